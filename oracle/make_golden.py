@@ -1,0 +1,231 @@
+"""Generate tests/golden/*.pt by EXECUTING THE REFERENCE'S OWN MODULES (authoring container only).
+
+TEST INFRASTRUCTURE ONLY.  Run:  python -m oracle.make_golden
+Requires /root/reference (read-only mount).  Each fixture stores the seeded
+inputs, the weights (state_dict of the reference module) and the reference's
+outputs, all fp32 CPU tensors.  The reference is imported unmodified via
+oracle/ref_loader.py; nothing from it is copied into this repository.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader                      # noqa: E402
+from oracle import tgsr_oracle as O                # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def randomize_bn(module, gen):
+    """Give every BatchNorm non-trivial eval statistics (SURVEY.md 8d cfg 2)."""
+    import torch.nn as nn
+    for m in module.modules():
+        if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=gen) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=gen) + 0.5)
+            m.weight.data.copy_(1 + 0.02 * torch.randn(m.weight.shape, generator=gen))
+            m.bias.data.copy_(0.05 * torch.randn(m.bias.shape, generator=gen))
+
+
+def clone_sd(m):
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def gen_attention(ns):
+    cases = []
+    g = torch.Generator().manual_seed(1001)
+    specs = [  # B, idf, cdf, ih, iw, T, mask kind
+        (1, 32, 256, 8, 8, 18, 'none'),
+        (4, 32, 256, 8, 8, 18, 'ragged'),
+        (3, 32, 256, 16, 8, 11, 'ragged'),
+        (2, 32, 256, 16, 16, 18, 'equal'),
+        (4, 64, 64, 8, 8, 32, 'ragged'),
+        (2, 128, 32, 4, 8, 48, 'ragged'),
+        (5, 32, 256, 6, 6, 7, 'ragged'),
+    ]
+    for (B, idf, cdf, ih, iw, T, mk) in specs:
+        att = ns.GlobalAttention.GlobalAttentionGeneral(idf, cdf)
+        att.conv_context.weight.data.copy_(torch.randn(idf, cdf, 1, 1, generator=g) * 0.1)
+        inp = torch.randn(B, idf, ih, iw, generator=g) * 0.5      # logits O(3): fp32 rounding stays < 1e-5 rel
+        ctx = torch.randn(B, cdf, T, generator=g) * 0.5
+        if mk == 'none':
+            mask = None
+        elif mk == 'equal':
+            mask = torch.zeros(B, T, dtype=torch.bool)
+        else:
+            lens = torch.randint(2, T + 1, (B,), generator=g)
+            lens[0] = T
+            mask = torch.arange(T)[None, :] >= lens[:, None]
+        att.applyMask(mask)
+        with torch.no_grad():
+            wctx, attn = att(inp, ctx)
+        cases.append(dict(inp=inp, ctx=ctx, w=att.conv_context.weight.data.clone(), mask=mask,
+                          wctx=wctx.clone(), attn=attn.clone()))
+    torch.save(cases, os.path.join(OUT, 'attention.pt'))
+
+
+def gen_func_attention(ns):
+    cases = []
+    g = torch.Generator().manual_seed(1002)
+    for (B, ndf, Tq, ih, iw, gamma) in [(2, 256, 18, 17, 17, 4.0), (3, 64, 7, 5, 6, 5.0)]:
+        q = torch.randn(B, ndf, Tq, generator=g) * 0.3
+        c = torch.randn(B, ndf, ih, iw, generator=g) * 0.3
+        w, a = ns.GlobalAttention.func_attention(q, c, gamma)
+        cases.append(dict(query=q, context=c, gamma1=gamma, wctx=w.clone(), attn=a.clone()))
+    torch.save(cases, os.path.join(OUT, 'func_attention.pt'))
+
+
+def gen_blocks(ns):
+    u = ns.util
+    g = torch.Generator().manual_seed(1003)
+    torch.manual_seed(1003)
+    out = {}
+    with torch.no_grad():
+        for name, mod, x in [
+            ('block3x3_3_32', u.Block3x3_relu(3, 32), torch.randn(2, 3, 16, 16, generator=g)),
+            ('block3x3_32_32', u.Block3x3_relu(32, 32), torch.randn(2, 32, 16, 8, generator=g)),
+            ('resblock_64', u.ResBlock(64), torch.randn(2, 64, 16, 16, generator=g)),
+            ('resblock_32', u.ResBlock(32), torch.randn(1, 32, 32, 32, generator=g)),
+            ('upblock_64_32', u.upBlock(64, 32), torch.randn(2, 64, 16, 8, generator=g)),
+            ('upblock_32_32', u.upBlock(32, 32), torch.randn(1, 32, 16, 16, generator=g)),
+            ('get_image', u.GET_IMAGE_G(32), torch.randn(2, 32, 16, 16, generator=g)),
+            ('get_image_noact', u.GET_IMAGE_G_noAct(32), torch.randn(2, 32, 16, 16, generator=g)),
+        ]:
+            randomize_bn(mod, g)
+            mod.eval()
+            out[name] = dict(sd=clone_sd(mod), x=x, y=mod(x).clone())
+        ca = u.CA_NET().eval()
+        s = torch.randn(3, 256, generator=g)
+        x = ca.relu(ca.fc(s))
+        out['ca_net'] = dict(sd=clone_sd(ca), x=s, mu=x[:, :100].clone(), logvar=x[:, 100:].clone())
+        ig = u.INIT_STAGE_G(32, 100)
+        randomize_bn(ig, g)
+        ig.eval()
+        z = torch.randn(2, 100, generator=g); c = torch.randn(2, 100, generator=g)
+        out['init_stage_g'] = dict(sd=clone_sd(ig), z=z, c=c, y=ig(z, c).clone())
+    torch.save(out, os.path.join(OUT, 'blocks.pt'))
+
+
+def gen_rnn(ns):
+    torch.manual_seed(100)                                     # test1.py:170
+    enc = ns.util.RNN_ENCODER(41, nhidden=256).eval()
+    caps_all = pickle.load(open(os.path.join(ref_loader.REF_ROOT, 'data/face/testset.pickle'), 'rb'))[0]
+    order = sorted(range(len(caps_all)), key=lambda i: -len(caps_all[i]))[:8]
+    lens = torch.tensor([len(caps_all[i]) for i in order])
+    caps = torch.zeros(len(order), 18, dtype=torch.int64)
+    for r, i in enumerate(order):
+        caps[r, :len(caps_all[i])] = torch.tensor(caps_all[i])
+    with torch.no_grad():
+        words, sent = enc(caps, lens, enc.init_hidden(len(order)))
+    torch.save(dict(sd=clone_sd(enc), captions=caps, cap_lens=lens, words=words.contiguous().clone(),
+                    sent=sent.clone()), os.path.join(OUT, 'rnn_encoder.pt'))
+
+
+def real_lr():
+    """data/face/000155.png -> Resize(288) -> CenterCrop(256) -> Resize(32) -> Normalize(.5,.5)
+    (datasets.py:1558-1563, :216)."""
+    from PIL import Image
+    from torchvision import transforms
+    img = Image.open(os.path.join(ref_loader.REF_ROOT, 'data/face/000155.png')).convert('RGB')
+    img = transforms.Compose([transforms.Resize(int(256 * 72 / 64)), transforms.CenterCrop(256)])(img)
+    lr = transforms.Resize([32, 32])(img)
+    norm = transforms.Compose([transforms.ToTensor(), transforms.Normalize((0.5,) * 3, (0.5,) * 3)])
+    return norm(lr)[None], norm(img)[None]
+
+
+def gen_face_x8(ns):
+    """Shipped Checkpoint/face_S8 weights, real LR image, real caption indices (B=1 and B=3 ragged)."""
+    ck = os.path.join(ref_loader.REF_ROOT, 'Checkpoint/face_S8')
+    sdL = torch.load(os.path.join(ck, 'netG_epoch_7.pth'), map_location='cpu', weights_only=False)
+    sdH = torch.load(os.path.join(ck, 'netGH_epoch_7.pth'), map_location='cpu', weights_only=False)
+    sdL = {k: v.float().clone() if v.is_floating_point() else v.clone() for k, v in sdL.items()}
+    sdH = {k: v.float().clone() if v.is_floating_point() else v.clone() for k, v in sdH.items()}
+    torch.save(dict(netG=sdL, netGH=sdH), os.path.join(OUT, 'face_S8_weights.pt'))
+
+    netGL = ns.model.G_SR_NET_low(); netGL.load_state_dict(sdL); netGL.eval()
+    with ref_loader.cuda_noop():
+        netGH = ns.model.NetG_highweight(weightmap=False, low='lr')
+    netGH.load_state_dict(sdH); netGH.eval()
+    rnn = torch.load(os.path.join(OUT, 'rnn_encoder.pt'))
+    torch.manual_seed(100)
+    enc = ns.util.RNN_ENCODER(41, nhidden=256).eval(); enc.load_state_dict(rnn['sd'])
+    lr1, hr1 = real_lr()
+    out = {}
+    for tag, idx in (('b1', [0]), ('b3', [0, 2, 5])):
+        caps = rnn['captions'][idx]; lens = rnn['cap_lens'][idx]
+        B = len(idx)
+        LR = lr1.repeat(B, 1, 1, 1).clone()
+        if B > 1:   # perturb the copies so images differ
+            g = torch.Generator().manual_seed(7)
+            LR = (LR + 0.05 * torch.randn(LR.shape, generator=g)).clamp(-1, 1)
+        with torch.no_grad():
+            words, sent = enc(caps, lens, enc.init_hidden(B))
+            mask = (caps == 0)[:, :words.size(2)]                 # trainer_objective.py:136-140
+            imgsL, atts, mu, logvar = netGL(LR, sent, words, mask)
+            fine, a, one = netGH(LR, imgsL, LR)
+        assert float(a) == 0.5 and float(one) == 1.0
+        if B == 1:     # full outputs; the 128^2 attention map is stored 4x-subsampled (size)
+            out[tag] = dict(LR=LR, captions=caps, cap_lens=lens, words=words.contiguous().clone(), sent=sent.clone(),
+                            mask=mask.clone(), imgsL=[t.clone() for t in imgsL],
+                            atts=[atts[0].clone(), atts[1].clone()], att2_sub4=atts[2][:, :, ::4, ::4].clone(),
+                            mu=mu.clone(), logvar=logvar.clone(), fine=[t.clone() for t in fine])
+        else:          # ragged batch (mask quirk through the whole net); small slices only
+            out[tag] = dict(LR=LR, captions=caps, cap_lens=lens, words=words.contiguous().clone(), sent=sent.clone(),
+                            mask=mask.clone(), imgL0=imgsL[0].clone(), att0=atts[0].clone(),
+                            att1_sub2=atts[1][:, :, ::2, ::2].clone(), fine0=fine[0].clone(),
+                            fine2_sub4=fine[2][:, :, ::4, ::4].clone(), mu=mu.clone(), logvar=logvar.clone())
+    out['hr'] = hr1
+    torch.save(out, os.path.join(OUT, 'face_x8.pt'))
+
+
+def gen_x16(ns):
+    """models16 (x16, weight-shared stages, tanh heads).  netGL is built with GF_DIM=8 to keep the
+    fixture small (it pins the WIRING of models16.py:5-39); NetG_high (models16.py:42-94) hard-codes
+    32 channels and is fed synthetic SRb pyramids."""
+    g = torch.Generator().manual_seed(1016)
+    torch.manual_seed(100)
+    ns.cfg.GAN.GF_DIM = 8
+    try:
+        netGL = ns.models16.G_SR_NET_low()
+    finally:
+        ns.cfg.GAN.GF_DIM = ref_loader.EVAL_CFG['GF_DIM']
+    randomize_bn(netGL, g); netGL.eval()
+    netGH = ns.models16.NetG_high(); randomize_bn(netGH, g); netGH.eval()
+    LR = O.synth_lr(2, 16, seed=116)
+    words = torch.randn(2, 256, 9, generator=g) * 0.2
+    sent = torch.randn(2, 256, generator=g) * 0.2
+    mask = torch.zeros(2, 9, dtype=torch.bool); mask[1, 6:] = True
+    LRh = O.synth_lr(1, 8, seed=117)
+    SRb = [O.synth_lr(1, 8 * 2 ** k, seed=118 + k) for k in range(1, 5)]
+    with torch.no_grad():
+        imgsL, atts, mu, logvar = netGL(LR, sent, words, mask)
+        fine = netGH(LRh, SRb, LRh, low=True)
+    torch.save(dict(sdL=netGL.state_dict(), sdH=netGH.state_dict(), LR=LR, words=words, sent=sent, mask=mask,
+                    imgsL=[t.clone() for t in imgsL[:3]], imgL3_sub2=imgsL[3][:, :, ::2, ::2].clone(),
+                    atts=[t.clone() for t in atts[:3]], att3_sub4=atts[3][:, :, ::4, ::4].clone(),
+                    LRh=LRh, SRb=SRb, fine=[t.clone() for t in fine]),
+               os.path.join(OUT, 'x16.pt'))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_loader.load()
+    gen_attention(ns)
+    gen_func_attention(ns)
+    gen_blocks(ns)
+    gen_rnn(ns)
+    gen_face_x8(ns)
+    gen_x16(ns)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,315 @@
+"""CPU oracle for the TGSR generator forward path (TEST INFRASTRUCTURE ONLY).
+
+A functional fp32 restatement of the reference's eval-mode arithmetic.  Every
+function takes an explicit ``state_dict`` (same keys as the reference modules)
+plus a key prefix, and cites the reference file:line it follows.  The
+arithmetic itself lives in PyTorch (the reference pins no version; this image
+has torch 2.11.0+cu128), so the restatement uses ``torch.nn.functional``
+primitives on CPU tensors in fp32 -- there are no nn.Module objects, no global
+``cfg`` and no hidden state here.
+
+Pinned against the reference's own modules by tests/golden/*.pt
+(see oracle/make_golden.py and tests/test_oracle_golden.py).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+BN_EPS = 1e-5  # nn.BatchNorm2d default, never overridden by the reference
+
+
+# --------------------------------------------------------------------------
+# Word-region attention
+# --------------------------------------------------------------------------
+def global_attention(inp: Tensor, context: Tensor, w_ctx: Tensor,
+                     mask: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """GlobalAttentionGeneral.forward -- GlobalAttention.py:87-130.
+
+    inp [B,idf,ih,iw], context [B,cdf,T], w_ctx [idf,cdf,1,1] (conv_context.weight),
+    mask bool [B,T] or None.  Returns (weightedContext [B,idf,ih,iw], attn [B,T,ih,iw]).
+
+    Mask quirk (GlobalAttention.py:109-112): the logits are laid out with row
+    ``r = b*Q + q`` but the mask is ``mask.repeat(Q, 1)`` whose row r is
+    ``mask[r % B]``.  Pixel q of image b is therefore masked with caption
+    ``(b*Q + q) % B``.  Restated here with explicit index arithmetic.
+    """
+    B, idf, ih, iw = inp.shape
+    Q = ih * iw
+    T = context.shape[2]
+    W = w_ctx.reshape(w_ctx.shape[0], w_ctx.shape[1])            # [idf, cdf]
+    source = torch.einsum('ic,bct->bit', W, context)             # :100-102  [B, idf, T]
+    target = inp.reshape(B, idf, Q)                              # :97
+    logits = torch.einsum('biq,bit->bqt', target, source)        # :107  [B, Q, T]
+    if mask is not None:
+        rows = torch.arange(B * Q, device=inp.device)            # r = b*Q + q
+        cap = rows % B                                           # :112 repeat(Q,1)
+        m = mask.to(torch.bool)[cap].reshape(B, Q, T)
+        logits = logits.masked_fill(m, float('-inf'))            # :113-116
+    attn = torch.softmax(logits, dim=2)                          # :118 (dim=1 of [B*Q,T])
+    attn_t = attn.transpose(1, 2).contiguous()                   # :122  [B, T, Q]
+    wctx = torch.einsum('bit,btq->biq', source, attn_t)          # :126
+    return wctx.reshape(B, idf, ih, iw), attn_t.reshape(B, T, ih, iw)
+
+
+def func_attention(query: Tensor, context: Tensor, gamma1: float) -> Tuple[Tensor, Tensor]:
+    """func_attention -- GlobalAttention.py:33-74 (DAMSM double softmax).
+
+    query [B,ndf,Tq], context [B,ndf,ih,iw] -> (weightedContext [B,ndf,Tq], attn [B,Tq,ih,iw]).
+    """
+    B, ndf, Tq = query.shape
+    ih, iw = context.shape[2], context.shape[3]
+    S = ih * iw
+    ctx = context.reshape(B, ndf, S)
+    a = torch.einsum('bds,bdt->bst', ctx, query)                 # :51  [B,S,Tq]
+    a = torch.softmax(a, dim=2)                                  # :54 over words
+    a = a.transpose(1, 2)                                        # :59  [B,Tq,S]
+    a = torch.softmax(a * gamma1, dim=2)                         # :62-63 over regions
+    wctx = torch.einsum('bds,bts->bdt', ctx, a)                  # :70
+    return wctx, a.reshape(B, Tq, ih, iw)
+
+
+# --------------------------------------------------------------------------
+# Generator building blocks
+# --------------------------------------------------------------------------
+def glu(x: Tensor) -> Tensor:
+    """GLU -- util.py:45-53."""
+    nc = x.shape[1]
+    assert nc % 2 == 0, 'channels dont divide 2!'
+    nc //= 2
+    return x[:, :nc] * torch.sigmoid(x[:, nc:])
+
+
+def _bn(sd: SD, p: str, x: Tensor) -> Tensor:
+    """nn.BatchNorm2d / BatchNorm1d in eval mode (running statistics)."""
+    return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'],
+                        sd[p + '.weight'], sd[p + '.bias'], False, 0.0, BN_EPS)
+
+
+def _conv(sd: SD, p: str, x: Tensor, pad: int) -> Tensor:
+    """conv3x3 / conv5x5, stride 1, no bias -- util.py:62-69."""
+    return F.conv2d(x, sd[p + '.weight'], None, 1, pad)
+
+
+def block3x3(sd: SD, p: str, x: Tensor) -> Tensor:
+    """conv3x3 -> BatchNorm2d -> GLU (Block3x3_relu / im2f / convin) -- util.py:102-107, :741-744."""
+    return glu(_bn(sd, p + '.1', _conv(sd, p + '.0', x, 1)))
+
+
+def res_block(sd: SD, p: str, x: Tensor) -> Tensor:
+    """ResBlock(batchnorm=True) -- util.py:110-130."""
+    y = glu(_bn(sd, p + '.block.1', _conv(sd, p + '.block.0', x, 1)))
+    y = _bn(sd, p + '.block.4', _conv(sd, p + '.block.3', y, 1))
+    return y + x
+
+
+def conv_bn_glu_conv_bn(sd: SD, p: str, x: Tensor) -> Tensor:
+    """residual24 / residual48: ResBlock body without the skip -- model.py:229-232."""
+    y = glu(_bn(sd, p + '.1', _conv(sd, p + '.0', x, 1)))
+    return _bn(sd, p + '.4', _conv(sd, p + '.3', y, 1))
+
+
+def up_block(sd: SD, p: str, x: Tensor) -> Tensor:
+    """upBlock: nearest x2 -> conv3x3 -> BN -> GLU -- util.py:74-80."""
+    x = F.interpolate(x, scale_factor=2, mode='nearest')
+    return glu(_bn(sd, p + '.2', _conv(sd, p + '.1', x, 1)))
+
+
+def get_image(sd: SD, p: str, h: Tensor, act: bool) -> Tensor:
+    """GET_IMAGE_G (tanh) util.py:894-905 / GET_IMAGE_G_noAct util.py:909-919."""
+    y = _conv(sd, p + '.img.0', h, 1)
+    return torch.tanh(y) if act else y
+
+
+def ca_net(sd: SD, p: str, sent: Tensor, c_dim: int, eps: Optional[Tensor] = None):
+    """CA_NET -- util.py:372-400.  ``eps`` replaces the reference's normal_() draw."""
+    x = glu(F.linear(sent, sd[p + '.fc.weight'], sd[p + '.fc.bias']))   # :384
+    mu, logvar = x[:, :c_dim], x[:, c_dim:]                               # :385-386
+    if eps is None:
+        eps = torch.zeros_like(mu)
+    c_code = eps * torch.exp(0.5 * logvar) + mu                           # :389-395
+    return c_code, mu, logvar
+
+
+def init_stage_gimgup(sd: SD, p: str, LR: Tensor, words: Tensor, mask, r_num: int):
+    """INIT_STAGE_GImgup.forward -- util.py:763-777."""
+    h = block3x3(sd, p + '.im2f', LR)                                     # :770
+    c, att = global_attention(h, words, sd[p + '.att.conv_context.weight'], mask)  # :772
+    x = torch.cat((h, c), 1)                                              # :773
+    for i in range(r_num):
+        x = res_block(sd, f'{p}.residual.{i}', x)                         # :774
+    return up_block(sd, p + '.upsample', x), att                          # :776
+
+
+def next_stage_g(sd: SD, p: str, h: Tensor, words: Tensor, mask, r_num: int):
+    """NEXT_STAGE_G.forward -- util.py:807-823."""
+    c, att = global_attention(h, words, sd[p + '.att.conv_context.weight'], mask)  # :816
+    x = torch.cat((h, c), 1)                                              # :817
+    for i in range(r_num):
+        x = res_block(sd, f'{p}.residual.{i}', x)                         # :818
+    return up_block(sd, p + '.upsample', x), att                          # :821
+
+
+def init_stage_g(sd: SD, p: str, z: Tensor, c: Tensor, ngf: int) -> Tensor:
+    """INIT_STAGE_G.forward (AttnGAN noise stage) -- util.py:404-443."""
+    x = torch.cat((c, z), 1)                                              # :430
+    x = F.linear(x, sd[p + '.fc.0.weight'])
+    x = glu(_bn(sd, p + '.fc.1', x))                                      # :432
+    x = x.reshape(-1, ngf, 4, 4)                                          # :433
+    for k in (1, 2, 3, 4):
+        x = up_block(sd, f'{p}.upsample{k}', x)                           # :435-441
+    return x
+
+
+# --------------------------------------------------------------------------
+# Whole nets
+# --------------------------------------------------------------------------
+def g_sr_net_low(sd: SD, LR: Tensor, sent: Tensor, words: Tensor, mask,
+                 variant: str = 'x8', r_num: int = 2, c_dim: int = 100,
+                 eps: Optional[Tensor] = None):
+    """G_SR_NET_low.forward -- model.py:48-78 (x8) / models16.py:16-39 (x16).
+
+    x16 shares one NEXT_STAGE_G for h_net2..4 and one GET_IMAGE_G (tanh) for all
+    heads (models16.py:13-14); in a state_dict the shared tensors appear under
+    every alias, so plain key lookups reproduce the sharing.
+    """
+    act = (variant == 'x16')
+    n_next = 3 if variant == 'x16' else 2
+    _, mu, logvar = ca_net(sd, 'ca_net', sent, c_dim, eps)               # c_code discarded, model.py:51
+    imgs: List[Tensor] = []
+    atts: List[Tensor] = []
+    feats: List[Tensor] = []
+    h, att = init_stage_gimgup(sd, 'h_net1', LR, words, mask, r_num)
+    imgs.append(get_image(sd, 'img_net1', h, act)); atts.append(att); feats.append(h)
+    for k in range(2, 2 + n_next):
+        h, att = next_stage_g(sd, f'h_net{k}', h, words, mask, r_num)
+        imgs.append(get_image(sd, f'img_net{k}', h, act)); atts.append(att); feats.append(h)
+    return imgs, atts, mu, logvar, feats
+
+
+def netg_high(sd: SD, LR: Tensor, SRb: Sequence[Tensor], LRb: Tensor, low: str = 'lr',
+              a: float = 0.5, one: float = 1.0, variant: str = 'x8',
+              x16_last: Tuple[str, str] = ('residual48', 'upscale8x')) -> List[Tensor]:
+    """NetG_highweight.forward(weightmap=False) -- model.py:264-298;
+    NetG_high.forward(cat=False) is the same graph with a=1 -- model.py:161-209.
+
+    ``a`` is the constant 0.5: ``nn.Parameter(...).cuda()`` (model.py:246-247)
+    is not a registered parameter.  low in {'lr','lrblur','lr-lrblur'} selects convin's input.
+    x16 (models16.py:145-179) reproduces the reference's reuse of residual48/upscale8x for
+    the last stage (x16_last default); its final add of SRb8 to a 256^2 tensor is a shape
+    error in the reference so the oracle adds SRb[3] there instead.
+    models16.NetG_high (models16.py:42-94) is x16_last=('residual816','upscale16x'), a=1.
+    """
+    if low == 'lrblur':
+        x = LRb
+    elif low == 'lr-lrblur':
+        x = LR - LRb
+    elif low == 'lr':
+        x = LR
+    else:
+        raise ValueError(low)
+    out = block3x3(sd, 'convin', x)                                       # :272
+    for i in range(6):
+        out = res_block(sd, f'residual.{i}', out)                         # :273
+    ims = []
+    out = up_block(sd, 'upscale2x', out)                                  # :275
+    ims.append(one * torch.tanh(_conv(sd, 'conv_output.0', out, 2)) + a * SRb[0])   # :280
+    out = up_block(sd, 'upscale4x', conv_bn_glu_conv_bn(sd, 'residual24', out))     # :283-284
+    ims.append(one * torch.tanh(_conv(sd, 'conv_output.0', out, 2)) + a * SRb[1])   # :288
+    out = up_block(sd, 'upscale8x', conv_bn_glu_conv_bn(sd, 'residual48', out))     # :291-292
+    ims.append(one * torch.tanh(_conv(sd, 'conv_output.0', out, 2)) + a * SRb[2])   # :297
+    if variant == 'x16':
+        out = up_block(sd, x16_last[1], conv_bn_glu_conv_bn(sd, x16_last[0], out))   # models16.py:172-173 / :89-90
+        ims.append(one * torch.tanh(_conv(sd, 'conv_output.0', out, 2)) + a * SRb[3])
+    return ims
+
+
+# --------------------------------------------------------------------------
+# Text encoder
+# --------------------------------------------------------------------------
+def _lstm_cell(x_proj: Tensor, h: Tensor, c: Tensor, w_hh: Tensor, H: int):
+    """One nn.LSTM step; gate order i,f,g,o (torch.nn.LSTM docs)."""
+    g = x_proj + h @ w_hh.t()
+    i = torch.sigmoid(g[0 * H:1 * H]); f = torch.sigmoid(g[1 * H:2 * H])
+    gg = torch.tanh(g[2 * H:3 * H]);   o = torch.sigmoid(g[3 * H:4 * H])
+    c = f * c + i * gg
+    h = o * torch.tanh(c)
+    return h, c
+
+
+def rnn_encoder(sd: SD, captions: Tensor, cap_lens: Tensor) -> Tuple[Tensor, Tensor]:
+    """RNN_ENCODER.forward (LSTM, 1 layer, bidirectional, eval) -- util.py:233-260.
+
+    captions int64 [B,Tcap]; cap_lens int64 [B] (sorted descending, datasets.py:75).
+    Packed-sequence semantics restated per caption: the forward direction runs
+    t=0..len-1, the reverse direction t=len-1..0, both from zero state
+    (init_hidden, util.py:222-231); outputs beyond len are zero and the output
+    width is max(cap_lens) (pad_packed_sequence, util.py:250).
+    Returns words_emb [B, 2H, Tmax], sent_emb [B, 2H].
+    """
+    emb_w = sd['encoder.weight']
+    H = sd['rnn.weight_hh_l0'].shape[1]
+    B = captions.shape[0]
+    lens = [int(v) for v in cap_lens.tolist()]
+    Tmax = max(lens)
+    words = torch.zeros(B, 2 * H, Tmax, dtype=torch.float32)
+    sent = torch.zeros(B, 2 * H, dtype=torch.float32)
+    for d, sfx in enumerate(('', '_reverse')):
+        w_ih = sd['rnn.weight_ih_l0' + sfx]; w_hh = sd['rnn.weight_hh_l0' + sfx]
+        bias = sd['rnn.bias_ih_l0' + sfx] + sd['rnn.bias_hh_l0' + sfx]
+        for b in range(B):
+            L = lens[b]
+            x = emb_w[captions[b, :L]]                       # :236 (dropout is identity in eval)
+            xp = x @ w_ih.t() + bias                         # [L, 4H]
+            h = torch.zeros(H); c = torch.zeros(H)
+            order = range(L) if d == 0 else range(L - 1, -1, -1)
+            for t in order:
+                h, c = _lstm_cell(xp[t], h, c, w_hh, H)
+                words[b, d * H:(d + 1) * H, t] = h           # :253 transpose(1,2)
+            sent[b, d * H:(d + 1) * H] = h                   # :256-259
+    return words, sent
+
+
+# --------------------------------------------------------------------------
+# Synthetic inputs and image metrics
+# --------------------------------------------------------------------------
+def synth_lr(batch: int, size: int, seed: int, kind: str = 'smooth') -> Tensor:
+    """'smooth': U(-1,1) at 4x4, bicubic to size, clamp; 'noise': iid U(-1,1)."""
+    g = torch.Generator().manual_seed(seed)
+    if kind == 'noise':
+        return torch.rand(batch, 3, size, size, generator=g) * 2 - 1
+    base = torch.rand(batch, 3, 4, 4, generator=g) * 2 - 1
+    return F.interpolate(base, size=(size, size), mode='bicubic', align_corners=False).clamp(-1, 1)
+
+
+def synth_captions(batch: int, ntoken: int, seed: int, words_num: int = 18, ragged: bool = False):
+    """iid tokens in [1,ntoken); lengths all words_num, or sorted-descending ragged 18..5."""
+    g = torch.Generator().manual_seed(seed)
+    caps = torch.randint(1, ntoken, (batch, words_num), generator=g)
+    if ragged:
+        lens = torch.randint(5, words_num + 1, (batch,), generator=g)
+        lens[0] = words_num
+        lens = torch.sort(lens, descending=True).values
+    else:
+        lens = torch.full((batch,), words_num, dtype=torch.int64)
+    for b in range(batch):
+        caps[b, int(lens[b]):] = 0
+    return caps, lens
+
+
+def to_uint8(img: Tensor) -> Tensor:
+    """trainer_objective.py:153-155 quantisation: round(clip((x+1)*127.5, 0, 255))."""
+    return torch.round(torch.clamp((img + 1.0) * 127.5, 0, 255)).to(torch.uint8)
+
+
+def psnr_u8(a: Tensor, b: Tensor) -> float:
+    """psnr -- trainer_objective.py:177-181 (on uint8 images)."""
+    diff = a.to(torch.float64) - b.to(torch.float64)
+    rmse = math.sqrt(float((diff ** 2).mean()))
+    return float('inf') if rmse == 0 else 20 * math.log10(255.0 / rmse)

@@ -1,0 +1,121 @@
+"""Pins the CPU oracle (oracle/tgsr_oracle.py) to outputs of the reference's own modules.
+
+The fixtures under tests/golden/ were produced by oracle/make_golden.py, which imports the
+unmodified reference from /root/reference.  CPU only; runs in seconds.
+"""
+import torch
+
+from oracle import tgsr_oracle as O
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
+
+
+def test_attention_cases(golden):
+    for c in golden('attention.pt'):
+        wctx, attn = O.global_attention(c['inp'], c['ctx'], c['w'], c['mask'])
+        close(attn, c['attn'], rtol=1e-5, atol=1e-7)
+        close(wctx, c['wctx'], rtol=1e-4, atol=5e-5)
+        # caption masking and the per-pixel argmax word index are bit-exact
+        assert torch.equal(attn == 0, c['attn'] == 0)
+        assert torch.equal(attn.argmax(1), c['attn'].argmax(1))
+
+
+def test_attention_mask_quirk(golden):
+    """GlobalAttention.py:109-112: pixel q of image b uses caption (b*Q+q) % B."""
+    c = golden('attention.pt')[1]
+    B, T, ih, iw = c['attn'].shape
+    Q = ih * iw
+    zero = (c['attn'] == 0).reshape(B, T, Q)
+    for b in range(B):
+        for q in (0, 1, 5, Q - 1):
+            assert torch.equal(zero[b, :, q], c['mask'][(b * Q + q) % B])
+
+
+def test_func_attention(golden):
+    for c in golden('func_attention.pt'):
+        w, a = O.func_attention(c['query'], c['context'], c['gamma1'])
+        close(w, c['wctx']); close(a, c['attn'], atol=1e-7)
+
+
+def test_blocks(golden):
+    g = golden('blocks.pt')
+    for name in ('block3x3_3_32', 'block3x3_32_32'):
+        sd = {'b.' + k: v for k, v in g[name]['sd'].items()}
+        close(O.block3x3(sd, 'b', g[name]['x']), g[name]['y'])
+    for name in ('resblock_64', 'resblock_32'):
+        sd = {'r.' + k: v for k, v in g[name]['sd'].items()}
+        close(O.res_block(sd, 'r', g[name]['x']), g[name]['y'], atol=1e-5)
+    for name in ('upblock_64_32', 'upblock_32_32'):
+        sd = {'u.' + k: v for k, v in g[name]['sd'].items()}
+        close(O.up_block(sd, 'u', g[name]['x']), g[name]['y'], atol=1e-5)
+    sd = {'h.' + k: v for k, v in g['get_image']['sd'].items()}
+    close(O.get_image(sd, 'h', g['get_image']['x'], True), g['get_image']['y'])
+    sd = {'h.' + k: v for k, v in g['get_image_noact']['sd'].items()}
+    close(O.get_image(sd, 'h', g['get_image_noact']['x'], False), g['get_image_noact']['y'])
+    sd = {'ca.' + k: v for k, v in g['ca_net']['sd'].items()}
+    _, mu, lv = O.ca_net(sd, 'ca', g['ca_net']['x'], 100)
+    close(mu, g['ca_net']['mu']); close(lv, g['ca_net']['logvar'])
+    sd = {'i.' + k: v for k, v in g['init_stage_g']['sd'].items()}
+    close(O.init_stage_g(sd, 'i', g['init_stage_g']['z'], g['init_stage_g']['c'], 32), g['init_stage_g']['y'],
+          atol=1e-5)
+
+
+def test_rnn_encoder(golden):
+    g = golden('rnn_encoder.pt')
+    words, sent = O.rnn_encoder(g['sd'], g['captions'], g['cap_lens'])
+    assert words.shape == g['words'].shape          # width = max(cap_lens), util.py:250
+    close(words, g['words'], atol=2e-6); close(sent, g['sent'], atol=2e-6)
+    # padded positions are exact zeros
+    for b, L in enumerate(g['cap_lens'].tolist()):
+        assert torch.count_nonzero(words[b, :, L:]) == 0
+
+
+def test_face_x8_checkpoint(golden):
+    w = golden('face_S8_weights.pt'); g = golden('face_x8.pt'); rnn = golden('rnn_encoder.pt')
+    c = g['b1']
+    words, sent = O.rnn_encoder(rnn['sd'], c['captions'], c['cap_lens'])
+    close(words, c['words'], atol=2e-6)
+    imgs, atts, mu, lv, _ = O.g_sr_net_low(w['netG'], c['LR'], c['sent'], c['words'], c['mask'])
+    for a, b in zip(imgs, c['imgsL']):
+        close(a, b, rtol=1e-4, atol=2e-5)
+    close(atts[0], c['atts'][0], atol=1e-6); close(atts[1], c['atts'][1], rtol=1e-4, atol=1e-6)
+    close(atts[2][:, :, ::4, ::4], c['att2_sub4'], rtol=1e-4, atol=1e-6)
+    close(mu, c['mu']); close(lv, c['logvar'])
+    fine = O.netg_high(w['netGH'], c['LR'], c['imgsL'], c['LR'], low='lr', a=0.5, one=1.0)
+    for a, b in zip(fine, c['fine']):
+        close(a, b, rtol=1e-4, atol=2e-5)
+    # ragged batch: exercises the mask quirk through the whole net
+    c = g['b3']
+    imgs, atts, mu, lv, _ = O.g_sr_net_low(w['netG'], c['LR'], c['sent'], c['words'], c['mask'])
+    close(imgs[0], c['imgL0'], rtol=1e-4, atol=2e-5); close(atts[0], c['att0'], atol=1e-6)
+    assert torch.equal(atts[0] == 0, c['att0'] == 0)
+    close(atts[1][:, :, ::2, ::2], c['att1_sub2'], rtol=1e-4, atol=1e-6)
+    fine = O.netg_high(w['netGH'], c['LR'], imgs, c['LR'], low='lr')
+    close(fine[0], c['fine0'], rtol=1e-4, atol=2e-5)
+    close(fine[2][:, :, ::4, ::4], c['fine2_sub4'], rtol=1e-4, atol=5e-5)
+
+
+def test_x16_wiring(golden):
+    g = golden('x16.pt')
+    imgs, atts, mu, lv, _ = O.g_sr_net_low(g['sdL'], g['LR'], g['sent'], g['words'], g['mask'], variant='x16')
+    assert len(imgs) == 4 and len(atts) == 4
+    for a, b in zip(imgs[:3], g['imgsL']):
+        close(a, b, rtol=1e-4, atol=2e-5)
+    close(imgs[3][:, :, ::2, ::2], g['imgL3_sub2'], rtol=1e-4, atol=2e-5)
+    for a, b in zip(atts[:3], g['atts']):
+        close(a, b, rtol=1e-4, atol=1e-6)
+    close(atts[3][:, :, ::4, ::4], g['att3_sub4'], rtol=1e-4, atol=1e-6)
+    fine = O.netg_high(g['sdH'], g['LRh'], g['SRb'], g['LRh'], low='lrblur', a=1.0, one=1.0, variant='x16',
+                       x16_last=('residual816', 'upscale16x'))
+    for a, b in zip(fine, g['fine']):
+        close(a, b, rtol=1e-4, atol=2e-5)
+
+
+def test_psnr_and_quantisation():
+    x = torch.tensor([[-1.0, 0.0, 1.0, 1.2]])
+    assert O.to_uint8(x).tolist() == [[0, 128, 255, 255]]       # round-half-even of 127.5 -> 128
+    a = torch.zeros(4, 4, dtype=torch.uint8); b = a.clone(); b[0, 0] = 16
+    import math
+    assert abs(O.psnr_u8(a, b) - 20 * math.log10(255.0 / 4.0)) < 1e-9
