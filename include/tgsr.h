@@ -1,0 +1,105 @@
+/*
+ * tgsr.h -- C ABI of libtgsr_sm100.so, the B200 (sm_100a) implementation of the TGSR
+ * text-conditioned SR generator forward path.
+ *
+ * The reference (cxm12/TGSR) has no FFI: the path sits behind plain torch.nn.Module classes
+ * (SURVEY.md section 8b).  Each entry point below replaces the arithmetic of the reference
+ * Python code cited next to it; the host-side mirror of the module API (tgsr_b200/*.py) binds
+ * these symbols with ctypes.  See INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer borrowed from the caller (torch tensors); the library
+ *     never allocates, frees or retains caller memory; workspaces are passed in;
+ *   - tensors are dense, row-major in the index order written in the comment;
+ *   - `stream` is a cudaStream_t (CUstream); work is enqueued, never synchronised;
+ *   - returns 0 (TGSR_OK) or a negative tgsr_status; never throws; launch errors are
+ *     captured with cudaGetLastError and returned as TGSR_ERR_CUDA (tgsr_last_cuda_error()).
+ *   - thread-safe with respect to distinct streams after tgsr_init(device).
+ */
+#ifndef TGSR_H_
+#define TGSR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* tgsr_stream_t; /* == cudaStream_t */
+
+typedef enum {
+  TGSR_OK = 0,
+  TGSR_ERR_BAD_SHAPE = -1,    /* a size is <= 0, misaligned or inconsistent                  */
+  TGSR_ERR_UNSUPPORTED = -2,  /* valid in the reference but outside this kernel's envelope   */
+  TGSR_ERR_CUDA = -3,         /* CUDA runtime/driver error, see tgsr_last_cuda_error()        */
+  TGSR_ERR_NULL = -4,         /* a required pointer is NULL                                  */
+  TGSR_ERR_NOT_INIT = -5      /* tgsr_init(device) has not been called for this device       */
+} tgsr_status;
+
+/* activation selectors for the conv entry points */
+enum { TGSR_ACT_NONE = 0, TGSR_ACT_GLU = 1, TGSR_ACT_TANH = 2 };
+
+int tgsr_version(void);
+const char* tgsr_error_string(int status);
+int tgsr_last_cuda_error(void); /* cudaError_t of the last TGSR_ERR_CUDA on this thread */
+/* One-time per device: kernel attributes (dynamic smem opt-in), TMA driver entry point, SM count. */
+int tgsr_init(int device);
+int tgsr_sm_count(void);
+
+/* ---- a1: GlobalAttentionGeneral.forward, GlobalAttention.py:87-130 (fp32 NCHW I/O) ---------
+ * input [B,idf,Q], context [B,cdf,T], w_ctx [idf,cdf] (conv_context.weight), mask uint8 [B,T] or
+ * NULL, wctx [B,idf,Q], attn [B,T,Q].  One fused kernel: word projection, logits, caption mask
+ * (reference row-order quirk: pixel q of image b uses caption (b*Q+q) % B), softmax over T,
+ * weighted sum.  idf <= 256, cdf <= 512 and cdf % 4 == 0, T <= 48. */
+int tgsr_attn_fwd_f32(const float* input, const float* context, const float* w_ctx,
+                      const uint8_t* mask, float* wctx, float* attn, int B, int idf, int cdf,
+                      int Q, int T, tgsr_stream_t stream);
+
+/* ---- a2: func_attention, GlobalAttention.py:33-74 (DAMSM double softmax), forward ----------
+ * query [B,ndf,Tq], context [B,ndf,S], wctx [B,ndf,Tq], attn [B,Tq,S].  Tq <= 48, S <= 1024. */
+int tgsr_func_attn_fwd_f32(const float* query, const float* context, float gamma1, float* wctx,
+                           float* attn, int B, int ndf, int Tq, int S, tgsr_stream_t stream);
+
+/* ---- a3/a4/a5/a8: conv (3x3 / 5x5, stride 1, same padding, no bias) with fused epilogue ----
+ * util.py:62-69 conv, nn.BatchNorm2d eval (folded to scale/shift), util.py:45-53 GLU,
+ * util.py:126-130 residual add, util.py:76 nearest x2 upsample of the INPUT, tanh image heads
+ * (util.py:899-901, model.py:224) and model.py:280 `one*y + a*SRb`.  fp32 NCHW.
+ *   x [B,Cin,H,W]; if up2x the convolution runs on the nearest-upsampled 2H x 2W image.
+ *   w [Cout,Cin,k,k]; scale/shift [Cout] or NULL (identity).
+ *   z = conv*scale + shift; act GLU: o[c] = z[c]*sigmoid(z[c+Cout/2]) (Cout/2 channels out);
+ *   act TANH: o = tanh(z).  Then o += residual (same shape as o, or NULL);
+ *   then o = out_scale*o + addend_scale*addend (addend same shape as o, or NULL).
+ *   y [B, Cout or Cout/2, Ho, Wo]. */
+int tgsr_conv2d_f32(const float* x, const float* w, const float* scale, const float* shift,
+                    const float* residual, const float* addend, float out_scale,
+                    float addend_scale, float* y, int B, int Cin, int H, int W, int Cout,
+                    int ksize, int up2x, int act, tgsr_stream_t stream);
+
+/* BatchNorm eval fold: scale = gamma/sqrt(var+eps), shift = beta - mean*scale (fp32, [C]). */
+int tgsr_bn_fold_f32(const float* gamma, const float* beta, const float* mean, const float* var,
+                     float eps, float* scale, float* shift, int C, tgsr_stream_t stream);
+
+/* ---- a12/a13: Linear (+bias) (+BatchNorm1d fold) + GLU, util.py:379-386 and :417-420 -------
+ * x [B,K], w [N,K], bias/scale/shift [N] or NULL; y [B,N/2] = GLU((x w^T + bias)*scale+shift). */
+int tgsr_linear_glu_f32(const float* x, const float* w, const float* bias, const float* scale,
+                        const float* shift, float* y, int B, int K, int N, tgsr_stream_t stream);
+/* CA_NET.reparametrize util.py:388-395: c = eps*exp(0.5*logvar)+mu; mulogvar [B,2*c_dim]. */
+int tgsr_ca_reparam_f32(const float* mulogvar, const float* eps, float* c_code, int B, int c_dim,
+                        tgsr_stream_t stream);
+
+/* ---- a11: RNN_ENCODER.forward, util.py:233-260 (Embedding -> 1-layer bi-LSTM, eval) --------
+ * captions int64 [B,Tcap]; cap_lens int64 [B] (device; any order); emb [ntoken,ninput];
+ * w_ih [2][4H,ninput], w_hh [2][4H,H], b_ih/b_hh [2][4H] (dir 0 = forward, 1 = reverse; gate
+ * order i,f,g,o).  xproj_ws: workspace of B*Tcap*2*4H floats.  words [B,2H,Tmax] (zero beyond
+ * each caption's length), sent [B,2H].  No host sync.  H <= 128. */
+int tgsr_lstm_bidir_fwd_f32(const int64_t* captions, const int64_t* cap_lens, const float* emb,
+                            const float* w_ih, const float* w_hh, const float* b_ih,
+                            const float* b_hh, float* xproj_ws, float* words, float* sent, int B,
+                            int Tcap, int Tmax, int ntoken, int ninput, int H,
+                            tgsr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGSR_H_ */

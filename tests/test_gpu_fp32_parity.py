@@ -1,0 +1,198 @@
+"""GPU parity of the fp32 CUDA path against the CPU oracle and the committed golden fixtures.
+Everything goes through the C ABI (tgsr_b200 modules -> ctypes -> libtgsr_sm100.so)."""
+import pytest
+import torch
+
+import tgsr_b200
+from oracle import tgsr_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    torch.testing.assert_close(a.detach().cpu(), b, rtol=rtol, atol=atol)
+
+
+@pytest.fixture(autouse=True)
+def _cfg():
+    tgsr_b200.set_eval_defaults()
+    tgsr_b200.set_precision('fp32')
+    yield
+
+
+def test_attention_golden(golden):
+    for c in golden('attention.pt'):
+        idf, cdf = c['w'].shape[0], c['w'].shape[1]
+        att = tgsr_b200.GlobalAttentionGeneral(idf, cdf).to(DEV)
+        att.conv_context.weight.data.copy_(c['w'])
+        att.applyMask(None if c['mask'] is None else c['mask'].to(DEV))
+        wctx, attn = att(c['inp'].to(DEV), c['ctx'].to(DEV))
+        close(attn, c['attn'], rtol=1e-5, atol=1e-7)          # north_star: 1e-5 relative on fp32 maps
+        close(wctx, c['wctx'], rtol=1e-4, atol=5e-5)
+        assert torch.equal(attn.cpu() == 0, c['attn'] == 0)   # caption masking bit-exact
+        assert torch.equal(attn.cpu().argmax(1), c['attn'].argmax(1))
+
+
+@pytest.mark.parametrize('B,idf,cdf,ih,iw,T,ragged', [
+    (1, 32, 256, 32, 32, 18, False), (4, 32, 256, 64, 64, 18, True), (3, 32, 256, 17, 13, 18, True),
+    (2, 64, 64, 32, 32, 32, True), (2, 128, 128, 16, 16, 48, True), (2, 256, 256, 8, 8, 18, False),
+    (7, 32, 256, 16, 16, 5, True), (2, 32, 32, 9, 7, 33, True)])
+def test_attention_vs_oracle(B, idf, cdf, ih, iw, T, ragged):
+    g = torch.Generator().manual_seed(B * 1000 + idf + T)
+    inp = torch.randn(B, idf, ih, iw, generator=g) * 0.5
+    ctx = torch.randn(B, cdf, T, generator=g) * 0.5
+    w = torch.randn(idf, cdf, 1, 1, generator=g) * (1.6 / cdf ** 0.5) * (32 / idf) ** 0.5
+    mask = None
+    if ragged:
+        lens = torch.randint(1, T + 1, (B,), generator=g); lens[0] = T
+        mask = torch.arange(T)[None] >= lens[:, None]
+    ref_w, ref_a = O.global_attention(inp, ctx, w, mask)
+    att = tgsr_b200.GlobalAttentionGeneral(idf, cdf).to(DEV)
+    att.conv_context.weight.data.copy_(w)
+    att.applyMask(None if mask is None else mask.to(DEV))
+    wctx, attn = att(inp.to(DEV), ctx.to(DEV))
+    close(attn, ref_a, rtol=1e-5, atol=1e-7)
+    close(wctx, ref_w, rtol=1e-4, atol=5e-5)
+    assert torch.equal(attn.cpu() == 0, ref_a == 0)
+    # argmax: exclude near-ties (top-2 margin below fp32 noise) by construction
+    top2 = ref_a.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-5
+    assert torch.equal(attn.cpu().argmax(1)[safe], ref_a.argmax(1)[safe])
+    close(attn.sum(1), torch.ones(B, ih, iw), rtol=0, atol=1e-5)          # rows sum to one
+
+
+def test_attention_errors():
+    att = tgsr_b200.GlobalAttentionGeneral(32, 256).to(DEV)
+    with pytest.raises(RuntimeError, match='unsupported'):
+        att(torch.zeros(1, 32, 4, 4, device=DEV), torch.zeros(1, 256, 49, device=DEV))
+    with pytest.raises(ValueError):
+        att(torch.zeros(2, 32, 4, 4, device=DEV), torch.zeros(1, 256, 5, device=DEV))
+
+
+def test_func_attention(golden):
+    for c in golden('func_attention.pt'):
+        w, a = tgsr_b200.func_attention(c['query'].to(DEV), c['context'].to(DEV), c['gamma1'])
+        close(w, c['wctx'], rtol=1e-4, atol=1e-5); close(a, c['attn'], rtol=1e-4, atol=1e-7)
+
+
+def test_blocks_golden(golden):
+    from tgsr_b200 import blocks
+    g = golden('blocks.pt')
+    mk = {'block3x3_3_32': lambda: blocks.Block3x3_relu(3, 32), 'block3x3_32_32': lambda: blocks.Block3x3_relu(32, 32),
+          'resblock_64': lambda: blocks.ResBlock(64), 'resblock_32': lambda: blocks.ResBlock(32),
+          'upblock_64_32': lambda: blocks.upBlock(64, 32), 'upblock_32_32': lambda: blocks.upBlock(32, 32),
+          'get_image': lambda: blocks.GET_IMAGE_G(32), 'get_image_noact': lambda: blocks.GET_IMAGE_G_noAct(32)}
+    for name, ctor in mk.items():
+        m = ctor(); m.load_state_dict(g[name]['sd'], strict=True); m.to(DEV).eval()
+        close(m(g[name]['x'].to(DEV)), g[name]['y'], rtol=1e-4, atol=2e-5)
+    ca = blocks.CA_NET(); ca.load_state_dict(g['ca_net']['sd'], strict=True); ca.to(DEV).eval()
+    c, mu, lv = ca(g['ca_net']['x'].to(DEV))
+    close(mu, g['ca_net']['mu'], rtol=1e-4, atol=1e-6); close(lv, g['ca_net']['logvar'], rtol=1e-4, atol=1e-6)
+    assert c.shape == mu.shape and torch.isfinite(c).all()
+    ig = blocks.INIT_STAGE_G(32, 100); ig.load_state_dict(g['init_stage_g']['sd'], strict=True); ig.to(DEV).eval()
+    close(ig(g['init_stage_g']['z'].to(DEV), g['init_stage_g']['c'].to(DEV)), g['init_stage_g']['y'], rtol=1e-4,
+          atol=2e-5)
+
+
+def test_train_mode_bn_raises():
+    from tgsr_b200 import blocks
+    m = blocks.ResBlock(32).to(DEV)          # training mode by default
+    with pytest.raises(RuntimeError, match='eval'):
+        m(torch.zeros(1, 32, 8, 8, device=DEV))
+
+
+def test_rnn_encoder_golden(golden):
+    from tgsr_b200.text_encoder import RNN_ENCODER
+    g = golden('rnn_encoder.pt')
+    enc = RNN_ENCODER(41, nhidden=256); enc.load_state_dict(g['sd'], strict=True); enc.to(DEV).eval()
+    B = g['captions'].shape[0]
+    words, sent = enc(g['captions'].to(DEV), g['cap_lens'].to(DEV), enc.init_hidden(B))
+    assert words.shape == g['words'].shape
+    close(words, g['words'], rtol=1e-4, atol=5e-6); close(sent, g['sent'], rtol=1e-4, atol=5e-6)
+    for b, L in enumerate(g['cap_lens'].tolist()):
+        assert torch.count_nonzero(words[b, :, L:]) == 0
+    # unsorted lengths and a CPU length list are handled too (no pack_padded_sequence constraint)
+    perm = torch.tensor([3, 0, 7, 1, 2, 6, 5, 4])
+    w2, s2 = enc(g['captions'][perm].to(DEV), g['cap_lens'][perm].tolist(), enc.init_hidden(B))
+    close(w2, g['words'][perm], rtol=1e-4, atol=5e-6); close(s2, g['sent'][perm], rtol=1e-4, atol=5e-6)
+
+
+def test_rnn_encoder_vs_oracle_big_vocab():
+    from tgsr_b200.text_encoder import RNN_ENCODER
+    torch.manual_seed(5)
+    enc = RNN_ENCODER(5450, nhidden=256).eval()
+    caps, lens = O.synth_captions(19, 5450, seed=3, ragged=True)
+    rw, rs = O.rnn_encoder(enc.state_dict(), caps, lens)
+    enc.to(DEV)
+    w, s = enc(caps.to(DEV), lens.to(DEV), enc.init_hidden(19))
+    close(w, rw, rtol=1e-4, atol=5e-6); close(s, rs, rtol=1e-4, atol=5e-6)
+
+
+def _face_nets(golden):
+    from tgsr_b200 import nets
+    w = golden('face_S8_weights.pt')
+    gl = nets.G_SR_NET_low(); gl.load_state_dict(w['netG'], strict=True); gl.to(DEV).eval()
+    gh = nets.NetG_highweight(weightmap=False, low='lr'); gh.load_state_dict(w['netGH'], strict=True); gh.to(DEV).eval()
+    return gl, gh
+
+
+def test_face_x8_checkpoint_fp32(golden):
+    """Shipped checkpoint + real image fixture, whole eval path (trainer_objective.py:134-146)."""
+    gl, gh = _face_nets(golden)
+    g = golden('face_x8.pt')
+    c = g['b1']
+    imgs, atts, mu, lv = gl(c['LR'].to(DEV), c['sent'].to(DEV), c['words'].to(DEV), c['mask'].to(DEV))
+    for a, b in zip(imgs, c['imgsL']):
+        close(a, b, rtol=1e-3, atol=1e-4)
+    close(atts[0], c['atts'][0], rtol=1e-4, atol=1e-6); close(atts[1], c['atts'][1], rtol=1e-3, atol=1e-6)
+    close(atts[2][:, :, ::4, ::4], c['att2_sub4'], rtol=1e-3, atol=1e-6)
+    close(mu, c['mu'], rtol=1e-4, atol=1e-6)
+    fine, a, one = gh(c['LR'].to(DEV), imgs, c['LR'].to(DEV))
+    assert float(a) == 0.5 and float(one) == 1.0
+    for x, y in zip(fine, c['fine']):
+        close(x, y, rtol=1e-3, atol=1e-4)
+    sr, ref = O.to_uint8(fine[-1].cpu()), O.to_uint8(c['fine'][-1])
+    assert (sr.int() - ref.int()).abs().max() <= 1
+    c = g['b3']                                                   # ragged batch -> mask quirk
+    imgs, atts, mu, lv = gl(c['LR'].to(DEV), c['sent'].to(DEV), c['words'].to(DEV), c['mask'].to(DEV))
+    close(imgs[0], c['imgL0'], rtol=1e-3, atol=1e-4); close(atts[0], c['att0'], rtol=1e-4, atol=1e-6)
+    assert torch.equal(atts[0].cpu() == 0, c['att0'] == 0)
+    fine, _, _ = gh(c['LR'].to(DEV), imgs, c['LR'].to(DEV))
+    close(fine[2][:, :, ::4, ::4], c['fine2_sub4'], rtol=1e-3, atol=2e-4)
+
+
+def test_x16_nets_fp32(golden):
+    from tgsr_b200 import nets16
+    g = golden('x16.pt')
+    tgsr_b200.cfg.GAN.GF_DIM = 8
+    try:
+        gl = nets16.G_SR_NET_low()
+    finally:
+        tgsr_b200.cfg.GAN.GF_DIM = 32
+    gl.load_state_dict(g['sdL'], strict=True); gl.to(DEV).eval()
+    imgs, atts, mu, lv = gl(g['LR'].to(DEV), g['sent'].to(DEV), g['words'].to(DEV), g['mask'].to(DEV))
+    assert len(imgs) == 4
+    for a, b in zip(imgs[:3], g['imgsL']):
+        close(a, b, rtol=1e-3, atol=1e-4)
+    for a, b in zip(atts[:3], g['atts']):
+        close(a, b, rtol=1e-3, atol=1e-6)
+    gh = nets16.NetG_high(); gh.load_state_dict(g['sdH'], strict=True); gh.to(DEV).eval()
+    fine = gh(g['LRh'].to(DEV), [t.to(DEV) for t in g['SRb']], g['LRh'].to(DEV), low=True)
+    for a, b in zip(fine, g['fine']):
+        close(a, b, rtol=1e-3, atol=1e-4)
+
+
+def test_conv_properties_full_size():
+    """Size-independent checks at the production size (256^2 output): linearity of the conv
+    path and equivalence of the fused upsample with an explicit nearest upsample."""
+    from tgsr_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x1 = torch.randn(2, 64, 128, 128, generator=g).to(DEV); x2 = torch.randn(2, 64, 128, 128, generator=g).to(DEV)
+    w = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).to(DEV)
+    y1 = ops.conv2d_fused(x1, w, None, None, 0, up2x=True); y2 = ops.conv2d_fused(x2, w, None, None, 0, up2x=True)
+    y12 = ops.conv2d_fused(x1 + x2, w, None, None, 0, up2x=True)
+    assert y12.shape == (2, 64, 256, 256)
+    torch.testing.assert_close(y12, y1 + y2, rtol=1e-4, atol=1e-4)
+    xu = x1.repeat_interleave(2, 2).repeat_interleave(2, 3).contiguous()
+    torch.testing.assert_close(ops.conv2d_fused(xu, w, None, None, 0), y1, rtol=0, atol=0)

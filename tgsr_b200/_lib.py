@@ -1,0 +1,95 @@
+"""ctypes binding of libtgsr_sm100.so (the C ABI in include/tgsr.h).
+
+The library is mandatory: importing a kernel entry point without the built .so, or on a host
+without a CUDA device, raises -- there is no CPU or PyTorch fallback for the arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libtgsr_sm100.so')
+
+ACT_NONE, ACT_GLU, ACT_TANH = 0, 1, 2
+
+_lib = None
+_lock = threading.Lock()
+_inited_devices = set()
+
+c_f32p = C.c_void_p
+_SIGS = {
+    'tgsr_version': ([], C.c_int),
+    'tgsr_error_string': ([C.c_int], C.c_char_p),
+    'tgsr_last_cuda_error': ([], C.c_int),
+    'tgsr_init': ([C.c_int], C.c_int),
+    'tgsr_sm_count': ([], C.c_int),
+    'tgsr_attn_fwd_f32': ([C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p], C.c_int),
+    'tgsr_func_attn_fwd_f32': ([C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p], C.c_int),
+    'tgsr_conv2d_f32': ([C.c_void_p] * 6 + [C.c_float, C.c_float, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p], C.c_int),
+    'tgsr_bn_fold_f32': ([C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p], C.c_int),
+    'tgsr_linear_glu_f32': ([C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p], C.c_int),
+    'tgsr_ca_reparam_f32': ([C.c_void_p] * 3 + [C.c_int] * 2 + [C.c_void_p], C.c_int),
+    'tgsr_lstm_bidir_fwd_f32': ([C.c_void_p] * 10 + [C.c_int] * 6 + [C.c_void_p], C.c_int),
+}
+
+
+def load() -> C.CDLL:
+    """dlopen the library (no GPU needed) and attach signatures."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise RuntimeError(
+                    'tgsr_b200: %s is missing -- build it with `python -m tgsr_b200.build` '
+                    '(there is no fallback path)' % LIB_PATH)
+            lib = C.CDLL(LIB_PATH)
+            for name, (argtypes, restype) in _SIGS.items():
+                fn = getattr(lib, name)          # AttributeError if the .so does not export it
+                fn.argtypes = argtypes
+                fn.restype = restype
+            _lib = lib
+    return _lib
+
+
+def declared_symbols():
+    return sorted(_SIGS)
+
+
+def _ensure_device(dev: torch.device) -> C.CDLL:
+    lib = load()
+    if dev.type != 'cuda':
+        raise RuntimeError('tgsr_b200 kernels need CUDA tensors (got %s); there is no CPU path' % dev)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _inited_devices:
+        with torch.cuda.device(idx):
+            check(lib.tgsr_init(idx), 'tgsr_init')
+        _inited_devices.add(idx)
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        lib = load()
+        msg = lib.tgsr_error_string(status).decode()
+        extra = ''
+        if status == -3:
+            extra = ' (cudaError %d)' % lib.tgsr_last_cuda_error()
+        raise RuntimeError('tgsr_b200: %s failed: %s%s' % (what, msg, extra))
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name: str, dev: torch.device, *args) -> None:
+    lib = _ensure_device(dev)
+    with torch.cuda.device(dev):
+        check(getattr(lib, name)(*args, stream_ptr()), name)

@@ -1,0 +1,267 @@
+"""Generator building blocks with the reference's constructors, forward signatures and
+state-dict keys (util.py).  torch.nn leaf modules (Conv2d, BatchNorm2d, Linear, ...) are used
+ONLY as parameter holders so that ``state_dict()`` / ``load_state_dict()`` match the shipped
+checkpoints key for key; their own forward() is never called -- every block's forward launches
+the fused sm_100a kernels through the C ABI.
+
+Eval-mode BatchNorm is folded to (scale, shift) once per weight version and cached outside the
+state dict.  Training-mode BatchNorm (batch statistics) is not implemented on this path.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .attention import GlobalAttentionGeneral as ATT_NET
+from .attention import conv1x1  # noqa: F401  (re-export, util.py:56)
+from .config import cfg
+from ._lib import ACT_GLU, ACT_NONE, ACT_TANH
+
+
+# ---------------------------------------------------------------- derived-parameter cache
+def _folded_bn(bn: Optional[nn.Module]):
+    """(scale, shift) for an eval-mode BatchNorm, cached on the module (not a buffer)."""
+    if bn is None:
+        return None, None
+    if bn.training:
+        raise RuntimeError('tgsr_b200: training-mode BatchNorm is not implemented on the CUDA path; call .eval()')
+    src = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple((t.data_ptr(), t._version, str(t.device)) for t in src)
+    cached = bn.__dict__.get('_tgsr_fold')
+    if cached is None or cached[0] != key:
+        scale, shift = ops.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
+        cached = (key, scale, shift)
+        bn.__dict__['_tgsr_fold'] = cached
+    return cached[1], cached[2]
+
+
+def _conv(x, conv: nn.Conv2d, bn, act, **kw):
+    scale, shift = _folded_bn(bn)
+    return ops.conv2d_fused(x, conv.weight.detach(), scale, shift, act, **kw)
+
+
+# ---------------------------------------------------------------- leaf helpers (util.py:45-69)
+class GLU(nn.Module):
+    """util.py:45-53.  Inside the blocks below GLU is fused into the conv epilogue; this
+    standalone module exists for constructor/state-dict parity."""
+
+    def forward(self, x):
+        nc = x.size(1)
+        assert nc % 2 == 0, 'channels dont divide 2!'
+        raise NotImplementedError('tgsr_b200: GLU only exists fused into conv/linear kernels')
+
+
+def conv3x3(in_planes, out_planes):
+    return nn.Conv2d(in_planes, out_planes, kernel_size=3, stride=1, padding=1, bias=False)
+
+
+def conv5x5(in_planes, out_planes):
+    return nn.Conv2d(in_planes, out_planes, kernel_size=5, stride=1, padding=2, bias=False)
+
+
+class _ConvBnGlu(nn.Sequential):
+    """[conv3x3, (BatchNorm2d), GLU] -> one kernel (Block3x3_relu, util.py:102-107)."""
+
+    def forward(self, x):
+        mods = list(self)
+        bn = mods[1] if isinstance(mods[1], nn.BatchNorm2d) else None
+        return _conv(x, mods[0], bn, ACT_GLU)
+
+
+class _UpBlock(nn.Sequential):
+    """[Upsample(nearest,2), conv3x3, (BatchNorm2d), GLU] -> one kernel; the upsample is folded
+    into the conv's input indexing (upBlock, util.py:74-80; upBlocknoBN :83-88)."""
+
+    def forward(self, x):
+        mods = list(self)
+        bn = mods[2] if isinstance(mods[2], nn.BatchNorm2d) else None
+        return _conv(x, mods[1], bn, ACT_GLU, up2x=True)
+
+
+class _ConvBnGluConvBn(nn.Sequential):
+    """[conv3x3, BN, GLU, conv3x3, BN] without skip (residual24/48, model.py:229-232)."""
+
+    def forward(self, x, residual=None):
+        mods = list(self)
+        if isinstance(mods[1], nn.BatchNorm2d):
+            y = _conv(x, mods[0], mods[1], ACT_GLU)
+            return _conv(y, mods[3], mods[4], ACT_NONE, residual=residual)
+        y = _conv(x, mods[0], None, ACT_GLU)
+        return _conv(y, mods[2], None, ACT_NONE, residual=residual)
+
+
+class _ImageHead(nn.Sequential):
+    """[conv, (Tanh)] image head.  ``forward(h, addend, a, one)`` fuses ``one*y + a*addend``."""
+
+    def forward(self, h, addend=None, a: float = 0.0, one: float = 1.0):
+        act = ACT_TANH if any(isinstance(m, nn.Tanh) for m in self) else ACT_NONE
+        return _conv(h, self[0], None, act, addend=addend, out_scale=one, addend_scale=a)
+
+
+def upBlock(in_planes, out_planes):
+    return _UpBlock(nn.Upsample(scale_factor=2, mode='nearest'), conv3x3(in_planes, out_planes * 2),
+                    nn.BatchNorm2d(out_planes * 2), GLU())
+
+
+def upBlocknoBN(in_planes, out_planes):
+    return _UpBlock(nn.Upsample(scale_factor=2, mode='nearest'), conv3x3(in_planes, out_planes * 2), GLU())
+
+
+def Block3x3_relu(in_planes, out_planes):
+    return _ConvBnGlu(conv3x3(in_planes, out_planes * 2), nn.BatchNorm2d(out_planes * 2), GLU())
+
+
+class ResBlock(nn.Module):
+    """util.py:110-130: x + BN(conv(GLU(BN(conv(x))))) as two fused kernels."""
+
+    def __init__(self, channel_num, batchnorm=True):
+        super().__init__()
+        if batchnorm:
+            self.block = _ConvBnGluConvBn(conv3x3(channel_num, channel_num * 2), nn.BatchNorm2d(channel_num * 2),
+                                          GLU(), conv3x3(channel_num, channel_num), nn.BatchNorm2d(channel_num))
+        else:
+            self.block = _ConvBnGluConvBn(conv3x3(channel_num, channel_num * 2), GLU(),
+                                          conv3x3(channel_num, channel_num))
+
+    def forward(self, x):
+        return self.block(x, residual=x)
+
+
+# ---------------------------------------------------------------- CA_NET (util.py:372-400)
+class CA_NET(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.t_dim = cfg.TEXT.EMBEDDING_DIM
+        self.c_dim = cfg.GAN.CONDITION_DIM
+        self.fc = nn.Linear(self.t_dim, self.c_dim * 4, bias=True)
+        self.relu = GLU()
+
+    def _mulogvar(self, text_embedding):
+        return ops.linear_glu(text_embedding, self.fc.weight.detach(), self.fc.bias.detach())
+
+    def encode(self, text_embedding):
+        x = self._mulogvar(text_embedding)
+        return x[:, :self.c_dim], x[:, self.c_dim:]
+
+    def reparametrize(self, mu, logvar):
+        eps = torch.randn(mu.shape, device=mu.device, dtype=torch.float32)     # util.py:390-393 normal_()
+        return ops.ca_reparam(torch.cat((mu, logvar), 1).contiguous(), eps)
+
+    def forward(self, text_embedding):
+        x = self._mulogvar(text_embedding)
+        eps = torch.randn((x.shape[0], self.c_dim), device=x.device, dtype=torch.float32)
+        c_code = ops.ca_reparam(x, eps)
+        return c_code, x[:, :self.c_dim], x[:, self.c_dim:]
+
+
+# ---------------------------------------------------------------- generator stages
+class _FcBnGlu(nn.Sequential):
+    """[Linear(no bias), BatchNorm1d, GLU] (INIT_STAGE_G.fc, util.py:417-420)."""
+
+    def forward(self, x):
+        scale, shift = _folded_bn(self[1])
+        return ops.linear_glu(x, self[0].weight.detach(), None, scale, shift)
+
+
+class INIT_STAGE_G(nn.Module):
+    """AttnGAN noise stage, util.py:404-443 (not reached by the shipped SR flows)."""
+
+    def __init__(self, ngf, ncf):
+        super().__init__()
+        self.gf_dim = ngf
+        self.in_dim = cfg.GAN.Z_DIM + ncf
+        self.define_module()
+
+    def define_module(self):
+        nz, ngf = self.in_dim, self.gf_dim
+        self.fc = _FcBnGlu(nn.Linear(nz, ngf * 4 * 4 * 2, bias=False), nn.BatchNorm1d(ngf * 4 * 4 * 2), GLU())
+        self.upsample1 = upBlock(ngf, ngf // 2)
+        self.upsample2 = upBlock(ngf // 2, ngf // 4)
+        self.upsample3 = upBlock(ngf // 4, ngf // 8)
+        self.upsample4 = upBlock(ngf // 8, ngf // 16)
+
+    def forward(self, z_code, c_code):
+        c_z_code = torch.cat((c_code, z_code), 1)
+        out_code = self.fc(c_z_code).view(-1, self.gf_dim, 4, 4)
+        out_code = self.upsample1(out_code)
+        out_code = self.upsample2(out_code)
+        out_code32 = self.upsample3(out_code)
+        return self.upsample4(out_code32)
+
+
+def _run_stage(stage, h_code, word_embs, mask):
+    """Shared body of INIT_STAGE_GImgup / NEXT_STAGE_G (util.py:769-776, :814-821)."""
+    stage.att.applyMask(mask)
+    c_code, att = stage.att(h_code, word_embs)
+    h_c_code = torch.cat((h_code, c_code), 1)
+    out_code = stage.residual(h_c_code)
+    return stage.upsample(out_code), att
+
+
+class INIT_STAGE_GImgup(nn.Module):
+    """util.py:726-777: image -> features, word attention, residual blocks, x2 upsample."""
+
+    def __init__(self, ngf, ncf, nef, batchnorm=True):
+        super().__init__()
+        self.gf_dim = ngf
+        self.in_dim = cfg.GAN.Z_DIM + ncf
+        self.ef_dim = nef
+        self.batchnorm = batchnorm
+        self.att = ATT_NET(self.gf_dim, self.ef_dim)
+        if batchnorm:
+            self.im2f = _ConvBnGlu(conv3x3(3, ngf * 2), nn.BatchNorm2d(ngf * 2), GLU())
+            self.upsample = upBlock(ngf * 2, ngf)
+        else:
+            self.im2f = _ConvBnGlu(conv3x3(3, ngf * 2), GLU())
+            self.upsample = upBlocknoBN(ngf * 2, ngf)
+        self.residual = nn.Sequential(*[ResBlock(ngf * 2, batchnorm) for _ in range(cfg.GAN.R_NUM)])
+
+    def forward(self, c_code0, LR, word_embs, mask):
+        return _run_stage(self, self.im2f(LR), word_embs, mask)
+
+
+class NEXT_STAGE_G(nn.Module):
+    """util.py:781-823."""
+
+    def __init__(self, ngf, nef, ncf, weightatten=False):
+        super().__init__()
+        if weightatten:
+            raise NotImplementedError('GlobalAttentionGeneral_weight is out of scope (unused by the SR flows)')
+        self.weightattn = weightatten
+        self.gf_dim = ngf
+        self.ef_dim = nef
+        self.cf_dim = ncf
+        self.num_residual = cfg.GAN.R_NUM
+        self.att = ATT_NET(ngf, self.ef_dim)
+        self.residual = nn.Sequential(*[ResBlock(ngf * 2) for _ in range(cfg.GAN.R_NUM)])
+        self.upsample = upBlock(ngf * 2, ngf)
+
+    def forward(self, h_code, c_code0, word_embs, mask):
+        return _run_stage(self, h_code, word_embs, mask)
+
+
+class GET_IMAGE_G(nn.Module):
+    """util.py:894-905: conv3x3(ngf,3) + tanh."""
+
+    def __init__(self, ngf):
+        super().__init__()
+        self.gf_dim = ngf
+        self.img = _ImageHead(conv3x3(ngf, 3), nn.Tanh())
+
+    def forward(self, h_code):
+        return self.img(h_code)
+
+
+class GET_IMAGE_G_noAct(nn.Module):
+    """util.py:909-919: conv3x3(ngf,3)."""
+
+    def __init__(self, ngf):
+        super().__init__()
+        self.gf_dim = ngf
+        self.img = _ImageHead(conv3x3(ngf, 3))
+
+    def forward(self, h_code):
+        return self.img(h_code)

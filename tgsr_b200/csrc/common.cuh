@@ -1,0 +1,31 @@
+// Shared helpers for libtgsr_sm100 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/tgsr.h"
+
+namespace tgsr {
+
+extern thread_local int g_last_cuda_error;
+extern int g_sm_count;      // 0 until tgsr_init
+extern int g_device;
+
+inline int cuda_fail(cudaError_t e) {
+  g_last_cuda_error = (int)e;
+  return TGSR_ERR_CUDA;
+}
+// Check the launch that was just enqueued (no sync).
+inline int launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? TGSR_OK : cuda_fail(e);
+}
+
+#define TGSR_REQUIRE_PTR(p) do { if ((p) == nullptr) return TGSR_ERR_NULL; } while (0)
+#define TGSR_REQUIRE(cond, code) do { if (!(cond)) return (code); } while (0)
+#define TGSR_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return tgsr::cuda_fail(e__); } while (0)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+}  // namespace tgsr

@@ -1,0 +1,172 @@
+// RNN_ENCODER forward: Embedding -> 1-layer bidirectional LSTM (eval), fp32.
+// reference: util.py:233-260 (forward), util.py:222-231 (zero initial state).
+//
+// Packed-sequence semantics are handled in-kernel from device-resident lengths (the reference
+// syncs the host with cap_lens.tolist(), util.py:239): the forward direction runs t=0..len-1,
+// the reverse direction t=len-1..0, outputs beyond len are zero, sent_emb is the final hidden
+// state of each direction.
+//
+// Three launches: (1) transpose W_hh so the recurrence reads it coalesced, (2) the input
+// projection for every token (one GEMM-like pass, W_ih read once per 8 tokens), (3) the
+// recurrence: one CTA per (direction, group of LSTM_BT captions), thread j owns gate row j.
+#include "common.cuh"
+
+namespace tgsr {
+
+constexpr int LSTM_TOK = 8;  // tokens per CTA in the input projection
+constexpr int LSTM_BT = 8;   // captions per CTA in the recurrence
+
+__global__ void lstm_transpose_whh(const float* __restrict__ w_hh, float* __restrict__ w_hhT, int H) {
+  // w_hh [2][4H][H] -> w_hhT [2][H][4H]
+  const int n = 2 * 4 * H * H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int d = i / (4 * H * H), r = i % (4 * H * H), j = r / H, k = r % H;
+    w_hhT[((size_t)d * H + k) * 4 * H + j] = w_hh[i];
+  }
+}
+
+// xproj[tok][d][j] = emb[cap[tok]] . w_ih[d][j] + b_ih[d][j] + b_hh[d][j]
+__global__ void __launch_bounds__(256)
+lstm_xproj_kernel(const int64_t* __restrict__ captions, const float* __restrict__ emb,
+                  const float* __restrict__ w_ih, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                  float* __restrict__ xproj, int ntok, int ntoken, int ninput, int H) {
+  extern __shared__ float xs[];  // [LSTM_TOK][ninput]
+  const int tok0 = blockIdx.x * LSTM_TOK;
+  for (int i = threadIdx.x; i < LSTM_TOK * ninput; i += blockDim.x) {
+    const int tk = i / ninput, k = i % ninput;
+    float v = 0.f;
+    if (tok0 + tk < ntok) {
+      long long id = captions[tok0 + tk];
+      if (id < 0) id = 0;
+      if (id >= ntoken) id = ntoken - 1;   // nn.Embedding would raise; clamp keeps the kernel memory-safe
+      v = __ldg(emb + (size_t)id * ninput + k);
+    }
+    xs[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarp = blockDim.x / 32;
+  const int rows = 2 * 4 * H;
+  for (int r = warp; r < rows; r += nwarp) {
+    const float* wr = w_ih + (size_t)r * ninput;
+    float acc[LSTM_TOK];
+#pragma unroll
+    for (int tk = 0; tk < LSTM_TOK; ++tk) acc[tk] = 0.f;
+    for (int k = lane; k < ninput; k += 32) {
+      const float wv = __ldg(wr + k);
+#pragma unroll
+      for (int tk = 0; tk < LSTM_TOK; ++tk) acc[tk] = fmaf(wv, xs[tk * ninput + k], acc[tk]);
+    }
+#pragma unroll
+    for (int tk = 0; tk < LSTM_TOK; ++tk)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[tk] += __shfl_xor_sync(0xffffffffu, acc[tk], o);
+    if (lane == 0) {
+      const float bsum = b_ih[r] + b_hh[r];
+#pragma unroll
+      for (int tk = 0; tk < LSTM_TOK; ++tk)
+        if (tok0 + tk < ntok) xproj[(size_t)(tok0 + tk) * rows + r] = acc[tk] + bsum;
+    }
+  }
+}
+
+// grid (2, ceil(B/LSTM_BT)); block 4H threads.
+__global__ void __launch_bounds__(512)
+lstm_recurrence_kernel(const int64_t* __restrict__ cap_lens, const float* __restrict__ xproj,
+                       const float* __restrict__ w_hhT, float* __restrict__ words, float* __restrict__ sent,
+                       int B, int Tcap, int Tmax, int H) {
+  extern __shared__ float sm[];
+  float* h_s = sm;                       // [LSTM_BT][H]
+  float* g_s = sm + LSTM_BT * H;         // [LSTM_BT][4H]
+  __shared__ int len_s[LSTM_BT];
+  const int d = blockIdx.x, b0 = blockIdx.y * LSTM_BT;
+  const int j = threadIdx.x, G = 4 * H;
+  if (j < LSTM_BT) {
+    int L = 0;
+    if (b0 + j < B) {
+      long long v = cap_lens[b0 + j];
+      L = (int)(v < 0 ? 0 : (v > Tcap ? Tcap : v));
+    }
+    len_s[j] = L;
+  }
+  for (int i = j; i < LSTM_BT * H; i += blockDim.x) h_s[i] = 0.f;
+  __syncthreads();
+  int maxlen = 0;
+#pragma unroll
+  for (int bb = 0; bb < LSTM_BT; ++bb) maxlen = max(maxlen, len_s[bb]);
+
+  // cell state: thread (bb, u) for tid < LSTM_BT*H keeps c in a register; with 4H threads and
+  // LSTM_BT*H cells each thread owns LSTM_BT/4 cells.
+  constexpr int CPT = LSTM_BT / 4;
+  float c_reg[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) c_reg[i] = 0.f;
+
+  const float* wT = w_hhT + (size_t)d * H * G;
+  for (int s = 0; s < maxlen; ++s) {
+    float acc[LSTM_BT];
+#pragma unroll
+    for (int bb = 0; bb < LSTM_BT; ++bb) {
+      const int L = len_s[bb];
+      const int t = d == 0 ? s : L - 1 - s;
+      acc[bb] = (s < L) ? __ldg(xproj + ((size_t)(b0 + bb) * Tcap + t) * 2 * G + (size_t)d * G + j) : 0.f;
+    }
+#pragma unroll 8
+    for (int k = 0; k < H; ++k) {
+      const float wv = __ldg(wT + (size_t)k * G + j);
+#pragma unroll
+      for (int bb = 0; bb < LSTM_BT; ++bb) acc[bb] = fmaf(wv, h_s[bb * H + k], acc[bb]);
+    }
+#pragma unroll
+    for (int bb = 0; bb < LSTM_BT; ++bb) g_s[bb * G + j] = acc[bb];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int cell = j + i * G;            // 0 .. LSTM_BT*H-1
+      const int bb = cell / H, u = cell % H;
+      const int L = len_s[bb];
+      if (s < L) {
+        const float* g = g_s + bb * G;
+        const float ig = 1.0f / (1.0f + expf(-g[u]));
+        const float fg = 1.0f / (1.0f + expf(-g[H + u]));
+        const float gg = tanhf(g[2 * H + u]);
+        const float og = 1.0f / (1.0f + expf(-g[3 * H + u]));
+        const float c = fmaf(fg, c_reg[i], ig * gg);
+        c_reg[i] = c;
+        const float h = og * tanhf(c);
+        h_s[bb * H + u] = h;
+        const int t = d == 0 ? s : L - 1 - s;
+        if (t < Tmax) words[((size_t)(b0 + bb) * 2 * H + d * H + u) * Tmax + t] = h;
+        if (s == L - 1) sent[(size_t)(b0 + bb) * 2 * H + d * H + u] = h;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace tgsr
+
+extern "C" int tgsr_lstm_bidir_fwd_f32(const int64_t* captions, const int64_t* cap_lens, const float* emb,
+                                       const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                       float* ws, float* words, float* sent, int B, int Tcap, int Tmax, int ntoken,
+                                       int ninput, int H, tgsr_stream_t stream) {
+  using namespace tgsr;
+  TGSR_REQUIRE_PTR(captions); TGSR_REQUIRE_PTR(cap_lens); TGSR_REQUIRE_PTR(emb); TGSR_REQUIRE_PTR(w_ih);
+  TGSR_REQUIRE_PTR(w_hh); TGSR_REQUIRE_PTR(b_ih); TGSR_REQUIRE_PTR(b_hh); TGSR_REQUIRE_PTR(ws);
+  TGSR_REQUIRE_PTR(words); TGSR_REQUIRE_PTR(sent);
+  TGSR_REQUIRE(B > 0 && Tcap > 0 && Tmax > 0 && Tmax <= Tcap && ntoken > 0 && ninput > 0 && H > 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE(H <= 128 && H % 32 == 0 && ninput <= 1024 && B <= 65535 * LSTM_BT, TGSR_ERR_UNSUPPORTED);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = 4 * H;
+  float* xproj = ws;
+  float* w_hhT = ws + (size_t)B * Tcap * 2 * G;
+  TGSR_CUDA(cudaMemsetAsync(words, 0, (size_t)B * 2 * H * Tmax * sizeof(float), st));
+  TGSR_CUDA(cudaMemsetAsync(sent, 0, (size_t)B * 2 * H * sizeof(float), st));
+  lstm_transpose_whh<<<64, 256, 0, st>>>(w_hh, w_hhT, H);
+  const int ntok = B * Tcap;
+  lstm_xproj_kernel<<<ceil_div(ntok, LSTM_TOK), 256, LSTM_TOK * ninput * sizeof(float), st>>>(
+      captions, emb, w_ih, b_ih, b_hh, xproj, ntok, ntoken, ninput, H);
+  const size_t smem = (size_t)(LSTM_BT * H + LSTM_BT * G) * sizeof(float);
+  lstm_recurrence_kernel<<<dim3(2, ceil_div(B, LSTM_BT)), G, smem, st>>>(cap_lens, xproj, w_hhT, words, sent, B,
+                                                                        Tcap, Tmax, H);
+  return launch_status();
+}

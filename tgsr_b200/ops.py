@@ -1,0 +1,126 @@
+"""Tensor-level wrappers over the C ABI (include/tgsr.h).  PyTorch is plumbing here: it owns the
+device memory and the stream; every arithmetic op below is a libtgsr_sm100 kernel."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GLU, ACT_NONE, ACT_TANH, call, ptr
+
+Tensor = torch.Tensor
+
+
+def _f32c(t: Tensor, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError('tgsr_b200: %s must be a CUDA tensor (no CPU path)' % name)
+    if t.dtype != torch.float32:
+        raise TypeError('tgsr_b200: %s must be float32, got %s' % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------ a1
+def attention_fwd(inp: Tensor, context: Tensor, w_ctx: Tensor, mask: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """GlobalAttentionGeneral.forward (GlobalAttention.py:87-130) -> (weightedContext, attn)."""
+    inp = _f32c(inp, 'input'); context = _f32c(context, 'context'); w_ctx = _f32c(w_ctx, 'conv_context.weight')
+    if inp.dim() != 4 or context.dim() != 3:
+        raise ValueError('expected input [B,idf,ih,iw] and context [B,cdf,T]')
+    B, idf, ih, iw = inp.shape
+    cdf, T = context.shape[1], context.shape[2]
+    if context.shape[0] != B or w_ctx.numel() != idf * cdf:
+        raise ValueError('attention shape mismatch: input %s context %s weight %s'
+                         % (tuple(inp.shape), tuple(context.shape), tuple(w_ctx.shape)))
+    m8 = None
+    if mask is not None:
+        if tuple(mask.shape) != (B, T):
+            raise ValueError('mask must be [B,T]=%s, got %s' % ((B, T), tuple(mask.shape)))
+        m8 = mask.to(device=inp.device, dtype=torch.uint8).contiguous()
+    wctx = torch.empty_like(inp)
+    attn = torch.empty((B, T, ih, iw), device=inp.device, dtype=torch.float32)
+    call('tgsr_attn_fwd_f32', inp.device, ptr(inp), ptr(context), ptr(w_ctx), ptr(m8), ptr(wctx), ptr(attn),
+         B, idf, cdf, ih * iw, T)
+    return wctx, attn
+
+
+# ------------------------------------------------------------------ a2
+def func_attention_fwd(query: Tensor, context: Tensor, gamma1: float) -> Tuple[Tensor, Tensor]:
+    """func_attention (GlobalAttention.py:33-74), forward only."""
+    query = _f32c(query, 'query'); context = _f32c(context, 'context')
+    B, ndf, Tq = query.shape
+    ih, iw = context.shape[2], context.shape[3]
+    wctx = torch.empty_like(query)
+    attn = torch.empty((B, Tq, ih, iw), device=query.device, dtype=torch.float32)
+    call('tgsr_func_attn_fwd_f32', query.device, ptr(query), ptr(context), float(gamma1), ptr(wctx), ptr(attn),
+         B, ndf, Tq, ih * iw)
+    return wctx, attn
+
+
+# ------------------------------------------------------------------ a3/a4/a5/a8
+def bn_fold(gamma: Tensor, beta: Tensor, mean: Tensor, var: Tensor, eps: float) -> Tuple[Tensor, Tensor]:
+    scale = torch.empty_like(gamma); shift = torch.empty_like(gamma)
+    call('tgsr_bn_fold_f32', gamma.device, ptr(gamma), ptr(beta), ptr(mean), ptr(var), float(eps), ptr(scale),
+         ptr(shift), gamma.numel())
+    return scale, shift
+
+
+def conv2d_fused(x: Tensor, w: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], act: int,
+                 residual: Optional[Tensor] = None, addend: Optional[Tensor] = None, out_scale: float = 1.0,
+                 addend_scale: float = 0.0, up2x: bool = False) -> Tensor:
+    x = _f32c(x, 'x'); w = _f32c(w, 'weight')
+    B, Cin, H, W = x.shape
+    Cout, Cin_w, k, k2 = w.shape
+    if Cin_w != Cin or k != k2:
+        raise ValueError('conv weight %s does not match input %s' % (tuple(w.shape), tuple(x.shape)))
+    if act == ACT_GLU and Cout % 2 != 0:
+        raise AssertionError('channels dont divide 2!')          # util.py:51
+    Cf = Cout // 2 if act == ACT_GLU else Cout
+    Ho, Wo = (2 * H, 2 * W) if up2x else (H, W)
+    y = torch.empty((B, Cf, Ho, Wo), device=x.device, dtype=torch.float32)
+    for nm, t in (('residual', residual), ('addend', addend)):
+        if t is not None and tuple(t.shape) != tuple(y.shape):
+            raise ValueError('%s shape %s != output shape %s' % (nm, tuple(t.shape), tuple(y.shape)))
+    residual = None if residual is None else _f32c(residual, 'residual')
+    addend = None if addend is None else _f32c(addend, 'addend')
+    call('tgsr_conv2d_f32', x.device, ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(residual), ptr(addend),
+         float(out_scale), float(addend_scale), ptr(y), B, Cin, H, W, Cout, k, int(up2x), act)
+    return y
+
+
+# ------------------------------------------------------------------ a12/a13
+def linear_glu(x: Tensor, w: Tensor, bias: Optional[Tensor], scale: Optional[Tensor] = None,
+               shift: Optional[Tensor] = None) -> Tensor:
+    x = _f32c(x, 'x'); w = _f32c(w, 'weight')
+    B, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError('linear weight %s does not match input %s' % (tuple(w.shape), tuple(x.shape)))
+    y = torch.empty((B, N // 2), device=x.device, dtype=torch.float32)
+    call('tgsr_linear_glu_f32', x.device, ptr(x), ptr(w), ptr(bias), ptr(scale), ptr(shift), ptr(y), B, K, N)
+    return y
+
+
+def ca_reparam(mulogvar: Tensor, eps: Tensor) -> Tensor:
+    B, two_c = mulogvar.shape
+    c = torch.empty((B, two_c // 2), device=mulogvar.device, dtype=torch.float32)
+    call('tgsr_ca_reparam_f32', mulogvar.device, ptr(mulogvar), ptr(_f32c(eps, 'eps')), ptr(c), B, two_c // 2)
+    return c
+
+
+# ------------------------------------------------------------------ a11
+def lstm_bidir(captions: Tensor, cap_lens: Tensor, emb: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor,
+               b_hh: Tensor, Tmax: int) -> Tuple[Tensor, Tensor]:
+    """Embedding + bidirectional LSTM.  w_ih [2,4H,ninput], w_hh [2,4H,H], b_* [2,4H] (stacked fwd, reverse)."""
+    dev = emb.device
+    captions = captions.to(device=dev, dtype=torch.int64).contiguous()
+    cap_lens = cap_lens.to(device=dev, dtype=torch.int64).contiguous()
+    B, Tcap = captions.shape
+    H = w_hh.shape[2]
+    ntoken, ninput = emb.shape
+    ws = torch.empty(B * Tcap * 8 * H + 8 * H * H, device=dev, dtype=torch.float32)
+    words = torch.empty((B, 2 * H, Tmax), device=dev, dtype=torch.float32)
+    sent = torch.empty((B, 2 * H), device=dev, dtype=torch.float32)
+    call('tgsr_lstm_bidir_fwd_f32', dev, ptr(captions), ptr(cap_lens), ptr(_f32c(emb, 'emb')), ptr(_f32c(w_ih, 'w_ih')),
+         ptr(_f32c(w_hh, 'w_hh')), ptr(_f32c(b_ih, 'b_ih')), ptr(_f32c(b_hh, 'b_hh')), ptr(ws), ptr(words), ptr(sent),
+         B, Tcap, Tmax, ntoken, ninput, H)
+    return words, sent
