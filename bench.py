@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- SR images/sec of the TGSR eval forward (text encoder -> G_SR_NET_low ->
+NetG_highweight) on B200, per BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+A step is one pass of the hot path over one batch of synthetic input (configs[1]: bird SR eval,
+batch 32 per GPU, 32x32 LR -> 256x256, 18-word captions, ntoken 5450, random-init weights with
+randomised BN statistics).  Multi-GPU = one process per GPU (torchrun), images sharded by rank,
+no collective on the data path (weak scaling); time = max over ranks, measured with CUDA events.
+
+Prints ONE JSON line on rank 0 (see the contract in the task statement):
+  value     : images/s, inputs resident in HBM
+  e2e       : same metric through SRPipeline.forward_host (pinned host buffers, H2D + D2H inside)
+  roofline  : the dominant conv kernel timed alone with CUDA events vs the measured bf16 peak
+  cpu_baseline : the CPU oracle (port of the reference's PyTorch path) on this box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 32
+NTOKEN = 5450
+WORDS = 18
+GFLOP_PER_IMAGE = 21.12          # reference FLOP count, 2*MAC, x8 nets
+METRIC = 'SR images/sec (eval fwd, x8 32->256, batch 32/GPU)'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default=None, choices=['bf16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], bf16=d['bf16_tflops'], bf16_sustained=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    source='measured')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def cpu_oracle_rate(n_images: int, budget_s: float, threads: int):
+    """Times the CPU oracle (PyTorch fp32 port of the reference path) on `n_images`-image batches
+    until `budget_s` seconds are used (at least 2 timed passes).  Returns (img/s, description)."""
+    import torch
+    from oracle import tgsr_oracle as O
+    import tgsr_b200
+    tgsr_b200.set_eval_defaults()
+    from tgsr_b200 import nets, text_encoder
+    torch.set_num_threads(threads)
+    torch.manual_seed(100)
+    enc = text_encoder.RNN_ENCODER(NTOKEN, nhidden=256).eval()
+    gl = nets.G_SR_NET_low().eval(); gh = nets.NetG_highweight(low='lr').eval()   # parameter holders only
+    sdE, sdL, sdH = enc.state_dict(), gl.state_dict(), gh.state_dict()
+    LR = O.synth_lr(n_images, 32, seed=101)
+    caps, lens = O.synth_captions(n_images, NTOKEN, seed=102, words_num=WORDS)
+
+    def one():
+        with torch.no_grad():
+            words, sent = O.rnn_encoder(sdE, caps, lens)
+            mask = (caps == 0)[:, :words.shape[2]]
+            imgs, atts, mu, lv, _ = O.g_sr_net_low(sdL, LR, sent, words, mask)
+            return O.netg_high(sdH, LR, imgs, LR, low='lr')
+    one()                                               # warm-up
+    t0 = time.perf_counter(); n = 0
+    while n < 2 or time.perf_counter() - t0 < budget_s:
+        one(); n += 1
+    dt = time.perf_counter() - t0
+    return n * n_images / dt, '%d passes of %d images (x8, 32->256, 18 words) in %.1f s' % (n, n_images, dt)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_img = 8
+    import torch
+    from oracle import tgsr_oracle as O                                     # noqa: F401
+    # each "step" = one 8-image pass; W warm-up + K timed
+    rate_s, times = None, []
+    import tgsr_b200
+    tgsr_b200.set_eval_defaults()
+    from tgsr_b200 import nets, text_encoder
+    torch.set_num_threads(cores)
+    torch.manual_seed(100)
+    enc = text_encoder.RNN_ENCODER(NTOKEN, nhidden=256).eval()
+    gl = nets.G_SR_NET_low().eval(); gh = nets.NetG_highweight(low='lr').eval()
+    sdE, sdL, sdH = enc.state_dict(), gl.state_dict(), gh.state_dict()
+    LR = O.synth_lr(n_img, 32, seed=101); caps, lens = O.synth_captions(n_img, NTOKEN, seed=102, words_num=WORDS)
+    steps = min(args.steps, 12); warm = min(args.warmup, 2)
+    for i in range(warm + steps):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            words, sent = O.rnn_encoder(sdE, caps, lens)
+            mask = (caps == 0)[:, :words.shape[2]]
+            imgs, atts, mu, lv, _ = O.g_sr_net_low(sdL, LR, sent, words, mask)
+            O.netg_high(sdH, LR, imgs, LR, low='lr')
+        if i >= warm:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = steps * n_img / total
+    sample = '%d steps of %d images per step (bounded sample of the batch-%d workload)' % (steps, n_img, BATCH_PER_GPU)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': warm, 'ms_per_step': 1e3 * total / steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'bird SR eval x8 (32->256), 18-word captions, ntoken 5450, random-init weights; '
+                               'CPU oracle (PyTorch fp32 port of the reference modules) on host cores'},
+        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import tgsr_b200
+    from tgsr_b200 import _lib
+    from tgsr_b200.pipeline import SRPipeline
+    from oracle import tgsr_oracle as O           # synthetic-input generators only (checker code, not timed)
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the product path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    tgsr_b200.set_eval_defaults()
+    precision = args.precision or tgsr_b200.DEFAULT_BENCH_PRECISION
+    tgsr_b200.set_precision(precision)
+
+    pipe = SRPipeline(NTOKEN, device=dev, variant='x8', low='lr', seed=100, randomize_bn=True)
+    B = BATCH_PER_GPU
+    LR_h = O.synth_lr(B, 32, seed=101 + rank).pin_memory()
+    caps_h, lens_h = O.synth_captions(B, NTOKEN, seed=102 + rank, words_num=WORDS)
+    caps_h, lens_h = caps_h.pin_memory(), lens_h.pin_memory()
+    LR, caps, lens = LR_h.to(dev), caps_h.to(dev), lens_h.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)     # 256 MiB > 126 MB L2
+
+    def step_device():
+        fine, _, _ = pipe.text_and_generate(LR, caps, lens, WORDS)
+        return fine
+
+    out_host = torch.empty((B, 3, 256, 256), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    lib = _lib.load()
+    launches0 = lib.tgsr_launch_count()
+    sampler = ClockSampler(local); sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s, e in ev:
+        flush.zero_()                         # L2 flush between timed iterations (outside the event pair)
+        s.record(); step_device(); e.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.tgsr_launch_count() - launches0
+    t_ms = sum(s.elapsed_time(e) for s, e in ev)
+    t = torch.tensor([t_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_ms = float(t.item())
+    value = world * B * args.steps / (t_ms * 1e-3)
+
+    # ---- end-to-end timing through the public API with host buffers
+    for _ in range(3):
+        pipe.forward_host(LR_h, caps_h, lens_h, out_host)
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s, e in ev2:
+        flush.zero_()
+        s.record(); pipe.forward_host(LR_h, caps_h, lens_h, out_host); e.record()
+    barrier()
+    t2 = torch.tensor([sum(s.elapsed_time(e) for s, e in ev2)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t2.item()) * 1e-3)
+    h2d = LR_h.numel() * 4 + caps_h.numel() * 8 + lens_h.numel() * 8
+    d2h = out_host.numel() * out_host.element_size()
+
+    # ---- roofline of the dominant kernel (timed alone, CUDA events, L2 flushed between launches)
+    pk = peaks()
+    roof = pipe.dominant_kernel_roofline(B, flush, pk) if rank == 0 else None
+    attn_roof = pipe.attention_roofline(B, flush, pk) if rank == 0 else None
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, sample = cpu_oracle_rate(4, 12.0, cores)
+        cpu_base = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': t_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if precision == 'bf16' else 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'bird SR eval (cfg/eval_birdSR_attn2.yml dims): text encoder + G_SR_NET_low + '
+                                   'NetG_highweight, x8 32->256, batch %d per GPU, 18-word captions, ntoken %d, '
+                                   'random-init weights, randomised BN stats' % (B, NTOKEN),
+                       'batch_per_gpu': B, 'parallelism': 'image-sharded replicas x%d (no collective)' % world,
+                       'l2': 'flushed between timed iterations (256 MiB write)', 'precision': precision,
+                       'gflop_per_image_reference': GFLOP_PER_IMAGE},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': int(launches),
+            'roofline': roof, 'roofline_attention': attn_roof,
+            'model_tflops': value * GFLOP_PER_IMAGE / 1e3, 'peaks': pk,
+        }
+        if cpu_base is not None:
+            line['cpu_baseline'] = cpu_base
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -46,6 +46,8 @@ int tgsr_last_cuda_error(void); /* cudaError_t of the last TGSR_ERR_CUDA on this
 /* One-time per device: kernel attributes (dynamic smem opt-in), TMA driver entry point, SM count. */
 int tgsr_init(int device);
 int tgsr_sm_count(void);
+/* Number of kernels this library has enqueued since load (monotonic; not thread-exact). */
+unsigned long long tgsr_launch_count(void);
 
 /* ---- a1: GlobalAttentionGeneral.forward, GlobalAttention.py:87-130 (fp32 NCHW I/O) ---------
  * input [B,idf,Q], context [B,cdf,T], w_ctx [idf,cdf] (conv_context.weight), mask uint8 [B,T] or
@@ -91,7 +93,7 @@ int tgsr_ca_reparam_f32(const float* mulogvar, const float* eps, float* c_code, 
 /* ---- a11: RNN_ENCODER.forward, util.py:233-260 (Embedding -> 1-layer bi-LSTM, eval) --------
  * captions int64 [B,Tcap]; cap_lens int64 [B] (device; any order); emb [ntoken,ninput];
  * w_ih [2][4H,ninput], w_hh [2][4H,H], b_ih/b_hh [2][4H] (dir 0 = forward, 1 = reverse; gate
- * order i,f,g,o).  xproj_ws: workspace of B*Tcap*2*4H floats.  words [B,2H,Tmax] (zero beyond
+ * order i,f,g,o).  xproj_ws: workspace of B*Tcap*8H + 8H*H floats.  words [B,2H,Tmax] (zero beyond
  * each caption's length), sent [B,2H].  No host sync.  H <= 128. */
 int tgsr_lstm_bidir_fwd_f32(const int64_t* captions, const int64_t* cap_lens, const float* emb,
                             const float* w_ih, const float* w_hh, const float* b_ih,

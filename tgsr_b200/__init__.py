@@ -6,6 +6,8 @@ from .attention import GlobalAttentionGeneral, func_attention  # noqa: F401
 __version__ = '0.1.0'
 
 _PRECISION = 'fp32'
+SMOKE_PRECISIONS = ('fp32',)
+DEFAULT_BENCH_PRECISION = 'fp32'      # switched to 'bf16' once the tcgen05 path is parity-green
 
 
 def set_precision(mode: str) -> None:

@@ -27,6 +27,7 @@ _SIGS = {
     'tgsr_last_cuda_error': ([], C.c_int),
     'tgsr_init': ([C.c_int], C.c_int),
     'tgsr_sm_count': ([], C.c_int),
+    'tgsr_launch_count': ([], C.c_ulonglong),
     'tgsr_attn_fwd_f32': ([C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p], C.c_int),
     'tgsr_func_attn_fwd_f32': ([C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p], C.c_int),
     'tgsr_conv2d_f32': ([C.c_void_p] * 6 + [C.c_float, C.c_float, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p], C.c_int),

@@ -5,6 +5,7 @@ namespace tgsr {
 thread_local int g_last_cuda_error = 0;
 int g_sm_count = 0;
 int g_device = -1;
+unsigned long long g_launches = 0;
 int init_attention(void);   // attention.cu
 int init_conv_tc(void);     // conv_tc.cu (tcgen05 path)
 }  // namespace tgsr
@@ -40,5 +41,7 @@ int tgsr_init(int device) {
 }
 
 int tgsr_sm_count(void) { return tgsr::g_sm_count; }
+
+unsigned long long tgsr_launch_count(void) { return tgsr::g_launches; }
 
 }  // extern "C"

@@ -9,13 +9,15 @@ namespace tgsr {
 extern thread_local int g_last_cuda_error;
 extern int g_sm_count;      // 0 until tgsr_init
 extern int g_device;
+extern unsigned long long g_launches;   // kernels enqueued by this library (bench.py's gpu_launches)
 
 inline int cuda_fail(cudaError_t e) {
   g_last_cuda_error = (int)e;
   return TGSR_ERR_CUDA;
 }
 // Check the launch that was just enqueued (no sync).
-inline int launch_status() {
+inline int launch_status(int n_kernels = 1) {
+  g_launches += (unsigned long long)n_kernels;
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? TGSR_OK : cuda_fail(e);
 }

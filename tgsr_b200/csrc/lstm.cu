@@ -168,5 +168,5 @@ extern "C" int tgsr_lstm_bidir_fwd_f32(const int64_t* captions, const int64_t* c
   const size_t smem = (size_t)(LSTM_BT * H + LSTM_BT * G) * sizeof(float);
   lstm_recurrence_kernel<<<dim3(2, ceil_div(B, LSTM_BT)), G, smem, st>>>(cap_lens, xproj, w_hhT, words, sent, B,
                                                                         Tcap, Tmax, H);
-  return launch_status();
+  return launch_status(3);
 }

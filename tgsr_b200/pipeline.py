@@ -1,0 +1,159 @@
+"""Eval-flow composition of the hot path: the body of condGANTrainer.gen_exampleSRHL
+(trainer_objective.py:134-146) -- text encoder -> mask -> G_SR_NET_low -> NetG_highweight --
+as one callable.  This is the user-facing call bench.py times end to end."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import nets, nets16
+from .config import cfg
+from .text_encoder import RNN_ENCODER
+
+
+class SRPipeline:
+    def __init__(self, n_words: int, device='cuda', variant: str = 'x8', low: str = 'lr', seed: Optional[int] = None,
+                 randomize_bn: bool = False):
+        """variant 'x8' -> model.py nets (TREE.BRANCH_NUM == 4), 'x16' -> models16.py
+        (trainer_objective.py:74-88).  Weights are random-init (seeded) unless load_* is called."""
+        if seed is not None:
+            torch.manual_seed(seed)
+        mod = nets if variant == 'x8' else nets16
+        self.variant = variant
+        self.device = torch.device(device)
+        self.text_encoder = RNN_ENCODER(n_words, nhidden=cfg.TEXT.EMBEDDING_DIM)
+        self.netGL = mod.G_SR_NET_low()
+        self.netGH = mod.NetG_highweight(weightmap=False, low=low)
+        if randomize_bn:
+            randomize_bn_stats([self.netGL, self.netGH], seed or 0)
+        for m in (self.text_encoder, self.netGL, self.netGH):
+            m.to(self.device).eval()
+        self._pinned = {}
+
+    def load_generators(self, sd_netG, sd_netGH):
+        self.netGL.load_state_dict(sd_netG, strict=True)
+        self.netGH.load_state_dict(sd_netGH, strict=True)
+
+    @torch.no_grad()
+    def forward_device(self, LR: torch.Tensor, captions: torch.Tensor, cap_lens, LRb: Optional[torch.Tensor] = None):
+        """Inputs on the device.  Returns (fine_imgs list, fake_imgL list, attention_maps list)."""
+        B = captions.shape[0]
+        hidden = None                                                     # zero state (init_hidden), built in-kernel
+        words_embs, sent_emb = self.text_encoder(captions, cap_lens, hidden)
+        mask = (captions == 0)                                            # trainer_objective.py:136
+        num_words = words_embs.size(2)
+        if mask.size(1) > num_words:
+            mask = mask[:, :num_words]
+        fake_imgL, attention_maps, mu, logvar = self.netGL(LR, sent_emb, words_embs, mask)
+        fine_im, a, one = self.netGH(LR, fake_imgL, LR if LRb is None else LRb)
+        return fine_im, fake_imgL, attention_maps
+
+    @torch.no_grad()
+    def text_and_generate(self, LR, captions, cap_lens, tmax: int):
+        """forward_device with max(cap_lens) known on the host: no device->host read anywhere."""
+        words_embs, sent_emb = self.text_encoder._forward_tmax(captions, cap_lens, tmax)
+        mask = (captions == 0)[:, :tmax]
+        fake_imgL, attention_maps, mu, logvar = self.netGL(LR, sent_emb, words_embs, mask)
+        fine_im, a, one = self.netGH(LR, fake_imgL, LR)
+        return fine_im, fake_imgL, attention_maps
+
+    # ------------------------------------------------------------------ roofline probes (bench.py)
+    @staticmethod
+    def _time_kernel(fn, flush, iters=20, warm=5):
+        for _ in range(warm):
+            fn()
+        ms = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            e.synchronize()
+            ms += s.elapsed_time(e)
+        return ms / iters
+
+    @torch.no_grad()
+    def dominant_kernel_roofline(self, B, flush, pk):
+        """The dominant kernel of the step: ResBlock conv1 of h_net3 (conv3x3 64->128 + BN + GLU at
+        128x128; 2*9*64*128*128^2 FLOP per image, util.py:115-117), timed alone."""
+        from . import get_precision
+        from .blocks import _conv
+        from ._lib import ACT_GLU
+        blk = self.netGL.h_net3.residual[0].block
+        H = W = 128
+        x = torch.randn(B, 64, H, W, device=self.device) * 0.5
+        flops = 2.0 * 9 * 64 * 128 * H * W * B
+        if get_precision() == 'bf16':
+            from . import tc
+            fn, kernel = tc.make_probe_conv(blk, x)
+        else:
+            fn, kernel = (lambda: _conv(x, blk[0], blk[1], ACT_GLU)), 'conv2d_f32_kernel<3,GLU> (CUDA-core fp32)'
+        ms = self._time_kernel(fn, flush)
+        ach = flops / (ms * 1e-3) / 1e12
+        return {'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': ach / pk['bf16'],
+                'traffic': None, 'kernel': kernel, 'ms_per_launch': ms, 'flops_per_launch': flops,
+                'peak_source': pk['source'] + ' cuBLAS bf16 burst (kernel timed alone)'}
+
+    @torch.no_grad()
+    def attention_roofline(self, B, flush, pk):
+        """Fused word attention at the h_net3 shape (Q=128^2, idf 32, cdf 256, T 18), timed alone.
+        Algorithmic bytes per SURVEY.md 8d: B*Q*(idf*e_in + idf*e_out + 4*T) + B*cdf*T*4 + idf*cdf*4 + B*T."""
+        from . import get_precision
+        att = self.netGL.h_net3.att
+        Q, idf, cdf, T = 128 * 128, 32, 256, 18
+        ctx = torch.randn(B, cdf, T, device=self.device) * 0.3
+        mask = torch.zeros(B, T, dtype=torch.bool, device=self.device)
+        att.applyMask(mask)
+        if get_precision() == 'bf16':
+            from . import tc
+            fn, e, kernel = tc.make_probe_attention(att, ctx, mask, B)
+        else:
+            x = torch.randn(B, idf, 128, 128, device=self.device) * 0.5
+            fn, e, kernel = (lambda: att(x, ctx)), 4, 'attn_fwd_f32_kernel (fp32 NCHW I/O)'
+        nbytes = B * Q * (idf * e + idf * e + 4 * T) + B * cdf * T * 4 + idf * cdf * 4 + B * T
+        ms = self._time_kernel(fn, flush)
+        ach = nbytes / (ms * 1e-3) / 1e9
+        return {'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
+                'traffic': None, 'kernel': kernel, 'ms_per_launch': ms, 'bytes_per_launch': nbytes,
+                'peak_source': pk['source'] + ' copy bandwidth'}
+
+    def _pin(self, name, t):
+        buf = self._pinned.get(name)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self._pinned[name] = buf
+        buf.copy_(t)
+        return buf
+
+    @torch.no_grad()
+    def forward_host(self, LR_host: torch.Tensor, captions_host: torch.Tensor, cap_lens_host: torch.Tensor,
+                     out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host buffers in, final SR image (fine_im[-1]) out on the host: H2D of the inputs, the whole
+        forward, D2H of the result, all on the current stream (synchronised before returning)."""
+        LR = LR_host.to(self.device, non_blocking=True)
+        caps = captions_host.to(self.device, non_blocking=True)
+        tmax = int(cap_lens_host.max())                                    # host-side, no device sync
+        lens = cap_lens_host.to(self.device, non_blocking=True)
+        words_embs, sent_emb = self.text_encoder._forward_tmax(caps, lens, tmax)
+        mask = (caps == 0)[:, :tmax]
+        fake_imgL, attention_maps, mu, logvar = self.netGL(LR, sent_emb, words_embs, mask)
+        fine_im, a, one = self.netGH(LR, fake_imgL, LR)
+        sr = fine_im[-1]
+        if out_host is None:
+            out_host = torch.empty(sr.shape, dtype=sr.dtype, pin_memory=True)
+        out_host.copy_(sr, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host
+
+
+def randomize_bn_stats(modules, seed: int):
+    """SURVEY.md 8d cfg 2: running_mean~N(0,0.1), running_var~U(0.5,1.5), gamma~N(1,0.02), beta=0."""
+    import torch.nn as nn
+    g = torch.Generator().manual_seed(1234 + seed)
+    for mod in modules:
+        for m in mod.modules():
+            if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+                m.weight.data.copy_(1 + 0.02 * torch.randn(m.weight.shape, generator=g))
+                m.bias.data.zero_()

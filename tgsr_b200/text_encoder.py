@@ -76,5 +76,9 @@ class RNN_ENCODER(nn.Module):
         else:
             tmax = int(max(cap_lens))
             cap_lens = torch.as_tensor(cap_lens, dtype=torch.int64)
+        return self._forward_tmax(captions, cap_lens, tmax)
+
+    def _forward_tmax(self, captions, cap_lens, tmax: int):
+        """Same as forward() when max(cap_lens) is already known on the host (no device read)."""
         w_ih, w_hh, b_ih, b_hh = self._stacked()
         return ops.lstm_bidir(captions, cap_lens, self.encoder.weight.detach(), w_ih, w_hh, b_ih, b_hh, tmax)
