@@ -101,6 +101,37 @@ int tgsr_lstm_bidir_fwd_f32(const int64_t* captions, const int64_t* cap_lens, co
                             int Tcap, int Tmax, int ntoken, int ninput, int H,
                             tgsr_stream_t stream);
 
+/* =============================== bf16 tensor-core path =====================================
+ * Activations live in HBM as "blocked planes": bf16 [B][P][H][W][8]; channel c is element c%8 of
+ * plane c/8.  A view of C channels inside a buffer with P planes per image is (ptr, P, p0): it
+ * covers planes [p0, p0 + C/8).  Channel concatenation (util.py:773,817) is therefore free: the
+ * producers write disjoint plane ranges of one buffer. */
+
+/* NCHW fp32 [B,C,H,W] <-> blocked bf16 view (edge conversions; the reference API is NCHW fp32). */
+int tgsr_nchw_to_blocked_bf16(const float* x, void* y, int B, int C, int H, int W, int yP, int yp0,
+                              tgsr_stream_t stream);
+int tgsr_blocked_to_nchw_f32(const void* x, float* y, int B, int C, int H, int W, int xP, int xp0,
+                             tgsr_stream_t stream);
+
+/* Weight prep: conv3x3 weight [Cout,Cin,3,3] fp32 -> packed bf16 UMMA operand image.
+ * up2x == 0: 9 taps, Cout*Cin*9 elements.  up2x == 1: the nearest-x2 upsample of util.py:76 is
+ * folded into the weights as four 2x2 sub-pixel phases (pre-summed in fp32, rounded once),
+ * Cout*Cin*16 elements. */
+int tgsr_pack_conv3x3_bf16(const float* w, void* packed, int Cout, int Cin, int up2x,
+                           tgsr_stream_t stream);
+
+/* a3/a4/a5: conv3x3 (+ folded BN scale/shift [Cout]) (+GLU) (+residual) on tcgen05 tensor cores,
+ * bf16 operands, fp32 accumulation in TMEM; util.py:62-65, :45-53, :110-130, :74-80.
+ * x view (xP,xp0) of Cin channels at HxW; y view (yP,yp0) of Cout (or Cout/2 with GLU) channels at
+ * HxW, or at 2Hx2W when up2x (wpacked must then come from tgsr_pack_conv3x3_bf16(up2x=1)).
+ * residual view (rP,rp0) or NULL (only with act NONE, no up2x).  Supported (Cin,Cout,act,up2x):
+ * (64,128,GLU,0) (64,64,NONE,0) (32,64,GLU,0) (32,32,NONE,0) (64,64,GLU,1) (32,64,GLU,1);
+ * H % 16 == 0, W % 8 == 0. */
+int tgsr_conv3x3_tc_bf16(const void* x, int xP, int xp0, const void* wpacked, const float* scale,
+                         const float* shift, const void* residual, int rP, int rp0, void* y, int yP,
+                         int yp0, int B, int Cin, int H, int W, int Cout, int up2x, int act,
+                         tgsr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,11 @@ _SIGS = {
     'tgsr_bn_fold_f32': ([C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p], C.c_int),
     'tgsr_linear_glu_f32': ([C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p], C.c_int),
     'tgsr_ca_reparam_f32': ([C.c_void_p] * 3 + [C.c_int] * 2 + [C.c_void_p], C.c_int),
+    'tgsr_nchw_to_blocked_bf16': ([C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p], C.c_int),
+    'tgsr_blocked_to_nchw_f32': ([C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p], C.c_int),
+    'tgsr_pack_conv3x3_bf16': ([C.c_void_p, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p], C.c_int),
+    'tgsr_conv3x3_tc_bf16': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                              C.c_void_p, C.c_int, C.c_int] + [C.c_int] * 7 + [C.c_void_p], C.c_int),
     'tgsr_lstm_bidir_fwd_f32': ([C.c_void_p] * 10 + [C.c_int] * 6 + [C.c_void_p], C.c_int),
 }
 

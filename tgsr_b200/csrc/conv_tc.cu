@@ -1,5 +1,494 @@
-// tcgen05 implicit-GEMM convolution path (bf16, blocked layout).  Filled in below.
+// tcgen05 implicit-GEMM 3x3 convolution on bf16 "blocked" activations, with the TGSR block
+// epilogues fused: folded BatchNorm, GLU, residual add, and the nearest-x2 upsample of upBlock
+// computed algebraically as four 2x2 sub-pixel phases (2.25x fewer MACs than convolving the
+// upsampled image).
+//
+// reference: util.py:62-65 (conv3x3), nn.BatchNorm2d (eval), util.py:45-53 (GLU),
+//            util.py:110-130 (ResBlock), util.py:74-80 (upBlock).
+//
+// Data layout in HBM ("blocked planes"): bf16 [B][P][H][W][8] -- channel c lives in plane c/8,
+// element c%8.  A pixel row of one plane is contiguous (W*16 B), so
+//   * one 4-D TMA box [8ch, TW+2, TH+2, planes] brings a whole halo patch into shared memory
+//     already in the UMMA no-swizzle K-major core-matrix layout (8 consecutive pixels x 16 B =
+//     one 128-B core matrix); out-of-bounds rows/columns are zero-filled by TMA = conv padding;
+//   * each of the 9 filter taps is just a different START ADDRESS into the same patch
+//     (descriptor start + (dy*PW+dx)*16 B), so the activations are read from L2/HBM once per
+//     tile (1.4x halo overhead) instead of 9x as with im2col;
+//   * the epilogue's per-thread 16-B stores (8 channels of one pixel) coalesce to full 128-B
+//     lines across the 8 pixels of a tile row.
+//
+// GEMM view per CTA tile: M = 128 pixels (16 rows x 8 cols), N = Cout (pre-GLU), K = taps*Cin.
+// Weights (B operand) are packed once on the host side of the ABI (tgsr_pack_*) into the exact
+// shared-memory image and stay resident in smem for the CTA's lifetime (persistent kernel).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> BN/GLU/residual -> bf16 -> global).
+// Pipelines: NSTAGE patch buffers (full/empty mbarriers) and 2 TMEM accumulator stages
+// (tmem_full/tmem_empty), so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
+#include "ptx_sm100.cuh"
+#include <cuda_bf16.h>
+
 namespace tgsr {
-int init_conv_tc() { return TGSR_OK; }
+
+using namespace ptx;
+
+constexpr int TC_TH = 16, TC_TW = 8;            // tile = 16 rows x 8 cols = 128 pixels (UMMA M)
+constexpr int TC_PH = TC_TH + 2, TC_PW = TC_TW + 2;
+constexpr int TC_PLANE_BYTES = TC_PH * TC_PW * 16;   // one 8-channel plane of the halo patch
+constexpr int TC_NSTAGE = 3;
+constexpr int TC_THREADS = 192;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+
+// ------------------------------------------------------------------------------------------
+// MMA op tables.  An op = one filter tap (or one tap x phase group of the 4-phase upsample):
+// A start offset inside the patch, N, accumulator column offset; B blocks are stored in op order.
+struct TcOp { int tap_r, tap_c, n_mul, dcol_mul; };   // N = n_mul*NPRE, dcol = dcol_mul*NPRE
+
+template <bool UP> struct OpTable;
+template <> struct OpTable<false> {
+  static constexpr int NOPS = 9;
+  __host__ __device__ static constexpr TcOp op(int i) { return TcOp{i / 3, i % 3, 1, 0}; }
+};
+// 4-phase nearest-x2 + conv3x3: low-res tap (r,c) in {0,1,2}^2 (offset -1..+1) feeds the output
+// parities ph = py*2+px listed below (see pack kernel for the pre-summed weights).
+template <> struct OpTable<true> {
+  static constexpr int NOPS = 11;
+  __host__ __device__ static constexpr TcOp op(int i) {
+    constexpr TcOp t[11] = {
+        {1, 1, 4, 0},                                          // centre: all four phases
+        {0, 1, 2, 0}, {2, 1, 2, 2},                            // up: ph0,ph1   down: ph2,ph3
+        {1, 0, 1, 0}, {1, 0, 1, 2}, {1, 2, 1, 1}, {1, 2, 1, 3},  // left: ph0, ph2   right: ph1, ph3
+        {0, 0, 1, 0}, {0, 2, 1, 1}, {2, 0, 1, 2}, {2, 2, 1, 3}};  // corners
+    return t[i];
+  }
+};
+
+template <int CIN, int NPRE, bool UP>
+struct TcCfg {
+  static constexpr int NPL = CIN / 8;                          // input planes
+  static constexpr int KSTEPS = CIN / 16;                      // UMMA K = 16
+  static constexpr int PATCH_BYTES = NPL * TC_PLANE_BYTES;
+  static constexpr int ACC_COLS = UP ? 4 * NPRE : NPRE;        // fp32 accumulator columns per stage
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;               // double-buffered (power of two)
+  static constexpr int WBYTES = (UP ? 16 : 9) * CIN * NPRE * 2;
+  static constexpr int NSCALE = NPRE;
+  static constexpr size_t SMEM = 1024 /*align slack*/ + WBYTES + TC_NSTAGE * PATCH_BYTES + 2 * NSCALE * 4 + 256;
+};
+
+struct TcParams {
+  const void* wpacked;
+  const float* scale;      // [NPRE] or null
+  const float* shift;
+  const __nv_bfloat16* residual;   // blocked, or null
+  __nv_bfloat16* out;              // blocked
+  int rP, rp0, yP, yp0;            // planes per image / first plane of the residual and output views
+  int xP, xp0;                     // input view (for the TMA plane coordinate)
+  int B, H, W;                     // INPUT spatial size
+  int tiles_x, tiles_y, ntiles;
+};
+
+__device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
+  uint4 r;
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+  r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
+  return r;
+}
+__device__ __forceinline__ void unpack8_bf16(const uint4& u, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+template <int CIN, int NPRE, bool UP, bool GLU>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+  using Cfg = TcCfg<CIN, NPRE, UP>;
+  using Ops = OpTable<UP>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* w_s = base;
+  unsigned char* patch_s = w_s + Cfg::WBYTES;
+  float* sc_s = reinterpret_cast<float*>(patch_s + TC_NSTAGE * Cfg::PATCH_BYTES);
+  float* sh_s = sc_s + Cfg::NSCALE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sh_s + Cfg::NSCALE);
+  uint64_t* full = bars;                       // [NSTAGE]
+  uint64_t* empty = bars + TC_NSTAGE;          // [NSTAGE]
+  uint64_t* wbar = bars + 2 * TC_NSTAGE;       // [1]
+  uint64_t* tfull = wbar + 1;                  // [2]
+  uint64_t* tempty = tfull + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(wbar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+    prefetch_tensormap(&tmap);
+  }
+  for (int i = threadIdx.x; i < Cfg::NSCALE; i += TC_THREADS) {
+    sc_s[i] = p.scale ? p.scale[i] : 1.0f;
+    sh_s[i] = p.shift ? p.shift[i] : 0.0f;
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, Cfg::WBYTES);
+      constexpr int CH = 32768;
+      for (int off = 0; off < Cfg::WBYTES; off += CH) {
+        const int n = Cfg::WBYTES - off < CH ? Cfg::WBYTES - off : CH;
+        bulk_g2s(w_s + off, reinterpret_cast<const unsigned char*>(p.wpacked) + off, n, wbar);
+      }
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int b = tile / tiles_per_img, r = tile % tiles_per_img;
+        const int y0 = (r / p.tiles_x) * TC_TH, x0 = (r % p.tiles_x) * TC_TW;
+        mbar_arrive_expect_tx(&full[s], Cfg::PATCH_BYTES);
+        tma_load_4d(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], 0, x0 - 1, y0 - 1, b * p.xP + p.xp0);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+      const uint32_t w_addr = smem_u32(w_s);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
+        const int acc = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], aph ^ 1);            // epilogue has drained this accumulator stage
+        mbar_wait(&full[s], ph);                     // patch landed
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(patch_s + s * Cfg::PATCH_BYTES);
+        const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
+        uint32_t b_off = 0;
+#pragma unroll
+        for (int o = 0; o < Ops::NOPS; ++o) {
+          constexpr int dummy = 0; (void)dummy;
+          const TcOp op = Ops::op(o);
+          const int N = op.n_mul * NPRE;
+          const uint32_t idesc = make_idesc_bf16(128, N);
+          const uint32_t a_tap = a_base + (op.tap_r * TC_PW + op.tap_c) * 16;
+#pragma unroll
+          for (int k = 0; k < Cfg::KSTEPS; ++k) {
+            const uint64_t adesc = make_smem_desc(a_tap + k * 2 * TC_PLANE_BYTES, TC_PLANE_BYTES, TC_PW * 16);
+            const uint64_t bdesc = make_smem_desc(w_addr + b_off + k * (N * 32), N * 16, 128);
+            umma_f16(d_base + op.dcol_mul * NPRE, adesc, bdesc, idesc, (o | k) != 0 ? 1u : 0u);
+          }
+          b_off += CIN * N * 2;
+        }
+        umma_commit(&empty[s]);                      // patch slot reusable once these MMAs retire
+        umma_commit(&tfull[acc]);                    // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ========================
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int m = quad * 32 + lane;                  // accumulator row = pixel within the tile
+    const int ty = m >> 3, tx = m & 7;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1, aph = (it >> 1) & 1;
+      const int b = tile / tiles_per_img, r = tile % tiles_per_img;
+      const int gy = (r / p.tiles_x) * TC_TH + ty, gx = (r % p.tiles_x) * TC_TW + tx;
+      mbar_wait(&tfull[acc], aph);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + ((uint32_t)(quad * 32) << 16);
+
+      if constexpr (!UP) {
+        constexpr int COUT = GLU ? NPRE / 2 : NPRE;            // channels written
+        const size_t pix = ((size_t)gy * p.W + gx) * 8;
+        const size_t plane_elems = (size_t)p.H * p.W * 8;
+        __nv_bfloat16* obase = p.out + ((size_t)b * p.yP + p.yp0) * plane_elems + pix;
+        const __nv_bfloat16* rbase =
+            p.residual ? p.residual + ((size_t)b * p.rP + p.rp0) * plane_elems + pix : nullptr;
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 32) {
+          uint32_t va[32];
+          tmem_ld32(t_base + c0, va);
+          uint32_t vg[32];
+          if constexpr (GLU) tmem_ld32(t_base + COUT + c0, vg);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                         // 4 planes of 8 channels
+            float o[8];
+            float res[8];
+            if (rbase) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(c0 / 8 + j) * plane_elems));
+              unpack8_bf16(u, res);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int c = c0 + j * 8 + e;
+              float z = fmaf(__uint_as_float(va[j * 8 + e]), sc_s[c], sh_s[c]);
+              if constexpr (GLU) {
+                const float g = fmaf(__uint_as_float(vg[j * 8 + e]), sc_s[COUT + c], sh_s[COUT + c]);
+                z *= fast_sigmoid(g);
+              }
+              if (rbase) z += res[e];
+              o[e] = z;
+            }
+            *reinterpret_cast<uint4*>(obase + (size_t)(c0 / 8 + j) * plane_elems) = pack8_bf16(o);
+          }
+        }
+      } else {
+        // 4-phase upsample: accumulator columns [ph*NPRE, (ph+1)*NPRE) hold output pixel
+        // (2*gy + ph/2, 2*gx + ph%2); GLU halves inside each phase block.
+        static_assert(!UP || (GLU && NPRE == 64), "upsample path is conv(C -> 64) + GLU -> 32 channels");
+        constexpr int COUT = NPRE / 2;                          // 32
+        const int Ho = 2 * p.H, Wo = 2 * p.W;
+        const size_t plane_elems = (size_t)Ho * Wo * 8;
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+          uint32_t va[32], vg[32];
+          tmem_ld32(t_base + ph * NPRE, va);
+          tmem_ld32(t_base + ph * NPRE + COUT, vg);
+          tmem_ld_wait();
+          const int oy = 2 * gy + (ph >> 1), ox = 2 * gx + (ph & 1);
+          __nv_bfloat16* obase = p.out + ((size_t)b * p.yP + p.yp0) * plane_elems + ((size_t)oy * Wo + ox) * 8;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int c = j * 8 + e;
+              const float z = fmaf(__uint_as_float(va[c]), sc_s[c], sh_s[c]);
+              const float g = fmaf(__uint_as_float(vg[c]), sc_s[COUT + c], sh_s[COUT + c]);
+              o[e] = z * fast_sigmoid(g);
+            }
+            *reinterpret_cast<uint4*>(obase + (size_t)j * plane_elems) = pack8_bf16(o);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight packing (runs once per weight version).  Packed image = for each op, for each K chunk
+// kc (8 input channels), for each group of 8 output rows: a 128-B core matrix [8 rows][8 k] bf16.
+//   byte offset(op, n, c) = op_base + (c/8)*(N_op*16) + (n/8)*128 + (n%8)*16 + (c%8)*2
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin) {
+  const int total = 9 * Cout * Cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % Cin, n = (i / Cin) % Cout, t = i / (Cin * Cout);
+    const float v = w[((size_t)n * Cin + c) * 9 + t];
+    const size_t off = (size_t)t * Cin * Cout + (size_t)(c / 8) * (Cout * 8) + (size_t)(n / 8) * 64 + (n % 8) * 8 + (c % 8);
+    out[off] = __float2bfloat16_rn(v);
+  }
+}
+
+// Row sets of the 3x3 kernel that collapse onto low-res offset r (0,1,2 = -1,0,+1) for output
+// parity py:  py=0: r=0 <- {ky 0}, r=1 <- {ky 1,2};  py=1: r=1 <- {ky 0,1}, r=2 <- {ky 2}.
+__device__ __forceinline__ int up_taps(int parity, int r, int (&ks)[2]) {
+  if (parity == 0) { if (r == 0) { ks[0] = 0; return 1; } if (r == 1) { ks[0] = 1; ks[1] = 2; return 2; } return 0; }
+  if (r == 1) { ks[0] = 0; ks[1] = 1; return 2; }
+  if (r == 2) { ks[0] = 2; return 1; }
+  return 0;
+}
+
+__global__ void pack_up2x_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin) {
+  // 11 ops; op o covers phases {ph = dcol_mul .. dcol_mul + n_mul - 1}; rows of op = [phase][Cout]
+  using Ops = OpTable<true>;
+  int op_base = 0;
+  for (int o = 0; o < Ops::NOPS; ++o) {
+    const TcOp op = Ops::op(o);
+    const int N = op.n_mul * Cout;
+    const int total = N * Cin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int c = i % Cin, nn = i / Cin;
+      const int phase = op.dcol_mul + nn / Cout, n = nn % Cout;
+      const int py = phase >> 1, px = phase & 1;
+      int kys[2], kxs[2];
+      const int ny = up_taps(py, op.tap_r, kys), nx = up_taps(px, op.tap_c, kxs);
+      float v = 0.f;                                        // pre-summed in fp32, rounded once
+      for (int a = 0; a < ny; ++a)
+        for (int bq = 0; bq < nx; ++bq) v += w[((size_t)n * Cin + c) * 9 + kys[a] * 3 + kxs[bq]];
+      const size_t off = (size_t)op_base + (size_t)(c / 8) * (N * 8) + (size_t)(nn / 8) * 64 + (nn % 8) * 8 + (c % 8);
+      out[off] = __float2bfloat16_rn(v);
+    }
+    op_base += N * Cin;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Layout converters between the reference's NCHW fp32 tensors and the blocked bf16 layout.
+__global__ void nchw_to_blocked_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C, int HW,
+                                       int P, int p0) {
+  // one thread per (b, plane, pixel): gathers 8 channels (coalesced across pixels), writes 16 B
+  const size_t total = (size_t)B * (C / 8) * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(i % HW);
+    const int pl = (int)((i / HW) % (C / 8));
+    const int b = (int)(i / ((size_t)HW * (C / 8)));
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __ldg(x + ((size_t)b * C + pl * 8 + e) * HW + pix);
+    *reinterpret_cast<uint4*>(y + (((size_t)b * P + p0 + pl) * HW + pix) * 8) = pack8_bf16(v);
+  }
+}
+__global__ void blocked_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int C, int HW,
+                                       int P, int p0) {
+  const size_t total = (size_t)B * (C / 8) * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(i % HW);
+    const int pl = (int)((i / HW) % (C / 8));
+    const int b = (int)(i / ((size_t)HW * (C / 8)));
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * P + p0 + pl) * HW + pix) * 8));
+    float v[8];
+    unpack8_bf16(u, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[((size_t)b * C + pl * 8 + e) * HW + pix] = v[e];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+template <int CIN, int NPRE, bool UP, bool GLU>
+static int set_tc_attr() {
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, NPRE, UP, GLU>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<CIN, NPRE, UP>::SMEM);
+  return e == cudaSuccess ? TGSR_OK : cuda_fail(e);
+}
+
+int init_conv_tc() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess) return cuda_fail(e);
+  if (q != cudaDriverEntryPointSuccess || fn == nullptr) return TGSR_ERR_UNSUPPORTED;
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  int s;
+  if ((s = set_tc_attr<64, 128, false, true>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<64, 64, false, false>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<32, 64, false, true>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<32, 32, false, false>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<64, 64, true, true>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<32, 64, true, true>()) != TGSR_OK) return s;
+  return TGSR_OK;
+}
+
+static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl) {
+  cuuint64_t gdim[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * P};
+  cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  cuuint32_t box[4] = {8, (cuuint32_t)TC_PW, (cuuint32_t)TC_PH, (cuuint32_t)npl};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return TGSR_ERR_CUDA; }
+  return TGSR_OK;
+}
+
+template <int CIN, int NPRE, bool UP, bool GLU>
+static int launch_tc(const CUtensorMap& tmap, const TcParams& p, cudaStream_t st) {
+  const int grid = p.ntiles < g_sm_count ? p.ntiles : g_sm_count;
+  conv3x3_tc_kernel<CIN, NPRE, UP, GLU><<<grid, TC_THREADS, TcCfg<CIN, NPRE, UP>::SMEM, st>>>(tmap, p);
+  return launch_status();
+}
+
+}  // namespace tgsr
+
+extern "C" int tgsr_conv3x3_tc_bf16(const void* x, int xP, int xp0, const void* wpacked, const float* scale,
+                                    const float* shift, const void* residual, int rP, int rp0, void* y, int yP,
+                                    int yp0, int B, int Cin, int H, int W, int Cout, int up2x, int act,
+                                    tgsr_stream_t stream) {
+  using namespace tgsr;
+  TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(wpacked); TGSR_REQUIRE_PTR(y);
+  TGSR_REQUIRE(g_sm_count > 0 && g_encode_tiled != nullptr, TGSR_ERR_NOT_INIT);
+  TGSR_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE((scale == nullptr) == (shift == nullptr), TGSR_ERR_NULL);
+  TGSR_REQUIRE(H % TC_TH == 0 && W % TC_TW == 0, TGSR_ERR_UNSUPPORTED);
+  TGSR_REQUIRE(act == TGSR_ACT_NONE || act == TGSR_ACT_GLU, TGSR_ERR_UNSUPPORTED);
+  const int npl = Cin / 8;
+  const int cout_planes = (act == TGSR_ACT_GLU ? Cout / 2 : Cout) / 8;
+  TGSR_REQUIRE(xp0 >= 0 && xp0 + npl <= xP && yp0 >= 0 && yp0 + cout_planes <= yP, TGSR_ERR_BAD_SHAPE);
+  if (residual) TGSR_REQUIRE(rp0 >= 0 && rp0 + cout_planes <= rP && !up2x && act == TGSR_ACT_NONE, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(wpacked) & 15) == 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE((long long)B * xP < (1LL << 31), TGSR_ERR_UNSUPPORTED);
+
+  CUtensorMap tmap;
+  int s = make_patch_tmap(&tmap, x, B, xP, H, W, npl);
+  if (s != TGSR_OK) return s;
+  TcParams p;
+  p.wpacked = wpacked; p.scale = scale; p.shift = shift;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.out = reinterpret_cast<__nv_bfloat16*>(y);
+  p.rP = rP; p.rp0 = rp0; p.yP = yP; p.yp0 = yp0; p.xP = xP; p.xp0 = xp0;
+  p.B = B; p.H = H; p.W = W;
+  p.tiles_x = W / TC_TW; p.tiles_y = H / TC_TH; p.ntiles = B * p.tiles_x * p.tiles_y;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool glu = act == TGSR_ACT_GLU;
+  if (!up2x) {
+    if (Cin == 64 && Cout == 128 && glu) return launch_tc<64, 128, false, true>(tmap, p, st);
+    if (Cin == 64 && Cout == 64 && !glu) return launch_tc<64, 64, false, false>(tmap, p, st);
+    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, false, true>(tmap, p, st);
+    if (Cin == 32 && Cout == 32 && !glu) return launch_tc<32, 32, false, false>(tmap, p, st);
+  } else {
+    if (Cin == 64 && Cout == 64 && glu) return launch_tc<64, 64, true, true>(tmap, p, st);
+    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, true, true>(tmap, p, st);
+  }
+  return TGSR_ERR_UNSUPPORTED;
+}
+
+extern "C" int tgsr_pack_conv3x3_bf16(const float* w, void* packed, int Cout, int Cin, int up2x,
+                                      tgsr_stream_t stream) {
+  using namespace tgsr;
+  TGSR_REQUIRE_PTR(w); TGSR_REQUIRE_PTR(packed);
+  TGSR_REQUIRE(Cout > 0 && Cin > 0 && Cout % 8 == 0 && Cin % 8 == 0, TGSR_ERR_BAD_SHAPE);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (up2x) pack_up2x_kernel<<<64, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin);
+  else pack_conv3x3_kernel<<<64, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin);
+  return launch_status();
+}
+
+extern "C" int tgsr_nchw_to_blocked_bf16(const float* x, void* y, int B, int C, int H, int W, int yP, int yp0,
+                                         tgsr_stream_t stream) {
+  using namespace tgsr;
+  TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(y);
+  TGSR_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0 && yp0 >= 0 && yp0 + C / 8 <= yP, TGSR_ERR_BAD_SHAPE);
+  const size_t total = (size_t)B * (C / 8) * H * W;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  nchw_to_blocked_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), B, C, H * W,
+                                                                  yP, yp0);
+  return launch_status();
+}
+
+extern "C" int tgsr_blocked_to_nchw_f32(const void* x, float* y, int B, int C, int H, int W, int xP, int xp0,
+                                        tgsr_stream_t stream) {
+  using namespace tgsr;
+  TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(y);
+  TGSR_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0 && xp0 >= 0 && xp0 + C / 8 <= xP, TGSR_ERR_BAD_SHAPE);
+  const size_t total = (size_t)B * (C / 8) * H * W;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  blocked_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), y, B, C,
+                                                                  H * W, xP, xp0);
+  return launch_status();
 }
