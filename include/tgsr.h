@@ -132,6 +132,30 @@ int tgsr_conv3x3_tc_bf16(const void* x, int xP, int xp0, const void* wpacked, co
                          int yp0, int B, int Cin, int H, int W, int Cout, int up2x, int act,
                          tgsr_stream_t stream);
 
+/* a8 image heads on tensor cores: GET_IMAGE_G / GET_IMAGE_G_noAct (conv3x3 32->3, util.py:894-919) and
+ * conv_output (conv5x5 32->3 + Tanh, model.py:223-226) with the fused `one*y + a*SRb` of model.py:280.
+ * x: blocked view of 32 channels; wpacked from tgsr_pack_head_bf16 (w [3,Cin,k,k] fp32);
+ * y fp32 NCHW [B,3,H,W] = out_scale * act(conv(x)) + addend_scale * addend (addend NCHW or NULL).
+ * act NONE or TANH; H % 16 == 0, W % 8 == 0. */
+int tgsr_pack_head_bf16(const float* w, void* packed, int Cin, int ksize, tgsr_stream_t stream);
+int tgsr_img_head_tc_bf16(const void* x, int xP, int xp0, const void* wpacked, const float* addend,
+                          float out_scale, float addend_scale, float* y, int B, int Cin, int H, int W,
+                          int ksize, int act, tgsr_stream_t stream);
+
+/* im2f / convin: conv3x3(3 -> 2C) + folded BN + GLU from the NCHW fp32 LR image (minus x_sub if not
+ * NULL: model.py:268-270 `LR - LRb`) into a blocked bf16 view of C channels; util.py:741-744,
+ * model.py:228.  w [2C,3,3,3], scale/shift [2C] or NULL.  C % 8 == 0, C <= 64. */
+int tgsr_conv_in_bf16(const float* x, const float* x_sub, const float* w, const float* scale,
+                      const float* shift, void* y, int yP, int yp0, int B, int H, int W, int C,
+                      tgsr_stream_t stream);
+
+/* a1 on blocked activations: reads the idf=32 channel view (xP,xp0), writes weightedContext as bf16
+ * into the view (yP,yp0) -- normally the next planes of the same concat buffer -- and the
+ * attention map attn fp32 [B,T,Q].  context fp32 [B,cdf,T]; mask as tgsr_attn_fwd_f32.  T <= 20. */
+int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const float* context, const float* w_ctx,
+                          const uint8_t* mask, void* y, int yP, int yp0, float* attn, int B, int idf,
+                          int cdf, int Q, int T, tgsr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

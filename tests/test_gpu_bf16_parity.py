@@ -1,0 +1,161 @@
+"""bf16 tensor-core pipeline vs the CPU oracle and the golden fixtures (through the C ABI).
+
+Tolerances (BASELINE.json north_star): bf16 SR image max-abs <= 2e-2 on the [-1,1] scale and
+|dPSNR| <= 0.05 dB against the fp32 reference; caption masking bit-exact; word argmax exact away
+from fp-noise ties.  Kernel-level checks compare against a bf16-faithful emulation (same rounded
+operands, fp32 accumulation), where only summation order and the last rounding differ."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import tgsr_b200
+from oracle import tgsr_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.fixture(autouse=True)
+def _cfg():
+    tgsr_b200.set_eval_defaults()
+    tgsr_b200.set_precision('bf16')
+    yield
+    tgsr_b200.set_precision('fp32')
+
+
+@pytest.mark.parametrize('k,tanh,with_add,B,H,W', [(3, False, False, 2, 32, 32), (3, True, False, 1, 16, 8),
+                                                    (5, True, True, 2, 32, 16), (5, False, True, 1, 64, 64),
+                                                    (5, True, True, 3, 128, 128)])
+def test_image_head_tc(k, tanh, with_add, B, H, W):
+    from tgsr_b200 import fast, tc
+    g = torch.Generator().manual_seed(k * 100 + H)
+    x = torch.randn(B, 32, H, W, generator=g)
+    w = torch.randn(3, 32, k, k, generator=g) * (1.0 / (k * 32 ** 0.5))
+    add = torch.randn(B, 3, H, W, generator=g) if with_add else None
+    ref = F.conv2d(bf(x), bf(w), None, 1, k // 2)
+    if tanh:
+        ref = torch.tanh(ref)
+    ref = 1.0 * ref + (0.5 * add if with_add else 0)
+    seq = torch.nn.Sequential(torch.nn.Conv2d(32, 3, k, 1, k // 2, bias=False), *([torch.nn.Tanh()] if tanh else [])).to(DEV)
+    seq[0].weight.data.copy_(w)
+    y = fast.image_head(tc.to_blocked(x.to(DEV)), seq, None if add is None else add.to(DEV), 0.5, 1.0).cpu()
+    torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)
+
+
+def test_conv_in_bf16(golden):
+    from tgsr_b200 import blocks, fast, tc
+    g = golden('blocks.pt')['block3x3_3_32']
+    m = blocks.Block3x3_relu(3, 32); m.load_state_dict(g['sd']); m.to(DEV).eval()
+    x = g['x']
+    out = tc.Blocked.empty(x.shape[0], 32, x.shape[2], x.shape[3], DEV, planes=8, p0=0)
+    fast.conv_in(m, x.to(DEV), out)
+    y = tc.to_nchw(out).cpu()
+    assert (y - g['y']).abs().max() <= 2 ** -8 * max(1.0, g['y'].abs().max().item())
+    # fused subtraction (model.py:268-270 LR - LRb)
+    xs = torch.randn(x.shape, generator=torch.Generator().manual_seed(1)) * 0.1
+    fast.conv_in(m, x.to(DEV), out, xs.to(DEV))
+    sd = {'b.' + k: v for k, v in g['sd'].items()}
+    ref = O.block3x3(sd, 'b', x - xs)
+    assert (tc.to_nchw(out).cpu() - ref).abs().max() <= 2 ** -8 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize('B,ih,iw,T,ragged', [(1, 32, 32, 18, False), (4, 64, 64, 18, True), (3, 16, 8, 7, True),
+                                               (5, 17, 3, 20, True)])
+def test_attention_blocked(B, ih, iw, T, ragged):
+    from tgsr_b200 import fast, tc
+    g = torch.Generator().manual_seed(B * 10 + T)
+    x = bf(torch.randn(B, 32, ih, iw, generator=g) * 0.5)
+    ctx = torch.randn(B, 256, T, generator=g) * 0.5
+    w = torch.randn(32, 256, 1, 1, generator=g) * 0.1
+    mask = None
+    if ragged:
+        lens = torch.randint(1, T + 1, (B,), generator=g); lens[0] = T
+        mask = torch.arange(T)[None] >= lens[:, None]
+    ref_w, ref_a = O.global_attention(x, ctx, w, mask)
+    att = tgsr_b200.GlobalAttentionGeneral(32, 256).to(DEV); att.conv_context.weight.data.copy_(w)
+    cat = tc.Blocked.empty(B, 64, ih, iw, DEV)
+    h = tc.to_blocked(x.to(DEV), out=cat.slice(0, 32))
+    attn = fast.attention(h, att, ctx.to(DEV), None if mask is None else mask.to(DEV), out=cat.slice(32, 32)).cpu()
+    torch.testing.assert_close(attn, ref_a, rtol=5e-5, atol=1e-7)
+    assert torch.equal(attn == 0, ref_a == 0)
+    top2 = ref_a.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-4
+    assert torch.equal(attn.argmax(1)[safe], ref_a.argmax(1)[safe])
+    wc = tc.to_nchw(cat.slice(32, 32)).cpu()
+    assert (wc - ref_w).abs().max() <= 2 ** -8 * max(1.0, ref_w.abs().max().item())
+    assert torch.equal(tc.to_nchw(cat.slice(0, 32)).cpu(), x)           # h_code planes untouched
+
+
+def _report(name, sr, ref, hr=None):
+    err = (sr - ref).abs().max().item()
+    msg = '%s: max-abs %.4f' % (name, err)
+    dp = None
+    if hr is not None:
+        p_ref = O.psnr_u8(O.to_uint8(ref), O.to_uint8(hr)); p_sr = O.psnr_u8(O.to_uint8(sr), O.to_uint8(hr))
+        dp = p_sr - p_ref
+        msg += '  PSNR fp32 %.3f dB, bf16 %.3f dB, delta %+.4f dB' % (p_ref, p_sr, dp)
+    print(msg)
+    return err, dp
+
+
+def test_face_x8_checkpoint_bf16(golden):
+    """Shipped checkpoint, real LR image: bf16 pipeline vs the reference's fp32 output."""
+    from tgsr_b200 import nets
+    w = golden('face_S8_weights.pt'); g = golden('face_x8.pt'); c = g['b1']
+    gl = nets.G_SR_NET_low(); gl.load_state_dict(w['netG']); gl.to(DEV).eval()
+    gh = nets.NetG_highweight(weightmap=False, low='lr'); gh.load_state_dict(w['netGH']); gh.to(DEV).eval()
+    LR = c['LR'].to(DEV)
+    imgs, atts, mu, lv = gl(LR, c['sent'].to(DEV), c['words'].to(DEV), c['mask'].to(DEV))
+    fine, a, one = gh(LR, imgs, LR)
+    torch.testing.assert_close(mu.cpu(), c['mu'], rtol=1e-4, atol=1e-6)
+    # stage-1 attention sees only the bf16-rounded im2f features: masks exact, maps close
+    assert torch.equal(atts[0].cpu() == 0, c['atts'][0] == 0)
+    assert (atts[0].cpu() - c['atts'][0]).abs().max() < 2e-2
+    top2 = c['atts'][0].topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 5e-2
+    assert torch.equal(atts[0].cpu().argmax(1)[safe], c['atts'][0].argmax(1)[safe])
+    for k in range(3):
+        _report('netGL img%d' % k, imgs[k].cpu(), c['imgsL'][k])
+    err, dp = _report('face x8 SR (fine[-1])', fine[-1].cpu(), c['fine'][-1], g['hr'])
+    assert err <= 2e-2, err
+    assert abs(dp) <= 0.05, dp
+    for k in range(3):
+        assert (imgs[k].cpu() - c['imgsL'][k]).abs().max() <= 2e-2
+
+
+def test_bird_config_bf16_vs_oracle():
+    """cfg 2 analogue at a test-sized batch: random-init weights, randomised BN stats, smooth LR."""
+    from tgsr_b200.pipeline import SRPipeline
+    pipe = SRPipeline(5450, device=DEV, variant='x8', low='lr', seed=100, randomize_bn=True)
+    B = 4
+    LR = O.synth_lr(B, 32, seed=21)
+    caps, lens = O.synth_captions(B, 5450, seed=22, ragged=True)
+    fine, imgsL, atts = pipe.forward_device(LR.to(DEV), caps.to(DEV), lens.to(DEV))
+    sd = lambda m: {k: v.cpu() for k, v in m.state_dict().items()}
+    words, sent = O.rnn_encoder(sd(pipe.text_encoder), caps, lens)
+    mask = (caps == 0)[:, :words.shape[2]]
+    r_imgs, r_atts, _, _, _ = O.g_sr_net_low(sd(pipe.netGL), LR, sent, words, mask)
+    r_fine = O.netg_high(sd(pipe.netGH), LR, r_imgs, LR, low='lr')
+    hr = F.interpolate(LR, size=(256, 256), mode='bicubic', align_corners=False).clamp(-1, 1)
+    err, dp = _report('bird cfg SR', fine[-1].cpu(), r_fine[-1], hr)
+    assert torch.equal(atts[0].cpu() == 0, r_atts[0] == 0)
+    assert err <= 2e-2, err
+    assert abs(dp) <= 0.05, dp
+
+
+def test_sharding_invariance_bf16():
+    """Image sharding (cfg 4): with equal-length captions, running the batch in two halves gives
+    bit-identical images to running it whole (no cross-image coupling, deterministic kernels)."""
+    from tgsr_b200.pipeline import SRPipeline
+    pipe = SRPipeline(300, device=DEV, variant='x8', low='lr', seed=3, randomize_bn=True)
+    LR = O.synth_lr(8, 32, seed=5).to(DEV)
+    caps, lens = O.synth_captions(8, 300, seed=6)
+    caps, lens = caps.to(DEV), lens.to(DEV)
+    whole = pipe.forward_device(LR, caps, lens)[0][-1]
+    a = pipe.forward_device(LR[:4], caps[:4], lens[:4])[0][-1]
+    b = pipe.forward_device(LR[4:], caps[4:], lens[4:])[0][-1]
+    assert torch.equal(whole, torch.cat((a, b), 0))

@@ -39,6 +39,12 @@ _SIGS = {
     'tgsr_pack_conv3x3_bf16': ([C.c_void_p, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p], C.c_int),
     'tgsr_conv3x3_tc_bf16': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                               C.c_void_p, C.c_int, C.c_int] + [C.c_int] * 7 + [C.c_void_p], C.c_int),
+    'tgsr_pack_head_bf16': ([C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p], C.c_int),
+    'tgsr_img_head_tc_bf16': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+                              + [C.c_int] * 6 + [C.c_void_p], C.c_int),
+    'tgsr_conv_in_bf16': ([C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_void_p], C.c_int),
+    'tgsr_attn_fwd_blocked': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                               C.c_int, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p], C.c_int),
     'tgsr_lstm_bidir_fwd_f32': ([C.c_void_p] * 10 + [C.c_int] * 6 + [C.c_void_p], C.c_int),
 }
 

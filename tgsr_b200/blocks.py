@@ -43,6 +43,17 @@ def _conv(x, conv: nn.Conv2d, bn, act, **kw):
     return ops.conv2d_fused(x, conv.weight.detach(), scale, shift, act, **kw)
 
 
+def _bf16():
+    from . import get_precision
+    return get_precision() == 'bf16'
+
+
+def _tc_ok(conv: nn.Conv2d, act, up2x, x) -> bool:
+    """bf16 mode and the layer is inside the tcgen05 kernel's envelope (else: fp32 CUDA-core kernel)."""
+    from . import tc
+    return _bf16() and tc.tc_supported(conv.weight.shape[1], conv.weight.shape[0], act, up2x, x.shape[2], x.shape[3])
+
+
 # ---------------------------------------------------------------- leaf helpers (util.py:45-69)
 class GLU(nn.Module):
     """util.py:45-53.  Inside the blocks below GLU is fused into the conv epilogue; this
@@ -68,6 +79,9 @@ class _ConvBnGlu(nn.Sequential):
     def forward(self, x):
         mods = list(self)
         bn = mods[1] if isinstance(mods[1], nn.BatchNorm2d) else None
+        if _tc_ok(mods[0], ACT_GLU, False, x):
+            from . import fast, tc
+            return tc.to_nchw(fast.conv_bn_act(tc.to_blocked(x), mods[0], bn, ACT_GLU))
         return _conv(x, mods[0], bn, ACT_GLU)
 
 
@@ -78,6 +92,9 @@ class _UpBlock(nn.Sequential):
     def forward(self, x):
         mods = list(self)
         bn = mods[2] if isinstance(mods[2], nn.BatchNorm2d) else None
+        if _tc_ok(mods[1], ACT_GLU, True, x):
+            from . import fast, tc
+            return tc.to_nchw(fast.up_block(tc.to_blocked(x), self))
         return _conv(x, mods[1], bn, ACT_GLU, up2x=True)
 
 
@@ -86,6 +103,13 @@ class _ConvBnGluConvBn(nn.Sequential):
 
     def forward(self, x, residual=None):
         mods = list(self)
+        if isinstance(mods[1], nn.BatchNorm2d) and _tc_ok(mods[0], ACT_GLU, False, x) \
+                and _tc_ok(mods[3], ACT_NONE, False, x):
+            from . import fast, tc
+            xb = tc.to_blocked(x)
+            y = fast.conv_bn_act(xb, mods[0], mods[1], ACT_GLU)
+            rb = xb if residual is x else (None if residual is None else tc.to_blocked(residual))
+            return tc.to_nchw(fast.conv_bn_act(y, mods[3], mods[4], ACT_NONE, residual=rb))
         if isinstance(mods[1], nn.BatchNorm2d):
             y = _conv(x, mods[0], mods[1], ACT_GLU)
             return _conv(y, mods[3], mods[4], ACT_NONE, residual=residual)
@@ -98,6 +122,10 @@ class _ImageHead(nn.Sequential):
 
     def forward(self, h, addend=None, a: float = 0.0, one: float = 1.0):
         act = ACT_TANH if any(isinstance(m, nn.Tanh) for m in self) else ACT_NONE
+        if _bf16() and h.shape[1] == 32 and self[0].weight.shape[0] == 3 and h.shape[2] % 16 == 0 \
+                and h.shape[3] % 8 == 0:
+            from . import fast, tc
+            return fast.image_head(tc.to_blocked(h), self, addend, a, one)
         return _conv(h, self[0], None, act, addend=addend, out_scale=one, addend_scale=a)
 
 
@@ -192,6 +220,18 @@ class INIT_STAGE_G(nn.Module):
         return self.upsample4(out_code32)
 
 
+def _run_stage_bf16(stage, h_code, LR, word_embs, mask):
+    """Module-level call in bf16 mode: NCHW fp32 in/out around the blocked tensor-core stage."""
+    from . import fast, tc
+    stage.att.applyMask(mask)
+    hb = None
+    if h_code is not None:
+        B, C, H, W = h_code.shape
+        hb = tc.to_blocked(h_code, out=tc.Blocked.empty(B, C, H, W, h_code.device, planes=2 * C // 8))
+    out, att = fast.stage(stage, hb, LR, word_embs, mask, None)
+    return tc.to_nchw(out), att
+
+
 def _run_stage(stage, h_code, word_embs, mask):
     """Shared body of INIT_STAGE_GImgup / NEXT_STAGE_G (util.py:769-776, :814-821)."""
     stage.att.applyMask(mask)
@@ -220,6 +260,9 @@ class INIT_STAGE_GImgup(nn.Module):
         self.residual = nn.Sequential(*[ResBlock(ngf * 2, batchnorm) for _ in range(cfg.GAN.R_NUM)])
 
     def forward(self, c_code0, LR, word_embs, mask):
+        from . import fast
+        if _bf16() and fast.stage_supported(self, LR.shape[2], LR.shape[3]):
+            return _run_stage_bf16(self, None, LR, word_embs, mask)
         return _run_stage(self, self.im2f(LR), word_embs, mask)
 
 
@@ -240,6 +283,9 @@ class NEXT_STAGE_G(nn.Module):
         self.upsample = upBlock(ngf * 2, ngf)
 
     def forward(self, h_code, c_code0, word_embs, mask):
+        from . import fast
+        if _bf16() and fast.stage_supported(self, h_code.shape[2], h_code.shape[3]):
+            return _run_stage_bf16(self, h_code, None, word_embs, mask)
         return _run_stage(self, h_code, word_embs, mask)
 
 

@@ -8,6 +8,7 @@ int g_device = -1;
 unsigned long long g_launches = 0;
 int init_attention(void);   // attention.cu
 int init_conv_tc(void);     // conv_tc.cu (tcgen05 path)
+int init_blocked_misc(void);  // blocked_misc.cu
 }  // namespace tgsr
 
 extern "C" {
@@ -37,7 +38,9 @@ int tgsr_init(int device) {
   tgsr::g_device = device;
   int s = tgsr::init_attention();
   if (s != TGSR_OK) return s;
-  return tgsr::init_conv_tc();
+  s = tgsr::init_conv_tc();
+  if (s != TGSR_OK) return s;
+  return tgsr::init_blocked_misc();
 }
 
 int tgsr_sm_count(void) { return tgsr::g_sm_count; }

@@ -34,9 +34,12 @@ namespace tgsr {
 using namespace ptx;
 
 constexpr int TC_TH = 16, TC_TW = 8;            // tile = 16 rows x 8 cols = 128 pixels (UMMA M)
-constexpr int TC_PH = TC_TH + 2, TC_PW = TC_TW + 2;
-constexpr int TC_PLANE_BYTES = TC_PH * TC_PW * 16;   // one 8-channel plane of the halo patch
 constexpr int TC_NSTAGE = 3;
+// kernel modes: what the op table / epilogue compute
+constexpr int MODE_CONV = 0;    // conv3x3 (+BN, +GLU, +residual) -> blocked bf16
+constexpr int MODE_UP = 1;      // nearest-x2 + conv3x3 + BN + GLU as four sub-pixel phases -> blocked bf16 at 2H x 2W
+constexpr int MODE_HEAD3 = 2;   // conv3x3 32->3 image head -> fp32 NCHW (+tanh, one*y + a*addend)
+constexpr int MODE_HEAD5 = 3;   // conv5x5 32->3 image head -> fp32 NCHW (+tanh, one*y + a*addend)
 constexpr int TC_THREADS = 192;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -49,14 +52,22 @@ static EncodeTiledFn g_encode_tiled = nullptr;
 // A start offset inside the patch, N, accumulator column offset; B blocks are stored in op order.
 struct TcOp { int tap_r, tap_c, n_mul, dcol_mul; };   // N = n_mul*NPRE, dcol = dcol_mul*NPRE
 
-template <bool UP> struct OpTable;
-template <> struct OpTable<false> {
+template <int MODE> struct OpTable;
+template <> struct OpTable<MODE_CONV> {
   static constexpr int NOPS = 9;
   __host__ __device__ static constexpr TcOp op(int i) { return TcOp{i / 3, i % 3, 1, 0}; }
 };
+template <> struct OpTable<MODE_HEAD3> {
+  static constexpr int NOPS = 9;
+  __host__ __device__ static constexpr TcOp op(int i) { return TcOp{i / 3, i % 3, 1, 0}; }
+};
+template <> struct OpTable<MODE_HEAD5> {
+  static constexpr int NOPS = 25;
+  __host__ __device__ static constexpr TcOp op(int i) { return TcOp{i / 5, i % 5, 1, 0}; }
+};
 // 4-phase nearest-x2 + conv3x3: low-res tap (r,c) in {0,1,2}^2 (offset -1..+1) feeds the output
 // parities ph = py*2+px listed below (see pack kernel for the pre-summed weights).
-template <> struct OpTable<true> {
+template <> struct OpTable<MODE_UP> {
   static constexpr int NOPS = 11;
   __host__ __device__ static constexpr TcOp op(int i) {
     constexpr TcOp t[11] = {
@@ -68,16 +79,23 @@ template <> struct OpTable<true> {
   }
 };
 
-template <int CIN, int NPRE, bool UP>
+template <int CIN, int NPRE, int MODE>
 struct TcCfg {
+  static constexpr bool UP = MODE == MODE_UP;
+  static constexpr bool HEAD = MODE == MODE_HEAD3 || MODE == MODE_HEAD5;
+  static constexpr int R = MODE == MODE_HEAD5 ? 2 : 1;         // halo radius
+  static constexpr int PH = TC_TH + 2 * R, PW = TC_TW + 2 * R;
+  static constexpr int PLANE_BYTES = PH * PW * 16;             // one 8-channel plane of the halo patch
   static constexpr int NPL = CIN / 8;                          // input planes
   static constexpr int KSTEPS = CIN / 16;                      // UMMA K = 16
-  static constexpr int PATCH_BYTES = NPL * TC_PLANE_BYTES;
-  static constexpr int ACC_COLS = UP ? 4 * NPRE : NPRE;        // fp32 accumulator columns per stage
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;               // double-buffered (power of two)
-  static constexpr int WBYTES = (UP ? 16 : 9) * CIN * NPRE * 2;
+  static constexpr int PATCH_BYTES = NPL * PLANE_BYTES;
+  static constexpr int ACC_COLS = UP ? 4 * NPRE : (NPRE < 32 ? 32 : NPRE);   // fp32 accumulator columns per stage
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;               // double-buffered (power of two >= 32)
+  static constexpr int NTAPB = UP ? 16 : OpTable<MODE>::NOPS;  // number of [NPRE x CIN] weight blocks
+  static constexpr int WBYTES = NTAPB * CIN * NPRE * 2;
   static constexpr int NSCALE = NPRE;
-  static constexpr size_t SMEM = 1024 /*align slack*/ + WBYTES + TC_NSTAGE * PATCH_BYTES + 2 * NSCALE * 4 + 256;
+  static constexpr size_t SMEM = 1024 /*align slack*/ + ((WBYTES + 1023) / 1024) * 1024 + TC_NSTAGE * PATCH_BYTES +
+                                 2 * NSCALE * 4 + 256;
 };
 
 struct TcParams {
@@ -90,6 +108,11 @@ struct TcParams {
   int xP, xp0;                     // input view (for the TMA plane coordinate)
   int B, H, W;                     // INPUT spatial size
   int tiles_x, tiles_y, ntiles;
+  // image-head epilogue (MODE_HEAD*): y = out_scale * act(conv) + addend_scale * addend, fp32 NCHW [B,3,H,W]
+  float* out_f32;
+  const float* addend;
+  float out_scale, addend_scale;
+  int act_tanh;
 };
 
 __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
@@ -107,15 +130,20 @@ __device__ __forceinline__ void unpack8_bf16(const uint4& u, float (&v)[8]) {
 }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-template <int CIN, int NPRE, bool UP, bool GLU>
+template <int CIN, int NPRE, int MODE, bool GLU>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
-  using Cfg = TcCfg<CIN, NPRE, UP>;
-  using Ops = OpTable<UP>;
+  using Cfg = TcCfg<CIN, NPRE, MODE>;
+  using Ops = OpTable<MODE>;
+  constexpr bool UP = Cfg::UP;
+  constexpr bool HEAD = Cfg::HEAD;
+  constexpr int TC_PW = Cfg::PW;
+  constexpr int TC_PLANE_BYTES = Cfg::PLANE_BYTES;
+  constexpr int WB_PAD = ((Cfg::WBYTES + 1023) / 1024) * 1024;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char* w_s = base;
-  unsigned char* patch_s = w_s + Cfg::WBYTES;
+  unsigned char* patch_s = w_s + WB_PAD;
   float* sc_s = reinterpret_cast<float*>(patch_s + TC_NSTAGE * Cfg::PATCH_BYTES);
   float* sh_s = sc_s + Cfg::NSCALE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sh_s + Cfg::NSCALE);
@@ -163,7 +191,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const int b = tile / tiles_per_img, r = tile % tiles_per_img;
         const int y0 = (r / p.tiles_x) * TC_TH, x0 = (r % p.tiles_x) * TC_TW;
         mbar_arrive_expect_tx(&full[s], Cfg::PATCH_BYTES);
-        tma_load_4d(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], 0, x0 - 1, y0 - 1, b * p.xP + p.xp0);
+        tma_load_4d(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], 0, x0 - Cfg::R, y0 - Cfg::R, b * p.xP + p.xp0);
       }
     }
   } else if (warp == 1) {
@@ -215,7 +243,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + ((uint32_t)(quad * 32) << 16);
 
-      if constexpr (!UP) {
+      if constexpr (HEAD) {
+        // image head: accumulator columns 0..2 are the RGB outputs (rows 3..15 of B are zero)
+        uint32_t v[16];
+        tmem_ld16(t_base, v);
+        tmem_ld_wait();
+        const size_t hw = (size_t)p.H * p.W;
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          float z = __uint_as_float(v[o]);
+          if (p.act_tanh) z = tanhf(z);
+          z *= p.out_scale;
+          const size_t oi = ((size_t)b * 3 + o) * hw + (size_t)gy * p.W + gx;
+          if (p.addend) z = fmaf(p.addend_scale, __ldg(p.addend + oi), z);
+          p.out_f32[oi] = z;
+        }
+      } else if constexpr (!UP) {
         constexpr int COUT = GLU ? NPRE / 2 : NPRE;            // channels written
         const size_t pix = ((size_t)gy * p.W + gx) * 8;
         const size_t plane_elems = (size_t)p.H * p.W * 8;
@@ -254,7 +297,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       } else {
         // 4-phase upsample: accumulator columns [ph*NPRE, (ph+1)*NPRE) hold output pixel
         // (2*gy + ph/2, 2*gx + ph%2); GLU halves inside each phase block.
-        static_assert(!UP || (GLU && NPRE == 64), "upsample path is conv(C -> 64) + GLU -> 32 channels");
+        static_assert(GLU && NPRE == 64, "upsample path is conv(C -> 64) + GLU -> 32 channels");
         constexpr int COUT = NPRE / 2;                          // 32
         const int Ho = 2 * p.H, Wo = 2 * p.W;
         const size_t plane_elems = (size_t)Ho * Wo * 8;
@@ -305,6 +348,17 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* 
   }
 }
 
+// Image heads: w [3][Cin][K][K] -> per tap a [16 x Cin] block whose rows 3..15 are zero.
+__global__ void pack_head_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int K) {
+  const int total = K * K * 16 * Cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % Cin, n = (i / Cin) % 16, t = i / (Cin * 16);
+    const float v = n < 3 ? w[((size_t)n * Cin + c) * K * K + t] : 0.f;
+    const size_t off = (size_t)t * Cin * 16 + (size_t)(c / 8) * (16 * 8) + (size_t)(n / 8) * 64 + (n % 8) * 8 + (c % 8);
+    out[off] = __float2bfloat16_rn(v);
+  }
+}
+
 // Row sets of the 3x3 kernel that collapse onto low-res offset r (0,1,2 = -1,0,+1) for output
 // parity py:  py=0: r=0 <- {ky 0}, r=1 <- {ky 1,2};  py=1: r=1 <- {ky 0,1}, r=2 <- {ky 2}.
 __device__ __forceinline__ int up_taps(int parity, int r, int (&ks)[2]) {
@@ -316,7 +370,7 @@ __device__ __forceinline__ int up_taps(int parity, int r, int (&ks)[2]) {
 
 __global__ void pack_up2x_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin) {
   // 11 ops; op o covers phases {ph = dcol_mul .. dcol_mul + n_mul - 1}; rows of op = [phase][Cout]
-  using Ops = OpTable<true>;
+  using Ops = OpTable<MODE_UP>;
   int op_base = 0;
   for (int o = 0; o < Ops::NOPS; ++o) {
     const TcOp op = Ops::op(o);
@@ -370,10 +424,10 @@ __global__ void blocked_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, floa
 }
 
 // ------------------------------------------------------------------------------------------
-template <int CIN, int NPRE, bool UP, bool GLU>
+template <int CIN, int NPRE, int MODE, bool GLU>
 static int set_tc_attr() {
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, NPRE, UP, GLU>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<CIN, NPRE, UP>::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, NPRE, MODE, GLU>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<CIN, NPRE, MODE>::SMEM);
   return e == cudaSuccess ? TGSR_OK : cuda_fail(e);
 }
 
@@ -385,16 +439,19 @@ int init_conv_tc() {
   if (q != cudaDriverEntryPointSuccess || fn == nullptr) return TGSR_ERR_UNSUPPORTED;
   g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
   int s;
-  if ((s = set_tc_attr<64, 128, false, true>()) != TGSR_OK) return s;
-  if ((s = set_tc_attr<64, 64, false, false>()) != TGSR_OK) return s;
-  if ((s = set_tc_attr<32, 64, false, true>()) != TGSR_OK) return s;
-  if ((s = set_tc_attr<32, 32, false, false>()) != TGSR_OK) return s;
-  if ((s = set_tc_attr<64, 64, true, true>()) != TGSR_OK) return s;
-  if ((s = set_tc_attr<32, 64, true, true>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<64, 128, MODE_CONV, true>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<64, 64, MODE_CONV, false>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<32, 64, MODE_CONV, true>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<32, 32, MODE_CONV, false>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<64, 64, MODE_UP, true>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<32, 64, MODE_UP, true>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<32, 16, MODE_HEAD3, false>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<32, 16, MODE_HEAD5, false>()) != TGSR_OK) return s;
   return TGSR_OK;
 }
 
-static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl) {
+static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl, int R = 1) {
+  const int TC_PW = TC_TW + 2 * R, TC_PH = TC_TH + 2 * R;
   cuuint64_t gdim[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * P};
   cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
   cuuint32_t box[4] = {8, (cuuint32_t)TC_PW, (cuuint32_t)TC_PH, (cuuint32_t)npl};
@@ -406,10 +463,10 @@ static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, i
   return TGSR_OK;
 }
 
-template <int CIN, int NPRE, bool UP, bool GLU>
+template <int CIN, int NPRE, int MODE, bool GLU>
 static int launch_tc(const CUtensorMap& tmap, const TcParams& p, cudaStream_t st) {
   const int grid = p.ntiles < g_sm_count ? p.ntiles : g_sm_count;
-  conv3x3_tc_kernel<CIN, NPRE, UP, GLU><<<grid, TC_THREADS, TcCfg<CIN, NPRE, UP>::SMEM, st>>>(tmap, p);
+  conv3x3_tc_kernel<CIN, NPRE, MODE, GLU><<<grid, TC_THREADS, TcCfg<CIN, NPRE, MODE>::SMEM, st>>>(tmap, p);
   return launch_status();
 }
 
@@ -444,16 +501,17 @@ extern "C" int tgsr_conv3x3_tc_bf16(const void* x, int xP, int xp0, const void* 
   p.rP = rP; p.rp0 = rp0; p.yP = yP; p.yp0 = yp0; p.xP = xP; p.xp0 = xp0;
   p.B = B; p.H = H; p.W = W;
   p.tiles_x = W / TC_TW; p.tiles_y = H / TC_TH; p.ntiles = B * p.tiles_x * p.tiles_y;
+  p.out_f32 = nullptr; p.addend = nullptr; p.out_scale = 1.f; p.addend_scale = 0.f; p.act_tanh = 0;
   cudaStream_t st = (cudaStream_t)stream;
   const bool glu = act == TGSR_ACT_GLU;
   if (!up2x) {
-    if (Cin == 64 && Cout == 128 && glu) return launch_tc<64, 128, false, true>(tmap, p, st);
-    if (Cin == 64 && Cout == 64 && !glu) return launch_tc<64, 64, false, false>(tmap, p, st);
-    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, false, true>(tmap, p, st);
-    if (Cin == 32 && Cout == 32 && !glu) return launch_tc<32, 32, false, false>(tmap, p, st);
+    if (Cin == 64 && Cout == 128 && glu) return launch_tc<64, 128, MODE_CONV, true>(tmap, p, st);
+    if (Cin == 64 && Cout == 64 && !glu) return launch_tc<64, 64, MODE_CONV, false>(tmap, p, st);
+    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, MODE_CONV, true>(tmap, p, st);
+    if (Cin == 32 && Cout == 32 && !glu) return launch_tc<32, 32, MODE_CONV, false>(tmap, p, st);
   } else {
-    if (Cin == 64 && Cout == 64 && glu) return launch_tc<64, 64, true, true>(tmap, p, st);
-    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, true, true>(tmap, p, st);
+    if (Cin == 64 && Cout == 64 && glu) return launch_tc<64, 64, MODE_UP, true>(tmap, p, st);
+    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, MODE_UP, true>(tmap, p, st);
   }
   return TGSR_ERR_UNSUPPORTED;
 }
@@ -467,6 +525,40 @@ extern "C" int tgsr_pack_conv3x3_bf16(const float* w, void* packed, int Cout, in
   if (up2x) pack_up2x_kernel<<<64, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin);
   else pack_conv3x3_kernel<<<64, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin);
   return launch_status();
+}
+
+extern "C" int tgsr_pack_head_bf16(const float* w, void* packed, int Cin, int ksize, tgsr_stream_t stream) {
+  using namespace tgsr;
+  TGSR_REQUIRE_PTR(w); TGSR_REQUIRE_PTR(packed);
+  TGSR_REQUIRE(Cin > 0 && Cin % 8 == 0 && (ksize == 3 || ksize == 5), TGSR_ERR_BAD_SHAPE);
+  pack_head_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cin, ksize);
+  return launch_status();
+}
+
+extern "C" int tgsr_img_head_tc_bf16(const void* x, int xP, int xp0, const void* wpacked, const float* addend,
+                                     float out_scale, float addend_scale, float* y, int B, int Cin, int H, int W,
+                                     int ksize, int act, tgsr_stream_t stream) {
+  using namespace tgsr;
+  TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(wpacked); TGSR_REQUIRE_PTR(y);
+  TGSR_REQUIRE(g_sm_count > 0 && g_encode_tiled != nullptr, TGSR_ERR_NOT_INIT);
+  TGSR_REQUIRE(B > 0 && H > 0 && W > 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE(Cin == 32 && (ksize == 3 || ksize == 5) && H % TC_TH == 0 && W % TC_TW == 0, TGSR_ERR_UNSUPPORTED);
+  TGSR_REQUIRE(act == TGSR_ACT_NONE || act == TGSR_ACT_TANH, TGSR_ERR_UNSUPPORTED);
+  TGSR_REQUIRE(xp0 >= 0 && xp0 + Cin / 8 <= xP, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE((long long)B * xP < (1LL << 31), TGSR_ERR_UNSUPPORTED);
+  CUtensorMap tmap;
+  int s = make_patch_tmap(&tmap, x, B, xP, H, W, Cin / 8, ksize / 2);
+  if (s != TGSR_OK) return s;
+  TcParams p;
+  p.wpacked = wpacked; p.scale = nullptr; p.shift = nullptr; p.residual = nullptr; p.out = nullptr;
+  p.rP = p.rp0 = p.yP = p.yp0 = 0; p.xP = xP; p.xp0 = xp0;
+  p.B = B; p.H = H; p.W = W;
+  p.tiles_x = W / TC_TW; p.tiles_y = H / TC_TH; p.ntiles = B * p.tiles_x * p.tiles_y;
+  p.out_f32 = y; p.addend = addend; p.out_scale = out_scale; p.addend_scale = addend_scale;
+  p.act_tanh = act == TGSR_ACT_TANH;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ksize == 3) return launch_tc<32, 16, MODE_HEAD3, false>(tmap, p, st);
+  return launch_tc<32, 16, MODE_HEAD5, false>(tmap, p, st);
 }
 
 extern "C" int tgsr_nchw_to_blocked_bf16(const float* x, void* y, int B, int C, int H, int W, int yP, int yp0,

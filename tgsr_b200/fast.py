@@ -1,0 +1,174 @@
+"""bf16 tensor-core execution of the generator modules (precision 'bf16').
+
+The module objects in blocks.py / nets.py own the parameters; the functions here run their
+forward on blocked-plane bf16 activations (tc.Blocked) so that consecutive layers chain in HBM
+without layout conversions, channel concatenation is a plane offset, and every conv is a tcgen05
+kernel.  Edge tensors stay in the reference's format: LR in and images / attention maps / mu /
+logvar out are NCHW fp32.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops, tc
+from ._lib import ACT_GLU, ACT_NONE, ACT_TANH, call, ptr
+from .tc import Blocked
+
+Tensor = torch.Tensor
+
+
+def _fold(bn):
+    from .blocks import _folded_bn
+    return _folded_bn(bn)
+
+
+# ---------------------------------------------------------------- single layers
+def conv_bn_act(x: Blocked, conv: nn.Conv2d, bn, act: int, residual: Optional[Blocked] = None, up2x: bool = False,
+                out: Optional[Blocked] = None) -> Blocked:
+    scale, shift = _fold(bn)
+    return tc.conv3x3_tc(x, conv, scale, shift, act, residual=residual, up2x=up2x, out=out)
+
+
+def conv_in(seq, x: Tensor, out: Blocked, x_sub: Optional[Tensor] = None) -> Blocked:
+    """[conv3x3(3,2C), BN, GLU] from the NCHW fp32 image (util.py:741-744, model.py:228)."""
+    conv = seq[0]
+    bn = seq[1] if isinstance(seq[1], nn.BatchNorm2d) else None
+    scale, shift = _fold(bn)
+    x = x.contiguous()
+    B, _, H, W = x.shape
+    C = conv.weight.shape[0] // 2
+    assert out.C == C and out.H == H and out.W == W
+    xs = None if x_sub is None else x_sub.contiguous()
+    call('tgsr_conv_in_bf16', x.device, ptr(x), ptr(xs), ptr(conv.weight.detach().contiguous()), ptr(scale), ptr(shift),
+         ptr(out.buf), out.P, out.p0, B, H, W, C)
+    return out
+
+
+def res_block(x: Blocked, rb) -> Blocked:
+    """ResBlock (util.py:110-130): two tcgen05 kernels, the skip add fused into the second."""
+    blk = rb.block
+    y = conv_bn_act(x, blk[0], blk[1], ACT_GLU)
+    return conv_bn_act(y, blk[3], blk[4], ACT_NONE, residual=x)
+
+
+def body_noskip(x: Blocked, seq) -> Blocked:
+    """residual24 / residual48 (model.py:229-232): conv-BN-GLU-conv-BN without skip."""
+    y = conv_bn_act(x, seq[0], seq[1], ACT_GLU)
+    return conv_bn_act(y, seq[3], seq[4], ACT_NONE)
+
+
+def up_block(x: Blocked, seq, out_planes: Optional[int] = None) -> Blocked:
+    """upBlock (util.py:74-80) as the 4-phase sub-pixel kernel; the output may be allocated with
+    extra planes so the next stage's attention can append c_code in place."""
+    conv, bn = seq[1], seq[2]
+    C = conv.weight.shape[0] // 2
+    out = Blocked.empty(x.B, C, 2 * x.H, 2 * x.W, x.device, planes=out_planes)
+    return conv_bn_act(x, conv, bn, ACT_GLU, up2x=True, out=out)
+
+
+def _packed_head(conv: nn.Conv2d) -> Tensor:
+    w = conv.weight
+    key = (w.data_ptr(), w._version, str(w.device))
+    cached = conv.__dict__.get('_tgsr_packed_head')
+    if cached is None or cached[0] != key:
+        k = w.shape[2]
+        packed = torch.empty(k * k * 16 * w.shape[1], device=w.device, dtype=torch.bfloat16)
+        call('tgsr_pack_head_bf16', w.device, ptr(w.detach().contiguous()), ptr(packed), w.shape[1], k)
+        cached = (key, packed)
+        conv.__dict__['_tgsr_packed_head'] = cached
+    return cached[1]
+
+
+def image_head(x: Blocked, head_seq, addend: Optional[Tensor] = None, a: float = 0.0, one: float = 1.0) -> Tensor:
+    """GET_IMAGE_G[_noAct].img / conv_output -> fp32 NCHW image (util.py:894-919, model.py:223-226,280)."""
+    conv = head_seq[0]
+    act = ACT_TANH if any(isinstance(m, nn.Tanh) for m in head_seq) else ACT_NONE
+    k = conv.weight.shape[2]
+    y = torch.empty((x.B, 3, x.H, x.W), device=x.device, dtype=torch.float32)
+    ad = None
+    if addend is not None:
+        if tuple(addend.shape) != tuple(y.shape):
+            raise ValueError('SRb shape %s != image shape %s' % (tuple(addend.shape), tuple(y.shape)))
+        ad = addend.contiguous()
+    call('tgsr_img_head_tc_bf16', x.device, ptr(x.buf), x.P, x.p0, ptr(_packed_head(conv)), ptr(ad), float(one), float(a),
+         ptr(y), x.B, x.C, x.H, x.W, k, act)
+    return y
+
+
+def attention(h: Blocked, att, words: Tensor, mask: Optional[Tensor], out: Blocked) -> Tensor:
+    """GlobalAttentionGeneral on blocked activations; c_code goes to `out` (normally the next planes
+    of h's own buffer).  Returns the fp32 attention map [B,T,ih,iw]."""
+    B, T = words.shape[0], words.shape[2]
+    idf, cdf = att.conv_context.weight.shape[0], att.conv_context.weight.shape[1]
+    attn = torch.empty((B, T, h.H, h.W), device=h.device, dtype=torch.float32)
+    m8 = None if mask is None else mask.to(device=h.device, dtype=torch.uint8).contiguous()
+    if idf == 32 and T <= 20:
+        call('tgsr_attn_fwd_blocked', h.device, ptr(h.buf), h.P, h.p0, ptr(words.contiguous()),
+             ptr(att.conv_context.weight.detach().contiguous()), ptr(m8), ptr(out.buf), out.P, out.p0, ptr(attn),
+             B, idf, cdf, h.H * h.W, T)
+        return attn
+    # outside the blocked kernel's envelope (long captions): fp32 kernel + layout conversion
+    wctx, attn = ops.attention_fwd(tc.to_nchw(h), words, att.conv_context.weight.detach(), mask)
+    tc.to_blocked(wctx, out=out)
+    return attn
+
+
+# ---------------------------------------------------------------- stages and nets
+def stage(st, h: Optional[Blocked], LR: Optional[Tensor], words: Tensor, mask, out_planes: Optional[int]):
+    """INIT_STAGE_GImgup (LR given) / NEXT_STAGE_G (h given); util.py:763-777 / :807-823.
+    `h` must be the first 32-channel view of a 64-channel buffer: c_code is appended in place."""
+    ngf = st.gf_dim
+    if h is None:
+        B, _, H, W = LR.shape
+        cat = Blocked.empty(B, 2 * ngf, H, W, LR.device)
+        h = conv_in(st.im2f, LR, cat.slice(0, ngf))
+    else:
+        assert h.p0 == 0 and h.P * 8 >= 2 * ngf, 'h_code must live in a concat-sized buffer'
+        cat = Blocked(h.buf, 0, 2 * ngf)
+    att = attention(h, st.att, words, mask, out=cat.slice(ngf, ngf))
+    x = cat
+    for rb in st.residual:
+        x = res_block(x, rb)
+    return up_block(x, st.upsample, out_planes=out_planes), att
+
+
+def stage_supported(st, H: int, W: int) -> bool:
+    return st.gf_dim == 32 and H % 16 == 0 and W % 8 == 0 and getattr(st, 'batchnorm', True)
+
+
+def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, heads, outmiddle: bool):
+    imgs: List[Tensor] = []
+    atts: List[Tensor] = []
+    feats: List[Blocked] = []
+    c_code, mu, logvar = net.ca_net(sent)
+    h = None
+    n = len(stages)
+    for i, (st, hd) in enumerate(zip(stages, heads)):
+        planes = 8 if i + 1 < n else 4                     # leave room for the next stage's c_code
+        h, att = stage(st, h, LR if i == 0 else None, words, mask, planes)
+        imgs.append(image_head(h, hd.img))
+        atts.append(att)
+        feats.append(h)
+    if outmiddle:
+        return imgs, atts, mu, logvar, [tc.to_nchw(f) for f in feats]
+    return imgs, atts, mu, logvar
+
+
+def netg_high(net, x: Tensor, x_sub: Optional[Tensor], SRb, a: float, one: float, tail, feats=None) -> List[Tensor]:
+    """Trunk of NetG_high / NetG_highweight (model.py:264-298).  `tail` = [(body, upscale), ...] after
+    the first upscale."""
+    B, _, H, W = x.shape
+    h = conv_in(net.convin, x, Blocked.empty(B, 32, H, W, x.device), x_sub)
+    for rb in net.residual:
+        h = res_block(h, rb)
+    h = up_block(h, net.upscale2x)
+    if feats is not None: feats.append(tc.to_nchw(h))
+    ims = [image_head(h, net.conv_output, SRb[0], a, one)]
+    for k, (body, up) in enumerate(tail):
+        h = up_block(body_noskip(h, body), up)
+        if feats is not None: feats.append(tc.to_nchw(h))
+        ims.append(image_head(h, net.conv_output, SRb[k + 1], a, one))
+    return ims

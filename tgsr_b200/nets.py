@@ -28,6 +28,12 @@ class G_SR_NET_low(nn.Module):
         self.img_net3 = GET_IMAGE_G_noAct(ngf)
 
     def forward(self, LR, sent_emb, word_embs, mask, outmiddle=False):
+        from . import fast, get_precision
+        if get_precision() == 'bf16' and fast.stage_supported(self.h_net1, LR.shape[2], LR.shape[3]):
+            for st in (self.h_net1, self.h_net2, self.h_net3):
+                st.att.applyMask(mask)                              # keep the stateful contract
+            return fast.g_sr_net_low(self, LR, sent_emb, word_embs, mask, [self.h_net1, self.h_net2, self.h_net3],
+                                     [self.img_net1, self.img_net2, self.img_net3], outmiddle)
         fake_imgs, att_maps = [], []
         c_code, mu, logvar = self.ca_net(sent_emb)              # c_code unused, model.py:51
         h_code1, att0 = self.h_net1(None, LR, word_embs, mask)
@@ -65,7 +71,14 @@ class _HighBase(nn.Module):
         self.residual48 = _ConvBnGluConvBn(conv3x3(ngf, ngf * 2), nn.BatchNorm2d(ngf * 2), GLU(), conv3x3(ngf, ngf),
                                            nn.BatchNorm2d(ngf))
 
-    def _trunk(self, x, SRb, a, one, feats=None):
+    def _trunk(self, x, SRb, a, one, feats=None, x_sub=None):
+        from . import fast, get_precision
+        if get_precision() == 'bf16' and self.convin[0].weight.shape[0] == 64 and x.shape[2] % 16 == 0 \
+                and x.shape[3] % 8 == 0:
+            return fast.netg_high(self, x, x_sub, SRb, a, one,
+                                  [(self.residual24, self.upscale4x), (self.residual48, self.upscale8x)], feats)
+        if x_sub is not None:
+            x = torch.sub(x, x_sub)
         out = self.convin(x)
         out = self.residual(out)
         out = self.upscale2x(out)
@@ -91,9 +104,8 @@ class NetG_high(_HighBase):
         self._build(cfg.GAN.GF_DIM)
 
     def forward(self, LR, SRb, LRb, low=False, outmiddle=False):
-        x = LRb if low else torch.sub(LR, LRb)
         feats = [] if outmiddle else None
-        ims = self._trunk(x, SRb, 1.0, 1.0, feats)
+        ims = self._trunk(LRb, SRb, 1.0, 1.0, feats) if low else self._trunk(LR, SRb, 1.0, 1.0, feats, x_sub=LRb)
         return (ims, feats) if outmiddle else ims
 
 
@@ -113,14 +125,17 @@ class NetG_highweight(_HighBase):
         self.one = torch.ones([1])
 
     def forward(self, LR, SRb, LRb):
+        x_sub = None
         if self.low == 'lrblur':
             x = LRb
         elif self.low == 'lr-lrblur':
-            x = torch.sub(LR, LRb)
+            x, x_sub = LR, LRb
         elif self.low == 'lr':
             x = LR
         else:
             raise ValueError(self.low)
-        ims = self._trunk(x, SRb, float(self.a), float(self.one))
+        ims = self._trunk(x, SRb, 0.5, 1.0, x_sub=x_sub)
         dev = ims[0].device
-        return ims, self.a.to(dev), self.one.to(dev)
+        if self.a.device != dev:
+            self.a, self.one = self.a.to(dev), self.one.to(dev)
+        return ims, self.a, self.one
