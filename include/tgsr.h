@@ -39,6 +39,8 @@ typedef enum {
 
 /* activation selectors for the conv entry points */
 enum { TGSR_ACT_NONE = 0, TGSR_ACT_GLU = 1, TGSR_ACT_TANH = 2 };
+/* 16-bit operand/storage format of the tensor-core path (both: tcgen05 kind::f16, fp32 accumulate) */
+enum { TGSR_FMT_BF16 = 0, TGSR_FMT_F16 = 1 };
 
 int tgsr_version(void);
 const char* tgsr_error_string(int status);
@@ -101,60 +103,62 @@ int tgsr_lstm_bidir_fwd_f32(const int64_t* captions, const int64_t* cap_lens, co
                             int Tcap, int Tmax, int ntoken, int ninput, int H,
                             tgsr_stream_t stream);
 
-/* =============================== bf16 tensor-core path =====================================
- * Activations live in HBM as "blocked planes": bf16 [B][P][H][W][8]; channel c is element c%8 of
+/* =============================== 16-bit tensor-core path ===================================
+ * Every entry point below takes `fmt` (TGSR_FMT_BF16 or TGSR_FMT_F16): the storage format of the
+ * blocked activations and packed weights it touches.
+ * Activations live in HBM as "blocked planes": 16-bit [B][P][H][W][8]; channel c is element c%8 of
  * plane c/8.  A view of C channels inside a buffer with P planes per image is (ptr, P, p0): it
  * covers planes [p0, p0 + C/8).  Channel concatenation (util.py:773,817) is therefore free: the
  * producers write disjoint plane ranges of one buffer. */
 
-/* NCHW fp32 [B,C,H,W] <-> blocked bf16 view (edge conversions; the reference API is NCHW fp32). */
-int tgsr_nchw_to_blocked_bf16(const float* x, void* y, int B, int C, int H, int W, int yP, int yp0,
-                              tgsr_stream_t stream);
-int tgsr_blocked_to_nchw_f32(const void* x, float* y, int B, int C, int H, int W, int xP, int xp0,
-                             tgsr_stream_t stream);
+/* NCHW fp32 [B,C,H,W] <-> blocked 16-bit view (edge conversions; the reference API is NCHW fp32). */
+int tgsr_nchw_to_blocked(const float* x, void* y, int B, int C, int H, int W, int yP, int yp0, int fmt,
+                         tgsr_stream_t stream);
+int tgsr_blocked_to_nchw(const void* x, float* y, int B, int C, int H, int W, int xP, int xp0, int fmt,
+                         tgsr_stream_t stream);
 
-/* Weight prep: conv3x3 weight [Cout,Cin,3,3] fp32 -> packed bf16 UMMA operand image.
+/* Weight prep: conv3x3 weight [Cout,Cin,3,3] fp32 -> packed 16-bit UMMA operand image.
  * up2x == 0: 9 taps, Cout*Cin*9 elements.  up2x == 1: the nearest-x2 upsample of util.py:76 is
  * folded into the weights as four 2x2 sub-pixel phases (pre-summed in fp32, rounded once),
  * Cout*Cin*16 elements. */
-int tgsr_pack_conv3x3_bf16(const float* w, void* packed, int Cout, int Cin, int up2x,
-                           tgsr_stream_t stream);
+int tgsr_pack_conv3x3(const float* w, void* packed, int Cout, int Cin, int up2x, int fmt,
+                      tgsr_stream_t stream);
 
 /* a3/a4/a5: conv3x3 (+ folded BN scale/shift [Cout]) (+GLU) (+residual) on tcgen05 tensor cores,
- * bf16 operands, fp32 accumulation in TMEM; util.py:62-65, :45-53, :110-130, :74-80.
+ * 16-bit operands, fp32 accumulation in TMEM; util.py:62-65, :45-53, :110-130, :74-80.
  * x view (xP,xp0) of Cin channels at HxW; y view (yP,yp0) of Cout (or Cout/2 with GLU) channels at
- * HxW, or at 2Hx2W when up2x (wpacked must then come from tgsr_pack_conv3x3_bf16(up2x=1)).
+ * HxW, or at 2Hx2W when up2x (wpacked must then come from tgsr_pack_conv3x3(up2x=1)).
  * residual view (rP,rp0) or NULL (only with act NONE, no up2x).  Supported (Cin,Cout,act,up2x):
  * (64,128,GLU,0) (64,64,NONE,0) (32,64,GLU,0) (32,32,NONE,0) (64,64,GLU,1) (32,64,GLU,1);
  * H % 16 == 0, W % 8 == 0. */
-int tgsr_conv3x3_tc_bf16(const void* x, int xP, int xp0, const void* wpacked, const float* scale,
-                         const float* shift, const void* residual, int rP, int rp0, void* y, int yP,
-                         int yp0, int B, int Cin, int H, int W, int Cout, int up2x, int act,
-                         tgsr_stream_t stream);
+int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const float* scale,
+                    const float* shift, const void* residual, int rP, int rp0, void* y, int yP, int yp0,
+                    int B, int Cin, int H, int W, int Cout, int up2x, int act, int fmt,
+                    tgsr_stream_t stream);
 
 /* a8 image heads on tensor cores: GET_IMAGE_G / GET_IMAGE_G_noAct (conv3x3 32->3, util.py:894-919) and
  * conv_output (conv5x5 32->3 + Tanh, model.py:223-226) with the fused `one*y + a*SRb` of model.py:280.
- * x: blocked view of 32 channels; wpacked from tgsr_pack_head_bf16 (w [3,Cin,k,k] fp32);
+ * x: blocked view of 32 channels; wpacked from tgsr_pack_head (w [3,Cin,k,k] fp32);
  * y fp32 NCHW [B,3,H,W] = out_scale * act(conv(x)) + addend_scale * addend (addend NCHW or NULL).
  * act NONE or TANH; H % 16 == 0, W % 8 == 0. */
-int tgsr_pack_head_bf16(const float* w, void* packed, int Cin, int ksize, tgsr_stream_t stream);
-int tgsr_img_head_tc_bf16(const void* x, int xP, int xp0, const void* wpacked, const float* addend,
-                          float out_scale, float addend_scale, float* y, int B, int Cin, int H, int W,
-                          int ksize, int act, tgsr_stream_t stream);
+int tgsr_pack_head(const float* w, void* packed, int Cin, int ksize, int fmt, tgsr_stream_t stream);
+int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpacked, const float* addend,
+                     float out_scale, float addend_scale, float* y, int B, int Cin, int H, int W,
+                     int ksize, int act, int fmt, tgsr_stream_t stream);
 
 /* im2f / convin: conv3x3(3 -> 2C) + folded BN + GLU from the NCHW fp32 LR image (minus x_sub if not
- * NULL: model.py:268-270 `LR - LRb`) into a blocked bf16 view of C channels; util.py:741-744,
+ * NULL: model.py:268-270 `LR - LRb`) into a blocked 16-bit view of C channels; util.py:741-744,
  * model.py:228.  w [2C,3,3,3], scale/shift [2C] or NULL.  C % 8 == 0, C <= 64. */
-int tgsr_conv_in_bf16(const float* x, const float* x_sub, const float* w, const float* scale,
-                      const float* shift, void* y, int yP, int yp0, int B, int H, int W, int C,
-                      tgsr_stream_t stream);
+int tgsr_conv_in_blocked(const float* x, const float* x_sub, const float* w, const float* scale,
+                         const float* shift, void* y, int yP, int yp0, int B, int H, int W, int C, int fmt,
+                         tgsr_stream_t stream);
 
-/* a1 on blocked activations: reads the idf=32 channel view (xP,xp0), writes weightedContext as bf16
+/* a1 on blocked activations: reads the idf=32 channel view (xP,xp0), writes weightedContext (16-bit)
  * into the view (yP,yp0) -- normally the next planes of the same concat buffer -- and the
  * attention map attn fp32 [B,T,Q].  context fp32 [B,cdf,T]; mask as tgsr_attn_fwd_f32.  T <= 20. */
 int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const float* context, const float* w_ctx,
                           const uint8_t* mask, void* y, int yP, int yp0, float* attn, int B, int idf,
-                          int cdf, int Q, int T, tgsr_stream_t stream);
+                          int cdf, int Q, int T, int fmt, tgsr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -11,11 +11,13 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 
 
-def bf(x):
-    return x.to(torch.bfloat16).to(torch.float32)
+def rounder(fmt):
+    dt = torch.float16 if fmt else torch.bfloat16
+    return lambda x: x.to(dt).to(torch.float32)
 
 
-def emulate(x, w, scale, shift, glu, res, up2x):
+def emulate(x, w, scale, shift, glu, res, up2x, fmt=0):
+    bf = rounder(fmt)
     xb = bf(x)
     if not up2x:
         z = F.conv2d(xb, bf(w), None, 1, 1)
@@ -56,8 +58,9 @@ CASES = [  # Cin, Cout, glu, up2x, residual, B, H, W
 ]
 
 
+@pytest.mark.parametrize('fmt', [0, 1], ids=['bf16', 'fp16'])
 @pytest.mark.parametrize('Cin,Cout,glu,up2x,use_res,B,H,W', CASES)
-def test_conv_tc_matches_bf16_emulation(Cin, Cout, glu, up2x, use_res, B, H, W):
+def test_conv_tc_matches_16bit_emulation(Cin, Cout, glu, up2x, use_res, B, H, W, fmt):
     from tgsr_b200 import tc
     from tgsr_b200._lib import ACT_GLU, ACT_NONE
     g = torch.Generator().manual_seed(Cin * 7 + Cout + H)
@@ -67,17 +70,17 @@ def test_conv_tc_matches_bf16_emulation(Cin, Cout, glu, up2x, use_res, B, H, W):
     shift = 0.1 * torch.randn(Cout, generator=g)
     Cf = Cout // 2 if glu else Cout
     res = torch.randn(B, Cf, H, W, generator=g) if use_res else None
-    ref = emulate(x, w, scale, shift, glu, res, up2x)
+    ref = emulate(x, w, scale, shift, glu, res, up2x, fmt)
 
     conv = torch.nn.Conv2d(Cin, Cout, 3, 1, 1, bias=False).to(DEV)
     conv.weight.data.copy_(w)
-    xb = tc.to_blocked(x.to(DEV))
-    rb = tc.to_blocked(res.to(DEV)) if use_res else None
+    xb = tc.to_blocked(x.to(DEV), fmt=fmt)
+    rb = tc.to_blocked(res.to(DEV), fmt=fmt) if use_res else None
     yb = tc.conv3x3_tc(xb, conv, scale.to(DEV), shift.to(DEV), ACT_GLU if glu else ACT_NONE, residual=rb, up2x=up2x)
     y = tc.to_nchw(yb).cpu()
     assert y.shape == ref.shape
     err = (y - ref).abs().max().item()
-    tol = 2 ** -8 * max(1.0, ref.abs().max().item())      # one bf16 rounding of the output
+    tol = 2 ** (-11 if fmt else -8) * max(1.0, ref.abs().max().item()) + 1e-4     # one rounding of the output
     assert err <= tol, 'max-abs %.4g > %.4g' % (err, tol)
 
 
@@ -88,7 +91,7 @@ def test_blocked_roundtrip_and_concat_views():
     buf.buf.zero_()
     tc.to_blocked(x.to(DEV), out=buf.slice(32, 32))       # write into the second channel half (concat)
     back = tc.to_nchw(buf.slice(32, 32)).cpu()
-    assert torch.equal(back, bf(x))
+    assert torch.equal(back, rounder(0)(x))
     assert torch.count_nonzero(tc.to_nchw(buf.slice(0, 32))) == 0
 
 

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libtgsr_sm100.so')
 
 ACT_NONE, ACT_GLU, ACT_TANH = 0, 1, 2
+FMT_BF16, FMT_F16 = 0, 1
 
 _lib = None
 _lock = threading.Lock()
@@ -34,17 +35,17 @@ _SIGS = {
     'tgsr_bn_fold_f32': ([C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p], C.c_int),
     'tgsr_linear_glu_f32': ([C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p], C.c_int),
     'tgsr_ca_reparam_f32': ([C.c_void_p] * 3 + [C.c_int] * 2 + [C.c_void_p], C.c_int),
-    'tgsr_nchw_to_blocked_bf16': ([C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p], C.c_int),
-    'tgsr_blocked_to_nchw_f32': ([C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p], C.c_int),
-    'tgsr_pack_conv3x3_bf16': ([C.c_void_p, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p], C.c_int),
-    'tgsr_conv3x3_tc_bf16': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                              C.c_void_p, C.c_int, C.c_int] + [C.c_int] * 7 + [C.c_void_p], C.c_int),
-    'tgsr_pack_head_bf16': ([C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p], C.c_int),
-    'tgsr_img_head_tc_bf16': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
-                              + [C.c_int] * 6 + [C.c_void_p], C.c_int),
-    'tgsr_conv_in_bf16': ([C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_void_p], C.c_int),
+    'tgsr_nchw_to_blocked': ([C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p], C.c_int),
+    'tgsr_blocked_to_nchw': ([C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p], C.c_int),
+    'tgsr_pack_conv3x3': ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p], C.c_int),
+    'tgsr_conv3x3_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                         C.c_void_p, C.c_int, C.c_int] + [C.c_int] * 8 + [C.c_void_p], C.c_int),
+    'tgsr_pack_head': ([C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
+    'tgsr_img_head_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+                         + [C.c_int] * 7 + [C.c_void_p], C.c_int),
+    'tgsr_conv_in_blocked': ([C.c_void_p] * 6 + [C.c_int] * 7 + [C.c_void_p], C.c_int),
     'tgsr_attn_fwd_blocked': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                               C.c_int, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p], C.c_int),
+                               C.c_int, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p], C.c_int),
     'tgsr_lstm_bidir_fwd_f32': ([C.c_void_p] * 10 + [C.c_int] * 6 + [C.c_void_p], C.c_int),
 }
 

@@ -44,8 +44,13 @@ def _conv(x, conv: nn.Conv2d, bn, act, **kw):
 
 
 def _bf16():
-    from . import get_precision
-    return get_precision() == 'bf16'
+    from . import is_16bit
+    return is_16bit()
+
+
+def _fmt():
+    from . import fmt_for
+    return fmt_for('low')
 
 
 def _tc_ok(conv: nn.Conv2d, act, up2x, x) -> bool:
@@ -81,7 +86,7 @@ class _ConvBnGlu(nn.Sequential):
         bn = mods[1] if isinstance(mods[1], nn.BatchNorm2d) else None
         if _tc_ok(mods[0], ACT_GLU, False, x):
             from . import fast, tc
-            return tc.to_nchw(fast.conv_bn_act(tc.to_blocked(x), mods[0], bn, ACT_GLU))
+            return tc.to_nchw(fast.conv_bn_act(tc.to_blocked(x, fmt=_fmt()), mods[0], bn, ACT_GLU))
         return _conv(x, mods[0], bn, ACT_GLU)
 
 
@@ -94,7 +99,7 @@ class _UpBlock(nn.Sequential):
         bn = mods[2] if isinstance(mods[2], nn.BatchNorm2d) else None
         if _tc_ok(mods[1], ACT_GLU, True, x):
             from . import fast, tc
-            return tc.to_nchw(fast.up_block(tc.to_blocked(x), self))
+            return tc.to_nchw(fast.up_block(tc.to_blocked(x, fmt=_fmt()), self))
         return _conv(x, mods[1], bn, ACT_GLU, up2x=True)
 
 
@@ -106,9 +111,9 @@ class _ConvBnGluConvBn(nn.Sequential):
         if isinstance(mods[1], nn.BatchNorm2d) and _tc_ok(mods[0], ACT_GLU, False, x) \
                 and _tc_ok(mods[3], ACT_NONE, False, x):
             from . import fast, tc
-            xb = tc.to_blocked(x)
+            xb = tc.to_blocked(x, fmt=_fmt())
             y = fast.conv_bn_act(xb, mods[0], mods[1], ACT_GLU)
-            rb = xb if residual is x else (None if residual is None else tc.to_blocked(residual))
+            rb = xb if residual is x else (None if residual is None else tc.to_blocked(residual, fmt=_fmt()))
             return tc.to_nchw(fast.conv_bn_act(y, mods[3], mods[4], ACT_NONE, residual=rb))
         if isinstance(mods[1], nn.BatchNorm2d):
             y = _conv(x, mods[0], mods[1], ACT_GLU)
@@ -125,7 +130,7 @@ class _ImageHead(nn.Sequential):
         if _bf16() and h.shape[1] == 32 and self[0].weight.shape[0] == 3 and h.shape[2] % 16 == 0 \
                 and h.shape[3] % 8 == 0:
             from . import fast, tc
-            return fast.image_head(tc.to_blocked(h), self, addend, a, one)
+            return fast.image_head(tc.to_blocked(h, fmt=_fmt()), self, addend, a, one)
         return _conv(h, self[0], None, act, addend=addend, out_scale=one, addend_scale=a)
 
 
@@ -227,8 +232,8 @@ def _run_stage_bf16(stage, h_code, LR, word_embs, mask):
     hb = None
     if h_code is not None:
         B, C, H, W = h_code.shape
-        hb = tc.to_blocked(h_code, out=tc.Blocked.empty(B, C, H, W, h_code.device, planes=2 * C // 8))
-    out, att = fast.stage(stage, hb, LR, word_embs, mask, None)
+        hb = tc.to_blocked(h_code, out=tc.Blocked.empty(B, C, H, W, h_code.device, planes=2 * C // 8, fmt=_fmt()))
+    out, att = fast.stage(stage, hb, LR, word_embs, mask, None, _fmt())
     return tc.to_nchw(out), att
 
 

@@ -6,31 +6,20 @@
 //     attention.cu, reading h_code from planes of the stage's concat buffer and writing c_code
 //     into the next planes of the SAME buffer (torch.cat of util.py:773,817 disappears).
 #include "common.cuh"
-#include <cuda_bf16.h>
+#include "fmt16.cuh"
 #include <math_constants.h>
 
 namespace tgsr {
 
-__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
-  uint4 r;
-  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
-  r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
-  r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
-  return r;
-}
-__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-}
+typedef uint16_t h16;
 
 // ---------------------------------------------------------------- conv_in
 // thread = (pixel, output plane of 8 channels): 8 GLU outputs = 16 pre-activation channels.
 constexpr int CI_MAXC = 64;   // max output channels C (weights [2C][3][3][3] in smem)
+template <int FMT>
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x, const float* __restrict__ xsub, const float* __restrict__ w,
-               const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+               const float* __restrict__ scale, const float* __restrict__ shift, h16* __restrict__ y,
                int B, int H, int W, int C, int yP, int yp0) {
   __shared__ float ws[2 * CI_MAXC * 27];
   __shared__ float sc[2 * CI_MAXC], sh[2 * CI_MAXC];
@@ -69,7 +58,7 @@ conv_in_kernel(const float* __restrict__ x, const float* __restrict__ xsub, cons
       g = fmaf(g, sc[cg], sh[cg]);
       o8[e] = a * (1.0f / (1.0f + __expf(-g)));
     }
-    *reinterpret_cast<uint4*>(y + (((size_t)b * yP + yp0 + pl) * HW + pix) * 8) = pack8(o8);
+    *reinterpret_cast<uint4*>(y + (((size_t)b * yP + yp0 + pl) * HW + pix) * 8) = pack8_16<FMT>(o8);
   }
 }
 
@@ -79,11 +68,11 @@ constexpr int AB_IDF = 32;
 constexpr int AB_TPAD = 20;
 
 // smem: S [32][20] f32 | ctx [cdf][T] f32 | maskbits [B] u64 | mbarrier
-template <int PIX>
+template <int PIX, int FMT>
 __global__ void __launch_bounds__(AB_THREADS)
-attn_blocked_kernel(const __nv_bfloat16* __restrict__ xin, int xP, int xp0, const float* __restrict__ context,
+attn_blocked_kernel(const h16* __restrict__ xin, int xP, int xp0, const float* __restrict__ context,
                     const float* __restrict__ w_ctx, const uint8_t* __restrict__ mask,
-                    __nv_bfloat16* __restrict__ yout, int yP, int yp0, float* __restrict__ attn, int B, int cdf, int Q,
+                    h16* __restrict__ yout, int yP, int yp0, float* __restrict__ attn, int B, int cdf, int Q,
                     int T, int chunk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* S = reinterpret_cast<float*>(smem_raw);
@@ -122,8 +111,8 @@ attn_blocked_kernel(const __nv_bfloat16* __restrict__ xin, int xP, int xp0, cons
 
   const float4* S4 = reinterpret_cast<const float4*>(S);
   const size_t plane = (size_t)Q * 8;
-  const __nv_bfloat16* xb = xin + ((size_t)b * xP + xp0) * plane;
-  __nv_bfloat16* yb = yout + ((size_t)b * yP + yp0) * plane;
+  const h16* xb = xin + ((size_t)b * xP + xp0) * plane;
+  h16* yb = yout + ((size_t)b * yP + yp0) * plane;
   float* ab = attn + (size_t)b * T * Q;
 
   for (int q = q_begin + tid * PIX; q < q_end; q += AB_THREADS * PIX) {
@@ -142,7 +131,7 @@ attn_blocked_kernel(const __nv_bfloat16* __restrict__ xin, int xP, int xp0, cons
     for (int pl = 0; pl < AB_IDF / 8; ++pl) {
       float x[PIX][8];
 #pragma unroll
-      for (int p = 0; p < PIX; ++p) unpack8(raw[pl][p], x[p]);
+      for (int p = 0; p < PIX; ++p) unpack8_16<FMT>(raw[pl][p], x[p]);
 #pragma unroll
       for (int e = 0; e < 8; ++e)
 #pragma unroll
@@ -198,40 +187,44 @@ attn_blocked_kernel(const __nv_bfloat16* __restrict__ xin, int xP, int xp0, cons
           }
           o[e] = acc;
         }
-        *reinterpret_cast<uint4*>(yb + pl * plane + (size_t)(q + p) * 8) = pack8(o);
+        *reinterpret_cast<uint4*>(yb + pl * plane + (size_t)(q + p) * 8) = pack8_16<FMT>(o);
       }
     }
   }
 }
 
 int init_blocked_misc() {
-  cudaError_t e = cudaFuncSetAttribute(attn_blocked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(attn_blocked_kernel<1, TGSR_FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   if (e != cudaSuccess) return cuda_fail(e);
-  e = cudaFuncSetAttribute(attn_blocked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  e = cudaFuncSetAttribute(attn_blocked_kernel<1, TGSR_FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   return e == cudaSuccess ? TGSR_OK : cuda_fail(e);
 }
 
 }  // namespace tgsr
 
-extern "C" int tgsr_conv_in_bf16(const float* x, const float* x_sub, const float* w, const float* scale,
-                                 const float* shift, void* y, int yP, int yp0, int B, int H, int W, int C,
-                                 tgsr_stream_t stream) {
+extern "C" int tgsr_conv_in_blocked(const float* x, const float* x_sub, const float* w, const float* scale,
+                                    const float* shift, void* y, int yP, int yp0, int B, int H, int W, int C,
+                                    int fmt, tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(w); TGSR_REQUIRE_PTR(y);
+  TGSR_REQUIRE(fmt == TGSR_FMT_BF16 || fmt == TGSR_FMT_F16, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && yp0 >= 0 && yp0 + C / 8 <= yP, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE((scale == nullptr) == (shift == nullptr), TGSR_ERR_NULL);
   TGSR_REQUIRE(C <= CI_MAXC, TGSR_ERR_UNSUPPORTED);
   const size_t total = (size_t)B * (C / 8) * H * W;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  conv_in_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_sub, w, scale, shift, reinterpret_cast<__nv_bfloat16*>(y),
-                                                          B, H, W, C, yP, yp0);
+  if (fmt == TGSR_FMT_F16)
+    conv_in_kernel<TGSR_FMT_F16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_sub, w, scale, shift, reinterpret_cast<h16*>(y), B, H, W, C, yP, yp0);
+  else
+    conv_in_kernel<TGSR_FMT_BF16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_sub, w, scale, shift, reinterpret_cast<h16*>(y), B, H, W, C, yP, yp0);
   return launch_status();
 }
 
 extern "C" int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const float* context, const float* w_ctx,
                                      const uint8_t* mask, void* y, int yP, int yp0, float* attn, int B, int idf,
-                                     int cdf, int Q, int T, tgsr_stream_t stream) {
+                                     int cdf, int Q, int T, int fmt, tgsr_stream_t stream) {
   using namespace tgsr;
+  TGSR_REQUIRE(fmt == TGSR_FMT_BF16 || fmt == TGSR_FMT_F16, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(context); TGSR_REQUIRE_PTR(w_ctx); TGSR_REQUIRE_PTR(y); TGSR_REQUIRE_PTR(attn);
   TGSR_REQUIRE(B > 0 && idf > 0 && cdf > 0 && Q > 0 && T > 0, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE(g_sm_count > 0, TGSR_ERR_NOT_INIT);
@@ -247,9 +240,12 @@ extern "C" int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const float
   const int chunk = unit * loops;
   dim3 grid(ceil_div(Q, chunk), B);
   cudaStream_t st = (cudaStream_t)stream;
-  auto xi = reinterpret_cast<const __nv_bfloat16*>(x);
-  auto yo = reinterpret_cast<__nv_bfloat16*>(y);
-  if (PIX == 2) attn_blocked_kernel<2><<<grid, AB_THREADS, smem, st>>>(xi, xP, xp0, context, w_ctx, mask, yo, yP, yp0, attn, B, cdf, Q, T, chunk);
-  else attn_blocked_kernel<1><<<grid, AB_THREADS, smem, st>>>(xi, xP, xp0, context, w_ctx, mask, yo, yP, yp0, attn, B, cdf, Q, T, chunk);
+  auto xi = reinterpret_cast<const h16*>(x);
+  auto yo = reinterpret_cast<h16*>(y);
+  (void)PIX;
+  if (fmt == TGSR_FMT_F16)
+    attn_blocked_kernel<1, TGSR_FMT_F16><<<grid, AB_THREADS, smem, st>>>(xi, xP, xp0, context, w_ctx, mask, yo, yP, yp0, attn, B, cdf, Q, T, chunk);
+  else
+    attn_blocked_kernel<1, TGSR_FMT_BF16><<<grid, AB_THREADS, smem, st>>>(xi, xP, xp0, context, w_ctx, mask, yo, yP, yp0, attn, B, cdf, Q, T, chunk);
   return launch_status();
 }

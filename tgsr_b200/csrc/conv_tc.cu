@@ -27,11 +27,12 @@
 // (tmem_full/tmem_empty), so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
-#include <cuda_bf16.h>
+#include "fmt16.cuh"
 
 namespace tgsr {
 
 using namespace ptx;
+typedef uint16_t h16;   // storage element of either 16-bit format
 
 constexpr int TC_TH = 16, TC_TW = 8;            // tile = 16 rows x 8 cols = 128 pixels (UMMA M)
 constexpr int TC_NSTAGE = 3;
@@ -102,8 +103,8 @@ struct TcParams {
   const void* wpacked;
   const float* scale;      // [NPRE] or null
   const float* shift;
-  const __nv_bfloat16* residual;   // blocked, or null
-  __nv_bfloat16* out;              // blocked
+  const h16* residual;   // blocked, or null
+  h16* out;              // blocked
   int rP, rp0, yP, yp0;            // planes per image / first plane of the residual and output views
   int xP, xp0;                     // input view (for the TMA plane coordinate)
   int B, H, W;                     // INPUT spatial size
@@ -115,22 +116,9 @@ struct TcParams {
   int act_tanh;
 };
 
-__device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
-  uint4 r;
-  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
-  r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
-  r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
-  return r;
-}
-__device__ __forceinline__ void unpack8_bf16(const uint4& u, float (&v)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-}
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-template <int CIN, int NPRE, int MODE, bool GLU>
+template <int CIN, int NPRE, int MODE, bool GLU, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   using Cfg = TcCfg<CIN, NPRE, MODE>;
@@ -215,7 +203,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           constexpr int dummy = 0; (void)dummy;
           const TcOp op = Ops::op(o);
           const int N = op.n_mul * NPRE;
-          const uint32_t idesc = make_idesc_bf16(128, N);
+          const uint32_t idesc = make_idesc_f16(128, N, Fmt16<FMT>::kUmmaFormat);
           const uint32_t a_tap = a_base + (op.tap_r * TC_PW + op.tap_c) * 16;
 #pragma unroll
           for (int k = 0; k < Cfg::KSTEPS; ++k) {
@@ -262,8 +250,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         constexpr int COUT = GLU ? NPRE / 2 : NPRE;            // channels written
         const size_t pix = ((size_t)gy * p.W + gx) * 8;
         const size_t plane_elems = (size_t)p.H * p.W * 8;
-        __nv_bfloat16* obase = p.out + ((size_t)b * p.yP + p.yp0) * plane_elems + pix;
-        const __nv_bfloat16* rbase =
+        h16* obase = p.out + ((size_t)b * p.yP + p.yp0) * plane_elems + pix;
+        const h16* rbase =
             p.residual ? p.residual + ((size_t)b * p.rP + p.rp0) * plane_elems + pix : nullptr;
 #pragma unroll
         for (int c0 = 0; c0 < COUT; c0 += 32) {
@@ -278,7 +266,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             float res[8];
             if (rbase) {
               const uint4 u = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(c0 / 8 + j) * plane_elems));
-              unpack8_bf16(u, res);
+              unpack8_16<FMT>(u, res);
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -291,7 +279,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
               if (rbase) z += res[e];
               o[e] = z;
             }
-            *reinterpret_cast<uint4*>(obase + (size_t)(c0 / 8 + j) * plane_elems) = pack8_bf16(o);
+            *reinterpret_cast<uint4*>(obase + (size_t)(c0 / 8 + j) * plane_elems) = pack8_16<FMT>(o);
           }
         }
       } else {
@@ -308,7 +296,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           tmem_ld32(t_base + ph * NPRE + COUT, vg);
           tmem_ld_wait();
           const int oy = 2 * gy + (ph >> 1), ox = 2 * gx + (ph & 1);
-          __nv_bfloat16* obase = p.out + ((size_t)b * p.yP + p.yp0) * plane_elems + ((size_t)oy * Wo + ox) * 8;
+          h16* obase = p.out + ((size_t)b * p.yP + p.yp0) * plane_elems + ((size_t)oy * Wo + ox) * 8;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float o[8];
@@ -319,7 +307,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
               const float g = fmaf(__uint_as_float(vg[c]), sc_s[COUT + c], sh_s[COUT + c]);
               o[e] = z * fast_sigmoid(g);
             }
-            *reinterpret_cast<uint4*>(obase + (size_t)j * plane_elems) = pack8_bf16(o);
+            *reinterpret_cast<uint4*>(obase + (size_t)j * plane_elems) = pack8_16<FMT>(o);
           }
         }
       }
@@ -338,24 +326,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 // Weight packing (runs once per weight version).  Packed image = for each op, for each K chunk
 // kc (8 input channels), for each group of 8 output rows: a 128-B core matrix [8 rows][8 k] bf16.
 //   byte offset(op, n, c) = op_base + (c/8)*(N_op*16) + (n/8)*128 + (n%8)*16 + (c%8)*2
-__global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin) {
+template <int FMT>
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, h16* __restrict__ out, int Cout, int Cin) {
   const int total = 9 * Cout * Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % Cin, n = (i / Cin) % Cout, t = i / (Cin * Cout);
     const float v = w[((size_t)n * Cin + c) * 9 + t];
     const size_t off = (size_t)t * Cin * Cout + (size_t)(c / 8) * (Cout * 8) + (size_t)(n / 8) * 64 + (n % 8) * 8 + (c % 8);
-    out[off] = __float2bfloat16_rn(v);
+    out[off] = Fmt16<FMT>::cvt(v);
   }
 }
 
 // Image heads: w [3][Cin][K][K] -> per tap a [16 x Cin] block whose rows 3..15 are zero.
-__global__ void pack_head_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int K) {
+template <int FMT>
+__global__ void pack_head_kernel(const float* __restrict__ w, h16* __restrict__ out, int Cin, int K) {
   const int total = K * K * 16 * Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % Cin, n = (i / Cin) % 16, t = i / (Cin * 16);
     const float v = n < 3 ? w[((size_t)n * Cin + c) * K * K + t] : 0.f;
     const size_t off = (size_t)t * Cin * 16 + (size_t)(c / 8) * (16 * 8) + (size_t)(n / 8) * 64 + (n % 8) * 8 + (c % 8);
-    out[off] = __float2bfloat16_rn(v);
+    out[off] = Fmt16<FMT>::cvt(v);
   }
 }
 
@@ -368,7 +358,8 @@ __device__ __forceinline__ int up_taps(int parity, int r, int (&ks)[2]) {
   return 0;
 }
 
-__global__ void pack_up2x_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin) {
+template <int FMT>
+__global__ void pack_up2x_kernel(const float* __restrict__ w, h16* __restrict__ out, int Cout, int Cin) {
   // 11 ops; op o covers phases {ph = dcol_mul .. dcol_mul + n_mul - 1}; rows of op = [phase][Cout]
   using Ops = OpTable<MODE_UP>;
   int op_base = 0;
@@ -386,7 +377,7 @@ __global__ void pack_up2x_kernel(const float* __restrict__ w, __nv_bfloat16* __r
       for (int a = 0; a < ny; ++a)
         for (int bq = 0; bq < nx; ++bq) v += w[((size_t)n * Cin + c) * 9 + kys[a] * 3 + kxs[bq]];
       const size_t off = (size_t)op_base + (size_t)(c / 8) * (N * 8) + (size_t)(nn / 8) * 64 + (nn % 8) * 8 + (c % 8);
-      out[off] = __float2bfloat16_rn(v);
+      out[off] = Fmt16<FMT>::cvt(v);
     }
     op_base += N * Cin;
   }
@@ -394,7 +385,8 @@ __global__ void pack_up2x_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 
 // ------------------------------------------------------------------------------------------
 // Layout converters between the reference's NCHW fp32 tensors and the blocked bf16 layout.
-__global__ void nchw_to_blocked_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C, int HW,
+template <int FMT>
+__global__ void nchw_to_blocked_kernel(const float* __restrict__ x, h16* __restrict__ y, int B, int C, int HW,
                                        int P, int p0) {
   // one thread per (b, plane, pixel): gathers 8 channels (coalesced across pixels), writes 16 B
   const size_t total = (size_t)B * (C / 8) * HW;
@@ -405,10 +397,11 @@ __global__ void nchw_to_blocked_kernel(const float* __restrict__ x, __nv_bfloat1
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = __ldg(x + ((size_t)b * C + pl * 8 + e) * HW + pix);
-    *reinterpret_cast<uint4*>(y + (((size_t)b * P + p0 + pl) * HW + pix) * 8) = pack8_bf16(v);
+    *reinterpret_cast<uint4*>(y + (((size_t)b * P + p0 + pl) * HW + pix) * 8) = pack8_16<FMT>(v);
   }
 }
-__global__ void blocked_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int C, int HW,
+template <int FMT>
+__global__ void blocked_to_nchw_kernel(const h16* __restrict__ x, float* __restrict__ y, int B, int C, int HW,
                                        int P, int p0) {
   const size_t total = (size_t)B * (C / 8) * HW;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -417,7 +410,7 @@ __global__ void blocked_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, floa
     const int b = (int)(i / ((size_t)HW * (C / 8)));
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * P + p0 + pl) * HW + pix) * 8));
     float v[8];
-    unpack8_bf16(u, v);
+    unpack8_16<FMT>(u, v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) y[((size_t)b * C + pl * 8 + e) * HW + pix] = v[e];
   }
@@ -426,8 +419,11 @@ __global__ void blocked_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, floa
 // ------------------------------------------------------------------------------------------
 template <int CIN, int NPRE, int MODE, bool GLU>
 static int set_tc_attr() {
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, NPRE, MODE, GLU>,
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_BF16>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<CIN, NPRE, MODE>::SMEM);
+  if (e != cudaSuccess) return cuda_fail(e);
+  e = cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_F16>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<CIN, NPRE, MODE>::SMEM);
   return e == cudaSuccess ? TGSR_OK : cuda_fail(e);
 }
 
@@ -450,13 +446,13 @@ int init_conv_tc() {
   return TGSR_OK;
 }
 
-static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl, int R = 1) {
+static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl, int fmt, int R = 1) {
   const int TC_PW = TC_TW + 2 * R, TC_PH = TC_TH + 2 * R;
   cuuint64_t gdim[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * P};
   cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
   cuuint32_t box[4] = {8, (cuuint32_t)TC_PW, (cuuint32_t)TC_PH, (cuuint32_t)npl};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+  CUresult r = g_encode_tiled(m, fmt == TGSR_FMT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return TGSR_ERR_CUDA; }
@@ -464,20 +460,26 @@ static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, i
 }
 
 template <int CIN, int NPRE, int MODE, bool GLU>
-static int launch_tc(const CUtensorMap& tmap, const TcParams& p, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& tmap, const TcParams& p, int fmt, cudaStream_t st) {
   const int grid = p.ntiles < g_sm_count ? p.ntiles : g_sm_count;
-  conv3x3_tc_kernel<CIN, NPRE, MODE, GLU><<<grid, TC_THREADS, TcCfg<CIN, NPRE, MODE>::SMEM, st>>>(tmap, p);
+  if (fmt == TGSR_FMT_F16)
+    conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_F16><<<grid, TC_THREADS, TcCfg<CIN, NPRE, MODE>::SMEM, st>>>(tmap, p);
+  else
+    conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_BF16><<<grid, TC_THREADS, TcCfg<CIN, NPRE, MODE>::SMEM, st>>>(tmap, p);
   return launch_status();
 }
 
 }  // namespace tgsr
 
-extern "C" int tgsr_conv3x3_tc_bf16(const void* x, int xP, int xp0, const void* wpacked, const float* scale,
-                                    const float* shift, const void* residual, int rP, int rp0, void* y, int yP,
-                                    int yp0, int B, int Cin, int H, int W, int Cout, int up2x, int act,
-                                    tgsr_stream_t stream) {
+#define TGSR_CHECK_FMT(fmt) TGSR_REQUIRE((fmt) == TGSR_FMT_BF16 || (fmt) == TGSR_FMT_F16, TGSR_ERR_UNSUPPORTED)
+
+extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const float* scale,
+                               const float* shift, const void* residual, int rP, int rp0, void* y, int yP,
+                               int yp0, int B, int Cin, int H, int W, int Cout, int up2x, int act, int fmt,
+                               tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(wpacked); TGSR_REQUIRE_PTR(y);
+  TGSR_CHECK_FMT(fmt);
   TGSR_REQUIRE(g_sm_count > 0 && g_encode_tiled != nullptr, TGSR_ERR_NOT_INIT);
   TGSR_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE((scale == nullptr) == (shift == nullptr), TGSR_ERR_NULL);
@@ -492,12 +494,12 @@ extern "C" int tgsr_conv3x3_tc_bf16(const void* x, int xP, int xp0, const void* 
   TGSR_REQUIRE((long long)B * xP < (1LL << 31), TGSR_ERR_UNSUPPORTED);
 
   CUtensorMap tmap;
-  int s = make_patch_tmap(&tmap, x, B, xP, H, W, npl);
+  int s = make_patch_tmap(&tmap, x, B, xP, H, W, npl, fmt);
   if (s != TGSR_OK) return s;
   TcParams p;
   p.wpacked = wpacked; p.scale = scale; p.shift = shift;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.out = reinterpret_cast<__nv_bfloat16*>(y);
+  p.residual = reinterpret_cast<const h16*>(residual);
+  p.out = reinterpret_cast<h16*>(y);
   p.rP = rP; p.rp0 = rp0; p.yP = yP; p.yp0 = yp0; p.xP = xP; p.xp0 = xp0;
   p.B = B; p.H = H; p.W = W;
   p.tiles_x = W / TC_TW; p.tiles_y = H / TC_TH; p.ntiles = B * p.tiles_x * p.tiles_y;
@@ -505,41 +507,53 @@ extern "C" int tgsr_conv3x3_tc_bf16(const void* x, int xP, int xp0, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   const bool glu = act == TGSR_ACT_GLU;
   if (!up2x) {
-    if (Cin == 64 && Cout == 128 && glu) return launch_tc<64, 128, MODE_CONV, true>(tmap, p, st);
-    if (Cin == 64 && Cout == 64 && !glu) return launch_tc<64, 64, MODE_CONV, false>(tmap, p, st);
-    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, MODE_CONV, true>(tmap, p, st);
-    if (Cin == 32 && Cout == 32 && !glu) return launch_tc<32, 32, MODE_CONV, false>(tmap, p, st);
+    if (Cin == 64 && Cout == 128 && glu) return launch_tc<64, 128, MODE_CONV, true>(tmap, p, fmt, st);
+    if (Cin == 64 && Cout == 64 && !glu) return launch_tc<64, 64, MODE_CONV, false>(tmap, p, fmt, st);
+    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, MODE_CONV, true>(tmap, p, fmt, st);
+    if (Cin == 32 && Cout == 32 && !glu) return launch_tc<32, 32, MODE_CONV, false>(tmap, p, fmt, st);
   } else {
-    if (Cin == 64 && Cout == 64 && glu) return launch_tc<64, 64, MODE_UP, true>(tmap, p, st);
-    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, MODE_UP, true>(tmap, p, st);
+    if (Cin == 64 && Cout == 64 && glu) return launch_tc<64, 64, MODE_UP, true>(tmap, p, fmt, st);
+    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, MODE_UP, true>(tmap, p, fmt, st);
   }
   return TGSR_ERR_UNSUPPORTED;
 }
 
-extern "C" int tgsr_pack_conv3x3_bf16(const float* w, void* packed, int Cout, int Cin, int up2x,
-                                      tgsr_stream_t stream) {
+extern "C" int tgsr_pack_conv3x3(const float* w, void* packed, int Cout, int Cin, int up2x, int fmt,
+                                 tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(w); TGSR_REQUIRE_PTR(packed);
+  TGSR_CHECK_FMT(fmt);
   TGSR_REQUIRE(Cout > 0 && Cin > 0 && Cout % 8 == 0 && Cin % 8 == 0, TGSR_ERR_BAD_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
-  if (up2x) pack_up2x_kernel<<<64, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin);
-  else pack_conv3x3_kernel<<<64, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cout, Cin);
+  h16* o = reinterpret_cast<h16*>(packed);
+  if (fmt == TGSR_FMT_F16) {
+    if (up2x) pack_up2x_kernel<TGSR_FMT_F16><<<64, 256, 0, st>>>(w, o, Cout, Cin);
+    else pack_conv3x3_kernel<TGSR_FMT_F16><<<64, 256, 0, st>>>(w, o, Cout, Cin);
+  } else {
+    if (up2x) pack_up2x_kernel<TGSR_FMT_BF16><<<64, 256, 0, st>>>(w, o, Cout, Cin);
+    else pack_conv3x3_kernel<TGSR_FMT_BF16><<<64, 256, 0, st>>>(w, o, Cout, Cin);
+  }
   return launch_status();
 }
 
-extern "C" int tgsr_pack_head_bf16(const float* w, void* packed, int Cin, int ksize, tgsr_stream_t stream) {
+extern "C" int tgsr_pack_head(const float* w, void* packed, int Cin, int ksize, int fmt, tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(w); TGSR_REQUIRE_PTR(packed);
+  TGSR_CHECK_FMT(fmt);
   TGSR_REQUIRE(Cin > 0 && Cin % 8 == 0 && (ksize == 3 || ksize == 5), TGSR_ERR_BAD_SHAPE);
-  pack_head_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), Cin, ksize);
+  if (fmt == TGSR_FMT_F16)
+    pack_head_kernel<TGSR_FMT_F16><<<32, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<h16*>(packed), Cin, ksize);
+  else
+    pack_head_kernel<TGSR_FMT_BF16><<<32, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<h16*>(packed), Cin, ksize);
   return launch_status();
 }
 
-extern "C" int tgsr_img_head_tc_bf16(const void* x, int xP, int xp0, const void* wpacked, const float* addend,
-                                     float out_scale, float addend_scale, float* y, int B, int Cin, int H, int W,
-                                     int ksize, int act, tgsr_stream_t stream) {
+extern "C" int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpacked, const float* addend,
+                                float out_scale, float addend_scale, float* y, int B, int Cin, int H, int W,
+                                int ksize, int act, int fmt, tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(wpacked); TGSR_REQUIRE_PTR(y);
+  TGSR_CHECK_FMT(fmt);
   TGSR_REQUIRE(g_sm_count > 0 && g_encode_tiled != nullptr, TGSR_ERR_NOT_INIT);
   TGSR_REQUIRE(B > 0 && H > 0 && W > 0, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE(Cin == 32 && (ksize == 3 || ksize == 5) && H % TC_TH == 0 && W % TC_TW == 0, TGSR_ERR_UNSUPPORTED);
@@ -547,7 +561,7 @@ extern "C" int tgsr_img_head_tc_bf16(const void* x, int xP, int xp0, const void*
   TGSR_REQUIRE(xp0 >= 0 && xp0 + Cin / 8 <= xP, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE((long long)B * xP < (1LL << 31), TGSR_ERR_UNSUPPORTED);
   CUtensorMap tmap;
-  int s = make_patch_tmap(&tmap, x, B, xP, H, W, Cin / 8, ksize / 2);
+  int s = make_patch_tmap(&tmap, x, B, xP, H, W, Cin / 8, fmt, ksize / 2);
   if (s != TGSR_OK) return s;
   TcParams p;
   p.wpacked = wpacked; p.scale = nullptr; p.shift = nullptr; p.residual = nullptr; p.out = nullptr;
@@ -557,30 +571,36 @@ extern "C" int tgsr_img_head_tc_bf16(const void* x, int xP, int xp0, const void*
   p.out_f32 = y; p.addend = addend; p.out_scale = out_scale; p.addend_scale = addend_scale;
   p.act_tanh = act == TGSR_ACT_TANH;
   cudaStream_t st = (cudaStream_t)stream;
-  if (ksize == 3) return launch_tc<32, 16, MODE_HEAD3, false>(tmap, p, st);
-  return launch_tc<32, 16, MODE_HEAD5, false>(tmap, p, st);
+  if (ksize == 3) return launch_tc<32, 16, MODE_HEAD3, false>(tmap, p, fmt, st);
+  return launch_tc<32, 16, MODE_HEAD5, false>(tmap, p, fmt, st);
 }
 
-extern "C" int tgsr_nchw_to_blocked_bf16(const float* x, void* y, int B, int C, int H, int W, int yP, int yp0,
-                                         tgsr_stream_t stream) {
+extern "C" int tgsr_nchw_to_blocked(const float* x, void* y, int B, int C, int H, int W, int yP, int yp0, int fmt,
+                                    tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(y);
+  TGSR_CHECK_FMT(fmt);
   TGSR_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0 && yp0 >= 0 && yp0 + C / 8 <= yP, TGSR_ERR_BAD_SHAPE);
   const size_t total = (size_t)B * (C / 8) * H * W;
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  nchw_to_blocked_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), B, C, H * W,
-                                                                  yP, yp0);
+  if (fmt == TGSR_FMT_F16)
+    nchw_to_blocked_kernel<TGSR_FMT_F16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<h16*>(y), B, C, H * W, yP, yp0);
+  else
+    nchw_to_blocked_kernel<TGSR_FMT_BF16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<h16*>(y), B, C, H * W, yP, yp0);
   return launch_status();
 }
 
-extern "C" int tgsr_blocked_to_nchw_f32(const void* x, float* y, int B, int C, int H, int W, int xP, int xp0,
-                                        tgsr_stream_t stream) {
+extern "C" int tgsr_blocked_to_nchw(const void* x, float* y, int B, int C, int H, int W, int xP, int xp0, int fmt,
+                                    tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(y);
+  TGSR_CHECK_FMT(fmt);
   TGSR_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0 && xp0 >= 0 && xp0 + C / 8 <= xP, TGSR_ERR_BAD_SHAPE);
   const size_t total = (size_t)B * (C / 8) * H * W;
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  blocked_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), y, B, C,
-                                                                  H * W, xP, xp0);
+  if (fmt == TGSR_FMT_F16)
+    blocked_to_nchw_kernel<TGSR_FMT_F16><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const h16*>(x), y, B, C, H * W, xP, xp0);
+  else
+    blocked_to_nchw_kernel<TGSR_FMT_BF16><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const h16*>(x), y, B, C, H * W, xP, xp0);
   return launch_status();
 }

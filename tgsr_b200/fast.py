@@ -42,8 +42,8 @@ def conv_in(seq, x: Tensor, out: Blocked, x_sub: Optional[Tensor] = None) -> Blo
     C = conv.weight.shape[0] // 2
     assert out.C == C and out.H == H and out.W == W
     xs = None if x_sub is None else x_sub.contiguous()
-    call('tgsr_conv_in_bf16', x.device, ptr(x), ptr(xs), ptr(conv.weight.detach().contiguous()), ptr(scale), ptr(shift),
-         ptr(out.buf), out.P, out.p0, B, H, W, C)
+    call('tgsr_conv_in_blocked', x.device, ptr(x), ptr(xs), ptr(conv.weight.detach().contiguous()), ptr(scale), ptr(shift),
+         ptr(out.buf), out.P, out.p0, B, H, W, C, out.fmt)
     return out
 
 
@@ -65,20 +65,21 @@ def up_block(x: Blocked, seq, out_planes: Optional[int] = None) -> Blocked:
     extra planes so the next stage's attention can append c_code in place."""
     conv, bn = seq[1], seq[2]
     C = conv.weight.shape[0] // 2
-    out = Blocked.empty(x.B, C, 2 * x.H, 2 * x.W, x.device, planes=out_planes)
+    out = Blocked.empty(x.B, C, 2 * x.H, 2 * x.W, x.device, planes=out_planes, fmt=x.fmt)
     return conv_bn_act(x, conv, bn, ACT_GLU, up2x=True, out=out)
 
 
-def _packed_head(conv: nn.Conv2d) -> Tensor:
+def _packed_head(conv: nn.Conv2d, fmt: int) -> Tensor:
     w = conv.weight
-    key = (w.data_ptr(), w._version, str(w.device))
-    cached = conv.__dict__.get('_tgsr_packed_head')
+    key = (w.data_ptr(), w._version, str(w.device), fmt)
+    name = '_tgsr_packed_head_%d' % fmt
+    cached = conv.__dict__.get(name)
     if cached is None or cached[0] != key:
         k = w.shape[2]
-        packed = torch.empty(k * k * 16 * w.shape[1], device=w.device, dtype=torch.bfloat16)
-        call('tgsr_pack_head_bf16', w.device, ptr(w.detach().contiguous()), ptr(packed), w.shape[1], k)
+        packed = torch.empty(k * k * 16 * w.shape[1], device=w.device, dtype=tc._DTYPES[fmt])
+        call('tgsr_pack_head', w.device, ptr(w.detach().contiguous()), ptr(packed), w.shape[1], k, fmt)
         cached = (key, packed)
-        conv.__dict__['_tgsr_packed_head'] = cached
+        conv.__dict__[name] = cached
     return cached[1]
 
 
@@ -93,8 +94,8 @@ def image_head(x: Blocked, head_seq, addend: Optional[Tensor] = None, a: float =
         if tuple(addend.shape) != tuple(y.shape):
             raise ValueError('SRb shape %s != image shape %s' % (tuple(addend.shape), tuple(y.shape)))
         ad = addend.contiguous()
-    call('tgsr_img_head_tc_bf16', x.device, ptr(x.buf), x.P, x.p0, ptr(_packed_head(conv)), ptr(ad), float(one), float(a),
-         ptr(y), x.B, x.C, x.H, x.W, k, act)
+    call('tgsr_img_head_tc', x.device, ptr(x.buf), x.P, x.p0, ptr(_packed_head(conv, x.fmt)), ptr(ad), float(one), float(a),
+         ptr(y), x.B, x.C, x.H, x.W, k, act, x.fmt)
     return y
 
 
@@ -108,7 +109,7 @@ def attention(h: Blocked, att, words: Tensor, mask: Optional[Tensor], out: Block
     if idf == 32 and T <= 20:
         call('tgsr_attn_fwd_blocked', h.device, ptr(h.buf), h.P, h.p0, ptr(words.contiguous()),
              ptr(att.conv_context.weight.detach().contiguous()), ptr(m8), ptr(out.buf), out.P, out.p0, ptr(attn),
-             B, idf, cdf, h.H * h.W, T)
+             B, idf, cdf, h.H * h.W, T, h.fmt)
         return attn
     # outside the blocked kernel's envelope (long captions): fp32 kernel + layout conversion
     wctx, attn = ops.attention_fwd(tc.to_nchw(h), words, att.conv_context.weight.detach(), mask)
@@ -117,13 +118,14 @@ def attention(h: Blocked, att, words: Tensor, mask: Optional[Tensor], out: Block
 
 
 # ---------------------------------------------------------------- stages and nets
-def stage(st, h: Optional[Blocked], LR: Optional[Tensor], words: Tensor, mask, out_planes: Optional[int]):
+def stage(st, h: Optional[Blocked], LR: Optional[Tensor], words: Tensor, mask, out_planes: Optional[int],
+          fmt: int = 0):
     """INIT_STAGE_GImgup (LR given) / NEXT_STAGE_G (h given); util.py:763-777 / :807-823.
     `h` must be the first 32-channel view of a 64-channel buffer: c_code is appended in place."""
     ngf = st.gf_dim
     if h is None:
         B, _, H, W = LR.shape
-        cat = Blocked.empty(B, 2 * ngf, H, W, LR.device)
+        cat = Blocked.empty(B, 2 * ngf, H, W, LR.device, fmt=fmt)
         h = conv_in(st.im2f, LR, cat.slice(0, ngf))
     else:
         assert h.p0 == 0 and h.P * 8 >= 2 * ngf, 'h_code must live in a concat-sized buffer'
@@ -139,7 +141,7 @@ def stage_supported(st, H: int, W: int) -> bool:
     return st.gf_dim == 32 and H % 16 == 0 and W % 8 == 0 and getattr(st, 'batchnorm', True)
 
 
-def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, heads, outmiddle: bool):
+def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, heads, outmiddle: bool, fmt: int = 0):
     imgs: List[Tensor] = []
     atts: List[Tensor] = []
     feats: List[Blocked] = []
@@ -148,7 +150,7 @@ def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, hea
     n = len(stages)
     for i, (st, hd) in enumerate(zip(stages, heads)):
         planes = 8 if i + 1 < n else 4                     # leave room for the next stage's c_code
-        h, att = stage(st, h, LR if i == 0 else None, words, mask, planes)
+        h, att = stage(st, h, LR if i == 0 else None, words, mask, planes, fmt)
         imgs.append(image_head(h, hd.img))
         atts.append(att)
         feats.append(h)
@@ -157,11 +159,12 @@ def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, hea
     return imgs, atts, mu, logvar
 
 
-def netg_high(net, x: Tensor, x_sub: Optional[Tensor], SRb, a: float, one: float, tail, feats=None) -> List[Tensor]:
+def netg_high(net, x: Tensor, x_sub: Optional[Tensor], SRb, a: float, one: float, tail, feats=None,
+              fmt: int = 0) -> List[Tensor]:
     """Trunk of NetG_high / NetG_highweight (model.py:264-298).  `tail` = [(body, upscale), ...] after
     the first upscale."""
     B, _, H, W = x.shape
-    h = conv_in(net.convin, x, Blocked.empty(B, 32, H, W, x.device), x_sub)
+    h = conv_in(net.convin, x, Blocked.empty(B, 32, H, W, x.device, fmt=fmt), x_sub)
     for rb in net.residual:
         h = res_block(h, rb)
     h = up_block(h, net.upscale2x)

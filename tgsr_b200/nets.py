@@ -28,12 +28,12 @@ class G_SR_NET_low(nn.Module):
         self.img_net3 = GET_IMAGE_G_noAct(ngf)
 
     def forward(self, LR, sent_emb, word_embs, mask, outmiddle=False):
-        from . import fast, get_precision
-        if get_precision() == 'bf16' and fast.stage_supported(self.h_net1, LR.shape[2], LR.shape[3]):
+        from . import fast, fmt_for, is_16bit
+        if is_16bit() and fast.stage_supported(self.h_net1, LR.shape[2], LR.shape[3]):
             for st in (self.h_net1, self.h_net2, self.h_net3):
                 st.att.applyMask(mask)                              # keep the stateful contract
             return fast.g_sr_net_low(self, LR, sent_emb, word_embs, mask, [self.h_net1, self.h_net2, self.h_net3],
-                                     [self.img_net1, self.img_net2, self.img_net3], outmiddle)
+                                     [self.img_net1, self.img_net2, self.img_net3], outmiddle, fmt_for('low'))
         fake_imgs, att_maps = [], []
         c_code, mu, logvar = self.ca_net(sent_emb)              # c_code unused, model.py:51
         h_code1, att0 = self.h_net1(None, LR, word_embs, mask)
@@ -72,11 +72,11 @@ class _HighBase(nn.Module):
                                            nn.BatchNorm2d(ngf))
 
     def _trunk(self, x, SRb, a, one, feats=None, x_sub=None):
-        from . import fast, get_precision
-        if get_precision() == 'bf16' and self.convin[0].weight.shape[0] == 64 and x.shape[2] % 16 == 0 \
+        from . import fast, fmt_for, is_16bit
+        if is_16bit() and self.convin[0].weight.shape[0] == 64 and x.shape[2] % 16 == 0 \
                 and x.shape[3] % 8 == 0:
             return fast.netg_high(self, x, x_sub, SRb, a, one,
-                                  [(self.residual24, self.upscale4x), (self.residual48, self.upscale8x)], feats)
+                                  [(self.residual24, self.upscale4x), (self.residual48, self.upscale8x)], feats, fmt_for('high'))
         if x_sub is not None:
             x = torch.sub(x, x_sub)
         out = self.convin(x)

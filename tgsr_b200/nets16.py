@@ -25,12 +25,12 @@ class G_SR_NET_low(nn.Module):
         self.img_net4 = self.img_net3 = self.img_net2 = self.img_net1 = GET_IMAGE_G(ngf)
 
     def forward(self, LR, sent_emb, word_embs, mask):
-        from . import fast, get_precision
-        if get_precision() == 'bf16' and fast.stage_supported(self.h_net1, LR.shape[2], LR.shape[3]):
+        from . import fast, fmt_for, is_16bit
+        if is_16bit() and fast.stage_supported(self.h_net1, LR.shape[2], LR.shape[3]):
             self.h_net1.att.applyMask(mask); self.h_net2.att.applyMask(mask)
             return fast.g_sr_net_low(self, LR, sent_emb, word_embs, mask,
                                      [self.h_net1, self.h_net2, self.h_net3, self.h_net4],
-                                     [self.img_net1, self.img_net2, self.img_net3, self.img_net4], False)
+                                     [self.img_net1, self.img_net2, self.img_net3, self.img_net4], False, fmt_for('low'))
         fake_imgs, att_maps = [], []
         c_code, mu, logvar = self.ca_net(sent_emb)
         h_code, att = self.h_net1(None, LR, word_embs, mask)

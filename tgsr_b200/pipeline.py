@@ -76,16 +76,20 @@ class SRPipeline:
     def dominant_kernel_roofline(self, B, flush, pk):
         """The dominant kernel of the step: ResBlock conv1 of h_net3 (conv3x3 64->128 + BN + GLU at
         128x128; 2*9*64*128*128^2 FLOP per image, util.py:115-117), timed alone."""
-        from . import get_precision
+        from . import get_precision, is_16bit
         from .blocks import _conv
         from ._lib import ACT_GLU
         blk = self.netGL.h_net3.residual[0].block
         H = W = 128
         x = torch.randn(B, 64, H, W, device=self.device) * 0.5
         flops = 2.0 * 9 * 64 * 128 * H * W * B
-        if get_precision() == 'bf16':
-            from . import tc
-            fn, kernel = tc.make_probe_conv(blk, x)
+        if is_16bit():
+            from . import fast, tc, fmt_for
+            from .blocks import _folded_bn
+            xb = tc.to_blocked(x, fmt=fmt_for('low'))
+            yb = tc.Blocked.empty(B, 64, H, W, self.device, fmt=xb.fmt)
+            fn = lambda: fast.conv_bn_act(xb, blk[0], blk[1], ACT_GLU, out=yb)
+            kernel = 'conv3x3_tc_kernel<64,128,CONV,GLU> (tcgen05, %s operands)' % ('fp16' if xb.fmt else 'bf16')
         else:
             fn, kernel = (lambda: _conv(x, blk[0], blk[1], ACT_GLU)), 'conv2d_f32_kernel<3,GLU> (CUDA-core fp32)'
         ms = self._time_kernel(fn, flush)
@@ -98,15 +102,18 @@ class SRPipeline:
     def attention_roofline(self, B, flush, pk):
         """Fused word attention at the h_net3 shape (Q=128^2, idf 32, cdf 256, T 18), timed alone.
         Algorithmic bytes per SURVEY.md 8d: B*Q*(idf*e_in + idf*e_out + 4*T) + B*cdf*T*4 + idf*cdf*4 + B*T."""
-        from . import get_precision
+        from . import get_precision, is_16bit
         att = self.netGL.h_net3.att
         Q, idf, cdf, T = 128 * 128, 32, 256, 18
         ctx = torch.randn(B, cdf, T, device=self.device) * 0.3
         mask = torch.zeros(B, T, dtype=torch.bool, device=self.device)
         att.applyMask(mask)
-        if get_precision() == 'bf16':
-            from . import tc
-            fn, e, kernel = tc.make_probe_attention(att, ctx, mask, B)
+        if is_16bit():
+            from . import fast, tc, fmt_for
+            cat = tc.Blocked.empty(B, 64, 128, 128, self.device, fmt=fmt_for('low'))
+            cat.buf.normal_(0, 0.5)
+            fn = lambda: fast.attention(cat.slice(0, 32), att, ctx, mask, out=cat.slice(32, 32))
+            e, kernel = 2, 'attn_blocked_kernel (16-bit blocked activations, fp32 maps)'
         else:
             x = torch.randn(B, idf, 128, 128, device=self.device) * 0.5
             fn, e, kernel = (lambda: att(x, ctx)), 4, 'attn_fwd_f32_kernel (fp32 NCHW I/O)'

@@ -7,24 +7,31 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from ._lib import ACT_GLU, ACT_NONE, call, ptr
+from ._lib import ACT_GLU, ACT_NONE, FMT_BF16, FMT_F16, call, ptr
 
 Tensor = torch.Tensor
 
 
+_DTYPES = {FMT_BF16: torch.bfloat16, FMT_F16: torch.float16}
+
+
 class Blocked:
-    """A view of C channels inside a blocked bf16 buffer [B, P, H, W, 8] starting at plane p0."""
+    """A view of C channels inside a blocked 16-bit buffer [B, P, H, W, 8] starting at plane p0."""
     __slots__ = ('buf', 'p0', 'C')
 
     def __init__(self, buf: Tensor, p0: int, C: int):
-        assert buf.dtype == torch.bfloat16 and buf.dim() == 5 and buf.shape[4] == 8 and buf.is_contiguous()
+        assert buf.dtype in (torch.bfloat16, torch.float16) and buf.dim() == 5 and buf.shape[4] == 8 and buf.is_contiguous()
         assert C % 8 == 0 and 0 <= p0 and p0 + C // 8 <= buf.shape[1]
         self.buf, self.p0, self.C = buf, p0, C
 
     @staticmethod
-    def empty(B: int, C: int, H: int, W: int, device, planes: Optional[int] = None, p0: int = 0) -> 'Blocked':
+    def empty(B: int, C: int, H: int, W: int, device, planes: Optional[int] = None, p0: int = 0,
+              fmt: int = FMT_BF16) -> 'Blocked':
         P = planes if planes is not None else C // 8
-        return Blocked(torch.empty((B, P, H, W, 8), device=device, dtype=torch.bfloat16), p0, C)
+        return Blocked(torch.empty((B, P, H, W, 8), device=device, dtype=_DTYPES[fmt]), p0, C)
+
+    @property
+    def fmt(self): return FMT_F16 if self.buf.dtype == torch.float16 else FMT_BF16
 
     @property
     def B(self): return self.buf.shape[0]
@@ -42,32 +49,32 @@ class Blocked:
         return Blocked(self.buf, self.p0 + c0 // 8, C)
 
 
-def to_blocked(x: Tensor, out: Optional[Blocked] = None) -> Blocked:
-    """NCHW fp32 -> blocked bf16 (round-to-nearest-even)."""
+def to_blocked(x: Tensor, out: Optional[Blocked] = None, fmt: int = FMT_BF16) -> Blocked:
+    """NCHW fp32 -> blocked 16-bit (round-to-nearest-even)."""
     x = x.contiguous()
     B, C, H, W = x.shape
     if out is None:
-        out = Blocked.empty(B, C, H, W, x.device)
-    call('tgsr_nchw_to_blocked_bf16', x.device, ptr(x), ptr(out.buf), B, C, H, W, out.P, out.p0)
+        out = Blocked.empty(B, C, H, W, x.device, fmt=fmt)
+    call('tgsr_nchw_to_blocked', x.device, ptr(x), ptr(out.buf), B, C, H, W, out.P, out.p0, out.fmt)
     return out
 
 
 def to_nchw(xb: Blocked) -> Tensor:
     y = torch.empty((xb.B, xb.C, xb.H, xb.W), device=xb.device, dtype=torch.float32)
-    call('tgsr_blocked_to_nchw_f32', xb.device, ptr(xb.buf), ptr(y), xb.B, xb.C, xb.H, xb.W, xb.P, xb.p0)
+    call('tgsr_blocked_to_nchw', xb.device, ptr(xb.buf), ptr(y), xb.B, xb.C, xb.H, xb.W, xb.P, xb.p0, xb.fmt)
     return y
 
 
-def packed_weights(conv: nn.Conv2d, up2x: bool) -> Tensor:
-    """bf16 UMMA operand image of a conv3x3 weight, cached per weight version (not in state_dict)."""
+def packed_weights(conv: nn.Conv2d, up2x: bool, fmt: int) -> Tensor:
+    """16-bit UMMA operand image of a conv3x3 weight, cached per weight version (not in state_dict)."""
     w = conv.weight
-    key = (w.data_ptr(), w._version, str(w.device), bool(up2x))
-    name = '_tgsr_packed_up' if up2x else '_tgsr_packed'
+    key = (w.data_ptr(), w._version, str(w.device), bool(up2x), fmt)
+    name = '_tgsr_packed_%d_%d' % (int(up2x), fmt)
     cached = conv.__dict__.get(name)
     if cached is None or cached[0] != key:
         Cout, Cin = w.shape[0], w.shape[1]
-        packed = torch.empty(Cout * Cin * (16 if up2x else 9), device=w.device, dtype=torch.bfloat16)
-        call('tgsr_pack_conv3x3_bf16', w.device, ptr(w.detach().contiguous()), ptr(packed), Cout, Cin, int(up2x))
+        packed = torch.empty(Cout * Cin * (16 if up2x else 9), device=w.device, dtype=_DTYPES[fmt])
+        call('tgsr_pack_conv3x3', w.device, ptr(w.detach().contiguous()), ptr(packed), Cout, Cin, int(up2x), fmt)
         cached = (key, packed)
         conv.__dict__[name] = cached
     return cached[1]
@@ -88,12 +95,12 @@ def conv3x3_tc(xb: Blocked, conv: nn.Conv2d, scale: Optional[Tensor], shift: Opt
     Cf = Cout // 2 if act == ACT_GLU else Cout
     Ho, Wo = (2 * xb.H, 2 * xb.W) if up2x else (xb.H, xb.W)
     if out is None:
-        out = Blocked.empty(xb.B, Cf, Ho, Wo, xb.device)
-    assert out.C == Cf and out.H == Ho and out.W == Wo and out.B == xb.B
-    wp = packed_weights(conv, up2x)
+        out = Blocked.empty(xb.B, Cf, Ho, Wo, xb.device, fmt=xb.fmt)
+    assert out.fmt == xb.fmt and out.C == Cf and out.H == Ho and out.W == Wo and out.B == xb.B
+    wp = packed_weights(conv, up2x, xb.fmt)
     rbuf, rP, rp0 = (residual.buf, residual.P, residual.p0) if residual is not None else (None, 0, 0)
     if residual is not None:
-        assert residual.C == Cf and residual.H == Ho and residual.W == Wo
-    call('tgsr_conv3x3_tc_bf16', xb.device, ptr(xb.buf), xb.P, xb.p0, ptr(wp), ptr(scale), ptr(shift), ptr(rbuf), rP, rp0,
-         ptr(out.buf), out.P, out.p0, xb.B, Cin, xb.H, xb.W, Cout, int(up2x), act)
+        assert residual.C == Cf and residual.H == Ho and residual.W == Wo and residual.fmt == xb.fmt
+    call('tgsr_conv3x3_tc', xb.device, ptr(xb.buf), xb.P, xb.p0, ptr(wp), ptr(scale), ptr(shift), ptr(rbuf), rP, rp0,
+         ptr(out.buf), out.P, out.p0, xb.B, Cin, xb.H, xb.W, Cout, int(up2x), act, xb.fmt)
     return out
