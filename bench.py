@@ -38,8 +38,8 @@ METRIC = 'SR images/sec (eval fwd, x8 32->256, batch 32/GPU)'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default=None, choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -219,12 +219,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing
+    sampler = ClockSampler(local); sampler.start()
+    t_wait = time.time()
+    while not sampler.lines and time.time() - t_wait < 3.0:      # nvidia-smi needs ~0.2 s to emit its first sample
+        time.sleep(0.05)
+    sampler.lines.clear()
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
     lib = _lib.load()
     launches0 = lib.tgsr_launch_count()
-    sampler = ClockSampler(local); sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for s, e in ev:
@@ -271,7 +275,7 @@ def run_ours(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': t_ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if precision == 'bf16' else 'f32',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16': 'bf16', 'fp16': 'f16', 'mixed16': 'bf16+f16 (16-bit tcgen05 operands, f32 accumulate)'}[precision],
             'data': 'synthetic',
             'config': {'workload': 'bird SR eval (cfg/eval_birdSR_attn2.yml dims): text encoder + G_SR_NET_low + '
                                    'NetG_highweight, x8 32->256, batch %d per GPU, 18-word captions, ntoken %d, '
