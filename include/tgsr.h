@@ -103,6 +103,16 @@ int tgsr_lstm_bidir_fwd_f32(const int64_t* captions, const int64_t* cap_lens, co
                             int Tcap, int Tmax, int ntoken, int ninput, int H,
                             tgsr_stream_t stream);
 
+/* Fast path of a11 for H == 128 (the TGSR encoder): the input projection becomes a table lookup.
+ * tgsr_lstm_prepare_f32 builds xtab [ntoken][2][4H] = emb.w_ih^T + b_ih + b_hh once per weight
+ * version; tgsr_lstm_bidir_fwd_tab_f32 runs the recurrence as one persistent cluster kernel
+ * (W_hh register-resident, h exchanged through distributed shared memory).  w_hh [2][4H,H]. */
+int tgsr_lstm_prepare_f32(const float* emb, const float* w_ih, const float* b_ih, const float* b_hh,
+                          float* xtab, int ntoken, int ninput, int H, tgsr_stream_t stream);
+int tgsr_lstm_bidir_fwd_tab_f32(const int64_t* captions, const int64_t* cap_lens, const float* xtab,
+                                const float* w_hh, float* words, float* sent, int B, int Tcap, int Tmax,
+                                int ntoken, int H, tgsr_stream_t stream);
+
 /* =============================== 16-bit tensor-core path ===================================
  * Every entry point below takes `fmt` (TGSR_FMT_BF16 or TGSR_FMT_F16): the storage format of the
  * blocked activations and packed weights it touches.
@@ -120,27 +130,28 @@ int tgsr_blocked_to_nchw(const void* x, float* y, int B, int C, int H, int W, in
 /* Weight prep: conv3x3 weight [Cout,Cin,3,3] fp32 -> packed 16-bit UMMA operand image.
  * up2x == 0: 9 taps, Cout*Cin*9 elements.  up2x == 1: the nearest-x2 upsample of util.py:76 is
  * folded into the weights as four 2x2 sub-pixel phases (pre-summed in fp32, rounded once),
- * Cout*Cin*16 elements. */
-int tgsr_pack_conv3x3(const float* w, void* packed, int Cout, int Cin, int up2x, int fmt,
-                      tgsr_stream_t stream);
+ * Cout*Cin*16 elements.  scale [Cout] (the folded BatchNorm scale, or NULL) is multiplied into the
+ * weights in fp32 before the single rounding, so the conv epilogue only adds the BN shift. */
+int tgsr_pack_conv3x3(const float* w, const float* scale, void* packed, int Cout, int Cin, int up2x,
+                      int fmt, tgsr_stream_t stream);
 
-/* a3/a4/a5: conv3x3 (+ folded BN scale/shift [Cout]) (+GLU) (+residual) on tcgen05 tensor cores,
+/* a3/a4/a5: conv3x3 (+ folded BN: scale in the packed weights, shift [Cout] here) (+GLU) (+residual) on tcgen05,
  * 16-bit operands, fp32 accumulation in TMEM; util.py:62-65, :45-53, :110-130, :74-80.
  * x view (xP,xp0) of Cin channels at HxW; y view (yP,yp0) of Cout (or Cout/2 with GLU) channels at
  * HxW, or at 2Hx2W when up2x (wpacked must then come from tgsr_pack_conv3x3(up2x=1)).
  * residual view (rP,rp0) or NULL (only with act NONE, no up2x).  Supported (Cin,Cout,act,up2x):
  * (64,128,GLU,0) (64,64,NONE,0) (32,64,GLU,0) (32,32,NONE,0) (64,64,GLU,1) (32,64,GLU,1);
  * H % 16 == 0, W % 8 == 0. */
-int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const float* scale,
-                    const float* shift, const void* residual, int rP, int rp0, void* y, int yP, int yp0,
-                    int B, int Cin, int H, int W, int Cout, int up2x, int act, int fmt,
-                    tgsr_stream_t stream);
+int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const float* shift,
+                    const void* residual, int rP, int rp0, void* y, int yP, int yp0, int B, int Cin, int H,
+                    int W, int Cout, int up2x, int act, int fmt, tgsr_stream_t stream);
 
 /* a8 image heads on tensor cores: GET_IMAGE_G / GET_IMAGE_G_noAct (conv3x3 32->3, util.py:894-919) and
  * conv_output (conv5x5 32->3 + Tanh, model.py:223-226) with the fused `one*y + a*SRb` of model.py:280.
  * x: blocked view of 32 channels; wpacked from tgsr_pack_head (w [3,Cin,k,k] fp32);
  * y fp32 NCHW [B,3,H,W] = out_scale * act(conv(x)) + addend_scale * addend (addend NCHW or NULL).
- * act NONE or TANH; H % 16 == 0, W % 8 == 0. */
+ * act NONE or TANH; W % 8 == 0 (any H).  The kx taps are folded into the MMA N dimension (N = 3k <= 16), so
+ * a kxk head issues k row-tap MMAs per K-step; packed weights hold k*16*Cin elements. */
 int tgsr_pack_head(const float* w, void* packed, int Cin, int ksize, int fmt, tgsr_stream_t stream);
 int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpacked, const float* addend,
                      float out_scale, float addend_scale, float* y, int B, int Cin, int H, int W,

@@ -1,0 +1,82 @@
+"""Launch individual hot kernels at bench shapes (B=32) for ncu captures and quick CUDA-event timing.
+
+    python scripts/probe_kernels.py conv128 | conv64res | up64 | head5 | head3 | attn | lstm  [--iters N]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import tgsr_b200
+from tgsr_b200 import fast, tc
+from tgsr_b200._lib import ACT_GLU, ACT_NONE
+from tgsr_b200.pipeline import SRPipeline
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('what')
+    ap.add_argument('--iters', type=int, default=5)
+    ap.add_argument('--size', type=int, default=128)
+    ap.add_argument('--batch', type=int, default=32)
+    a = ap.parse_args()
+    tgsr_b200.set_eval_defaults(); tgsr_b200.set_precision('mixed16')
+    dev = torch.device('cuda')
+    pipe = SRPipeline(5450, device=dev, seed=100, randomize_bn=True)
+    B, S = a.batch, a.size
+    st = pipe.netGL.h_net3
+    rb = st.residual[0].block
+    flops = None
+    if a.what == 'conv128':
+        x = tc.to_blocked(torch.randn(B, 64, S, S, device=dev) * 0.5)
+        out = tc.Blocked.empty(B, 64, S, S, dev)
+        fn = lambda: fast.conv_bn_act(x, rb[0], rb[1], ACT_GLU, out=out)
+        flops = 2 * 9 * 64 * 128 * S * S * B
+    elif a.what == 'conv64res':
+        x = tc.to_blocked(torch.randn(B, 64, S, S, device=dev) * 0.5)
+        r = tc.to_blocked(torch.randn(B, 64, S, S, device=dev) * 0.5)
+        out = tc.Blocked.empty(B, 64, S, S, dev)
+        fn = lambda: fast.conv_bn_act(x, rb[3], rb[4], ACT_NONE, residual=r, out=out)
+        flops = 2 * 9 * 64 * 64 * S * S * B
+    elif a.what == 'up64':
+        x = tc.to_blocked(torch.randn(B, 64, S, S, device=dev) * 0.5)
+        out = tc.Blocked.empty(B, 32, 2 * S, 2 * S, dev)
+        fn = lambda: fast.conv_bn_act(x, st.upsample[1], st.upsample[2], ACT_GLU, up2x=True, out=out)
+        flops = 2 * 9 * 64 * 64 * 4 * S * S * B          # reference FLOPs (executed: 4/9 of it)
+    elif a.what in ('head5', 'head3'):
+        x = tc.to_blocked(torch.randn(B, 32, 2 * S, 2 * S, device=dev) * 0.5, fmt=1)
+        seq = pipe.netGH.conv_output if a.what == 'head5' else pipe.netGL.img_net3.img
+        add = torch.randn(B, 3, 2 * S, 2 * S, device=dev)
+        fn = lambda: fast.image_head(x, seq, add, 0.5, 1.0)
+        k = 5 if a.what == 'head5' else 3
+        flops = 2 * k * k * 32 * 3 * 4 * S * S * B
+    elif a.what == 'attn':
+        cat = tc.Blocked.empty(B, 64, S, S, dev); cat.buf.normal_(0, 0.5)
+        ctx = torch.randn(B, 256, 18, device=dev) * 0.3
+        mask = torch.zeros(B, 18, dtype=torch.bool, device=dev)
+        fn = lambda: fast.attention(cat.slice(0, 32), st.att, ctx, mask, out=cat.slice(32, 32))
+    elif a.what == 'lstm':
+        caps = torch.randint(1, 5450, (B, 18), device=dev); lens = torch.full((B,), 18, device=dev)
+        fn = lambda: pipe.text_encoder._forward_tmax(caps, lens, 18)
+    else:
+        raise SystemExit('unknown kernel ' + a.what)
+    flush = torch.empty(64 * 1024 * 1024, device=dev)
+    for _ in range(3):
+        fn()
+    ms = 0.0
+    for _ in range(a.iters):
+        flush.zero_()
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); e.synchronize()
+        ms += s.elapsed_time(e)
+    ms /= a.iters
+    msg = '%s B=%d S=%d: %.1f us/launch' % (a.what, B, S, ms * 1e3)
+    if flops:
+        msg += '  %.1f TFLOP/s (reference FLOPs)' % (flops / ms / 1e9)
+    print(msg)
+
+
+if __name__ == '__main__':
+    main()

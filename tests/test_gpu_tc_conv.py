@@ -19,6 +19,7 @@ def rounder(fmt):
 def emulate(x, w, scale, shift, glu, res, up2x, fmt=0):
     bf = rounder(fmt)
     xb = bf(x)
+    w = w * scale[:, None, None, None]          # BN scale is folded into the weights before rounding
     if not up2x:
         z = F.conv2d(xb, bf(w), None, 1, 1)
     else:
@@ -37,7 +38,7 @@ def emulate(x, w, scale, shift, glu, res, up2x, fmt=0):
                                 acc = acc + w[:, :, ky, kx]
                         w3[:, :, r, c] = acc
                 z[:, :, py::2, px::2] = F.conv2d(xb, bf(w3), None, 1, 1)
-    z = z * scale[None, :, None, None] + shift[None, :, None, None]
+    z = z + shift[None, :, None, None]
     if glu:
         n = z.shape[1] // 2
         z = z[:, :n] * torch.sigmoid(z[:, n:])

@@ -37,8 +37,8 @@ _SIGS = {
     'tgsr_ca_reparam_f32': ([C.c_void_p] * 3 + [C.c_int] * 2 + [C.c_void_p], C.c_int),
     'tgsr_nchw_to_blocked': ([C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p], C.c_int),
     'tgsr_blocked_to_nchw': ([C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p], C.c_int),
-    'tgsr_pack_conv3x3': ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p], C.c_int),
-    'tgsr_conv3x3_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+    'tgsr_pack_conv3x3': ([C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p], C.c_int),
+    'tgsr_conv3x3_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                          C.c_void_p, C.c_int, C.c_int] + [C.c_int] * 8 + [C.c_void_p], C.c_int),
     'tgsr_pack_head': ([C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     'tgsr_img_head_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
@@ -46,6 +46,8 @@ _SIGS = {
     'tgsr_conv_in_blocked': ([C.c_void_p] * 6 + [C.c_int] * 7 + [C.c_void_p], C.c_int),
     'tgsr_attn_fwd_blocked': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                C.c_int, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p], C.c_int),
+    'tgsr_lstm_prepare_f32': ([C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p], C.c_int),
+    'tgsr_lstm_bidir_fwd_tab_f32': ([C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p], C.c_int),
     'tgsr_lstm_bidir_fwd_f32': ([C.c_void_p] * 10 + [C.c_int] * 6 + [C.c_void_p], C.c_int),
 }
 

@@ -127,8 +127,7 @@ class _ImageHead(nn.Sequential):
 
     def forward(self, h, addend=None, a: float = 0.0, one: float = 1.0):
         act = ACT_TANH if any(isinstance(m, nn.Tanh) for m in self) else ACT_NONE
-        if _bf16() and h.shape[1] == 32 and self[0].weight.shape[0] == 3 and h.shape[2] % 16 == 0 \
-                and h.shape[3] % 8 == 0:
+        if _bf16() and h.shape[1] == 32 and self[0].weight.shape[0] == 3 and h.shape[3] % 8 == 0:
             from . import fast, tc
             return fast.image_head(tc.to_blocked(h, fmt=_fmt()), self, addend, a, one)
         return _conv(h, self[0], None, act, addend=addend, out_scale=one, addend_scale=a)

@@ -41,7 +41,7 @@ constexpr int MODE_CONV = 0;    // conv3x3 (+BN, +GLU, +residual) -> blocked bf1
 constexpr int MODE_UP = 1;      // nearest-x2 + conv3x3 + BN + GLU as four sub-pixel phases -> blocked bf16 at 2H x 2W
 constexpr int MODE_HEAD3 = 2;   // conv3x3 32->3 image head -> fp32 NCHW (+tanh, one*y + a*addend)
 constexpr int MODE_HEAD5 = 3;   // conv5x5 32->3 image head -> fp32 NCHW (+tanh, one*y + a*addend)
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -58,13 +58,15 @@ template <> struct OpTable<MODE_CONV> {
   static constexpr int NOPS = 9;
   __host__ __device__ static constexpr TcOp op(int i) { return TcOp{i / 3, i % 3, 1, 0}; }
 };
+// Image heads (Cout = 3): the kx taps are folded into N (column n = o*K + kx of a row-tap ky), so a KxK
+// head needs K MMA ops instead of K*K; the epilogue sums the K shifted partials per output.
 template <> struct OpTable<MODE_HEAD3> {
-  static constexpr int NOPS = 9;
-  __host__ __device__ static constexpr TcOp op(int i) { return TcOp{i / 3, i % 3, 1, 0}; }
+  static constexpr int NOPS = 3;
+  __host__ __device__ static constexpr TcOp op(int i) { return TcOp{i, 0, 1, 0}; }
 };
 template <> struct OpTable<MODE_HEAD5> {
-  static constexpr int NOPS = 25;
-  __host__ __device__ static constexpr TcOp op(int i) { return TcOp{i / 5, i % 5, 1, 0}; }
+  static constexpr int NOPS = 5;
+  __host__ __device__ static constexpr TcOp op(int i) { return TcOp{i, 0, 1, 0}; }
 };
 // 4-phase nearest-x2 + conv3x3: low-res tap (r,c) in {0,1,2}^2 (offset -1..+1) feeds the output
 // parities ph = py*2+px listed below (see pack kernel for the pre-summed weights).
@@ -85,7 +87,14 @@ struct TcCfg {
   static constexpr bool UP = MODE == MODE_UP;
   static constexpr bool HEAD = MODE == MODE_HEAD3 || MODE == MODE_HEAD5;
   static constexpr int R = MODE == MODE_HEAD5 ? 2 : 1;         // halo radius
-  static constexpr int PH = TC_TH + 2 * R, PW = TC_TW + 2 * R;
+  static constexpr int KS = 2 * R + 1;                         // filter size
+  static constexpr int PW = TC_TW + 2 * R;
+  // Conv/up tiles: 16 rows x 8 cols, accumulator row m = (y, x) and 8-row groups are PW*16 B apart.
+  // Head tiles: accumulator row m = LINEAR patch pixel (y*PW + x'), i.e. M walks the patch contiguously
+  // (8-row groups 128 B apart) and covers TH = 128/PW output rows; columns x' >= 8 are halo-only rows.
+  static constexpr int TH = HEAD ? 128 / PW : TC_TH;           // output rows per tile (10 / 12 for 5x5 / 3x3 heads)
+  static constexpr int PH = HEAD ? TH + 2 * R + 1 : TC_TH + 2 * R;   // +1 row: the linear M window overruns the last row
+  static constexpr int SBO_A = HEAD ? 128 : PW * 16;
   static constexpr int PLANE_BYTES = PH * PW * 16;             // one 8-channel plane of the halo patch
   static constexpr int NPL = CIN / 8;                          // input planes
   static constexpr int KSTEPS = CIN / 16;                      // UMMA K = 16
@@ -95,8 +104,9 @@ struct TcCfg {
   static constexpr int NTAPB = UP ? 16 : OpTable<MODE>::NOPS;  // number of [NPRE x CIN] weight blocks
   static constexpr int WBYTES = NTAPB * CIN * NPRE * 2;
   static constexpr int NSCALE = NPRE;
+  static constexpr int PBUF_BYTES = HEAD ? 2 * 128 * 16 * 4 : 0;   // head epilogue exchange buffer (double-buffered)
   static constexpr size_t SMEM = 1024 /*align slack*/ + ((WBYTES + 1023) / 1024) * 1024 + TC_NSTAGE * PATCH_BYTES +
-                                 2 * NSCALE * 4 + 256;
+                                 2 * NSCALE * 4 + 256 + PBUF_BYTES;
 };
 
 struct TcParams {
@@ -141,20 +151,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   uint64_t* tfull = wbar + 1;                  // [2]
   uint64_t* tempty = tfull + 2;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* pbuf = reinterpret_cast<float*>(tmem_slot + 4);   // [2][128][16] (heads only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(wbar, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], HEAD ? 4 : 8); }
     fence_barrier_init();
     prefetch_tensormap(&tmap);
   }
-  for (int i = threadIdx.x; i < Cfg::NSCALE; i += TC_THREADS) {
-    sc_s[i] = p.scale ? p.scale[i] : 1.0f;
-    sh_s[i] = p.shift ? p.shift[i] : 0.0f;
-  }
+  for (int i = threadIdx.x; i < Cfg::NSCALE; i += TC_THREADS) sh_s[i] = p.shift ? p.shift[i] : 0.0f;
+  (void)sc_s;   // the BN scale is folded into the packed weights (tgsr_pack_conv3x3)
   if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -177,7 +186,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         const int b = tile / tiles_per_img, r = tile % tiles_per_img;
-        const int y0 = (r / p.tiles_x) * TC_TH, x0 = (r % p.tiles_x) * TC_TW;
+        const int y0 = (r / p.tiles_x) * Cfg::TH, x0 = (r % p.tiles_x) * TC_TW;
         mbar_arrive_expect_tx(&full[s], Cfg::PATCH_BYTES);
         tma_load_4d(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], 0, x0 - Cfg::R, y0 - Cfg::R, b * p.xP + p.xp0);
       }
@@ -207,7 +216,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           const uint32_t a_tap = a_base + (op.tap_r * TC_PW + op.tap_c) * 16;
 #pragma unroll
           for (int k = 0; k < Cfg::KSTEPS; ++k) {
-            const uint64_t adesc = make_smem_desc(a_tap + k * 2 * TC_PLANE_BYTES, TC_PLANE_BYTES, TC_PW * 16);
+            const uint64_t adesc = make_smem_desc(a_tap + k * 2 * TC_PLANE_BYTES, TC_PLANE_BYTES, Cfg::SBO_A);
             const uint64_t bdesc = make_smem_desc(w_addr + b_off + k * (N * 32), N * 16, 128);
             umma_f16(d_base + op.dcol_mul * NPRE, adesc, bdesc, idesc, (o | k) != 0 ? 1u : 0u);
           }
@@ -218,95 +227,143 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       }
     }
   } else {
-    // ================================ epilogue (warps 2..5) ========================
+    // ================================ epilogue (warps 2..9) ========================
+    // Two warps per TMEM lane quadrant: `half` selects which half of the output channels (or which
+    // sub-pixel phases / RGB outputs) this warp produces, so two warps per SM sub-partition work on
+    // every tile and the per-tile epilogue latency halves.
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;                // 0: warps 2..5, 1: warps 6..9
     const int m = quad * 32 + lane;                  // accumulator row = pixel within the tile
     const int ty = m >> 3, tx = m & 7;
+    const float4* sh4 = reinterpret_cast<const float4*>(sh_s);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int acc = it & 1, aph = (it >> 1) & 1;
       const int b = tile / tiles_per_img, r = tile % tiles_per_img;
       const int gy = (r / p.tiles_x) * TC_TH + ty, gx = (r % p.tiles_x) * TC_TW + tx;
-      mbar_wait(&tfull[acc], aph);
-      tc_fence_after();
       const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + ((uint32_t)(quad * 32) << 16);
 
       if constexpr (HEAD) {
-        // image head: accumulator columns 0..2 are the RGB outputs (rows 3..15 of B are zero)
-        uint32_t v[16];
-        tmem_ld16(t_base, v);
-        tmem_ld_wait();
+        // Image head.  Accumulator row m = linear patch pixel (y*PW + x'), column o*K + kx holds the partial
+        // sum over (ky, c) for output o and tap column kx.  out[y][x][o] = sum_kx P[y*PW + x + kx][o*K + kx].
+        // Warps 2..5 move the accumulator to shared memory (then release TMEM); after one named barrier all
+        // 256 epilogue threads produce one (pixel, o) output each.
+        constexpr int K = Cfg::KS, NPIX = Cfg::TH * TC_TW;       // valid outputs per tile (80 / 96)
+        float* pb = pbuf + acc * (128 * 16);
+        const int et = threadIdx.x - 64;                        // 0..255
+        constexpr int NITEM = (3 * NPIX + 255) / 256;           // (pixel, o) outputs per thread: 1 (5x5) or 2 (3x3)
         const size_t hw = (size_t)p.H * p.W;
+        size_t oi[NITEM]; float ad[NITEM]; bool valid[NITEM]; int m0[NITEM], oo[NITEM];
 #pragma unroll
-        for (int o = 0; o < 3; ++o) {
-          float z = __uint_as_float(v[o]);
-          if (p.act_tanh) z = tanhf(z);
-          z *= p.out_scale;
-          const size_t oi = ((size_t)b * 3 + o) * hw + (size_t)gy * p.W + gx;
-          if (p.addend) z = fmaf(p.addend_scale, __ldg(p.addend + oi), z);
-          p.out_f32[oi] = z;
+        for (int q = 0; q < NITEM; ++q) {
+          const int item = et + q * 256;
+          const int o = item / NPIX, pidx = item % NPIX;        // output channel, pixel within the tile
+          const int oy = (r / p.tiles_x) * Cfg::TH + pidx / TC_TW, ox = (r % p.tiles_x) * TC_TW + pidx % TC_TW;
+          valid[q] = o < 3 && oy < p.H;
+          oi[q] = ((size_t)b * 3 + o) * hw + (size_t)oy * p.W + ox;
+          m0[q] = (pidx / TC_TW) * Cfg::PW + (pidx % TC_TW);
+          oo[q] = o;
+          ad[q] = (valid[q] && p.addend) ? __ldg(p.addend + oi[q]) : 0.f;   // fetched before the accumulator wait
         }
+        if (half == 0) {
+          mbar_wait(&tfull[acc], aph);
+          tc_fence_after();
+          uint32_t v[16];
+          tmem_ld16(t_base, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          float4* dst = reinterpret_cast<float4*>(pb + m * 16);
+          dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+          dst[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+          dst[2] = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+          dst[3] = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);             // TMEM stage is free again
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps only
+#pragma unroll
+        for (int q = 0; q < NITEM; ++q) {
+          if (valid[q]) {
+            float z = 0.f;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) z += pb[(m0[q] + kx) * 16 + oo[q] * K + kx];
+            if (p.act_tanh) z = tanhf(z);
+            __stcs(p.out_f32 + oi[q], fmaf(p.addend_scale, ad[q], z * p.out_scale));
+          }
+        }
+        continue;                                               // (tempty already signalled)
       } else if constexpr (!UP) {
         constexpr int COUT = GLU ? NPRE / 2 : NPRE;            // channels written
+        constexpr int CW = COUT / 2;                           // channels per epilogue warp (32 or 16)
+        const int c0 = half * CW;
         const size_t pix = ((size_t)gy * p.W + gx) * 8;
         const size_t plane_elems = (size_t)p.H * p.W * 8;
-        h16* obase = p.out + ((size_t)b * p.yP + p.yp0) * plane_elems + pix;
-        const h16* rbase =
-            p.residual ? p.residual + ((size_t)b * p.rP + p.rp0) * plane_elems + pix : nullptr;
+        h16* obase = p.out + ((size_t)b * p.yP + p.yp0 + c0 / 8) * plane_elems + pix;
+        uint4 rres[CW / 8];
+        if (p.residual) {                                      // prefetch the skip tensor before the MMA wait
+          const h16* rbase = p.residual + ((size_t)b * p.rP + p.rp0 + c0 / 8) * plane_elems + pix;
 #pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 32) {
-          uint32_t va[32];
+          for (int j = 0; j < CW / 8; ++j) rres[j] = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)j * plane_elems));
+        }
+        mbar_wait(&tfull[acc], aph);
+        tc_fence_after();
+        uint32_t va[CW], vg[CW];
+        if constexpr (CW == 32) {
           tmem_ld32(t_base + c0, va);
-          uint32_t vg[32];
           if constexpr (GLU) tmem_ld32(t_base + COUT + c0, vg);
-          tmem_ld_wait();
+        } else {
+          tmem_ld16(t_base + c0, va);
+          if constexpr (GLU) tmem_ld16(t_base + COUT + c0, vg);
+        }
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {                         // 4 planes of 8 channels
-            float o[8];
-            float res[8];
-            if (rbase) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(c0 / 8 + j) * plane_elems));
-              unpack8_16<FMT>(u, res);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int c = c0 + j * 8 + e;
-              float z = fmaf(__uint_as_float(va[j * 8 + e]), sc_s[c], sh_s[c]);
-              if constexpr (GLU) {
-                const float g = fmaf(__uint_as_float(vg[j * 8 + e]), sc_s[COUT + c], sh_s[COUT + c]);
-                z *= fast_sigmoid(g);
-              }
-              if (rbase) z += res[e];
-              o[e] = z;
-            }
-            *reinterpret_cast<uint4*>(obase + (size_t)(c0 / 8 + j) * plane_elems) = pack8_16<FMT>(o);
+        for (int j = 0; j < CW / 8; ++j) {                      // planes of 8 channels
+          float o[8], res[8];
+          if (p.residual) unpack8_16<FMT>(rres[j], res);
+          const float4 sa0 = sh4[(c0 + j * 8) / 4], sa1 = sh4[(c0 + j * 8) / 4 + 1];
+          const float sa[8] = {sa0.x, sa0.y, sa0.z, sa0.w, sa1.x, sa1.y, sa1.z, sa1.w};
+          float sg[8];
+          if constexpr (GLU) {
+            const float4 g0 = sh4[(COUT + c0 + j * 8) / 4], g1 = sh4[(COUT + c0 + j * 8) / 4 + 1];
+            sg[0] = g0.x; sg[1] = g0.y; sg[2] = g0.z; sg[3] = g0.w; sg[4] = g1.x; sg[5] = g1.y; sg[6] = g1.z; sg[7] = g1.w;
           }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float z = __uint_as_float(va[j * 8 + e]) + sa[e];
+            if constexpr (GLU) z *= fast_sigmoid(__uint_as_float(vg[j * 8 + e]) + sg[e]);
+            if (p.residual) z += res[e];
+            o[e] = z;
+          }
+          *reinterpret_cast<uint4*>(obase + (size_t)j * plane_elems) = pack8_16<FMT>(o);
         }
       } else {
         // 4-phase upsample: accumulator columns [ph*NPRE, (ph+1)*NPRE) hold output pixel
-        // (2*gy + ph/2, 2*gx + ph%2); GLU halves inside each phase block.
+        // (2*gy + ph/2, 2*gx + ph%2); GLU halves inside each phase block.  half h -> phases 2h, 2h+1
+        // (= output row 2*gy + h, both columns: one 32-byte run per plane).
         static_assert(GLU && NPRE == 64, "upsample path is conv(C -> 64) + GLU -> 32 channels");
         constexpr int COUT = NPRE / 2;                          // 32
         const int Ho = 2 * p.H, Wo = 2 * p.W;
         const size_t plane_elems = (size_t)Ho * Wo * 8;
+        mbar_wait(&tfull[acc], aph);
+        tc_fence_after();
 #pragma unroll
-        for (int ph = 0; ph < 4; ++ph) {
+        for (int q = 0; q < 2; ++q) {
+          const int ph = half * 2 + q;
           uint32_t va[32], vg[32];
           tmem_ld32(t_base + ph * NPRE, va);
           tmem_ld32(t_base + ph * NPRE + COUT, vg);
           tmem_ld_wait();
-          const int oy = 2 * gy + (ph >> 1), ox = 2 * gx + (ph & 1);
+          const int oy = 2 * gy + half, ox = 2 * gx + q;
           h16* obase = p.out + ((size_t)b * p.yP + p.yp0) * plane_elems + ((size_t)oy * Wo + ox) * 8;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
+            const float4 sa0 = sh4[j * 2], sa1 = sh4[j * 2 + 1], g0 = sh4[(COUT + j * 8) / 4], g1 = sh4[(COUT + j * 8) / 4 + 1];
+            const float sa[8] = {sa0.x, sa0.y, sa0.z, sa0.w, sa1.x, sa1.y, sa1.z, sa1.w};
+            const float sg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
             float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int c = j * 8 + e;
-              const float z = fmaf(__uint_as_float(va[c]), sc_s[c], sh_s[c]);
-              const float g = fmaf(__uint_as_float(vg[c]), sc_s[COUT + c], sh_s[COUT + c]);
-              o[e] = z * fast_sigmoid(g);
-            }
+            for (int e = 0; e < 8; ++e)
+              o[e] = (__uint_as_float(va[j * 8 + e]) + sa[e]) * fast_sigmoid(__uint_as_float(vg[j * 8 + e]) + sg[e]);
             *reinterpret_cast<uint4*>(obase + (size_t)j * plane_elems) = pack8_16<FMT>(o);
           }
         }
@@ -327,24 +384,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 // kc (8 input channels), for each group of 8 output rows: a 128-B core matrix [8 rows][8 k] bf16.
 //   byte offset(op, n, c) = op_base + (c/8)*(N_op*16) + (n/8)*128 + (n%8)*16 + (c%8)*2
 template <int FMT>
-__global__ void pack_conv3x3_kernel(const float* __restrict__ w, h16* __restrict__ out, int Cout, int Cin) {
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, const float* __restrict__ scale, h16* __restrict__ out,
+                                    int Cout, int Cin) {
   const int total = 9 * Cout * Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % Cin, n = (i / Cin) % Cout, t = i / (Cin * Cout);
-    const float v = w[((size_t)n * Cin + c) * 9 + t];
+    const float v = w[((size_t)n * Cin + c) * 9 + t] * (scale ? scale[n] : 1.0f);   // BN scale folded, fp32
     const size_t off = (size_t)t * Cin * Cout + (size_t)(c / 8) * (Cout * 8) + (size_t)(n / 8) * 64 + (n % 8) * 8 + (c % 8);
     out[off] = Fmt16<FMT>::cvt(v);
   }
 }
 
-// Image heads: w [3][Cin][K][K] -> per tap a [16 x Cin] block whose rows 3..15 are zero.
+// Image heads: w [3][Cin][K][K] -> per ROW tap ky a [16 x Cin] block; row n = o*K + kx (n < 3K), rest zero.
 template <int FMT>
 __global__ void pack_head_kernel(const float* __restrict__ w, h16* __restrict__ out, int Cin, int K) {
-  const int total = K * K * 16 * Cin;
+  const int total = K * 16 * Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i % Cin, n = (i / Cin) % 16, t = i / (Cin * 16);
-    const float v = n < 3 ? w[((size_t)n * Cin + c) * K * K + t] : 0.f;
-    const size_t off = (size_t)t * Cin * 16 + (size_t)(c / 8) * (16 * 8) + (size_t)(n / 8) * 64 + (n % 8) * 8 + (c % 8);
+    const int c = i % Cin, n = (i / Cin) % 16, ky = i / (Cin * 16);
+    float v = 0.f;
+    if (n < 3 * K) {
+      const int o = n / K, kx = n % K;
+      v = w[(((size_t)o * Cin + c) * K + ky) * K + kx];
+    }
+    const size_t off = (size_t)ky * Cin * 16 + (size_t)(c / 8) * (16 * 8) + (size_t)(n / 8) * 64 + (n % 8) * 8 + (c % 8);
     out[off] = Fmt16<FMT>::cvt(v);
   }
 }
@@ -359,7 +421,8 @@ __device__ __forceinline__ int up_taps(int parity, int r, int (&ks)[2]) {
 }
 
 template <int FMT>
-__global__ void pack_up2x_kernel(const float* __restrict__ w, h16* __restrict__ out, int Cout, int Cin) {
+__global__ void pack_up2x_kernel(const float* __restrict__ w, const float* __restrict__ scale, h16* __restrict__ out,
+                                 int Cout, int Cin) {
   // 11 ops; op o covers phases {ph = dcol_mul .. dcol_mul + n_mul - 1}; rows of op = [phase][Cout]
   using Ops = OpTable<MODE_UP>;
   int op_base = 0;
@@ -376,6 +439,7 @@ __global__ void pack_up2x_kernel(const float* __restrict__ w, h16* __restrict__ 
       float v = 0.f;                                        // pre-summed in fp32, rounded once
       for (int a = 0; a < ny; ++a)
         for (int bq = 0; bq < nx; ++bq) v += w[((size_t)n * Cin + c) * 9 + kys[a] * 3 + kxs[bq]];
+      if (scale) v *= scale[n];
       const size_t off = (size_t)op_base + (size_t)(c / 8) * (N * 8) + (size_t)(nn / 8) * 64 + (nn % 8) * 8 + (c % 8);
       out[off] = Fmt16<FMT>::cvt(v);
     }
@@ -446,8 +510,10 @@ int init_conv_tc() {
   return TGSR_OK;
 }
 
-static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl, int fmt, int R = 1) {
-  const int TC_PW = TC_TW + 2 * R, TC_PH = TC_TH + 2 * R;
+static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl, int fmt, int R = 1,
+                           int head = 0) {
+  const int TC_PW = TC_TW + 2 * R;
+  const int TC_PH = head ? (128 / TC_PW) + 2 * R + 1 : TC_TH + 2 * R;
   cuuint64_t gdim[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * P};
   cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
   cuuint32_t box[4] = {8, (cuuint32_t)TC_PW, (cuuint32_t)TC_PH, (cuuint32_t)npl};
@@ -473,16 +539,14 @@ static int launch_tc(const CUtensorMap& tmap, const TcParams& p, int fmt, cudaSt
 
 #define TGSR_CHECK_FMT(fmt) TGSR_REQUIRE((fmt) == TGSR_FMT_BF16 || (fmt) == TGSR_FMT_F16, TGSR_ERR_UNSUPPORTED)
 
-extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const float* scale,
-                               const float* shift, const void* residual, int rP, int rp0, void* y, int yP,
-                               int yp0, int B, int Cin, int H, int W, int Cout, int up2x, int act, int fmt,
-                               tgsr_stream_t stream) {
+extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const float* shift,
+                               const void* residual, int rP, int rp0, void* y, int yP, int yp0, int B, int Cin,
+                               int H, int W, int Cout, int up2x, int act, int fmt, tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(wpacked); TGSR_REQUIRE_PTR(y);
   TGSR_CHECK_FMT(fmt);
   TGSR_REQUIRE(g_sm_count > 0 && g_encode_tiled != nullptr, TGSR_ERR_NOT_INIT);
   TGSR_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, TGSR_ERR_BAD_SHAPE);
-  TGSR_REQUIRE((scale == nullptr) == (shift == nullptr), TGSR_ERR_NULL);
   TGSR_REQUIRE(H % TC_TH == 0 && W % TC_TW == 0, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(act == TGSR_ACT_NONE || act == TGSR_ACT_GLU, TGSR_ERR_UNSUPPORTED);
   const int npl = Cin / 8;
@@ -497,7 +561,7 @@ extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpack
   int s = make_patch_tmap(&tmap, x, B, xP, H, W, npl, fmt);
   if (s != TGSR_OK) return s;
   TcParams p;
-  p.wpacked = wpacked; p.scale = scale; p.shift = shift;
+  p.wpacked = wpacked; p.scale = nullptr; p.shift = shift;
   p.residual = reinterpret_cast<const h16*>(residual);
   p.out = reinterpret_cast<h16*>(y);
   p.rP = rP; p.rp0 = rp0; p.yP = yP; p.yp0 = yp0; p.xP = xP; p.xp0 = xp0;
@@ -518,8 +582,8 @@ extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpack
   return TGSR_ERR_UNSUPPORTED;
 }
 
-extern "C" int tgsr_pack_conv3x3(const float* w, void* packed, int Cout, int Cin, int up2x, int fmt,
-                                 tgsr_stream_t stream) {
+extern "C" int tgsr_pack_conv3x3(const float* w, const float* scale, void* packed, int Cout, int Cin, int up2x,
+                                 int fmt, tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(w); TGSR_REQUIRE_PTR(packed);
   TGSR_CHECK_FMT(fmt);
@@ -527,11 +591,11 @@ extern "C" int tgsr_pack_conv3x3(const float* w, void* packed, int Cout, int Cin
   cudaStream_t st = (cudaStream_t)stream;
   h16* o = reinterpret_cast<h16*>(packed);
   if (fmt == TGSR_FMT_F16) {
-    if (up2x) pack_up2x_kernel<TGSR_FMT_F16><<<64, 256, 0, st>>>(w, o, Cout, Cin);
-    else pack_conv3x3_kernel<TGSR_FMT_F16><<<64, 256, 0, st>>>(w, o, Cout, Cin);
+    if (up2x) pack_up2x_kernel<TGSR_FMT_F16><<<64, 256, 0, st>>>(w, scale, o, Cout, Cin);
+    else pack_conv3x3_kernel<TGSR_FMT_F16><<<64, 256, 0, st>>>(w, scale, o, Cout, Cin);
   } else {
-    if (up2x) pack_up2x_kernel<TGSR_FMT_BF16><<<64, 256, 0, st>>>(w, o, Cout, Cin);
-    else pack_conv3x3_kernel<TGSR_FMT_BF16><<<64, 256, 0, st>>>(w, o, Cout, Cin);
+    if (up2x) pack_up2x_kernel<TGSR_FMT_BF16><<<64, 256, 0, st>>>(w, scale, o, Cout, Cin);
+    else pack_conv3x3_kernel<TGSR_FMT_BF16><<<64, 256, 0, st>>>(w, scale, o, Cout, Cin);
   }
   return launch_status();
 }
@@ -556,18 +620,20 @@ extern "C" int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpac
   TGSR_CHECK_FMT(fmt);
   TGSR_REQUIRE(g_sm_count > 0 && g_encode_tiled != nullptr, TGSR_ERR_NOT_INIT);
   TGSR_REQUIRE(B > 0 && H > 0 && W > 0, TGSR_ERR_BAD_SHAPE);
-  TGSR_REQUIRE(Cin == 32 && (ksize == 3 || ksize == 5) && H % TC_TH == 0 && W % TC_TW == 0, TGSR_ERR_UNSUPPORTED);
+  TGSR_REQUIRE(Cin == 32 && (ksize == 3 || ksize == 5) && W % TC_TW == 0, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(act == TGSR_ACT_NONE || act == TGSR_ACT_TANH, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(xp0 >= 0 && xp0 + Cin / 8 <= xP, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE((long long)B * xP < (1LL << 31), TGSR_ERR_UNSUPPORTED);
   CUtensorMap tmap;
-  int s = make_patch_tmap(&tmap, x, B, xP, H, W, Cin / 8, fmt, ksize / 2);
+  int s = make_patch_tmap(&tmap, x, B, xP, H, W, Cin / 8, fmt, ksize / 2, 1);
   if (s != TGSR_OK) return s;
   TcParams p;
   p.wpacked = wpacked; p.scale = nullptr; p.shift = nullptr; p.residual = nullptr; p.out = nullptr;
   p.rP = p.rp0 = p.yP = p.yp0 = 0; p.xP = xP; p.xp0 = xp0;
   p.B = B; p.H = H; p.W = W;
   p.tiles_x = W / TC_TW; p.tiles_y = H / TC_TH; p.ntiles = B * p.tiles_x * p.tiles_y;
+  const int th = 128 / (TC_TW + 2 * (ksize / 2));            // output rows per head tile
+  p.tiles_y = (H + th - 1) / th; p.ntiles = B * p.tiles_x * p.tiles_y;
   p.out_f32 = y; p.addend = addend; p.out_scale = out_scale; p.addend_scale = addend_scale;
   p.act_tanh = act == TGSR_ACT_TANH;
   cudaStream_t st = (cudaStream_t)stream;

@@ -36,7 +36,7 @@ lstm_xproj_kernel(const int64_t* __restrict__ captions, const float* __restrict_
     const int tk = i / ninput, k = i % ninput;
     float v = 0.f;
     if (tok0 + tk < ntok) {
-      long long id = captions[tok0 + tk];
+      long long id = captions ? captions[tok0 + tk] : (long long)(tok0 + tk);
       if (id < 0) id = 0;
       if (id >= ntoken) id = ntoken - 1;   // nn.Embedding would raise; clamp keeps the kernel memory-safe
       v = __ldg(emb + (size_t)id * ninput + k);
@@ -143,7 +143,153 @@ lstm_recurrence_kernel(const int64_t* __restrict__ cap_lens, const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Persistent cluster recurrence (H = 128).  A cluster of 2 CTAs owns LC_BT captions of one
+// direction for all time steps.  CTA `rank` owns hidden units [64*rank, 64*rank+64): thread r holds
+// gate row (g = r/64, u = 64*rank + r%64) of W_hh ENTIRELY IN REGISTERS (128 floats), so the
+// recurrent GEMV reads no weights from memory after the prologue.  The input projection is a
+// gather from the precomputed table xtab[token][dir][4H] = E.W_ih^T + b_ih + b_hh.  Each step the
+// new h of a CTA's 64 units is written to both CTAs' shared memory (DSMEM) and one cluster barrier
+// publishes it.
+constexpr int LC_BT = 4;
+constexpr int LC_H = 128;
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void st_remote_f32(const float* local_smem_ptr, uint32_t target_rank, float v) {
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local_smem_ptr);
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(target_rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+lstm_cluster_kernel(const int64_t* __restrict__ captions, const int64_t* __restrict__ cap_lens,
+                    const float* __restrict__ xtab, const float* __restrict__ w_hh, float* __restrict__ words,
+                    float* __restrict__ sent, int B, int Tcap, int Tmax, int ntoken) {
+  constexpr int H = LC_H, G = 4 * H;
+  __shared__ __align__(16) float h_s[2][H][LC_BT];      // double-buffered hidden state, [unit][caption]
+  __shared__ float g_s[4][64][LC_BT];                   // this CTA's gate pre-activations
+  __shared__ int len_s[LC_BT];
+  const uint32_t rank = cluster_rank();
+  const int d = blockIdx.y, b0 = blockIdx.z * LC_BT;
+  const int r = threadIdx.x, g = r >> 6, ul = r & 63, u = (int)rank * 64 + ul, row = g * H + u;
+
+  if (r < LC_BT) {
+    int L = 0;
+    if (b0 + r < B) {
+      const long long v = cap_lens[b0 + r];
+      L = (int)(v < 0 ? 0 : (v > Tcap ? Tcap : v));
+    }
+    len_s[r] = L;
+  }
+  for (int i = r; i < H * LC_BT; i += 256) (&h_s[0][0][0])[i] = 0.f;
+  float w[H];                                           // W_hh[d][row][:] in registers
+  {
+    const float4* wr = reinterpret_cast<const float4*>(w_hh + ((size_t)d * G + row) * H);
+#pragma unroll
+    for (int k4 = 0; k4 < H / 4; ++k4) {
+      const float4 v = __ldg(wr + k4);
+      w[4 * k4] = v.x; w[4 * k4 + 1] = v.y; w[4 * k4 + 2] = v.z; w[4 * k4 + 3] = v.w;
+    }
+  }
+  __syncthreads();
+  int maxlen = 0;
+#pragma unroll
+  for (int bb = 0; bb < LC_BT; ++bb) maxlen = max(maxlen, len_s[bb]);
+  cluster_sync_all();                                   // both CTAs initialised before any remote store
+
+  float c_reg = 0.f;                                    // cell (unit ul, caption g): 64 x 4 cells = 256 threads
+  const int cb = g;                                     // caption handled by this thread in the cell update
+  // input projection of step s for the 4 captions: a gather from the table, issued one step ahead so
+  // its L2/HBM latency hides behind the recurrent GEMV of the previous step.
+  auto gather = [&](int s, float (&xv)[LC_BT]) {
+#pragma unroll
+    for (int bb = 0; bb < LC_BT; ++bb) {
+      const int L = len_s[bb];
+      xv[bb] = 0.f;
+      if (s < L) {
+        const int t = d == 0 ? s : L - 1 - s;
+        long long id = captions[(size_t)(b0 + bb) * Tcap + t];
+        id = id < 0 ? 0 : (id >= ntoken ? ntoken - 1 : id);
+        xv[bb] = __ldg(xtab + ((size_t)id * 2 + d) * G + row);
+      }
+    }
+  };
+  float xcur[LC_BT], xnext[LC_BT];
+  gather(0, xcur);
+  for (int s = 0; s < maxlen; ++s) {
+    const int cur = s & 1, nxt = cur ^ 1;
+    gather(s + 1, xnext);
+    float acc[LC_BT];
+#pragma unroll
+    for (int bb = 0; bb < LC_BT; ++bb) acc[bb] = xcur[bb];
+    const float4* h4 = reinterpret_cast<const float4*>(&h_s[cur][0][0]);
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      const float4 hv = h4[k];                          // broadcast: h[k] of the 4 captions
+      acc[0] = fmaf(w[k], hv.x, acc[0]); acc[1] = fmaf(w[k], hv.y, acc[1]);
+      acc[2] = fmaf(w[k], hv.z, acc[2]); acc[3] = fmaf(w[k], hv.w, acc[3]);
+    }
+#pragma unroll
+    for (int bb = 0; bb < LC_BT; ++bb) g_s[g][ul][bb] = acc[bb];
+    __syncthreads();
+    {
+      const int L = len_s[cb];
+      if (s < L) {
+        const float ig = 1.0f / (1.0f + expf(-g_s[0][ul][cb]));
+        const float fg = 1.0f / (1.0f + expf(-g_s[1][ul][cb]));
+        const float gg = tanhf(g_s[2][ul][cb]);
+        const float og = 1.0f / (1.0f + expf(-g_s[3][ul][cb]));
+        c_reg = fmaf(fg, c_reg, ig * gg);
+        const float h = og * tanhf(c_reg);
+        h_s[nxt][u][cb] = h;
+        st_remote_f32(&h_s[nxt][u][cb], rank ^ 1u, h);
+        const int t = d == 0 ? s : L - 1 - s;
+        if (t < Tmax) words[((size_t)(b0 + cb) * 2 * H + d * H + u) * Tmax + t] = h;
+        if (s == L - 1) sent[(size_t)(b0 + cb) * 2 * H + d * H + u] = h;
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < LC_BT; ++bb) xcur[bb] = xnext[bb];
+    cluster_sync_all();
+  }
+}
+
 }  // namespace tgsr
+
+extern "C" int tgsr_lstm_prepare_f32(const float* emb, const float* w_ih, const float* b_ih, const float* b_hh,
+                                     float* xtab, int ntoken, int ninput, int H, tgsr_stream_t stream) {
+  using namespace tgsr;
+  TGSR_REQUIRE_PTR(emb); TGSR_REQUIRE_PTR(w_ih); TGSR_REQUIRE_PTR(b_ih); TGSR_REQUIRE_PTR(b_hh); TGSR_REQUIRE_PTR(xtab);
+  TGSR_REQUIRE(ntoken > 0 && ninput > 0 && H > 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE(ninput <= 1024, TGSR_ERR_UNSUPPORTED);
+  lstm_xproj_kernel<<<ceil_div(ntoken, LSTM_TOK), 256, LSTM_TOK * ninput * sizeof(float), (cudaStream_t)stream>>>(
+      nullptr, emb, w_ih, b_ih, b_hh, xtab, ntoken, ntoken, ninput, H);
+  return launch_status();
+}
+
+extern "C" int tgsr_lstm_bidir_fwd_tab_f32(const int64_t* captions, const int64_t* cap_lens, const float* xtab,
+                                           const float* w_hh, float* words, float* sent, int B, int Tcap, int Tmax,
+                                           int ntoken, int H, tgsr_stream_t stream) {
+  using namespace tgsr;
+  TGSR_REQUIRE_PTR(captions); TGSR_REQUIRE_PTR(cap_lens); TGSR_REQUIRE_PTR(xtab); TGSR_REQUIRE_PTR(w_hh);
+  TGSR_REQUIRE_PTR(words); TGSR_REQUIRE_PTR(sent);
+  TGSR_REQUIRE(B > 0 && Tcap > 0 && Tmax > 0 && Tmax <= Tcap && ntoken > 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE(H == LC_H && B <= 65535 * LC_BT, TGSR_ERR_UNSUPPORTED);
+  cudaStream_t st = (cudaStream_t)stream;
+  TGSR_CUDA(cudaMemsetAsync(words, 0, (size_t)B * 2 * H * Tmax * sizeof(float), st));
+  TGSR_CUDA(cudaMemsetAsync(sent, 0, (size_t)B * 2 * H * sizeof(float), st));
+  lstm_cluster_kernel<<<dim3(2, 2, ceil_div(B, LC_BT)), 256, 0, st>>>(captions, cap_lens, xtab, w_hh, words, sent, B,
+                                                                      Tcap, Tmax, ntoken);
+  return launch_status();
+}
 
 extern "C" int tgsr_lstm_bidir_fwd_f32(const int64_t* captions, const int64_t* cap_lens, const float* emb,
                                        const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,

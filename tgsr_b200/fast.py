@@ -76,7 +76,7 @@ def _packed_head(conv: nn.Conv2d, fmt: int) -> Tensor:
     cached = conv.__dict__.get(name)
     if cached is None or cached[0] != key:
         k = w.shape[2]
-        packed = torch.empty(k * k * 16 * w.shape[1], device=w.device, dtype=tc._DTYPES[fmt])
+        packed = torch.empty(k * 16 * w.shape[1], device=w.device, dtype=tc._DTYPES[fmt])
         call('tgsr_pack_head', w.device, ptr(w.detach().contiguous()), ptr(packed), w.shape[1], k, fmt)
         cached = (key, packed)
         conv.__dict__[name] = cached

@@ -124,3 +124,26 @@ def lstm_bidir(captions: Tensor, cap_lens: Tensor, emb: Tensor, w_ih: Tensor, w_
          ptr(_f32c(w_hh, 'w_hh')), ptr(_f32c(b_ih, 'b_ih')), ptr(_f32c(b_hh, 'b_hh')), ptr(ws), ptr(words), ptr(sent),
          B, Tcap, Tmax, ntoken, ninput, H)
     return words, sent
+
+
+def lstm_prepare(emb: Tensor, w_ih: Tensor, b_ih: Tensor, b_hh: Tensor) -> Tensor:
+    """xtab [ntoken, 2, 4H] = emb @ w_ih^T + b_ih + b_hh (weight prep for lstm_bidir_tab)."""
+    ntoken, ninput = emb.shape
+    H = w_ih.shape[1] // 4
+    xtab = torch.empty((ntoken, 2, 4 * H), device=emb.device, dtype=torch.float32)
+    call('tgsr_lstm_prepare_f32', emb.device, ptr(_f32c(emb, 'emb')), ptr(_f32c(w_ih, 'w_ih')), ptr(_f32c(b_ih, 'b_ih')),
+         ptr(_f32c(b_hh, 'b_hh')), ptr(xtab), ntoken, ninput, H)
+    return xtab
+
+
+def lstm_bidir_tab(captions: Tensor, cap_lens: Tensor, xtab: Tensor, w_hh: Tensor, Tmax: int) -> Tuple[Tensor, Tensor]:
+    dev = xtab.device
+    captions = captions.to(device=dev, dtype=torch.int64).contiguous()
+    cap_lens = cap_lens.to(device=dev, dtype=torch.int64).contiguous()
+    B, Tcap = captions.shape
+    H = w_hh.shape[2]
+    words = torch.empty((B, 2 * H, Tmax), device=dev, dtype=torch.float32)
+    sent = torch.empty((B, 2 * H), device=dev, dtype=torch.float32)
+    call('tgsr_lstm_bidir_fwd_tab_f32', dev, ptr(captions), ptr(cap_lens), ptr(xtab), ptr(_f32c(w_hh, 'w_hh')), ptr(words),
+         ptr(sent), B, Tcap, Tmax, xtab.shape[0], H)
+    return words, sent

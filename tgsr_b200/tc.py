@@ -65,17 +65,18 @@ def to_nchw(xb: Blocked) -> Tensor:
     return y
 
 
-def packed_weights(conv: nn.Conv2d, up2x: bool, fmt: int) -> Tensor:
-    """16-bit UMMA operand image of a conv3x3 weight, cached per weight version (not in state_dict)."""
+def packed_weights(conv: nn.Conv2d, up2x: bool, fmt: int, scale: Optional[Tensor] = None) -> Tensor:
+    """16-bit UMMA operand image of a conv3x3 weight with the folded BN scale multiplied in (fp32, one
+    rounding); cached per weight / BN version (not in state_dict)."""
     w = conv.weight
-    key = (w.data_ptr(), w._version, str(w.device), bool(up2x), fmt)
+    key = (w.data_ptr(), w._version, str(w.device), bool(up2x), fmt, None if scale is None else scale.data_ptr())
     name = '_tgsr_packed_%d_%d' % (int(up2x), fmt)
     cached = conv.__dict__.get(name)
     if cached is None or cached[0] != key:
         Cout, Cin = w.shape[0], w.shape[1]
         packed = torch.empty(Cout * Cin * (16 if up2x else 9), device=w.device, dtype=_DTYPES[fmt])
-        call('tgsr_pack_conv3x3', w.device, ptr(w.detach().contiguous()), ptr(packed), Cout, Cin, int(up2x), fmt)
-        cached = (key, packed)
+        call('tgsr_pack_conv3x3', w.device, ptr(w.detach().contiguous()), ptr(scale), ptr(packed), Cout, Cin, int(up2x), fmt)
+        cached = (key, packed, scale)      # keep `scale` alive so its data_ptr stays unique
         conv.__dict__[name] = cached
     return cached[1]
 
@@ -97,10 +98,10 @@ def conv3x3_tc(xb: Blocked, conv: nn.Conv2d, scale: Optional[Tensor], shift: Opt
     if out is None:
         out = Blocked.empty(xb.B, Cf, Ho, Wo, xb.device, fmt=xb.fmt)
     assert out.fmt == xb.fmt and out.C == Cf and out.H == Ho and out.W == Wo and out.B == xb.B
-    wp = packed_weights(conv, up2x, xb.fmt)
+    wp = packed_weights(conv, up2x, xb.fmt, scale)
     rbuf, rP, rp0 = (residual.buf, residual.P, residual.p0) if residual is not None else (None, 0, 0)
     if residual is not None:
         assert residual.C == Cf and residual.H == Ho and residual.W == Wo and residual.fmt == xb.fmt
-    call('tgsr_conv3x3_tc', xb.device, ptr(xb.buf), xb.P, xb.p0, ptr(wp), ptr(scale), ptr(shift), ptr(rbuf), rP, rp0,
+    call('tgsr_conv3x3_tc', xb.device, ptr(xb.buf), xb.P, xb.p0, ptr(wp), ptr(shift), ptr(rbuf), rP, rp0,
          ptr(out.buf), out.P, out.p0, xb.B, Cin, xb.H, xb.W, Cout, int(up2x), act, xb.fmt)
     return out

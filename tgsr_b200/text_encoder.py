@@ -60,10 +60,15 @@ class RNN_ENCODER(nn.Module):
         cached = self.__dict__.get('_tgsr_stacked')
         if cached is None or cached[0] != key:
             d = [t.detach() for t in src]
-            cached = (key, torch.stack((d[0], d[1])).contiguous(), torch.stack((d[2], d[3])).contiguous(),
-                      torch.stack((d[4], d[5])).contiguous(), torch.stack((d[6], d[7])).contiguous())
+            cached = [key, torch.stack((d[0], d[1])).contiguous(), torch.stack((d[2], d[3])).contiguous(),
+                      torch.stack((d[4], d[5])).contiguous(), torch.stack((d[6], d[7])).contiguous(), None, None]
             self.__dict__['_tgsr_stacked'] = cached
-        return cached[1:]
+        ek = (self.encoder.weight.data_ptr(), self.encoder.weight._version)
+        if self.nhidden == 128 and cached[1].is_cuda and (cached[5] is None or cached[6] != ek):
+            # weight prep (derived, not in state_dict): input-projection lookup table
+            cached[5] = ops.lstm_prepare(self.encoder.weight.detach(), cached[1], cached[3], cached[4])
+            cached[6] = ek
+        return cached[1:6]
 
     def forward(self, captions, cap_lens, hidden, mask=None):
         """captions int64 [B, n_steps]; cap_lens [B]; hidden = init_hidden(B) (zeros, as in every
@@ -80,5 +85,7 @@ class RNN_ENCODER(nn.Module):
 
     def _forward_tmax(self, captions, cap_lens, tmax: int):
         """Same as forward() when max(cap_lens) is already known on the host (no device read)."""
-        w_ih, w_hh, b_ih, b_hh = self._stacked()
+        w_ih, w_hh, b_ih, b_hh, xtab = self._stacked()
+        if xtab is not None:
+            return ops.lstm_bidir_tab(captions, cap_lens, xtab, w_hh, tmax)
         return ops.lstm_bidir(captions, cap_lens, self.encoder.weight.detach(), w_ih, w_hh, b_ih, b_hh, tmax)
