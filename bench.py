@@ -41,8 +41,9 @@ def parse():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default=None, choices=['bf16', 'fp32'])
+    ap.add_argument('--precision', default=None, choices=['fp32', 'bf16', 'fp16', 'mixed16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of CUDA-graph replay')
     return ap.parse_args()
 
 
@@ -207,9 +208,15 @@ def run_ours(args):
     LR, caps, lens = LR_h.to(dev), caps_h.to(dev), lens_h.to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)     # 256 MiB > 126 MB L2
 
+    use_graph = not args.no_graph
+    if use_graph:                      # capture once; the resident inputs become the graph's static inputs
+        pipe.forward_graph(LR, caps, lens, WORDS)
+        LR, caps, lens = pipe.static_inputs(B, WORDS, WORDS, 32)
+
     def step_device():
-        fine, _, _ = pipe.text_and_generate(LR, caps, lens, WORDS)
-        return fine
+        if use_graph:
+            return pipe.forward_graph(LR, caps, lens, WORDS)[0]
+        return pipe.text_and_generate(LR, caps, lens, WORDS)[0]
 
     out_host = torch.empty((B, 3, 256, 256), dtype=torch.float32).pin_memory()
 
@@ -237,6 +244,8 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     launches = lib.tgsr_launch_count() - launches0
+    if use_graph:                       # replays do not pass through the library's counter
+        launches = pipe.last_graph_kernels * args.steps
     t_ms = sum(s.elapsed_time(e) for s, e in ev)
     t = torch.tensor([t_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -246,12 +255,12 @@ def run_ours(args):
 
     # ---- end-to-end timing through the public API with host buffers
     for _ in range(3):
-        pipe.forward_host(LR_h, caps_h, lens_h, out_host)
+        pipe.forward_host(LR_h, caps_h, lens_h, out_host, use_graph)
     barrier()
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for s, e in ev2:
         flush.zero_()
-        s.record(); pipe.forward_host(LR_h, caps_h, lens_h, out_host); e.record()
+        s.record(); pipe.forward_host(LR_h, caps_h, lens_h, out_host, use_graph); e.record()
     barrier()
     t2 = torch.tensor([sum(s.elapsed_time(e) for s, e in ev2)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -282,6 +291,7 @@ def run_ours(args):
                                    'random-init weights, randomised BN stats' % (B, NTOKEN),
                        'batch_per_gpu': B, 'parallelism': 'image-sharded replicas x%d (no collective)' % world,
                        'l2': 'flushed between timed iterations (256 MiB write)', 'precision': precision,
+                       'launch': 'CUDA-graph replay' if use_graph else 'per-kernel launches from Python',
                        'gflop_per_image_reference': GFLOP_PER_IMAGE},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},

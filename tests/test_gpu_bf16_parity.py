@@ -167,3 +167,23 @@ def test_sharding_invariance_bf16():
     a = pipe.forward_device(LR[:4], caps[:4], lens[:4])[0][-1]
     b = pipe.forward_device(LR[4:], caps[4:], lens[4:])[0][-1]
     assert torch.equal(whole, torch.cat((a, b), 0))
+
+
+def test_graph_replay_matches_eager():
+    """CUDA-graph replay (one launch per forward) is bit-identical to per-kernel launches."""
+    from tgsr_b200.pipeline import SRPipeline
+    pipe = SRPipeline(300, device=DEV, variant='x8', low='lr', seed=3, randomize_bn=True)
+    LR = O.synth_lr(4, 32, seed=5).to(DEV)
+    caps, lens = O.synth_captions(4, 300, seed=6, ragged=True)
+    caps, lens = caps.to(DEV), lens.to(DEV)
+    tmax = int(lens.max())
+    eager = [t.clone() for t in pipe.text_and_generate(LR, caps, lens, tmax)[0]]
+    rep = pipe.forward_graph(LR, caps, lens, tmax)[0]
+    for a, b in zip(eager, rep):
+        assert torch.equal(a, b)
+    LR2 = O.synth_lr(4, 32, seed=9).to(DEV)                      # new inputs through the same graph
+    rep2 = [t.clone() for t in pipe.forward_graph(LR2, caps, lens, tmax)[0]]
+    eager2 = pipe.text_and_generate(LR2, caps, lens, tmax)[0]
+    for a, b in zip(eager2, rep2):
+        assert torch.equal(a, b)
+    assert pipe.last_graph_kernels >= 40

@@ -104,7 +104,22 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_fn_cache = {}
+
+
 def call(name: str, dev: torch.device, *args) -> None:
-    lib = _ensure_device(dev)
-    with torch.cuda.device(dev):
-        check(getattr(lib, name)(*args, stream_ptr()), name)
+    """Enqueue one C-ABI entry point on torch's current stream of `dev` (hot path: keep it lean)."""
+    idx = dev.index
+    if dev.type != 'cuda' or idx is None or idx not in _inited_devices:
+        _ensure_device(dev)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(load(), name)
+    if idx != torch.cuda.current_device():
+        with torch.cuda.device(idx):
+            status = fn(*args, C.c_void_p(torch.cuda.current_stream(idx).cuda_stream))
+    else:
+        status = fn(*args, C.c_void_p(torch.cuda.current_stream(idx).cuda_stream))
+    if status != 0:
+        check(status, name)

@@ -35,7 +35,6 @@ using namespace ptx;
 typedef uint16_t h16;   // storage element of either 16-bit format
 
 constexpr int TC_TH = 16, TC_TW = 8;            // tile = 16 rows x 8 cols = 128 pixels (UMMA M)
-constexpr int TC_NSTAGE = 3;
 // kernel modes: what the op table / epilogue compute
 constexpr int MODE_CONV = 0;    // conv3x3 (+BN, +GLU, +residual) -> blocked bf16
 constexpr int MODE_UP = 1;      // nearest-x2 + conv3x3 + BN + GLU as four sub-pixel phases -> blocked bf16 at 2H x 2W
@@ -104,9 +103,15 @@ struct TcCfg {
   static constexpr int NTAPB = UP ? 16 : OpTable<MODE>::NOPS;  // number of [NPRE x CIN] weight blocks
   static constexpr int WBYTES = NTAPB * CIN * NPRE * 2;
   static constexpr int NSCALE = NPRE;
+  // Patch-ring depth: as many stages as fit next to the resident weights (TMA latency ~1-2 us must be
+  // covered by stages in flight: small-channel layers and heads spend < 0.5 us of MMA time per tile).
+  static constexpr int WB_PAD_ = ((WBYTES + 1023) / 1024) * 1024;
+  static constexpr int STAGE_ROOM = (232448 - 1024 - WB_PAD_ - 2 * NSCALE * 4 - 512 - (HEAD ? 2 * 128 * 16 * 4 : 0)) / PATCH_BYTES;
+  static constexpr int NSTAGE = STAGE_ROOM > 12 ? 12 : STAGE_ROOM;
+  static_assert(NSTAGE >= 2, "not enough shared memory for a double-buffered patch ring");
   static constexpr int PBUF_BYTES = HEAD ? 2 * 128 * 16 * 4 : 0;   // head epilogue exchange buffer (double-buffered)
-  static constexpr size_t SMEM = 1024 /*align slack*/ + ((WBYTES + 1023) / 1024) * 1024 + TC_NSTAGE * PATCH_BYTES +
-                                 2 * NSCALE * 4 + 256 + PBUF_BYTES;
+  static constexpr size_t SMEM = 1024 /*align slack*/ + ((WBYTES + 1023) / 1024) * 1024 + NSTAGE * PATCH_BYTES +
+                                 2 * NSCALE * 4 + 512 + PBUF_BYTES;
 };
 
 struct TcParams {
@@ -138,6 +143,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   constexpr int TC_PW = Cfg::PW;
   constexpr int TC_PLANE_BYTES = Cfg::PLANE_BYTES;
   constexpr int WB_PAD = ((Cfg::WBYTES + 1023) / 1024) * 1024;
+  constexpr int TC_NSTAGE = Cfg::NSTAGE;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char* w_s = base;
@@ -151,7 +157,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   uint64_t* tfull = wbar + 1;                  // [2]
   uint64_t* tempty = tfull + 2;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* pbuf = reinterpret_cast<float*>(tmem_slot + 4);   // [2][128][16] (heads only)
+  float* pbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~uintptr_t(127));   // [2][128][16] (heads only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 

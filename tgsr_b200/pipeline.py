@@ -58,6 +58,59 @@ class SRPipeline:
         fine_im, a, one = self.netGH(LR, fake_imgL, LR)
         return fine_im, fake_imgL, attention_maps
 
+    # ------------------------------------------------------------------ CUDA-graph replay
+    @torch.no_grad()
+    def forward_graph(self, LR, captions, cap_lens, tmax: int):
+        """Same result as text_and_generate, but the ~50 kernel launches of one forward are captured
+        once per input signature into a CUDA graph and replayed with a single launch.  Inputs are copied
+        into the graph's static buffers unless they already ARE those buffers (see static_inputs()).
+        The returned tensors are the graph's static outputs: they are overwritten by the next replay."""
+        from . import get_precision
+        key = (tuple(LR.shape), tuple(captions.shape), int(tmax), get_precision())
+        e = self._graphs.get(key) if hasattr(self, '_graphs') else None
+        if e is None:
+            e = self._capture(key, LR, captions, cap_lens, tmax)
+        if LR.data_ptr() != e['LR'].data_ptr():
+            e['LR'].copy_(LR, non_blocking=True)
+        if captions.data_ptr() != e['caps'].data_ptr():
+            e['caps'].copy_(captions, non_blocking=True)
+        if cap_lens.data_ptr() != e['lens'].data_ptr():
+            e['lens'].copy_(cap_lens, non_blocking=True)
+        e['graph'].replay()
+        return e['out']
+
+    def static_inputs(self, B: int, tmax: int, Tcap: int = 18, size: int = 32):
+        """The static input buffers of the graph for this signature (fill them in place to skip copies)."""
+        from . import get_precision
+        key = ((B, 3, size, size), (B, Tcap), int(tmax), get_precision())
+        e = getattr(self, '_graphs', {}).get(key)
+        return None if e is None else (e['LR'], e['caps'], e['lens'])
+
+    def _capture(self, key, LR, captions, cap_lens, tmax):
+        if not hasattr(self, '_graphs'):
+            self._graphs = {}
+        ent = {'LR': LR.detach().clone(), 'caps': captions.detach().clone().to(torch.int64),
+               'lens': cap_lens.detach().clone().to(device=self.device, dtype=torch.int64)}
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):                 # warm every weight-prep cache (BN fold, packed operands, LSTM table)
+                self.text_and_generate(ent['LR'], ent['caps'], ent['lens'], tmax)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        from . import _lib
+        lib = _lib.load()
+        n0 = lib.tgsr_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            ent['out'] = self.text_and_generate(ent['LR'], ent['caps'], ent['lens'], tmax)
+        ent['graph'] = g
+        ent['n_kernels'] = int(lib.tgsr_launch_count() - n0)     # libtgsr kernels inside one replay
+        self.last_graph_kernels = ent['n_kernels']
+        self._graphs[key] = ent
+        return ent
+
     # ------------------------------------------------------------------ roofline probes (bench.py)
     @staticmethod
     def _time_kernel(fn, flush, iters=20, warm=5):
@@ -134,17 +187,25 @@ class SRPipeline:
 
     @torch.no_grad()
     def forward_host(self, LR_host: torch.Tensor, captions_host: torch.Tensor, cap_lens_host: torch.Tensor,
-                     out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     out_host: Optional[torch.Tensor] = None, use_graph: bool = True) -> torch.Tensor:
         """Host buffers in, final SR image (fine_im[-1]) out on the host: H2D of the inputs, the whole
         forward, D2H of the result, all on the current stream (synchronised before returning)."""
-        LR = LR_host.to(self.device, non_blocking=True)
-        caps = captions_host.to(self.device, non_blocking=True)
         tmax = int(cap_lens_host.max())                                    # host-side, no device sync
-        lens = cap_lens_host.to(self.device, non_blocking=True)
-        words_embs, sent_emb = self.text_encoder._forward_tmax(caps, lens, tmax)
-        mask = (caps == 0)[:, :tmax]
-        fake_imgL, attention_maps, mu, logvar = self.netGL(LR, sent_emb, words_embs, mask)
-        fine_im, a, one = self.netGH(LR, fake_imgL, LR)
+        if use_graph:
+            st = self.static_inputs(LR_host.shape[0], tmax, captions_host.shape[1], LR_host.shape[2])
+            if st is None:
+                self.forward_graph(LR_host.to(self.device), captions_host.to(self.device),
+                                   cap_lens_host.to(self.device), tmax)
+                st = self.static_inputs(LR_host.shape[0], tmax, captions_host.shape[1], LR_host.shape[2])
+            st[0].copy_(LR_host, non_blocking=True)                        # H2D straight into the graph's inputs
+            st[1].copy_(captions_host, non_blocking=True)
+            st[2].copy_(cap_lens_host, non_blocking=True)
+            fine_im = self.forward_graph(st[0], st[1], st[2], tmax)[0]
+        else:
+            LR = LR_host.to(self.device, non_blocking=True)
+            caps = captions_host.to(self.device, non_blocking=True)
+            lens = cap_lens_host.to(self.device, non_blocking=True)
+            fine_im = self.text_and_generate(LR, caps, lens, tmax)[0]
         sr = fine_im[-1]
         if out_host is None:
             out_host = torch.empty(sr.shape, dtype=sr.dtype, pin_memory=True)
