@@ -57,51 +57,51 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every 5 ms, own thread)."""
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self.t = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            names = {'hw_slowdown': N.nvmlClocksEventReasonHwSlowdown if hasattr(N, 'nvmlClocksEventReasonHwSlowdown') else 0x8,
+                     'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
+            get_reasons = getattr(N, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                getattr(N, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+            while not self._stop.is_set():
+                self.samples.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+                time.sleep(0.005)
+        except Exception as e:                      # noqa: BLE001
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def clear(self):
+        self.samples.clear(); self.reasons.clear()
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(',')]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx = float(f[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        sm.sort()
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+        self._stop.set()
+        if self.t is not None:
+            self.t.join(timeout=2)
+        sm = sorted(self.samples)
+        out = {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+               'samples': len(sm)}
+        if self.err:
+            out['error'] = self.err
+        return out
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -226,14 +226,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing
-    sampler = ClockSampler(local); sampler.start()
-    t_wait = time.time()
-    while not sampler.lines and time.time() - t_wait < 3.0:      # nvidia-smi needs ~0.2 s to emit its first sample
-        time.sleep(0.05)
-    sampler.lines.clear()
+    sampler = ClockSampler(int(os.environ.get('CUDA_VISIBLE_DEVICES', '0,1,2,3,4,5,6,7').split(',')[local])
+                           if os.environ.get('CUDA_VISIBLE_DEVICES') else local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
+    sampler.clear()                     # keep only samples taken under the timed region's load
     lib = _lib.load()
     launches0 = lib.tgsr_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

@@ -194,7 +194,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const int b = tile / tiles_per_img, r = tile % tiles_per_img;
         const int y0 = (r / p.tiles_x) * Cfg::TH, x0 = (r % p.tiles_x) * TC_TW;
         mbar_arrive_expect_tx(&full[s], Cfg::PATCH_BYTES);
-        tma_load_4d(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], 0, x0 - Cfg::R, y0 - Cfg::R, b * p.xP + p.xp0);
+        tma_load_3d(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], (x0 - Cfg::R) * 8, y0 - Cfg::R, b * p.xP + p.xp0);
       }
     }
   } else if (warp == 1) {
@@ -520,11 +520,15 @@ static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, i
                            int head = 0) {
   const int TC_PW = TC_TW + 2 * R;
   const int TC_PH = head ? (128 / TC_PW) + 2 * R + 1 : TC_TH + 2 * R;
-  cuuint64_t gdim[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * P};
-  cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-  cuuint32_t box[4] = {8, (cuuint32_t)TC_PW, (cuuint32_t)TC_PH, (cuuint32_t)npl};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = g_encode_tiled(m, fmt == TGSR_FMT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+  // A pixel row of one plane is W*8 contiguous 16-bit elements, so (x, c%8) is described as ONE inner
+  // dimension: the box's inner run is PW*16 bytes (160/192 B) instead of 16 B, which is what the TMA
+  // engine's per-row cost wants; the bytes landing in shared memory are identical to a [8,PW,PH,planes] box.
+  cuuint64_t gdim[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)B * P};
+  cuuint64_t gstr[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  cuuint32_t box[3] = {(cuuint32_t)TC_PW * 8, (cuuint32_t)TC_PH, (cuuint32_t)npl};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode_tiled(m, fmt == TGSR_FMT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                              const_cast<void*>(x), gdim, gstr, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return TGSR_ERR_CUDA; }
