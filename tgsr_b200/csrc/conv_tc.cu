@@ -180,42 +180,46 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // The whole warp runs the loop (uniform control flow); one elected lane issues.
+    if (elect_one()) {
       mbar_arrive_expect_tx(wbar, Cfg::WBYTES);
       constexpr int CH = 32768;
       for (int off = 0; off < Cfg::WBYTES; off += CH) {
         const int n = Cfg::WBYTES - off < CH ? Cfg::WBYTES - off : CH;
         bulk_g2s(w_s + off, reinterpret_cast<const unsigned char*>(p.wpacked) + off, n, wbar);
       }
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        const int b = tile / tiles_per_img, r = tile % tiles_per_img;
-        const int y0 = (r / p.tiles_x) * Cfg::TH, x0 = (r % p.tiles_x) * TC_TW;
+    }
+    __syncwarp();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      const int b = tile / tiles_per_img, r = tile % tiles_per_img;
+      const int y0 = (r / p.tiles_x) * Cfg::TH, x0 = (r % p.tiles_x) * TC_TW;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full[s], Cfg::PATCH_BYTES);
         tma_load_3d(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], (x0 - Cfg::R) * 8, y0 - Cfg::R, b * p.xP + p.xp0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      mbar_wait(wbar, 0);
+    mbar_wait(wbar, 0);
+    tc_fence_after();
+    const uint32_t w_addr = smem_u32(w_s);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
+      const int acc = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], aph ^ 1);            // epilogue has drained this accumulator stage
+      mbar_wait(&full[s], ph);                     // patch landed
       tc_fence_after();
-      const uint32_t w_addr = smem_u32(w_s);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
-        const int acc = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(&tempty[acc], aph ^ 1);            // epilogue has drained this accumulator stage
-        mbar_wait(&full[s], ph);                     // patch landed
-        tc_fence_after();
+      if (elect_one()) {
         const uint32_t a_base = smem_u32(patch_s + s * Cfg::PATCH_BYTES);
         const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
         uint32_t b_off = 0;
 #pragma unroll
         for (int o = 0; o < Ops::NOPS; ++o) {
-          constexpr int dummy = 0; (void)dummy;
           const TcOp op = Ops::op(o);
           const int N = op.n_mul * NPRE;
           const uint32_t idesc = make_idesc_f16(128, N, Fmt16<FMT>::kUmmaFormat);
@@ -231,6 +235,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         umma_commit(&empty[s]);                      // patch slot reusable once these MMAs retire
         umma_commit(&tfull[acc]);                    // accumulator ready for the epilogue
       }
+      __syncwarp();
     }
   } else {
     // ================================ epilogue (warps 2..9) ========================
