@@ -9,6 +9,7 @@ unsigned long long g_launches = 0;
 int init_attention(void);   // attention.cu
 int init_conv_tc(void);     // conv_tc.cu (tcgen05 path)
 int init_blocked_misc(void);  // blocked_misc.cu
+int init_lstm(void);          // lstm.cu
 }  // namespace tgsr
 
 extern "C" {
@@ -40,7 +41,9 @@ int tgsr_init(int device) {
   if (s != TGSR_OK) return s;
   s = tgsr::init_conv_tc();
   if (s != TGSR_OK) return s;
-  return tgsr::init_blocked_misc();
+  s = tgsr::init_blocked_misc();
+  if (s != TGSR_OK) return s;
+  return tgsr::init_lstm();
 }
 
 int tgsr_sm_count(void) { return tgsr::g_sm_count; }

@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "fmt16.cuh"
+#include <cstdlib>
 
 namespace tgsr {
 
@@ -46,6 +47,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode_tiled = nullptr;
+static int g_tc_debug = 0;
 
 // ------------------------------------------------------------------------------------------
 // MMA op tables.  An op = one filter tap (or one tap x phase group of the 4-phase upsample):
@@ -87,29 +89,33 @@ struct TcCfg {
   static constexpr bool HEAD = MODE == MODE_HEAD3 || MODE == MODE_HEAD5;
   static constexpr int R = MODE == MODE_HEAD5 ? 2 : 1;         // halo radius
   static constexpr int KS = 2 * R + 1;                         // filter size
-  static constexpr int PW = TC_TW + 2 * R;
-  // Conv/up tiles: 16 rows x 8 cols, accumulator row m = (y, x) and 8-row groups are PW*16 B apart.
-  // Head tiles: accumulator row m = LINEAR patch pixel (y*PW + x'), i.e. M walks the patch contiguously
-  // (8-row groups 128 B apart) and covers TH = 128/PW output rows; columns x' >= 8 are halo-only rows.
-  static constexpr int TH = HEAD ? 128 / PW : TC_TH;           // output rows per tile (10 / 12 for 5x5 / 3x3 heads)
-  static constexpr int PH = HEAD ? TH + 2 * R + 1 : TC_TH + 2 * R;   // +1 row: the linear M window overruns the last row
+  // Conv/up tiles: 16 rows x 8 cols; accumulator row m = (y, x), 8-row groups are PW*16 B apart.
+  // Head tiles: the patch is 16 pixels wide and M walks it LINEARLY (m = y*16 + x', 8 rows of 16, 8-row groups
+  // 128 B apart).  Columns x' < TWO = 16-2R are outputs, the rest is halo, so every output's kx neighbours
+  // (x'+kx <= 15) sit in the same patch row = the same warp (a warp owns 2 rows): the epilogue combines the
+  // kx-folded partial sums with warp shuffles, no shared-memory exchange.
+  static constexpr int PW = HEAD ? 16 : TC_TW + 2 * R;
+  static constexpr int TWO = HEAD ? 16 - 2 * R : TC_TW;        // output columns per tile (12 / 14 for 5x5 / 3x3 heads)
+  static constexpr int TH = HEAD ? 8 : TC_TH;                  // output rows per tile
+  static constexpr int PH = TH + 2 * R;
   static constexpr int SBO_A = HEAD ? 128 : PW * 16;
+  static constexpr int NACC = HEAD ? 4 : 2;                    // TMEM accumulator stages
   static constexpr int PLANE_BYTES = PH * PW * 16;             // one 8-channel plane of the halo patch
   static constexpr int NPL = CIN / 8;                          // input planes
   static constexpr int KSTEPS = CIN / 16;                      // UMMA K = 16
   static constexpr int PATCH_BYTES = NPL * PLANE_BYTES;
   static constexpr int ACC_COLS = UP ? 4 * NPRE : (NPRE < 32 ? 32 : NPRE);   // fp32 accumulator columns per stage
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;               // double-buffered (power of two >= 32)
+  static constexpr int TMEM_COLS = NACC * ACC_COLS;            // power of two >= 32
   static constexpr int NTAPB = UP ? 16 : OpTable<MODE>::NOPS;  // number of [NPRE x CIN] weight blocks
   static constexpr int WBYTES = NTAPB * CIN * NPRE * 2;
   static constexpr int NSCALE = NPRE;
   // Patch-ring depth: as many stages as fit next to the resident weights (TMA latency ~1-2 us must be
   // covered by stages in flight: small-channel layers and heads spend < 0.5 us of MMA time per tile).
   static constexpr int WB_PAD_ = ((WBYTES + 1023) / 1024) * 1024;
-  static constexpr int STAGE_ROOM = (232448 - 1024 - WB_PAD_ - 2 * NSCALE * 4 - 512 - (HEAD ? 2 * 128 * 16 * 4 : 0)) / PATCH_BYTES;
+  static constexpr int STAGE_ROOM = (232448 - 1024 - WB_PAD_ - 2 * NSCALE * 4 - 512) / PATCH_BYTES;
   static constexpr int NSTAGE = STAGE_ROOM > 12 ? 12 : STAGE_ROOM;
   static_assert(NSTAGE >= 2, "not enough shared memory for a double-buffered patch ring");
-  static constexpr int PBUF_BYTES = HEAD ? 2 * 128 * 16 * 4 : 0;   // head epilogue exchange buffer (double-buffered)
+  static constexpr int PBUF_BYTES = 0;
   static constexpr size_t SMEM = 1024 /*align slack*/ + ((WBYTES + 1023) / 1024) * 1024 + NSTAGE * PATCH_BYTES +
                                  2 * NSCALE * 4 + 512 + PBUF_BYTES;
 };
@@ -129,6 +135,7 @@ struct TcParams {
   const float* addend;
   float out_scale, addend_scale;
   int act_tanh;
+  int debug;   // profiling aid (TGSR_TC_DEBUG env): 1 skip MMAs, 2 skip epilogue work, 4 skip TMA patch loads
 };
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -154,17 +161,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   uint64_t* full = bars;                       // [NSTAGE]
   uint64_t* empty = bars + TC_NSTAGE;          // [NSTAGE]
   uint64_t* wbar = bars + 2 * TC_NSTAGE;       // [1]
-  uint64_t* tfull = wbar + 1;                  // [2]
-  uint64_t* tempty = tfull + 2;                // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* pbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~uintptr_t(127));   // [2][128][16] (heads only)
+  uint64_t* tfull = wbar + 1;                  // [NACC <= 4]
+  uint64_t* tempty = tfull + 4;                // [NACC <= 4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(wbar, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], HEAD ? 4 : 8); }
+    for (int a = 0; a < Cfg::NACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], HEAD ? 4 : 8); }
     fence_barrier_init();
     prefetch_tensormap(&tmap);
   }
@@ -195,8 +201,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
       mbar_wait(&empty[s], ph ^ 1);
       const int b = tile / tiles_per_img, r = tile % tiles_per_img;
-      const int y0 = (r / p.tiles_x) * Cfg::TH, x0 = (r % p.tiles_x) * TC_TW;
-      if (elect_one()) {
+      const int y0 = (r / p.tiles_x) * Cfg::TH, x0 = (r % p.tiles_x) * Cfg::TWO;
+      if (p.debug & 4) {
+        if (elect_one()) mbar_arrive(&full[s]);
+      } else if (elect_one()) {
         mbar_arrive_expect_tx(&full[s], Cfg::PATCH_BYTES);
         tma_load_3d(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], (x0 - Cfg::R) * 8, y0 - Cfg::R, b * p.xP + p.xp0);
       }
@@ -210,25 +218,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
-      const int acc = it & 1, aph = (it >> 1) & 1;
+      const int acc = it % Cfg::NACC, aph = (it / Cfg::NACC) & 1;
       mbar_wait(&tempty[acc], aph ^ 1);            // epilogue has drained this accumulator stage
       mbar_wait(&full[s], ph);                     // patch landed
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_base = smem_u32(patch_s + s * Cfg::PATCH_BYTES);
+      if (p.debug & 1) {
+        if (elect_one()) { mbar_arrive(&empty[s]); mbar_arrive(&tfull[acc]); }
+      } else if (elect_one()) {
+        // Descriptors are "per-tile base + compile-time constant": only the 14-bit start-address field of
+        // the low word changes between MMAs, so each one costs a single 32-bit add on the issuing thread.
+        const uint32_t a_lo0 = (smem_u32(patch_s + s * Cfg::PATCH_BYTES) >> 4) | ((uint32_t)(TC_PLANE_BYTES >> 4) << 16);
+        constexpr uint32_t a_hi = (uint32_t)(Cfg::SBO_A >> 4) | (1u << 14);
+        constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
+        const uint32_t b_lo0 = w_addr >> 4;
         const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
-        uint32_t b_off = 0;
+        uint32_t b_off = 0;                         // compile-time after unrolling
 #pragma unroll
         for (int o = 0; o < Ops::NOPS; ++o) {
           const TcOp op = Ops::op(o);
           const int N = op.n_mul * NPRE;
           const uint32_t idesc = make_idesc_f16(128, N, Fmt16<FMT>::kUmmaFormat);
-          const uint32_t a_tap = a_base + (op.tap_r * TC_PW + op.tap_c) * 16;
 #pragma unroll
           for (int k = 0; k < Cfg::KSTEPS; ++k) {
-            const uint64_t adesc = make_smem_desc(a_tap + k * 2 * TC_PLANE_BYTES, TC_PLANE_BYTES, Cfg::SBO_A);
-            const uint64_t bdesc = make_smem_desc(w_addr + b_off + k * (N * 32), N * 16, 128);
-            umma_f16(d_base + op.dcol_mul * NPRE, adesc, bdesc, idesc, (o | k) != 0 ? 1u : 0u);
+            const uint32_t a_lo = a_lo0 + (uint32_t)(((op.tap_r * TC_PW + op.tap_c) * 16 + k * 2 * TC_PLANE_BYTES) >> 4);
+            const uint32_t b_lo = b_lo0 + (uint32_t)((b_off + k * (N * 32)) >> 4) + ((uint32_t)((N * 16) >> 4) << 16);
+            umma_f16(d_base + op.dcol_mul * NPRE, make_desc64(a_lo, a_hi), make_desc64(b_lo, b_hi), idesc,
+                     (o | k) != 0 ? 1u : 0u);
           }
           b_off += CIN * N * 2;
         }
@@ -249,57 +264,54 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     const float4* sh4 = reinterpret_cast<const float4*>(sh_s);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1, aph = (it >> 1) & 1;
+      const int acc = it % Cfg::NACC, aph = (it / Cfg::NACC) & 1;
+      if (HEAD && (it & 1) != half) continue;        // heads: the two warp groups take alternate tiles
       const int b = tile / tiles_per_img, r = tile % tiles_per_img;
       const int gy = (r / p.tiles_x) * TC_TH + ty, gx = (r % p.tiles_x) * TC_TW + tx;
       const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + ((uint32_t)(quad * 32) << 16);
+      if (p.debug & 2) {
+        mbar_wait(&tfull[acc], aph);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        continue;
+      }
 
       if constexpr (HEAD) {
-        // Image head.  Accumulator row m = linear patch pixel (y*PW + x'), column o*K + kx holds the partial
-        // sum over (ky, c) for output o and tap column kx.  out[y][x][o] = sum_kx P[y*PW + x + kx][o*K + kx].
-        // Warps 2..5 move the accumulator to shared memory (then release TMEM); after one named barrier all
-        // 256 epilogue threads produce one (pixel, o) output each.
-        constexpr int K = Cfg::KS, NPIX = Cfg::TH * TC_TW;       // valid outputs per tile (80 / 96)
-        float* pb = pbuf + acc * (128 * 16);
-        const int et = threadIdx.x - 64;                        // 0..255
-        constexpr int NITEM = (3 * NPIX + 255) / 256;           // (pixel, o) outputs per thread: 1 (5x5) or 2 (3x3)
+        // Image head.  Accumulator row m = (y, x') = (m/16, m%16) of the 16-wide patch; column o*K + kx holds
+        // the partial sum over (ky, c) for output o and tap column kx:
+        //   out[y][x'][o] = sum_kx P[(y, x'+kx)][o*K + kx]  -> lane shuffles by kx inside the warp.
+        constexpr int K = Cfg::KS;
+        const int hy = m >> 4, hx = m & 15;
+        const int oy = (r / p.tiles_x) * Cfg::TH + hy, ox = (r % p.tiles_x) * Cfg::TWO + hx;
+        const bool valid = hx < Cfg::TWO && ox < p.W && oy < p.H;
         const size_t hw = (size_t)p.H * p.W;
-        size_t oi[NITEM]; float ad[NITEM]; bool valid[NITEM]; int m0[NITEM], oo[NITEM];
+        const size_t oi = (size_t)b * 3 * hw + (size_t)oy * p.W + ox;
+        float ad[3] = {0.f, 0.f, 0.f};
+        if (valid && p.addend) {                                // fetched before the accumulator wait
 #pragma unroll
-        for (int q = 0; q < NITEM; ++q) {
-          const int item = et + q * 256;
-          const int o = item / NPIX, pidx = item % NPIX;        // output channel, pixel within the tile
-          const int oy = (r / p.tiles_x) * Cfg::TH + pidx / TC_TW, ox = (r % p.tiles_x) * TC_TW + pidx % TC_TW;
-          valid[q] = o < 3 && oy < p.H;
-          oi[q] = ((size_t)b * 3 + o) * hw + (size_t)oy * p.W + ox;
-          m0[q] = (pidx / TC_TW) * Cfg::PW + (pidx % TC_TW);
-          oo[q] = o;
-          ad[q] = (valid[q] && p.addend) ? __ldg(p.addend + oi[q]) : 0.f;   // fetched before the accumulator wait
+          for (int o = 0; o < 3; ++o) ad[o] = __ldg(p.addend + oi + o * hw);
         }
-        if (half == 0) {
-          mbar_wait(&tfull[acc], aph);
-          tc_fence_after();
-          uint32_t v[16];
-          tmem_ld16(t_base, v);
-          tmem_ld_wait();
-          tc_fence_before();
-          float4* dst = reinterpret_cast<float4*>(pb + m * 16);
-          dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-          dst[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-          dst[2] = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
-          dst[3] = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);             // TMEM stage is free again
+        mbar_wait(&tfull[acc], aph);
+        tc_fence_after();
+        uint32_t v[16];
+        tmem_ld16(t_base, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);               // TMEM stage is free again
+        float z[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          z[o] = __uint_as_float(v[o * K]);
+#pragma unroll
+          for (int kx = 1; kx < K; ++kx) z[o] += __shfl_down_sync(0xffffffffu, __uint_as_float(v[o * K + kx]), kx);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps only
+        if (valid) {
 #pragma unroll
-        for (int q = 0; q < NITEM; ++q) {
-          if (valid[q]) {
-            float z = 0.f;
-#pragma unroll
-            for (int kx = 0; kx < K; ++kx) z += pb[(m0[q] + kx) * 16 + oo[q] * K + kx];
-            if (p.act_tanh) z = tanhf(z);
-            __stcs(p.out_f32 + oi[q], fmaf(p.addend_scale, ad[q], z * p.out_scale));
+          for (int o = 0; o < 3; ++o) {
+            float t = z[o];
+            if (p.act_tanh) t = tanhf(t);
+            __stcs(p.out_f32 + oi + o * hw, fmaf(p.addend_scale, ad[o], t * p.out_scale));
           }
         }
         continue;                                               // (tempty already signalled)
@@ -509,6 +521,7 @@ int init_conv_tc() {
   if (e != cudaSuccess) return cuda_fail(e);
   if (q != cudaDriverEntryPointSuccess || fn == nullptr) return TGSR_ERR_UNSUPPORTED;
   g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  if (const char* d = getenv("TGSR_TC_DEBUG")) g_tc_debug = atoi(d);
   int s;
   if ((s = set_tc_attr<64, 128, MODE_CONV, true>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<64, 64, MODE_CONV, false>()) != TGSR_OK) return s;
@@ -523,8 +536,8 @@ int init_conv_tc() {
 
 static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl, int fmt, int R = 1,
                            int head = 0) {
-  const int TC_PW = TC_TW + 2 * R;
-  const int TC_PH = head ? (128 / TC_PW) + 2 * R + 1 : TC_TH + 2 * R;
+  const int TC_PW = head ? 16 : TC_TW + 2 * R;
+  const int TC_PH = (head ? 8 : TC_TH) + 2 * R;
   // A pixel row of one plane is W*8 contiguous 16-bit elements, so (x, c%8) is described as ONE inner
   // dimension: the box's inner run is PW*16 bytes (160/192 B) instead of 16 B, which is what the TMA
   // engine's per-row cost wants; the bytes landing in shared memory are identical to a [8,PW,PH,planes] box.
@@ -583,6 +596,7 @@ extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpack
   p.B = B; p.H = H; p.W = W;
   p.tiles_x = W / TC_TW; p.tiles_y = H / TC_TH; p.ntiles = B * p.tiles_x * p.tiles_y;
   p.out_f32 = nullptr; p.addend = nullptr; p.out_scale = 1.f; p.addend_scale = 0.f; p.act_tanh = 0;
+  p.debug = g_tc_debug;
   cudaStream_t st = (cudaStream_t)stream;
   const bool glu = act == TGSR_ACT_GLU;
   if (!up2x) {
@@ -635,7 +649,7 @@ extern "C" int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpac
   TGSR_CHECK_FMT(fmt);
   TGSR_REQUIRE(g_sm_count > 0 && g_encode_tiled != nullptr, TGSR_ERR_NOT_INIT);
   TGSR_REQUIRE(B > 0 && H > 0 && W > 0, TGSR_ERR_BAD_SHAPE);
-  TGSR_REQUIRE(Cin == 32 && (ksize == 3 || ksize == 5) && W % TC_TW == 0, TGSR_ERR_UNSUPPORTED);
+  TGSR_REQUIRE(Cin == 32 && (ksize == 3 || ksize == 5) && W % 8 == 0, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(act == TGSR_ACT_NONE || act == TGSR_ACT_TANH, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(xp0 >= 0 && xp0 + Cin / 8 <= xP, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE((long long)B * xP < (1LL << 31), TGSR_ERR_UNSUPPORTED);
@@ -647,10 +661,11 @@ extern "C" int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpac
   p.rP = p.rp0 = p.yP = p.yp0 = 0; p.xP = xP; p.xp0 = xp0;
   p.B = B; p.H = H; p.W = W;
   p.tiles_x = W / TC_TW; p.tiles_y = H / TC_TH; p.ntiles = B * p.tiles_x * p.tiles_y;
-  const int th = 128 / (TC_TW + 2 * (ksize / 2));            // output rows per head tile
-  p.tiles_y = (H + th - 1) / th; p.ntiles = B * p.tiles_x * p.tiles_y;
+  const int two = 16 - 2 * (ksize / 2);                      // output columns per head tile (8 rows x two cols)
+  p.tiles_x = (W + two - 1) / two; p.tiles_y = (H + 7) / 8; p.ntiles = B * p.tiles_x * p.tiles_y;
   p.out_f32 = y; p.addend = addend; p.out_scale = out_scale; p.addend_scale = addend_scale;
   p.act_tanh = act == TGSR_ACT_TANH;
+  p.debug = g_tc_debug;
   cudaStream_t st = (cudaStream_t)stream;
   if (ksize == 3) return launch_tc<32, 16, MODE_HEAD3, false>(tmap, p, fmt, st);
   return launch_tc<32, 16, MODE_HEAD5, false>(tmap, p, fmt, st);

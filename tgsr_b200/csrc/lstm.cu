@@ -177,6 +177,7 @@ lstm_cluster_kernel(const int64_t* __restrict__ captions, const int64_t* __restr
   __shared__ __align__(16) float h_s[2][H][LC_BT];      // double-buffered hidden state, [unit][caption]
   __shared__ float g_s[4][64][LC_BT];                   // this CTA's gate pre-activations
   __shared__ int len_s[LC_BT];
+  __shared__ int tok_s[LC_BT * 64];                     // token ids of this cluster's captions (Tcap <= 64)
   const uint32_t rank = cluster_rank();
   const int d = blockIdx.y, b0 = blockIdx.z * LC_BT;
   const int r = threadIdx.x, g = r >> 6, ul = r & 63, u = (int)rank * 64 + ul, row = g * H + u;
@@ -207,29 +208,33 @@ lstm_cluster_kernel(const int64_t* __restrict__ captions, const int64_t* __restr
 
   float c_reg = 0.f;                                    // cell (unit ul, caption g): 64 x 4 cells = 256 threads
   const int cb = g;                                     // caption handled by this thread in the cell update
-  // input projection of step s for the 4 captions: a gather from the table, issued one step ahead so
-  // its L2/HBM latency hides behind the recurrent GEMV of the previous step.
-  auto gather = [&](int s, float (&xv)[LC_BT]) {
+  // Input projections of ALL steps for this CTA's 256 gate rows: gathered from the table into shared
+  // memory up front (independent loads, full memory-level parallelism), so the serial step loop below
+  // touches no global memory except its outputs.
+  extern __shared__ float xs[];                         // [maxlen][LC_BT][256]
+  for (int i = r; i < LC_BT * Tcap; i += 256) {
+    const int bb = i / Tcap, t = i % Tcap;
+    long long id = (b0 + bb < B) ? captions[(size_t)(b0 + bb) * Tcap + t] : 0;
+    tok_s[i] = (int)(id < 0 ? 0 : (id >= ntoken ? ntoken - 1 : id));
+  }
+  __syncthreads();
+  for (int s = 0; s < maxlen; ++s) {
 #pragma unroll
     for (int bb = 0; bb < LC_BT; ++bb) {
       const int L = len_s[bb];
-      xv[bb] = 0.f;
+      float v = 0.f;
       if (s < L) {
         const int t = d == 0 ? s : L - 1 - s;
-        long long id = captions[(size_t)(b0 + bb) * Tcap + t];
-        id = id < 0 ? 0 : (id >= ntoken ? ntoken - 1 : id);
-        xv[bb] = __ldg(xtab + ((size_t)id * 2 + d) * G + row);
+        v = __ldg(xtab + ((size_t)tok_s[bb * Tcap + t] * 2 + d) * G + row);
       }
+      xs[(s * LC_BT + bb) * 256 + r] = v;
     }
-  };
-  float xcur[LC_BT], xnext[LC_BT];
-  gather(0, xcur);
+  }
   for (int s = 0; s < maxlen; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
-    gather(s + 1, xnext);
     float acc[LC_BT];
 #pragma unroll
-    for (int bb = 0; bb < LC_BT; ++bb) acc[bb] = xcur[bb];
+    for (int bb = 0; bb < LC_BT; ++bb) acc[bb] = xs[(s * LC_BT + bb) * 256 + r];
     const float4* h4 = reinterpret_cast<const float4*>(&h_s[cur][0][0]);
 #pragma unroll
     for (int k = 0; k < H; ++k) {
@@ -256,10 +261,14 @@ lstm_cluster_kernel(const int64_t* __restrict__ captions, const int64_t* __restr
         if (s == L - 1) sent[(size_t)(b0 + cb) * 2 * H + d * H + u] = h;
       }
     }
-#pragma unroll
-    for (int bb = 0; bb < LC_BT; ++bb) xcur[bb] = xnext[bb];
     cluster_sync_all();
   }
+}
+
+int init_lstm() {
+  cudaError_t e = cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       48 * LC_BT * 256 * 4);
+  return e == cudaSuccess ? TGSR_OK : cuda_fail(e);
 }
 
 }  // namespace tgsr
@@ -282,12 +291,13 @@ extern "C" int tgsr_lstm_bidir_fwd_tab_f32(const int64_t* captions, const int64_
   TGSR_REQUIRE_PTR(captions); TGSR_REQUIRE_PTR(cap_lens); TGSR_REQUIRE_PTR(xtab); TGSR_REQUIRE_PTR(w_hh);
   TGSR_REQUIRE_PTR(words); TGSR_REQUIRE_PTR(sent);
   TGSR_REQUIRE(B > 0 && Tcap > 0 && Tmax > 0 && Tmax <= Tcap && ntoken > 0, TGSR_ERR_BAD_SHAPE);
-  TGSR_REQUIRE(H == LC_H && B <= 65535 * LC_BT, TGSR_ERR_UNSUPPORTED);
+  TGSR_REQUIRE(H == LC_H && B <= 65535 * LC_BT && Tcap <= 48, TGSR_ERR_UNSUPPORTED);
   cudaStream_t st = (cudaStream_t)stream;
   TGSR_CUDA(cudaMemsetAsync(words, 0, (size_t)B * 2 * H * Tmax * sizeof(float), st));
   TGSR_CUDA(cudaMemsetAsync(sent, 0, (size_t)B * 2 * H * sizeof(float), st));
-  lstm_cluster_kernel<<<dim3(2, 2, ceil_div(B, LC_BT)), 256, 0, st>>>(captions, cap_lens, xtab, w_hh, words, sent, B,
-                                                                      Tcap, Tmax, ntoken);
+  const size_t xs_bytes = (size_t)Tcap * LC_BT * 256 * sizeof(float);
+  lstm_cluster_kernel<<<dim3(2, 2, ceil_div(B, LC_BT)), 256, xs_bytes, st>>>(captions, cap_lens, xtab, w_hh, words, sent,
+                                                                             B, Tcap, Tmax, ntoken);
   return launch_status();
 }
 

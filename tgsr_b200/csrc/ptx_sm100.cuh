@@ -148,6 +148,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;   // descriptor version 1 (Blackwell)
   return d;                 // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
 }
+__device__ __forceinline__ uint64_t make_desc64(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32, A and B = `fmt` (0 = f16, 1 = bf16), both K-major, M x N.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, uint32_t fmt) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
