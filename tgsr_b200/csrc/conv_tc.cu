@@ -96,15 +96,16 @@ struct TcCfg {
   // kx-folded partial sums with warp shuffles, no shared-memory exchange.
   static constexpr int PW = HEAD ? 16 : TC_TW + 2 * R;
   static constexpr int TWO = HEAD ? 16 - 2 * R : TC_TW;        // output columns per tile (12 / 14 for 5x5 / 3x3 heads)
-  static constexpr int TH = HEAD ? 8 : TC_TH;                  // output rows per tile
+  static constexpr int MB = HEAD ? 4 : 1;                      // M=128 blocks per tile (heads: 4 x (8 rows x 16 px))
+  static constexpr int TH = HEAD ? 8 * MB : TC_TH;             // output rows per tile
   static constexpr int PH = TH + 2 * R;
   static constexpr int SBO_A = HEAD ? 128 : PW * 16;
-  static constexpr int NACC = HEAD ? 4 : 2;                    // TMEM accumulator stages
+  static constexpr int NACC = 2;                               // TMEM accumulator stages
   static constexpr int PLANE_BYTES = PH * PW * 16;             // one 8-channel plane of the halo patch
   static constexpr int NPL = CIN / 8;                          // input planes
   static constexpr int KSTEPS = CIN / 16;                      // UMMA K = 16
   static constexpr int PATCH_BYTES = NPL * PLANE_BYTES;
-  static constexpr int ACC_COLS = UP ? 4 * NPRE : (NPRE < 32 ? 32 : NPRE);   // fp32 accumulator columns per stage
+  static constexpr int ACC_COLS = UP ? 4 * NPRE : (HEAD ? 32 * (HEAD ? 4 : 1) : NPRE);   // fp32 accumulator columns per stage
   static constexpr int TMEM_COLS = NACC * ACC_COLS;            // power of two >= 32
   static constexpr int NTAPB = UP ? 16 : OpTable<MODE>::NOPS;  // number of [NPRE x CIN] weight blocks
   static constexpr int WBYTES = NTAPB * CIN * NPRE * 2;
@@ -170,7 +171,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(wbar, 1);
-    for (int a = 0; a < Cfg::NACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], HEAD ? 4 : 8); }
+    for (int a = 0; a < Cfg::NACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
     fence_barrier_init();
     prefetch_tensormap(&tmap);
   }
@@ -232,20 +233,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
         const uint32_t b_lo0 = w_addr >> 4;
         const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
-        uint32_t b_off = 0;                         // compile-time after unrolling
 #pragma unroll
-        for (int o = 0; o < Ops::NOPS; ++o) {
-          const TcOp op = Ops::op(o);
-          const int N = op.n_mul * NPRE;
-          const uint32_t idesc = make_idesc_f16(128, N, Fmt16<FMT>::kUmmaFormat);
+        for (int j = 0; j < Cfg::MB; ++j) {         // heads: 4 M-blocks of 8 patch rows each per tile
+          uint32_t b_off = 0;                       // compile-time after unrolling
 #pragma unroll
-          for (int k = 0; k < Cfg::KSTEPS; ++k) {
-            const uint32_t a_lo = a_lo0 + (uint32_t)(((op.tap_r * TC_PW + op.tap_c) * 16 + k * 2 * TC_PLANE_BYTES) >> 4);
-            const uint32_t b_lo = b_lo0 + (uint32_t)((b_off + k * (N * 32)) >> 4) + ((uint32_t)((N * 16) >> 4) << 16);
-            umma_f16(d_base + op.dcol_mul * NPRE, make_desc64(a_lo, a_hi), make_desc64(b_lo, b_hi), idesc,
-                     (o | k) != 0 ? 1u : 0u);
+          for (int o = 0; o < Ops::NOPS; ++o) {
+            const TcOp op = Ops::op(o);
+            const int N = op.n_mul * NPRE;
+            const uint32_t idesc = make_idesc_f16(128, N, Fmt16<FMT>::kUmmaFormat);
+#pragma unroll
+            for (int k = 0; k < Cfg::KSTEPS; ++k) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)((((j * 8 + op.tap_r) * TC_PW + op.tap_c) * 16 + k * 2 * TC_PLANE_BYTES) >> 4);
+              const uint32_t b_lo = b_lo0 + (uint32_t)((b_off + k * (N * 32)) >> 4) + ((uint32_t)((N * 16) >> 4) << 16);
+              umma_f16(d_base + op.dcol_mul * NPRE + j * 32, make_desc64(a_lo, a_hi), make_desc64(b_lo, b_hi), idesc,
+                       (o | k) != 0 ? 1u : 0u);
+            }
+            b_off += CIN * N * 2;
           }
-          b_off += CIN * N * 2;
         }
         umma_commit(&empty[s]);                      // patch slot reusable once these MMAs retire
         umma_commit(&tfull[acc]);                    // accumulator ready for the epilogue
@@ -265,7 +269,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int acc = it % Cfg::NACC, aph = (it / Cfg::NACC) & 1;
-      if (HEAD && (it & 1) != half) continue;        // heads: the two warp groups take alternate tiles
       const int b = tile / tiles_per_img, r = tile % tiles_per_img;
       const int gy = (r / p.tiles_x) * TC_TH + ty, gx = (r % p.tiles_x) * TC_TW + tx;
       const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + ((uint32_t)(quad * 32) << 16);
@@ -277,41 +280,48 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       }
 
       if constexpr (HEAD) {
-        // Image head.  Accumulator row m = (y, x') = (m/16, m%16) of the 16-wide patch; column o*K + kx holds
-        // the partial sum over (ky, c) for output o and tap column kx:
+        // Image head.  A tile is MB=4 accumulator blocks (columns j*32..) of 8 patch rows each; accumulator row
+        // m = (y, x') = (m/16, m%16) of the 16-wide patch; column o*K + kx holds the partial sum over (ky, c):
         //   out[y][x'][o] = sum_kx P[(y, x'+kx)][o*K + kx]  -> lane shuffles by kx inside the warp.
+        // Warp group `half` produces blocks 2*half and 2*half+1.
         constexpr int K = Cfg::KS;
         const int hy = m >> 4, hx = m & 15;
-        const int oy = (r / p.tiles_x) * Cfg::TH + hy, ox = (r % p.tiles_x) * Cfg::TWO + hx;
-        const bool valid = hx < Cfg::TWO && ox < p.W && oy < p.H;
+        const int ox = (r % p.tiles_x) * Cfg::TWO + hx;
         const size_t hw = (size_t)p.H * p.W;
-        const size_t oi = (size_t)b * 3 * hw + (size_t)oy * p.W + ox;
-        float ad[3] = {0.f, 0.f, 0.f};
-        if (valid && p.addend) {                                // fetched before the accumulator wait
+        bool valid[2]; size_t oi[2]; float ad[2][3];
 #pragma unroll
-          for (int o = 0; o < 3; ++o) ad[o] = __ldg(p.addend + oi + o * hw);
+        for (int q = 0; q < 2; ++q) {
+          const int oy = (r / p.tiles_x) * Cfg::TH + (half * 2 + q) * 8 + hy;
+          valid[q] = hx < Cfg::TWO && ox < p.W && oy < p.H;
+          oi[q] = (size_t)b * 3 * hw + (size_t)oy * p.W + ox;
+#pragma unroll
+          for (int o = 0; o < 3; ++o) ad[q][o] = (valid[q] && p.addend) ? __ldg(p.addend + oi[q] + o * hw) : 0.f;
         }
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
-        uint32_t v[16];
-        tmem_ld16(t_base, v);
+        uint32_t v[2][16];
+        tmem_ld16(t_base + (half * 2) * 32, v[0]);
+        tmem_ld16(t_base + (half * 2 + 1) * 32, v[1]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);               // TMEM stage is free again
-        float z[3];
 #pragma unroll
-        for (int o = 0; o < 3; ++o) {
-          z[o] = __uint_as_float(v[o * K]);
-#pragma unroll
-          for (int kx = 1; kx < K; ++kx) z[o] += __shfl_down_sync(0xffffffffu, __uint_as_float(v[o * K + kx]), kx);
-        }
-        if (valid) {
+        for (int q = 0; q < 2; ++q) {
+          float z[3];
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
-            float t = z[o];
-            if (p.act_tanh) t = tanhf(t);
-            __stcs(p.out_f32 + oi + o * hw, fmaf(p.addend_scale, ad[o], t * p.out_scale));
+            z[o] = __uint_as_float(v[q][o * K]);
+#pragma unroll
+            for (int kx = 1; kx < K; ++kx) z[o] += __shfl_down_sync(0xffffffffu, __uint_as_float(v[q][o * K + kx]), kx);
+          }
+          if (valid[q]) {
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              float t = z[o];
+              if (p.act_tanh) t = tanhf(t);
+              __stcs(p.out_f32 + oi[q] + o * hw, fmaf(p.addend_scale, ad[q][o], t * p.out_scale));
+            }
           }
         }
         continue;                                               // (tempty already signalled)
@@ -537,7 +547,7 @@ int init_conv_tc() {
 static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl, int fmt, int R = 1,
                            int head = 0) {
   const int TC_PW = head ? 16 : TC_TW + 2 * R;
-  const int TC_PH = (head ? 8 : TC_TH) + 2 * R;
+  const int TC_PH = (head ? 32 : TC_TH) + 2 * R;
   // A pixel row of one plane is W*8 contiguous 16-bit elements, so (x, c%8) is described as ONE inner
   // dimension: the box's inner run is PW*16 bytes (160/192 B) instead of 16 B, which is what the TMA
   // engine's per-row cost wants; the bytes landing in shared memory are identical to a [8,PW,PH,planes] box.
@@ -661,8 +671,8 @@ extern "C" int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpac
   p.rP = p.rp0 = p.yP = p.yp0 = 0; p.xP = xP; p.xp0 = xp0;
   p.B = B; p.H = H; p.W = W;
   p.tiles_x = W / TC_TW; p.tiles_y = H / TC_TH; p.ntiles = B * p.tiles_x * p.tiles_y;
-  const int two = 16 - 2 * (ksize / 2);                      // output columns per head tile (8 rows x two cols)
-  p.tiles_x = (W + two - 1) / two; p.tiles_y = (H + 7) / 8; p.ntiles = B * p.tiles_x * p.tiles_y;
+  const int two = 16 - 2 * (ksize / 2);                      // output columns per head tile (32 rows x two cols)
+  p.tiles_x = (W + two - 1) / two; p.tiles_y = (H + 31) / 32; p.ntiles = B * p.tiles_x * p.tiles_y;
   p.out_f32 = y; p.addend = addend; p.out_scale = out_scale; p.addend_scale = addend_scale;
   p.act_tanh = act == TGSR_ACT_TANH;
   p.debug = g_tc_debug;

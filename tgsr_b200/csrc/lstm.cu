@@ -218,6 +218,7 @@ lstm_cluster_kernel(const int64_t* __restrict__ captions, const int64_t* __restr
     tok_s[i] = (int)(id < 0 ? 0 : (id >= ntoken ? ntoken - 1 : id));
   }
   __syncthreads();
+#pragma unroll 6
   for (int s = 0; s < maxlen; ++s) {
 #pragma unroll
     for (int bb = 0; bb < LC_BT; ++bb) {
