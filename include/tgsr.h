@@ -164,12 +164,22 @@ int tgsr_conv_in_blocked(const float* x, const float* x_sub, const float* w, con
                          const float* shift, void* y, int yP, int yp0, int B, int H, int W, int C, int fmt,
                          tgsr_stream_t stream);
 
-/* a1 on blocked activations: reads the idf=32 channel view (xP,xp0), writes weightedContext (16-bit)
- * into the view (yP,yp0) -- normally the next planes of the same concat buffer -- and the
- * attention map attn fp32 [B,T,Q].  context fp32 [B,cdf,T]; mask as tgsr_attn_fwd_f32.  T <= 20. */
-int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const float* context, const float* w_ctx,
-                          const uint8_t* mask, void* y, int yP, int yp0, float* attn, int B, int idf,
-                          int cdf, int Q, int T, int fmt, tgsr_stream_t stream);
+/* a1 on blocked activations (GlobalAttention.py:87-130), two entry points.
+ * tgsr_attn_project: the word projection S[b] = w_ctx . context[b] (conv_context, GlobalAttention.py:99-101) in
+ * fp32, written as the per-lane tensor-core operand image `sfrag` (tgsr_attn_sfrag_bytes(B) bytes, caller-owned
+ * workspace).  It depends on the caption only: one call per (captions, conv_context weight), reused by every
+ * pixel tile.  context fp32 [B,cdf,T], w_ctx fp32 [idf,cdf]; idf == 32, T <= 24, cdf % 4 == 0.
+ * tgsr_attn_fwd_blocked: reads the idf=32 channel view (xP,xp0), writes weightedContext (16-bit) into the view
+ * (yP,yp0) -- normally the next planes of the same concat buffer -- and the attention map attn fp32 [B,T,Q]; caption
+ * mask uint8 [B,T] or NULL with the reference's row-order quirk (pixel q of image b uses caption (b*Q+q) % B).
+ * Logits, mask, softmax and the weighted sum are one persistent kernel (TMA-fed, warp-level tensor cores, S split
+ * into three 16-bit pieces so the fp32 maps keep fp32 accuracy).  Q % 32 == 0. */
+size_t tgsr_attn_sfrag_bytes(int B);
+int tgsr_attn_project(const float* context, const float* w_ctx, void* sfrag, int B, int idf, int cdf, int T,
+                      int fmt, tgsr_stream_t stream);
+int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const void* sfrag, const uint8_t* mask, void* y,
+                          int yP, int yp0, float* attn, int B, int idf, int Q, int T, int fmt,
+                          tgsr_stream_t stream);
 
 #ifdef __cplusplus
 }

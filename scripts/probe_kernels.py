@@ -21,6 +21,8 @@ def main():
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--size', type=int, default=128)
     ap.add_argument('--batch', type=int, default=32)
+    ap.add_argument('--flush', default='write', choices=['write', 'read', 'none'],
+                    help='L2 state before each timed launch: 256 MiB memset (dirty lines), 256 MiB read (clean lines), nothing (warm)')
     a = ap.parse_args()
     tgsr_b200.set_eval_defaults(); tgsr_b200.set_precision('mixed16')
     dev = torch.device('cuda')
@@ -29,6 +31,7 @@ def main():
     st = pipe.netGL.h_net3
     rb = st.residual[0].block
     flops = None
+    nbytes = None
     if a.what == 'conv128':
         x = tc.to_blocked(torch.randn(B, 64, S, S, device=dev) * 0.5)
         out = tc.Blocked.empty(B, 64, S, S, dev)
@@ -52,29 +55,63 @@ def main():
         fn = lambda: fast.image_head(x, seq, add, 0.5, 1.0)
         k = 5 if a.what == 'head5' else 3
         flops = 2 * k * k * 32 * 3 * 4 * S * S * B
-    elif a.what == 'attn':
+    elif a.what in ('attn', 'attnproj'):
+        # attn: the per-pixel kernel alone (word projection precomputed, as inside a forward);
+        # attnproj: projection + per-pixel kernel (a stand-alone GlobalAttentionGeneral call)
         cat = tc.Blocked.empty(B, 64, S, S, dev); cat.buf.normal_(0, 0.5)
         ctx = torch.randn(B, 256, 18, device=dev) * 0.3
-        mask = torch.zeros(B, 18, dtype=torch.bool, device=dev)
-        fn = lambda: fast.attention(cat.slice(0, 32), st.att, ctx, mask, out=cat.slice(32, 32))
+        mask = torch.zeros(B, 18, dtype=torch.uint8, device=dev)
+        sfrag = fast.attention_project(st.att, ctx, cat.fmt) if a.what == 'attn' else None
+        fn = lambda: fast.attention(cat.slice(0, 32), st.att, ctx, mask, out=cat.slice(32, 32), sfrag=sfrag)
+        nbytes = B * S * S * (32 * 2 + 32 * 2 + 4 * 18) + B * 256 * 18 * 4 + 32 * 256 * 4 + B * 18
+    elif a.what == 'null':                      # calibration: a trivially small kernel in the same harness
+        from tgsr_b200 import ops
+        v = torch.ones(64, device=dev)
+        fn = lambda: ops.bn_fold(v, v, v, v, 1e-5)
     elif a.what == 'lstm':
         caps = torch.randint(1, 5450, (B, 18), device=dev); lens = torch.full((B,), 18, device=dev)
         fn = lambda: pipe.text_encoder._forward_tmax(caps, lens, 18)
     else:
         raise SystemExit('unknown kernel ' + a.what)
-    flush = torch.empty(64 * 1024 * 1024, device=dev)
-    for _ in range(3):
-        fn()
-    ms = 0.0
-    for _ in range(a.iters):
-        flush.zero_()
-        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
-        s.record(); fn(); e.record(); e.synchronize()
-        ms += s.elapsed_time(e)
-    ms /= a.iters
+    # Device time without launch latency: two CUDA graphs, N x [L2 flush, op] and N x [L2 flush]; the
+    # difference of their CUDA-event durations / N is the L2-cold duration of the op.
+    flush = torch.empty(64 * 1024 * 1024, device=dev)          # 256 MiB > 126 MB L2
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.synchronize()
+    N = a.iters
+    g_both, g_flush = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    sink = torch.zeros(1, device=dev)
+
+    def do_flush():
+        if a.flush == 'write':
+            flush.zero_()
+        elif a.flush == 'read':
+            torch.sum(flush, dim=0, keepdim=True, out=sink)
+    do_flush(); torch.cuda.synchronize()
+    with torch.cuda.graph(g_both):
+        for _ in range(N):
+            do_flush(); fn()
+    with torch.cuda.graph(g_flush):
+        for _ in range(N):
+            do_flush()
+
+    def timed(g):
+        best = 1e9
+        for _ in range(3):
+            s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+            s.record(); g.replay(); e.record(); e.synchronize()
+            best = min(best, s.elapsed_time(e))
+        return best
+    timed(g_both); timed(g_flush)
+    ms = (timed(g_both) - timed(g_flush)) / N
     msg = '%s B=%d S=%d: %.1f us/launch' % (a.what, B, S, ms * 1e3)
     if flops:
         msg += '  %.1f TFLOP/s (reference FLOPs)' % (flops / ms / 1e9)
+    if nbytes:
+        msg += '  %.0f GB/s (algorithmic bytes)' % (nbytes / ms / 1e6)
     print(msg)
 
 

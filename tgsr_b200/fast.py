@@ -99,19 +99,35 @@ def image_head(x: Blocked, head_seq, addend: Optional[Tensor] = None, a: float =
     return y
 
 
-def attention(h: Blocked, att, words: Tensor, mask: Optional[Tensor], out: Blocked) -> Tensor:
+def attention_project(att, words: Tensor, fmt: int) -> Tensor:
+    """S = conv_context(words) (GlobalAttention.py:99-101) as the tensor-core operand image of the blocked
+    attention kernel; depends on the caption only, so a forward computes it once per stage up front."""
+    B, cdf, T = words.shape
+    w = att.conv_context.weight
+    sfrag = torch.empty(B * 48 * 32, device=words.device, dtype=torch.int32)
+    call('tgsr_attn_project', words.device, ptr(words.contiguous()), ptr(w.detach().contiguous()), ptr(sfrag),
+         B, w.shape[0], cdf, T, fmt)
+    return sfrag
+
+
+def attention_blocked_supported(idf: int, T: int, Q: int) -> bool:
+    return idf == 32 and T <= 24 and Q % 32 == 0
+
+
+def attention(h: Blocked, att, words: Tensor, mask: Optional[Tensor], out: Blocked, sfrag: Optional[Tensor] = None) -> Tensor:
     """GlobalAttentionGeneral on blocked activations; c_code goes to `out` (normally the next planes
     of h's own buffer).  Returns the fp32 attention map [B,T,ih,iw]."""
     B, T = words.shape[0], words.shape[2]
     idf, cdf = att.conv_context.weight.shape[0], att.conv_context.weight.shape[1]
-    attn = torch.empty((B, T, h.H, h.W), device=h.device, dtype=torch.float32)
-    m8 = None if mask is None else mask.to(device=h.device, dtype=torch.uint8).contiguous()
-    if idf == 32 and T <= 20:
-        call('tgsr_attn_fwd_blocked', h.device, ptr(h.buf), h.P, h.p0, ptr(words.contiguous()),
-             ptr(att.conv_context.weight.detach().contiguous()), ptr(m8), ptr(out.buf), out.P, out.p0, ptr(attn),
-             B, idf, cdf, h.H * h.W, T, h.fmt)
+    m8 = mask if mask is None or mask.dtype == torch.uint8 else mask.to(device=h.device, dtype=torch.uint8).contiguous()
+    if attention_blocked_supported(idf, T, h.H * h.W):
+        if sfrag is None:
+            sfrag = attention_project(att, words, h.fmt)
+        attn = torch.empty((B, T, h.H, h.W), device=h.device, dtype=torch.float32)
+        call('tgsr_attn_fwd_blocked', h.device, ptr(h.buf), h.P, h.p0, ptr(sfrag), ptr(m8), ptr(out.buf), out.P, out.p0,
+             ptr(attn), B, idf, h.H * h.W, T, h.fmt)
         return attn
-    # outside the blocked kernel's envelope (long captions): fp32 kernel + layout conversion
+    # outside the blocked kernel's envelope (long captions, odd sizes): fp32 kernel + layout conversion
     wctx, attn = ops.attention_fwd(tc.to_nchw(h), words, att.conv_context.weight.detach(), mask)
     tc.to_blocked(wctx, out=out)
     return attn
@@ -119,7 +135,7 @@ def attention(h: Blocked, att, words: Tensor, mask: Optional[Tensor], out: Block
 
 # ---------------------------------------------------------------- stages and nets
 def stage(st, h: Optional[Blocked], LR: Optional[Tensor], words: Tensor, mask, out_planes: Optional[int],
-          fmt: int = 0):
+          fmt: int = 0, sfrag: Optional[Tensor] = None):
     """INIT_STAGE_GImgup (LR given) / NEXT_STAGE_G (h given); util.py:763-777 / :807-823.
     `h` must be the first 32-channel view of a 64-channel buffer: c_code is appended in place."""
     ngf = st.gf_dim
@@ -130,7 +146,7 @@ def stage(st, h: Optional[Blocked], LR: Optional[Tensor], words: Tensor, mask, o
     else:
         assert h.p0 == 0 and h.P * 8 >= 2 * ngf, 'h_code must live in a concat-sized buffer'
         cat = Blocked(h.buf, 0, 2 * ngf)
-    att = attention(h, st.att, words, mask, out=cat.slice(ngf, ngf))
+    att = attention(h, st.att, words, mask, out=cat.slice(ngf, ngf), sfrag=sfrag)
     x = cat
     for rb in st.residual:
         x = res_block(x, rb)
@@ -146,11 +162,18 @@ def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, hea
     atts: List[Tensor] = []
     feats: List[Blocked] = []
     c_code, mu, logvar = net.ca_net(sent)
+    if mask is not None and mask.dtype != torch.uint8:       # one conversion per forward, not one per stage
+        mask = mask.to(device=LR.device, dtype=torch.uint8).contiguous()
     h = None
     n = len(stages)
+    # the word projections depend on the captions only: all stages' operand images first
+    size = LR.shape[2] * LR.shape[3]
+    sfrags = [attention_project(st.att, words, fmt)
+              if attention_blocked_supported(st.att.conv_context.weight.shape[0], words.shape[2], size * 4 ** i) else None
+              for i, st in enumerate(stages)]
     for i, (st, hd) in enumerate(zip(stages, heads)):
         planes = 8 if i + 1 < n else 4                     # leave room for the next stage's c_code
-        h, att = stage(st, h, LR if i == 0 else None, words, mask, planes, fmt)
+        h, att = stage(st, h, LR if i == 0 else None, words, mask, planes, fmt, sfrags[i])
         imgs.append(image_head(h, hd.img))
         atts.append(att)
         feats.append(h)
