@@ -113,17 +113,32 @@ class SRPipeline:
 
     # ------------------------------------------------------------------ roofline probes (bench.py)
     @staticmethod
-    def _time_kernel(fn, flush, iters=20, warm=5):
-        for _ in range(warm):
-            fn()
-        ms = 0.0
-        for _ in range(iters):
-            flush.zero_()
-            s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
-            s.record(); fn(); e.record()
-            e.synchronize()
-            ms += s.elapsed_time(e)
-        return ms / iters
+    def _time_kernel(fn, flush, iters=20, warm=3):
+        """L2-cold device time of one op, free of launch latency: two CUDA graphs, `iters` x [L2-flushing
+        memset, op] and `iters` x [memset]; the difference of their CUDA-event durations / iters."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warm):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g_both, g_flush = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_both):
+            for _ in range(iters):
+                flush.zero_(); fn()
+        with torch.cuda.graph(g_flush):
+            for _ in range(iters):
+                flush.zero_()
+
+        def timed(g):
+            best = float('inf')
+            for _ in range(4):
+                s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+                s.record(); g.replay(); e.record(); e.synchronize()
+                best = min(best, s.elapsed_time(e))
+            return best
+        return (timed(g_both) - timed(g_flush)) / iters
 
     @torch.no_grad()
     def dominant_kernel_roofline(self, B, flush, pk):
@@ -148,7 +163,7 @@ class SRPipeline:
         ms = self._time_kernel(fn, flush)
         ach = flops / (ms * 1e-3) / 1e12
         return {'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': ach / pk['bf16'],
-                'traffic': None, 'kernel': kernel, 'ms_per_launch': ms, 'flops_per_launch': flops,
+                'traffic': _ncu_traffic('conv3x3_tc_kernel<64,128,CONV,GLU> B=32 128x128') if (B == 32 and is_16bit()) else None, 'kernel': kernel, 'ms_per_launch': ms, 'flops_per_launch': flops,
                 'peak_source': pk['source'] + ' cuBLAS bf16 burst (kernel timed alone)'}
 
     @torch.no_grad()
@@ -165,8 +180,10 @@ class SRPipeline:
             from . import fast, tc, fmt_for
             cat = tc.Blocked.empty(B, 64, 128, 128, self.device, fmt=fmt_for('low'))
             cat.buf.normal_(0, 0.5)
-            fn = lambda: fast.attention(cat.slice(0, 32), att, ctx, mask, out=cat.slice(32, 32))
-            e, kernel = 2, 'attn_blocked_kernel (16-bit blocked activations, fp32 maps)'
+            m8 = mask.to(torch.uint8)
+            sfrag = fast.attention_project(att, ctx, cat.fmt)        # per-caption operand image, as inside a forward
+            fn = lambda: fast.attention(cat.slice(0, 32), att, ctx, m8, out=cat.slice(32, 32), sfrag=sfrag)
+            e, kernel = 2, 'attn_blocked_kernel (16-bit blocked activations, fp32 maps; word projection precomputed per caption)'
         else:
             x = torch.randn(B, idf, 128, 128, device=self.device) * 0.5
             fn, e, kernel = (lambda: att(x, ctx)), 4, 'attn_fwd_f32_kernel (fp32 NCHW I/O)'
@@ -174,7 +191,7 @@ class SRPipeline:
         ms = self._time_kernel(fn, flush)
         ach = nbytes / (ms * 1e-3) / 1e9
         return {'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
-                'traffic': None, 'kernel': kernel, 'ms_per_launch': ms, 'bytes_per_launch': nbytes,
+                'traffic': _ncu_traffic('attn_blocked_kernel B=32 128x128 T=18') if (B == 32 and is_16bit()) else None, 'kernel': kernel, 'ms_per_launch': ms, 'bytes_per_launch': nbytes,
                 'peak_source': pk['source'] + ' copy bandwidth'}
 
     def _pin(self, name, t):
@@ -212,6 +229,17 @@ class SRPipeline:
         out_host.copy_(sr, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_host
+
+
+def _ncu_traffic(key: str):
+    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json)."""
+    import json, os
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', 'ncu_traffic.json')
+    try:
+        e = json.load(open(p))[key]
+        return e['read'] + e['write']
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def randomize_bn_stats(modules, seed: int):
