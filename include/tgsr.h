@@ -60,6 +60,17 @@ int tgsr_attn_fwd_f32(const float* input, const float* context, const float* w_c
                       const uint8_t* mask, float* wctx, float* attn, int B, int idf, int cdf,
                       int Q, int T, tgsr_stream_t stream);
 
+/* a1 at fp32 accuracy on the warp-level tensor-core path (3xTF32 split operands, fp32 accumulate): the word
+ * projection runs once per caption into `ws` (tgsr_attn_f32_ws_floats(B, idf, T) floats, caller-owned), then one
+ * persistent kernel streams the pixels with float4-only global accesses.  Same tensors and semantics as
+ * tgsr_attn_fwd_f32.  Envelope (tgsr_attn_f32_tc_supported): idf % 8 == 0, idf <= 256, T <= 48, Q % 32 == 0 and the
+ * operand images fit shared memory ((idf/8) * ceil8(T)/8 <= ~120). */
+size_t tgsr_attn_f32_ws_floats(int B, int idf, int T);
+int tgsr_attn_f32_tc_supported(int B, int idf, int cdf, int Q, int T, int has_mask);
+int tgsr_attn_fwd_f32_tc(const float* input, const float* context, const float* w_ctx, const uint8_t* mask,
+                         float* ws, float* wctx, float* attn, int B, int idf, int cdf, int Q, int T,
+                         tgsr_stream_t stream);
+
 /* ---- a2: func_attention, GlobalAttention.py:33-74 (DAMSM double softmax), forward ----------
  * query [B,ndf,Tq], context [B,ndf,S], wctx [B,ndf,Tq], attn [B,Tq,S].  Tq <= 48, S <= 1024. */
 int tgsr_func_attn_fwd_f32(const float* query, const float* context, float gamma1, float* wctx,

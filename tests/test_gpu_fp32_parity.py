@@ -62,6 +62,20 @@ def test_attention_vs_oracle(B, idf, cdf, ih, iw, T, ragged):
     close(attn.sum(1), torch.ones(B, ih, iw), rtol=0, atol=1e-5)          # rows sum to one
 
 
+def test_attention_cuda_core_kernel_kept():
+    """The CUDA-core fp32 kernel (used outside the tensor-core envelope) on a shape the tensor-core path would take."""
+    from tgsr_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    inp = torch.randn(2, 32, 16, 16, generator=g) * 0.5; ctx = torch.randn(2, 256, 18, generator=g) * 0.5
+    w = torch.randn(32, 256, 1, 1, generator=g) * 0.1
+    mask = torch.arange(18)[None] >= torch.tensor([18, 7])[:, None]
+    ref_w, ref_a = O.global_attention(inp, ctx, w, mask)
+    for tcores in (False, True):
+        wctx, attn = ops.attention_fwd(inp.to(DEV), ctx.to(DEV), w.to(DEV), mask.to(DEV), tensor_cores=tcores)
+        close(attn, ref_a, rtol=1e-5, atol=1e-7); close(wctx, ref_w, rtol=1e-4, atol=5e-5)
+        assert torch.equal(attn.cpu() == 0, ref_a == 0)
+
+
 def test_attention_errors():
     att = tgsr_b200.GlobalAttentionGeneral(32, 256).to(DEV)
     with pytest.raises(RuntimeError, match='unsupported'):

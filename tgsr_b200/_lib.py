@@ -30,6 +30,9 @@ _SIGS = {
     'tgsr_sm_count': ([], C.c_int),
     'tgsr_launch_count': ([], C.c_ulonglong),
     'tgsr_attn_fwd_f32': ([C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p], C.c_int),
+    'tgsr_attn_f32_ws_floats': ([C.c_int] * 3, C.c_size_t),
+    'tgsr_attn_f32_tc_supported': ([C.c_int] * 6, C.c_int),
+    'tgsr_attn_fwd_f32_tc': ([C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p], C.c_int),
     'tgsr_func_attn_fwd_f32': ([C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p], C.c_int),
     'tgsr_conv2d_f32': ([C.c_void_p] * 6 + [C.c_float, C.c_float, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p], C.c_int),
     'tgsr_bn_fold_f32': ([C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p], C.c_int),

@@ -11,6 +11,7 @@ int init_conv_tc(void);     // conv_tc.cu (tcgen05 path)
 int init_blocked_misc(void);  // blocked_misc.cu
 int init_lstm(void);          // lstm.cu
 int init_attention_mma(void);  // attention_mma.cu
+int init_attention_f32_mma(void);  // attention_f32_mma.cu
 }  // namespace tgsr
 
 extern "C" {
@@ -45,6 +46,8 @@ int tgsr_init(int device) {
   s = tgsr::init_blocked_misc();
   if (s != TGSR_OK) return s;
   s = tgsr::init_attention_mma();
+  if (s != TGSR_OK) return s;
+  s = tgsr::init_attention_f32_mma();
   if (s != TGSR_OK) return s;
   return tgsr::init_lstm();
 }

@@ -21,8 +21,10 @@ def _f32c(t: Tensor, name: str) -> Tensor:
 
 
 # ------------------------------------------------------------------ a1
-def attention_fwd(inp: Tensor, context: Tensor, w_ctx: Tensor, mask: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
-    """GlobalAttentionGeneral.forward (GlobalAttention.py:87-130) -> (weightedContext, attn)."""
+def attention_fwd(inp: Tensor, context: Tensor, w_ctx: Tensor, mask: Optional[Tensor],
+                  tensor_cores: bool = True) -> Tuple[Tensor, Tensor]:
+    """GlobalAttentionGeneral.forward (GlobalAttention.py:87-130) -> (weightedContext, attn).
+    tensor_cores=False keeps the CUDA-core kernel even inside the tensor-core kernel's envelope (tests)."""
     inp = _f32c(inp, 'input'); context = _f32c(context, 'context'); w_ctx = _f32c(w_ctx, 'conv_context.weight')
     if inp.dim() != 4 or context.dim() != 3:
         raise ValueError('expected input [B,idf,ih,iw] and context [B,cdf,T]')
@@ -38,8 +40,15 @@ def attention_fwd(inp: Tensor, context: Tensor, w_ctx: Tensor, mask: Optional[Te
         m8 = mask.to(device=inp.device, dtype=torch.uint8).contiguous()
     wctx = torch.empty_like(inp)
     attn = torch.empty((B, T, ih, iw), device=inp.device, dtype=torch.float32)
-    call('tgsr_attn_fwd_f32', inp.device, ptr(inp), ptr(context), ptr(w_ctx), ptr(m8), ptr(wctx), ptr(attn),
-         B, idf, cdf, ih * iw, T)
+    lib = _lib.load()
+    if tensor_cores and lib.tgsr_attn_f32_tc_supported(B, idf, cdf, ih * iw, T, int(m8 is not None)):
+        # tensor-core path (3xTF32, fp32 accuracy): per-caption projection workspace + persistent pixel kernel
+        ws = torch.empty(lib.tgsr_attn_f32_ws_floats(B, idf, T), device=inp.device, dtype=torch.float32)
+        call('tgsr_attn_fwd_f32_tc', inp.device, ptr(inp), ptr(context), ptr(w_ctx), ptr(m8), ptr(ws), ptr(wctx), ptr(attn),
+             B, idf, cdf, ih * iw, T)
+    else:
+        call('tgsr_attn_fwd_f32', inp.device, ptr(inp), ptr(context), ptr(w_ctx), ptr(m8), ptr(wctx), ptr(attn),
+             B, idf, cdf, ih * iw, T)
     return wctx, attn
 
 

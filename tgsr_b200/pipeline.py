@@ -114,31 +114,8 @@ class SRPipeline:
     # ------------------------------------------------------------------ roofline probes (bench.py)
     @staticmethod
     def _time_kernel(fn, flush, iters=20, warm=3):
-        """L2-cold device time of one op, free of launch latency: two CUDA graphs, `iters` x [L2-flushing
-        memset, op] and `iters` x [memset]; the difference of their CUDA-event durations / iters."""
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warm):
-                fn()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        g_both, g_flush = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_both):
-            for _ in range(iters):
-                flush.zero_(); fn()
-        with torch.cuda.graph(g_flush):
-            for _ in range(iters):
-                flush.zero_()
-
-        def timed(g):
-            best = float('inf')
-            for _ in range(4):
-                s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
-                s.record(); g.replay(); e.record(); e.synchronize()
-                best = min(best, s.elapsed_time(e))
-            return best
-        return (timed(g_both) - timed(g_flush)) / iters
+        from .timing import cold_time_ms
+        return cold_time_ms(fn, flush, iters=iters, warm=warm)
 
     @torch.no_grad()
     def dominant_kernel_roofline(self, B, flush, pk):
