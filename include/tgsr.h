@@ -192,6 +192,11 @@ int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const void* sfrag, con
                           int yP, int yp0, float* attn, int B, int idf, int Q, int T, int fmt,
                           tgsr_stream_t stream);
 
+/* Eval-flow edge: uint8 image quantisation of trainer_objective.py:153-155 on the device,
+ * y[i] = uint8(round_half_even(clamp((x[i] + 1.0f) * 127.5f, 0, 255))), fp32 arithmetic as numpy does it.
+ * x fp32 (16-byte aligned), y uint8 (4-byte aligned), n elements. */
+int tgsr_quantize_u8(const float* x, uint8_t* y, size_t n, tgsr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

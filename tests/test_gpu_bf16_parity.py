@@ -187,3 +187,29 @@ def test_graph_replay_matches_eager():
     for a, b in zip(eager2, rep2):
         assert torch.equal(a, b)
     assert pipe.last_graph_kernels >= 40
+
+
+@pytest.mark.gpu
+def test_quantize_u8_and_pipelined_host_api():
+    """Device-side uint8 quantisation (trainer_objective.py:153-155) is bit-exact with the numpy formula, and the
+    pipelined submit/result API returns the same image as the blocking call."""
+    import numpy as np
+    from tgsr_b200 import ops
+    from tgsr_b200.pipeline import SRPipeline
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 3, 37, 41, generator=g) * 0.8
+    x[0, 0, 0, :8] = torch.tensor([-1.0, 1.0, -1.5, 1.5, 0.0, 1.0 / 127.5 * 0.5 - 1.0, 0.0039215689, -0.99607843])
+    ref = np.round(np.maximum(0, np.minimum(255, (x.numpy() + 1.0) * 127.5))).astype(np.uint8)
+    got = ops.quantize_u8(x.to(DEV)).cpu().numpy()
+    assert np.array_equal(got, ref)
+    tgsr_b200.set_precision('mixed16')
+    pipe = SRPipeline(50, device=DEV, seed=3, randomize_bn=True)
+    B = 4
+    LR = O.synth_lr(B, 32, seed=7).pin_memory()
+    caps, lens = O.synth_captions(B, 50, seed=8, words_num=18)
+    caps, lens = caps.pin_memory(), lens.pin_memory()
+    blocking = pipe.forward_host(LR, caps, lens).clone()
+    t1 = pipe.submit(LR, caps, lens, out='fp32'); t2 = pipe.submit(LR, caps, lens, out='uint8'); t3 = pipe.submit(LR, caps, lens, out='uint8')
+    assert torch.equal(pipe.result(t1), blocking)
+    u8 = np.round(np.maximum(0, np.minimum(255, (blocking.numpy() + 1.0) * 127.5))).astype(np.uint8)
+    assert np.array_equal(pipe.result(t2).numpy(), u8) and np.array_equal(pipe.result(t3).numpy(), u8)

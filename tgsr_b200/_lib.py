@@ -47,6 +47,7 @@ _SIGS = {
     'tgsr_img_head_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
                          + [C.c_int] * 7 + [C.c_void_p], C.c_int),
     'tgsr_conv_in_blocked': ([C.c_void_p] * 6 + [C.c_int] * 7 + [C.c_void_p], C.c_int),
+    'tgsr_quantize_u8': ([C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p], C.c_int),
     'tgsr_attn_sfrag_bytes': ([C.c_int], C.c_size_t),
     'tgsr_attn_project': ([C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p], C.c_int),
     'tgsr_attn_fwd_blocked': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

@@ -182,15 +182,20 @@ def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, hea
     return imgs, atts, mu, logvar
 
 
-def netg_high(net, x: Tensor, x_sub: Optional[Tensor], SRb, a: float, one: float, tail, feats=None,
-              fmt: int = 0) -> List[Tensor]:
-    """Trunk of NetG_high / NetG_highweight (model.py:264-298).  `tail` = [(body, upscale), ...] after
-    the first upscale."""
+def netg_high_trunk(net, x: Tensor, x_sub: Optional[Tensor], fmt: int = 0) -> Blocked:
+    """First, text-independent part of NetG_high / NetG_highweight (model.py:264-279): convin, six ResBlocks and
+    upscale2x.  It needs nothing from the text encoder or G_SR_NET_low, so the eval pipeline runs it on a second
+    stream next to them."""
     B, _, H, W = x.shape
     h = conv_in(net.convin, x, Blocked.empty(B, 32, H, W, x.device, fmt=fmt), x_sub)
     for rb in net.residual:
         h = res_block(h, rb)
-    h = up_block(h, net.upscale2x)
+    return up_block(h, net.upscale2x)
+
+
+def netg_high_finish(net, h: Blocked, SRb, a: float, one: float, tail, feats=None) -> List[Tensor]:
+    """Rest of the trunk (model.py:280-298): image heads with the fused `one*y + a*SRb`, residual24/48 bodies and
+    upscale4x/8x.  `tail` = [(body, upscale), ...] after the first upscale."""
     if feats is not None: feats.append(tc.to_nchw(h))
     ims = [image_head(h, net.conv_output, SRb[0], a, one)]
     for k, (body, up) in enumerate(tail):
@@ -198,3 +203,9 @@ def netg_high(net, x: Tensor, x_sub: Optional[Tensor], SRb, a: float, one: float
         if feats is not None: feats.append(tc.to_nchw(h))
         ims.append(image_head(h, net.conv_output, SRb[k + 1], a, one))
     return ims
+
+
+def netg_high(net, x: Tensor, x_sub: Optional[Tensor], SRb, a: float, one: float, tail, feats=None,
+              fmt: int = 0) -> List[Tensor]:
+    """Trunk of NetG_high / NetG_highweight (model.py:264-298)."""
+    return netg_high_finish(net, netg_high_trunk(net, x, x_sub, fmt), SRb, a, one, tail, feats)

@@ -156,3 +156,16 @@ def lstm_bidir_tab(captions: Tensor, cap_lens: Tensor, xtab: Tensor, w_hh: Tenso
     call('tgsr_lstm_bidir_fwd_tab_f32', dev, ptr(captions), ptr(cap_lens), ptr(xtab), ptr(_f32c(w_hh, 'w_hh')), ptr(words),
          ptr(sent), B, Tcap, Tmax, xtab.shape[0], H)
     return words, sent
+
+
+# ------------------------------------------------------------------ eval-flow edge
+def quantize_u8(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """uint8 image of trainer_objective.py:153-155: round(clip((x + 1) * 127.5, 0, 255)), same shape as x."""
+    x = _f32c(x, 'x')
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
+    elif out.dtype != torch.uint8 or out.numel() != x.numel() or not out.is_contiguous() or out.device != x.device:
+        raise ValueError('out must be a contiguous uint8 tensor with as many elements as x on the same device')
+    import ctypes as C
+    call('tgsr_quantize_u8', x.device, ptr(x), ptr(out), C.c_size_t(x.numel()))
+    return out

@@ -30,6 +30,9 @@ class SRPipeline:
         for m in (self.text_encoder, self.netGL, self.netGH):
             m.to(self.device).eval()
         self._pinned = {}
+        self._side = None
+        self._copy_stream = None
+        self._slots, self._tickets, self._ticket = {}, {}, 0
 
     def load_generators(self, sd_netG, sd_netGH):
         self.netGL.load_state_dict(sd_netG, strict=True)
@@ -51,11 +54,31 @@ class SRPipeline:
 
     @torch.no_grad()
     def text_and_generate(self, LR, captions, cap_lens, tmax: int):
-        """forward_device with max(cap_lens) known on the host: no device->host read anywhere."""
+        """forward_device with max(cap_lens) known on the host: no device->host read anywhere.
+        In the 16-bit modes the text-independent head of NetG_highweight (convin, 6 ResBlocks, upscale2x at 32x32 --
+        small grids) runs on a second stream next to the text encoder (a latency-bound cluster kernel) and the
+        first G_SR_NET_low stage; the streams join before the first high-frequency image head."""
+        from . import fast, fmt_for, is_16bit
+        gh = self.netGH
+        overlap = (is_16bit() and self.variant == 'x8' and gh.low == 'lr' and LR.shape[2] % 16 == 0 and LR.shape[3] % 8 == 0
+                   and gh.convin[0].weight.shape[0] == 64)
+        if overlap:
+            cur = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                h_high = fast.netg_high_trunk(gh, LR, None, fmt_for('high'))
         words_embs, sent_emb = self.text_encoder._forward_tmax(captions, cap_lens, tmax)
         mask = (captions == 0)[:, :tmax]
         fake_imgL, attention_maps, mu, logvar = self.netGL(LR, sent_emb, words_embs, mask)
-        fine_im, a, one = self.netGH(LR, fake_imgL, LR)
+        if overlap:
+            cur.wait_stream(self._side)
+            h_high.buf.record_stream(cur)
+            fine_im = fast.netg_high_finish(gh, h_high, fake_imgL, 0.5, 1.0,
+                                            [(gh.residual24, gh.upscale4x), (gh.residual48, gh.upscale8x)])
+        else:
+            fine_im, a, one = gh(LR, fake_imgL, LR)
         return fine_im, fake_imgL, attention_maps
 
     # ------------------------------------------------------------------ CUDA-graph replay
@@ -179,6 +202,62 @@ class SRPipeline:
         buf.copy_(t)
         return buf
 
+    # ------------------------------------------------------------------ pipelined host API
+    @torch.no_grad()
+    def submit(self, LR_host: torch.Tensor, captions_host: torch.Tensor, cap_lens_host: torch.Tensor,
+               out: str = 'uint8') -> int:
+        """Enqueue one batch from pinned host buffers and return a ticket for `result`.  Two output slots
+        alternate: the device->host copy of batch i runs on a copy stream while batch i+1 computes.
+        out='uint8': the saved-image format of trainer_objective.py:153-155, quantised on the device
+        ([B,3,H,W] uint8); out='fp32': the raw SR tensor."""
+        tmax = int(cap_lens_host.max())                                    # host-side, no device sync
+        B, size, Tcap = LR_host.shape[0], LR_host.shape[2], captions_host.shape[1]
+        st = self.static_inputs(B, tmax, Tcap, size)
+        if st is None:
+            self.forward_graph(LR_host.to(self.device), captions_host.to(self.device), cap_lens_host.to(self.device), tmax)
+            st = self.static_inputs(B, tmax, Tcap, size)
+        cur = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        st[0].copy_(LR_host, non_blocking=True)                            # H2D straight into the graph's inputs
+        st[1].copy_(captions_host, non_blocking=True)
+        st[2].copy_(cap_lens_host, non_blocking=True)
+        sr = self.forward_graph(st[0], st[1], st[2], tmax)[0][-1]
+        key = (tuple(sr.shape), out)
+        slots = self._slots.get(key)
+        if slots is None:
+            slots = []
+            for _ in range(2):
+                s = _Slot()
+                dt = torch.uint8 if out == 'uint8' else torch.float32
+                s.dev = torch.empty(sr.shape, device=self.device, dtype=dt)
+                s.host = torch.empty(sr.shape, dtype=dt, pin_memory=True)
+                s.done = torch.cuda.Event(); s.copied = torch.cuda.Event()
+                s.copied.record(cur)
+                slots.append(s)
+            self._slots[key] = slots
+        self._ticket += 1
+        s = slots[self._ticket & 1]
+        cur.wait_event(s.copied)                                           # the slot's previous copy has left the device
+        if out == 'uint8':
+            from . import ops
+            ops.quantize_u8(sr, s.dev)
+        else:
+            s.dev.copy_(sr, non_blocking=True)
+        s.done.record(cur)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(s.done)
+            s.host.copy_(s.dev, non_blocking=True)
+            s.copied.record(self._copy_stream)
+        self._tickets[self._ticket] = s
+        return self._ticket
+
+    def result(self, ticket: int) -> torch.Tensor:
+        """Block until the batch of `ticket` is in host memory; the buffer is reused two submits later."""
+        s = self._tickets.pop(ticket)
+        s.copied.synchronize()
+        return s.host
+
     @torch.no_grad()
     def forward_host(self, LR_host: torch.Tensor, captions_host: torch.Tensor, cap_lens_host: torch.Tensor,
                      out_host: Optional[torch.Tensor] = None, use_graph: bool = True) -> torch.Tensor:
@@ -206,6 +285,10 @@ class SRPipeline:
         out_host.copy_(sr, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_host
+
+
+class _Slot:
+    __slots__ = ('dev', 'host', 'done', 'copied')
 
 
 def _ncu_traffic(key: str):
