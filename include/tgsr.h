@@ -192,6 +192,42 @@ int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const void* sfrag, con
                           int yP, int yp0, float* attn, int B, int idf, int Q, int T, int fmt,
                           tgsr_stream_t stream);
 
+/* ============================ training-mode generator (fp32 NCHW) ===============================
+ * The reference trains through autograd + cuDNN; these are the explicit forward/backward kernels of the same
+ * arithmetic (nn.BatchNorm2d batch statistics, GLU util.py:45-53, ResBlock skip util.py:126-130, nn.Upsample(2)
+ * util.py:76, conv3x3/conv5x5 util.py:62-69, tanh head + `one*y + a*SRb` model.py:224,280, GlobalAttention.py:87-130). */
+
+/* BatchNorm2d train-mode statistics of x [B,C,HW]: mean[c], invstd[c] = 1/sqrt(biased var + eps); updates
+ * running_mean / running_var (unbiased var, momentum) in place when not NULL. */
+int tgsr_bn_stats_f32(const float* x, float* mean, float* invstd, float* running_mean, float* running_var,
+                      float momentum, float eps, int B, int C, int HW, tgsr_stream_t stream);
+/* y = act(gamma*(x-mean)*invstd + beta) (+ residual, shaped like y).  act NONE: y [B,C,HW]; act GLU: y [B,C/2,HW]. */
+int tgsr_bn_act_f32(const float* x, const float* mean, const float* invstd, const float* gamma,
+                    const float* beta, const float* residual, float* y, int B, int C, int HW, int act,
+                    tgsr_stream_t stream);
+/* Backward of tgsr_bn_act_f32 through the batch statistics: dx [B,C,HW], dgamma [C], dbeta [C] from dy (shape of y).
+ * (The residual's gradient is dy itself.) */
+int tgsr_bn_act_bwd_f32(const float* x, const float* mean, const float* invstd, const float* gamma,
+                        const float* beta, const float* dy, float* dx, float* dgamma, float* dbeta, int B,
+                        int C, int HW, int act, tgsr_stream_t stream);
+/* wt[ci][co][k-1-ky][k-1-kx] = w[co][ci][ky][kx]: tgsr_conv2d_f32(dy, wt) is the data gradient of conv(x, w). */
+int tgsr_conv_weight_flip_f32(const float* w, float* wt, int Cout, int Cin, int ksize, tgsr_stream_t stream);
+/* Backward of the nearest x2 upsample folded into a conv: y [BC,H,W] = 2x2 block sums of x [BC,2H,2W]. */
+int tgsr_sumpool2x2_f32(const float* x, float* y, int BC, int H, int W, tgsr_stream_t stream);
+/* dw [Cout,Cin,k,k] = weight gradient of conv(x [B,Cin,H,W] (nearest-upsampled x2 if up2x), w) given dy
+ * [B,Cout,Ho,Wo]; dw is overwritten. */
+int tgsr_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, int B, int Cin, int H, int W, int Cout,
+                          int ksize, int up2x, tgsr_stream_t stream);
+/* y = one*tanh(conv) + a*srb (model.py:224,280): dconv = dy*one*(1-t^2), t = (y - a*srb)/one; dsrb = a*dy if not NULL.
+ * srb may be NULL (a plain tanh head). */
+int tgsr_tanh_head_bwd_f32(const float* y, const float* srb, const float* dy, float one, float a, float* dconv,
+                           float* dsrb, size_t n, tgsr_stream_t stream);
+/* Backward of a1: d_input [B,idf,Q] and d_w_ctx [idf,cdf] from d_wctx [B,idf,Q] (and d_attn [B,T,Q] or NULL), with
+ * the forward's attention map `attn`.  ws: 2 * tgsr_attn_f32_ws_floats(B, idf, T) floats.  No gradient to `context`. */
+int tgsr_attn_bwd_f32(const float* input, const float* context, const float* w_ctx, const float* attn,
+                      const float* d_wctx, const float* d_attn, float* ws, float* d_input, float* d_w_ctx,
+                      int B, int idf, int cdf, int Q, int T, tgsr_stream_t stream);
+
 /* Eval-flow edge: uint8 image quantisation of trainer_objective.py:153-155 on the device,
  * y[i] = uint8(round_half_even(clamp((x[i] + 1.0f) * 127.5f, 0, 255))), fp32 arithmetic as numpy does it.
  * x fp32 (16-byte aligned), y uint8 (4-byte aligned), n elements. */

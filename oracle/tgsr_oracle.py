@@ -86,8 +86,25 @@ def glu(x: Tensor) -> Tensor:
     return x[:, :nc] * torch.sigmoid(x[:, nc:])
 
 
+BN_TRAIN = False   # set by train_mode(): nn.BatchNorm2d in train() mode (batch statistics), for the training-step checks
+
+
+class train_mode:
+    """Context manager: the block functions below use batch statistics, as the reference modules do in train() mode."""
+
+    def __enter__(self):
+        global BN_TRAIN
+        self._old, BN_TRAIN = BN_TRAIN, True
+
+    def __exit__(self, *a):
+        global BN_TRAIN
+        BN_TRAIN = self._old
+
+
 def _bn(sd: SD, p: str, x: Tensor) -> Tensor:
-    """nn.BatchNorm2d / BatchNorm1d in eval mode (running statistics)."""
+    """nn.BatchNorm2d / BatchNorm1d in eval mode (running statistics), or batch statistics under train_mode()."""
+    if BN_TRAIN:
+        return F.batch_norm(x, None, None, sd[p + '.weight'], sd[p + '.bias'], True, 0.0, BN_EPS)
     return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'],
                         sd[p + '.weight'], sd[p + '.bias'], False, 0.0, BN_EPS)
 

@@ -109,11 +109,15 @@ def test_blocks_golden(golden):
           atol=2e-5)
 
 
-def test_train_mode_bn_raises():
+def test_train_mode_needs_fp32():
     from tgsr_b200 import blocks
-    m = blocks.ResBlock(32).to(DEV)          # training mode by default
-    with pytest.raises(RuntimeError, match='eval'):
-        m(torch.zeros(1, 32, 8, 8, device=DEV))
+    m = blocks.ResBlock(64).to(DEV)          # training mode by default
+    tgsr_b200.set_precision('mixed16')
+    try:
+        with pytest.raises(RuntimeError, match='fp32'):
+            m(torch.zeros(1, 64, 16, 8, device=DEV))
+    finally:
+        tgsr_b200.set_precision('fp32')
 
 
 def test_rnn_encoder_golden(golden):

@@ -1,0 +1,183 @@
+"""Training-mode parity (-m gpu): the explicit forward/backward kernels of the generator blocks (csrc/train_ops.cu,
+csrc/attention_bwd.cu) against torch.autograd over the CPU oracle (the reference arithmetic with BatchNorm in train()
+mode).  fp32; tolerances cover summation-order differences only."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import tgsr_b200
+from oracle import tgsr_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(autouse=True)
+def _fp32():
+    tgsr_b200.set_eval_defaults()
+    tgsr_b200.set_precision('fp32')
+    yield
+
+
+def close(a, b, rtol=2e-4, atol=2e-5):
+    torch.testing.assert_close(a.detach().cpu(), b.detach(), rtol=rtol, atol=atol)
+
+
+def _randomize(mod, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in mod.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.copy_(1 + 0.2 * torch.randn(m.weight.shape, generator=g))
+            m.bias.data.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+
+
+def _oracle_sd(mod):
+    return {k: (v.detach().cpu().clone().requires_grad_(True) if v.is_floating_point() else v.cpu().clone())
+            for k, v in mod.state_dict().items()}
+
+
+def _check_param_grads(mod, sd, rtol=1e-3, atol=2e-5, skip=()):
+    n = 0
+    for name, p in mod.named_parameters():
+        if any(s in name for s in skip):
+            continue
+        ref = sd[name].grad
+        if ref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert p.grad is not None, name
+        scale = max(1.0, float(ref.abs().max()))
+        torch.testing.assert_close(p.grad.cpu(), ref, rtol=rtol, atol=atol * scale, msg=lambda m, name=name: name + ': ' + m)
+        n += 1
+    assert n > 0
+
+
+@pytest.mark.parametrize('C,H,W,B', [(32, 16, 16, 3), (64, 8, 24, 2)])
+def test_resblock_train(C, H, W, B):
+    from tgsr_b200 import blocks
+    torch.manual_seed(C + H)
+    m = blocks.ResBlock(C).to(DEV).train(); _randomize(m, 1)
+    sd = _oracle_sd(m)
+    rm0 = m.block[1].running_mean.clone()
+    x = torch.randn(B, C, H, W) * 0.7
+    xg = x.to(DEV).requires_grad_(True); xr = x.clone().requires_grad_(True)
+    y = m(xg)
+    with O.train_mode():
+        yr = O.res_block(sd, '', xr) if False else None
+    # the oracle's key prefix convention is '<p>.block.0'; ResBlock.state_dict keys are 'block.0.weight'
+    sdp = {'r.' + k: v for k, v in sd.items()}
+    with O.train_mode():
+        yr = O.res_block(sdp, 'r', xr)
+    close(y, yr)
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(2))
+    y.backward(gy.to(DEV)); yr.backward(gy)
+    close(xg.grad, xr.grad, rtol=1e-3, atol=2e-5)
+    _check_param_grads(m, sd)
+    # running statistics follow nn.BatchNorm2d.train(): momentum 0.1, unbiased variance
+    z = F.conv2d(x, sd['block.0.weight'].detach(), None, 1, 1)
+    exp_rm = 0.9 * rm0.cpu() + 0.1 * z.mean((0, 2, 3))
+    close(m.block[1].running_mean, exp_rm, rtol=1e-4, atol=1e-6)
+    exp_rv = 0.9 * torch.ones(2 * C) + 0.1 * z.var((0, 2, 3), unbiased=True)
+    close(m.block[1].running_var, exp_rv, rtol=1e-4, atol=1e-6)
+    assert int(m.block[1].num_batches_tracked) == 1
+
+
+def test_upblock_and_heads_train():
+    from tgsr_b200 import blocks
+    torch.manual_seed(3)
+    up = blocks.upBlock(64, 32).to(DEV).train(); _randomize(up, 4)
+    sd = {'u.' + k: v for k, v in _oracle_sd(up).items()}
+    x = torch.randn(2, 64, 8, 12) * 0.5
+    xg = x.to(DEV).requires_grad_(True); xr = x.clone().requires_grad_(True)
+    y = up(xg)
+    with O.train_mode():
+        yr = O.up_block(sd, 'u', xr)
+    close(y, yr)
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(5))
+    y.backward(gy.to(DEV)); yr.backward(gy)
+    close(xg.grad, xr.grad, rtol=1e-3, atol=2e-5)
+    _check_param_grads(up, {k[2:]: v for k, v in sd.items()})
+    # conv5x5 + tanh head with the fused one*y + a*SRb (model.py:223-226,280)
+    head = blocks._ImageHead(blocks.conv5x5(32, 3), torch.nn.Tanh()).to(DEV).train()
+    w = head[0].weight.detach().cpu().clone().requires_grad_(True)
+    h = torch.randn(2, 32, 16, 20) * 0.5; srb = torch.randn(2, 3, 16, 20) * 0.3
+    hg = h.to(DEV).requires_grad_(True); sg = srb.to(DEV).requires_grad_(True)
+    hr = h.clone().requires_grad_(True); sr = srb.clone().requires_grad_(True)
+    out = head(hg, sg, 0.5, 1.0)
+    ref = 1.0 * torch.tanh(F.conv2d(hr, w, None, 1, 2)) + 0.5 * sr
+    close(out, ref)
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(6))
+    out.backward(go.to(DEV)); ref.backward(go)
+    close(hg.grad, hr.grad, rtol=1e-3, atol=2e-5); close(sg.grad, sr.grad); close(head[0].weight.grad, w.grad, rtol=1e-3, atol=5e-5)
+    # conv3x3 head without activation (GET_IMAGE_G_noAct, util.py:909-919)
+    g3 = blocks.GET_IMAGE_G_noAct(32).to(DEV).train()
+    w3 = g3.img[0].weight.detach().cpu().clone().requires_grad_(True)
+    hg2 = h.to(DEV).requires_grad_(True); hr2 = h.clone().requires_grad_(True)
+    o3 = g3(hg2); r3 = F.conv2d(hr2, w3, None, 1, 1)
+    close(o3, r3)
+    o3.backward(go.to(DEV)); r3.backward(go)
+    close(hg2.grad, hr2.grad, rtol=1e-3, atol=2e-5); close(g3.img[0].weight.grad, w3.grad, rtol=1e-3, atol=5e-5)
+
+
+@pytest.mark.parametrize('B,idf,cdf,ih,iw,T,ragged', [(3, 32, 256, 16, 16, 18, True), (2, 32, 256, 9, 7, 18, False),
+                                                       (2, 64, 64, 16, 8, 30, True)])
+def test_attention_train(B, idf, cdf, ih, iw, T, ragged):
+    g = torch.Generator().manual_seed(B + T)
+    inp = torch.randn(B, idf, ih, iw, generator=g) * 0.5
+    ctx = torch.randn(B, cdf, T, generator=g) * 0.5
+    w = torch.randn(idf, cdf, 1, 1, generator=g) * (1.6 / cdf ** 0.5)
+    mask = None
+    if ragged:
+        lens = torch.randint(2, T + 1, (B,), generator=g); lens[0] = T
+        mask = torch.arange(T)[None] >= lens[:, None]
+    att = tgsr_b200.GlobalAttentionGeneral(idf, cdf).to(DEV).train()
+    att.conv_context.weight.data.copy_(w)
+    att.applyMask(None if mask is None else mask.to(DEV))
+    xg = inp.to(DEV).requires_grad_(True)
+    wctx, attn = att(xg, ctx.to(DEV))
+    xr = inp.clone().requires_grad_(True); wr = w.clone().requires_grad_(True)
+    ref_w, ref_a = O.global_attention(xr, ctx, wr, mask)
+    close(wctx, ref_w, rtol=1e-4, atol=5e-5); close(attn, ref_a, rtol=1e-5, atol=1e-7)
+    g1 = torch.randn(ref_w.shape, generator=g); g2 = torch.randn(ref_a.shape, generator=g)
+    (wctx * g1.to(DEV)).sum().backward(retain_graph=True)
+    (ref_w * g1).sum().backward(retain_graph=True)
+    close(xg.grad, xr.grad, rtol=1e-3, atol=2e-5)
+    close(att.conv_context.weight.grad, wr.grad, rtol=1e-3, atol=1e-4)
+    # gradient through the returned attention maps as well
+    xg.grad = None; att.conv_context.weight.grad = None; xr.grad = None; wr.grad = None
+    ((wctx * g1.to(DEV)).sum() + (attn * g2.to(DEV)).sum()).backward()
+    ((ref_w * g1).sum() + (ref_a * g2).sum()).backward()
+    close(xg.grad, xr.grad, rtol=1e-3, atol=2e-5)
+    close(att.conv_context.weight.grad, wr.grad, rtol=1e-3, atol=1e-4)
+
+
+def test_generator_train_step_grads():
+    """Whole G_SR_NET_low + NetG_highweight in train() mode on a 16x16 LR batch: outputs, the MSE loss against a target
+    pyramid and every parameter gradient against autograd over the oracle."""
+    from tgsr_b200 import nets
+    torch.manual_seed(11)
+    gl = nets.G_SR_NET_low().to(DEV).train(); gh = nets.NetG_highweight(low='lr').to(DEV).train()
+    _randomize(gl, 12); _randomize(gh, 13)
+    sdl, sdh = _oracle_sd(gl), _oracle_sd(gh)
+    B, T = 2, 18
+    LR = O.synth_lr(B, 16, seed=14)
+    g = torch.Generator().manual_seed(15)
+    words = torch.randn(B, 256, T, generator=g) * 0.5; sent = torch.randn(B, 256, generator=g) * 0.5
+    mask = torch.zeros(B, T, dtype=torch.bool); mask[1, 12:] = True
+    targets = [torch.randn(B, 3, 16 * 2 ** (k + 1), 16 * 2 ** (k + 1), generator=g) * 0.5 for k in range(3)]
+
+    imgs, atts, mu, lv = gl(LR.to(DEV), sent.to(DEV), words.to(DEV), mask.to(DEV))
+    fine, a, one = gh(LR.to(DEV), imgs, LR.to(DEV))
+    loss = sum(F.mse_loss(f, t.to(DEV)) for f, t in zip(fine, targets)) + sum(F.mse_loss(f, t.to(DEV)) for f, t in zip(imgs, targets))
+    loss.backward()
+
+    with O.train_mode():
+        r_imgs, r_atts, r_mu, r_lv, _ = O.g_sr_net_low(sdl, LR, sent, words, mask)
+        r_fine = O.netg_high(sdh, LR, r_imgs, LR, low='lr')
+    r_loss = sum(F.mse_loss(f, t) for f, t in zip(r_fine, targets)) + sum(F.mse_loss(f, t) for f, t in zip(r_imgs, targets))
+    r_loss.backward()
+    for k in range(3):
+        close(imgs[k], r_imgs[k], rtol=1e-3, atol=1e-4); close(fine[k], r_fine[k], rtol=1e-3, atol=1e-4)
+    close(loss, r_loss, rtol=1e-4, atol=1e-6)
+    _check_param_grads(gl, sdl, rtol=5e-3, atol=2e-4, skip=('ca_net',))
+    _check_param_grads(gh, sdh, rtol=5e-3, atol=2e-4)

@@ -36,4 +36,8 @@ class GlobalAttentionGeneral(nn.Module):
 
     def forward(self, input, context):
         """input: batch x idf x ih x iw; context: batch x cdf x sourceL."""
-        return ops.attention_fwd(input, context, self.conv_context.weight.detach(), self.mask)
+        w = self.conv_context.weight
+        if self.training and torch.is_grad_enabled() and (input.requires_grad or w.requires_grad):
+            from .train import AttentionFn
+            return AttentionFn.apply(input, w, context.detach(), self.mask)
+        return ops.attention_fwd(input, context, w.detach(), self.mask)

@@ -5,7 +5,8 @@ checkpoints key for key; their own forward() is never called -- every block's fo
 the fused sm_100a kernels through the C ABI.
 
 Eval-mode BatchNorm is folded to (scale, shift) once per weight version and cached outside the
-state dict.  Training-mode BatchNorm (batch statistics) is not implemented on this path.
+state dict.  In train() mode (or whenever autograd records and a gradient is needed) the fp32 blocks run the
+training kernels of tgsr_b200/train.py: batch-statistics BatchNorm and explicit backward kernels.
 """
 from __future__ import annotations
 
@@ -39,6 +40,9 @@ def _folded_bn(bn: Optional[nn.Module]):
 
 
 def _conv(x, conv: nn.Conv2d, bn, act, **kw):
+    from . import train
+    if train.wants_grad(x, conv, bn):               # train() mode / autograd recording: explicit fwd+bwd kernels
+        return train.conv_bn_act(x, conv, bn, act, **kw)
     scale, shift = _folded_bn(bn)
     return ops.conv2d_fused(x, conv.weight.detach(), scale, shift, act, **kw)
 

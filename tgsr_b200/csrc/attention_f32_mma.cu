@@ -381,6 +381,14 @@ size_t attn_f32_ws_floats(int B, int idf, int T) {
   return (size_t)B * idf * NT * 8;
 }
 
+int attn_project_f32_launch(const float* context, const float* w_ctx, float* S, int B, int idf, int cdf, int T, cudaStream_t st) {
+  dim3 grid(B, idf / 8);
+  if (T <= 24) attn_project_f32_kernel<3><<<grid, 256, 0, st>>>(context, w_ctx, S, idf, cdf, T);
+  else if (T <= 32) attn_project_f32_kernel<4><<<grid, 256, 0, st>>>(context, w_ctx, S, idf, cdf, T);
+  else attn_project_f32_kernel<6><<<grid, 256, 0, st>>>(context, w_ctx, S, idf, cdf, T);
+  return launch_status();
+}
+
 int attn_f32_mma_launch(const float* x, const float* context, const float* w_ctx, const uint8_t* mask, float* S, float* wctx,
                         float* attn, int B, int idf, int cdf, int Q, int T, cudaStream_t st) {
   if (T <= 24) return af_launch<3>(x, context, w_ctx, mask, S, wctx, attn, B, idf, cdf, Q, T, st);
