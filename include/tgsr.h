@@ -228,6 +228,39 @@ int tgsr_attn_bwd_f32(const float* input, const float* context, const float* w_c
                       const float* d_wctx, const float* d_attn, float* ws, float* d_input, float* d_w_ctx,
                       int B, int idf, int cdf, int Q, int T, tgsr_stream_t stream);
 
+/* ---- a2 / a14: DAMSM matching losses (miscc/losses.py:21-136; func_attention GlobalAttention.py:33-74), fp32 ----
+ * One CTA per (image j, caption i) pair replaces the reference's Python loop over captions.
+ * feats [n_img,256,S] (region features, S = 17*17), words [n_cap,256,T], cap_lens int64 [n_cap] or NULL (all T words).
+ * Outputs, any may be NULL: sim [n_img,n_cap] = log sum_t exp(gamma2 * cos(w_t, c_t)) (losses.py:102-109);
+ * attn [pair,T,S] (second softmax, rows >= cap_len are zero); p [pair,S,24] (first softmax, for the backward);
+ * c [pair,256,T] (weightedContext).  pair = j*n_cap + i.  diag != 0: pairs (b,b) only, pair = b (func_attention).
+ * ndf == 256, T <= 24, S <= 1024. */
+int tgsr_damsm_pairs_fwd_f32(const float* feats, const float* words, const int64_t* cap_lens, float gamma1,
+                             float gamma2, float eps, float* sim, float* attn, float* p, float* c, int n_img,
+                             int n_cap, int ndf, int S, int T, int diag, tgsr_stream_t stream);
+/* Both cross entropies over scores = gamma3 * sim [B,B] (class_mask uint8 [B,B] or NULL: masked -> -inf, no gradient):
+ * loss2[0] = CE over rows (image -> caption), loss2[1] = CE over columns; d0/d1 [B,B] = d loss / d sim. */
+int tgsr_damsm_ce_f32(const float* sim, const uint8_t* class_mask, const int64_t* labels, float gamma3,
+                      float* loss2, float* d0, float* d1, int B, tgsr_stream_t stream);
+/* d_feats [n_img,256,S] = d (g0*loss0 + g1*loss1) / d feats through the pair kernel.  words_t [n_cap,T,256] is words
+ * transposed; g0, g1 device scalars; dcT [pairs,24,256] and draw [pairs,24,S] are caller-owned scratch. */
+int tgsr_damsm_pairs_bwd_f32(const float* feats, const float* words, const float* words_t, const int64_t* cap_lens,
+                             const float* attn, const float* p, const float* c, const float* d0, const float* d1,
+                             const float* g0, const float* g1, float gamma1, float gamma2, float eps, float* dcT,
+                             float* draw, float* d_feats, int n_img, int n_cap, int ndf, int S, int T,
+                             tgsr_stream_t stream);
+/* sent_loss (losses.py:21-62): sim [B,B] = cos(cnn_code[j], rnn_code[i]); its gradient to cnn_code given d0/d1 of
+ * tgsr_damsm_ce_f32. */
+int tgsr_sent_sim_f32(const float* cnn_code, const float* rnn_code, float eps, float* sim, int B, int D,
+                      tgsr_stream_t stream);
+int tgsr_sent_bwd_f32(const float* cnn_code, const float* rnn_code, const float* sim, const float* d0,
+                      const float* d1, const float* g0, const float* g1, float eps, float* d_cnn, int B, int D,
+                      tgsr_stream_t stream);
+/* nn.MSELoss (losses.py:779-784): loss[0] += mean((a-b)^2) (caller zeroes loss so terms accumulate); grad or NULL. */
+int tgsr_mse_f32(const float* a, const float* b, float* loss, float* grad, size_t n, tgsr_stream_t stream);
+/* grad = g[0] * 2 (a - b) / n  (g: device scalar, the upstream gradient of the mean). */
+int tgsr_mse_bwd_f32(const float* a, const float* b, const float* g, float* grad, size_t n, tgsr_stream_t stream);
+
 /* Eval-flow edge: uint8 image quantisation of trainer_objective.py:153-155 on the device,
  * y[i] = uint8(round_half_even(clamp((x[i] + 1.0f) * 127.5f, 0, 255))), fp32 arithmetic as numpy does it.
  * x fp32 (16-byte aligned), y uint8 (4-byte aligned), n elements. */

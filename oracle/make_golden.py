@@ -214,15 +214,55 @@ def gen_x16(ns):
                os.path.join(OUT, 'x16.pt'))
 
 
+def gen_losses(ns):
+    """words_loss / sent_loss / MSE of the UNMODIFIED miscc/losses.py (gamma 4/5/10, cfg/DAMSM/bird.yml:23-25) with
+    autograd gradients to the image side: the pin for tgsr_b200/losses.py and the oracle's restatement."""
+    from miscc import losses as L
+    L.server = 1                                            # bool masks (uint8 masked_fill_ fails on torch 2.x)
+    ns.cfg.TRAIN.SMOOTH.GAMMA1, ns.cfg.TRAIN.SMOOTH.GAMMA2, ns.cfg.TRAIN.SMOOTH.GAMMA3 = 4.0, 5.0, 10.0
+    ns.cfg.TRAIN.SMOOTH.LAMBDA = 1.0
+    import numpy as np
+    cases = []
+    g = torch.Generator().manual_seed(1007)
+    for (B, T, ragged, with_cls) in [(3, 18, True, False), (4, 12, True, True), (2, 18, False, False)]:
+        feats = (torch.randn(B, 256, 17, 17, generator=g) * 0.4).half().float().requires_grad_(True)   # fp16-exact: small fixture
+        words = torch.randn(B, 256, T, generator=g) * 0.4
+        cnn = (torch.randn(B, 256, generator=g) * 0.5).requires_grad_(True)
+        sent = torch.randn(B, 256, generator=g) * 0.5
+        lens = torch.randint(3, T + 1, (B,), generator=g) if ragged else torch.full((B,), T)
+        lens = torch.sort(lens, descending=True).values
+        labels = torch.arange(B)
+        cls = np.array([0, 1, 0, 2][:B]) if with_cls else None
+        w0, w1, att = L.words_loss(feats, words, labels, lens, cls, B)
+        s0, s1 = L.sent_loss(cnn, sent, labels, cls, B)
+        gw = torch.tensor([0.7, 1.3]); gs = torch.tensor([1.1, 0.6])
+        (gw[0] * w0 + gw[1] * w1 + gs[0] * s0 + gs[1] * s1).backward()
+        fake = [torch.randn(B, 3, 4 * 2 ** k, 4 * 2 ** k, generator=g).requires_grad_(True) for k in range(3)]
+        real = [torch.randn(B, 3, 4 * 2 ** k, 4 * 2 ** k, generator=g) for k in range(3)]
+        mse = L.MSE(fake, real)
+        (1.7 * mse).backward()
+        cases.append(dict(feats=feats.detach().half(), words=words, cnn=cnn.detach().clone(), sent=sent, lens=lens, labels=labels,
+                          class_ids=None if cls is None else cls.tolist(), w0=w0.detach(), w1=w1.detach(), s0=s0.detach(),
+                          s1=s1.detach(), att=[a.detach().clone() for a in att], gw=gw, gs=gs, d_feats=feats.grad.clone(),
+                          d_cnn=cnn.grad.clone(), fake=[f.detach().clone() for f in fake], real=real, mse=mse.detach(),
+                          d_fake=[f.grad.clone() for f in fake], gamma=(4.0, 5.0, 10.0)))
+    torch.save(cases, os.path.join(OUT, 'losses.pt'))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == 'losses':
+        gen_losses(ns)
+        print('losses.pt', os.path.getsize(os.path.join(OUT, 'losses.pt')))
+        return
     gen_attention(ns)
     gen_func_attention(ns)
     gen_blocks(ns)
     gen_rnn(ns)
     gen_face_x8(ns)
     gen_x16(ns)
+    gen_losses(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -248,6 +248,66 @@ def netg_high(sd: SD, LR: Tensor, SRb: Sequence[Tensor], LRb: Tensor, low: str =
 
 
 # --------------------------------------------------------------------------
+# DAMSM matching losses (training step)
+# --------------------------------------------------------------------------
+def cosine_similarity(x1: Tensor, x2: Tensor, dim: int = 1, eps: float = 1e-8) -> Tensor:
+    """miscc/losses.py:12-18."""
+    w12 = torch.sum(x1 * x2, dim)
+    w1 = torch.norm(x1, 2, dim)
+    w2 = torch.norm(x2, 2, dim)
+    return (w12 / (w1 * w2).clamp(min=eps)).squeeze()
+
+
+def _class_masks(class_ids, B: int) -> Optional[Tensor]:
+    """miscc/losses.py:24-34 / :73-77, :117-120."""
+    if class_ids is None:
+        return None
+    ids = torch.as_tensor(class_ids)
+    m = ids[:, None] == ids[None, :]
+    m.fill_diagonal_(False)
+    return m
+
+
+def sent_loss(cnn_code: Tensor, rnn_code: Tensor, labels: Tensor, class_ids, gamma3: float, eps: float = 1e-8):
+    """miscc/losses.py:21-62 for [B, nef] codes."""
+    B = cnn_code.shape[0]
+    c, r = cnn_code.unsqueeze(0), rnn_code.unsqueeze(0)                  # :37-39
+    cn = torch.norm(c, 2, dim=2, keepdim=True); rn = torch.norm(r, 2, dim=2, keepdim=True)   # :42-43
+    scores0 = torch.bmm(c, r.transpose(1, 2))                            # :45
+    norm0 = torch.bmm(cn, rn.transpose(1, 2))                            # :46
+    scores0 = (scores0 / norm0.clamp(min=eps) * gamma3).squeeze(0)       # :47-50
+    masks = _class_masks(class_ids, B)
+    if masks is not None:
+        scores0.data.masked_fill_(masks, -float('inf'))                  # :51-55
+    scores1 = scores0.transpose(0, 1)
+    return F.cross_entropy(scores0, labels), F.cross_entropy(scores1, labels)   # :57-59
+
+
+def words_loss(img_features: Tensor, words_emb: Tensor, labels: Tensor, cap_lens, class_ids, gamma1: float, gamma2: float,
+               gamma3: float):
+    """miscc/losses.py:65-136 (the per-caption Python loop, verbatim in structure)."""
+    B = img_features.shape[0]
+    att_maps, sims = [], []
+    lens = [int(v) for v in (cap_lens.tolist() if torch.is_tensor(cap_lens) else cap_lens)]
+    for i in range(B):
+        n = lens[i]
+        word = words_emb[i, :, :n].unsqueeze(0).contiguous().repeat(B, 1, 1)            # :79-83
+        wei, attn = func_attention(word, img_features, gamma1)                          # :92
+        att_maps.append(attn[i].unsqueeze(0).contiguous())                              # :93
+        w2 = word.transpose(1, 2).contiguous().view(B * n, -1)                          # :95-98
+        c2 = wei.transpose(1, 2).contiguous().view(B * n, -1)
+        row_sim = cosine_similarity(w2, c2).view(B, n)                                  # :102-104
+        row_sim = torch.log(torch.exp(row_sim * gamma2).sum(dim=1, keepdim=True))       # :107-109
+        sims.append(row_sim)
+    sim = torch.cat(sims, 1) * gamma3                                                   # :116, :124
+    masks = _class_masks(class_ids, B)
+    if masks is not None:
+        sim.data.masked_fill_(masks, -float('inf'))                                     # :125-129
+    sim1 = sim.transpose(0, 1)
+    return F.cross_entropy(sim, labels), F.cross_entropy(sim1, labels), att_maps       # :131-136
+
+
+# --------------------------------------------------------------------------
 # Text encoder
 # --------------------------------------------------------------------------
 def _lstm_cell(x_proj: Tensor, h: Tensor, c: Tensor, w_hh: Tensor, H: int):

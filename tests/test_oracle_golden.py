@@ -119,3 +119,20 @@ def test_psnr_and_quantisation():
     a = torch.zeros(4, 4, dtype=torch.uint8); b = a.clone(); b[0, 0] = 16
     import math
     assert abs(O.psnr_u8(a, b) - 20 * math.log10(255.0 / 4.0)) < 1e-9
+
+
+def test_losses_oracle_matches_reference(golden):
+    """The oracle's words_loss / sent_loss restatement against the UNMODIFIED miscc/losses.py outputs and autograd
+    gradients (tests/golden/losses.pt, oracle/make_golden.py gen_losses)."""
+    for c in golden('losses.pt'):
+        g1, g2, g3 = c['gamma']
+        feats = c['feats'].float().requires_grad_(True); cnn = c['cnn'].clone().requires_grad_(True)
+        w0, w1, att = O.words_loss(feats, c['words'], c['labels'], c['lens'], c['class_ids'], g1, g2, g3)
+        s0, s1 = O.sent_loss(cnn, c['sent'], c['labels'], c['class_ids'], g3)
+        for a, b in ((w0, c['w0']), (w1, c['w1']), (s0, c['s0']), (s1, c['s1'])):
+            torch.testing.assert_close(a.detach(), b, rtol=1e-5, atol=1e-6)
+        for a, b in zip(att, c['att']):
+            torch.testing.assert_close(a.detach(), b, rtol=1e-5, atol=1e-8)
+        (c['gw'][0] * w0 + c['gw'][1] * w1 + c['gs'][0] * s0 + c['gs'][1] * s1).backward()
+        torch.testing.assert_close(feats.grad, c['d_feats'], rtol=1e-4, atol=1e-7)
+        torch.testing.assert_close(cnn.grad, c['d_cnn'], rtol=1e-4, atol=1e-7)

@@ -55,6 +55,13 @@ _SIGS = {
     'tgsr_conv2d_wgrad_f32': ([C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p], C.c_int),
     'tgsr_tanh_head_bwd_f32': ([C.c_void_p] * 3 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p], C.c_int),
     'tgsr_attn_bwd_f32': ([C.c_void_p] * 9 + [C.c_int] * 5 + [C.c_void_p], C.c_int),
+    'tgsr_damsm_pairs_fwd_f32': ([C.c_void_p] * 3 + [C.c_float] * 3 + [C.c_void_p] * 4 + [C.c_int] * 6 + [C.c_void_p], C.c_int),
+    'tgsr_damsm_ce_f32': ([C.c_void_p] * 3 + [C.c_float] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p], C.c_int),
+    'tgsr_damsm_pairs_bwd_f32': ([C.c_void_p] * 11 + [C.c_float] * 3 + [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p], C.c_int),
+    'tgsr_sent_sim_f32': ([C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p], C.c_int),
+    'tgsr_sent_bwd_f32': ([C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p], C.c_int),
+    'tgsr_mse_f32': ([C.c_void_p] * 4 + [C.c_size_t, C.c_void_p], C.c_int),
+    'tgsr_mse_bwd_f32': ([C.c_void_p] * 4 + [C.c_size_t, C.c_void_p], C.c_int),
     'tgsr_quantize_u8': ([C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p], C.c_int),
     'tgsr_attn_sfrag_bytes': ([C.c_int], C.c_size_t),
     'tgsr_attn_project': ([C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p], C.c_int),

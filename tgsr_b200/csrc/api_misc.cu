@@ -13,6 +13,7 @@ int init_lstm(void);          // lstm.cu
 int init_attention_mma(void);  // attention_mma.cu
 int init_attention_f32_mma(void);  // attention_f32_mma.cu
 int init_attention_bwd(void);      // attention_bwd.cu
+int init_damsm(void);              // damsm.cu
 }  // namespace tgsr
 
 extern "C" {
@@ -51,6 +52,8 @@ int tgsr_init(int device) {
   s = tgsr::init_attention_f32_mma();
   if (s != TGSR_OK) return s;
   s = tgsr::init_attention_bwd();
+  if (s != TGSR_OK) return s;
+  s = tgsr::init_damsm();
   if (s != TGSR_OK) return s;
   return tgsr::init_lstm();
 }
