@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""bench_train.py -- generator training step of BASELINE.json configs[4] (SURVEY.md 8d cfg 5).
+
+    python bench_train.py [--steps K] [--warmup W] [--batch B]          (1 GPU)
+    torchrun --nproc-per-node N ... bench_train.py --gpus N ...         (N GPUs, NCCL gradient all-reduce)
+
+One step = G_SR_NET_low + NetG_highweight forward in train() mode (batch-statistics BatchNorm) on a synthetic batch,
+DAMSM word/sentence ranking loss on the final 256x256 image (frozen random-init Inception-v3 image encoder and frozen text
+encoder) + MSE against the real pyramid, backward, flat-bucket gradient all-reduce, fused Adam(2e-4, (0.5, 0.999)).
+fp32 (the training kernels are CUDA-core fp32 in round 1).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=32, help='images per GPU')
+    a = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import tgsr_b200
+    from tgsr_b200 import _lib, nets
+    from tgsr_b200.text_encoder import RNN_ENCODER
+    from tgsr_b200.train_step import FrozenImageEncoder, GeneratorTrainStep
+    from oracle import tgsr_oracle as O                    # synthetic-input generators only
+
+    world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0')); local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench_train.py: no CUDA device -- the product path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    tgsr_b200.set_eval_defaults(); tgsr_b200.set_precision('fp32')
+    from tgsr_b200.config import cfg
+    cfg.TRAIN.SMOOTH.GAMMA1, cfg.TRAIN.SMOOTH.GAMMA2, cfg.TRAIN.SMOOTH.GAMMA3 = 4.0, 5.0, 10.0
+    torch.manual_seed(100)                                  # identical replicas
+    gl = nets.G_SR_NET_low().to(dev); gh = nets.NetG_highweight(low='lr').to(dev)
+    enc = RNN_ENCODER(5450, nhidden=256).to(dev).eval()
+    img = FrozenImageEncoder().to(dev)
+    ts = GeneratorTrainStep(gl, gh, enc, img)
+    B = a.batch
+    LR = O.synth_lr(B, 32, seed=201 + rank).to(dev)
+    real = [torch.nn.functional.interpolate(LR, scale_factor=2 ** (k + 1), mode='bicubic').clamp(-1, 1) for k in range(3)]
+    caps, lens = O.synth_captions(B, 5450, seed=202 + rank, words_num=18)
+    caps, lens = caps.to(dev), lens.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        out = ts.step(LR, real, caps, lens, 18)
+    barrier()
+    lib = _lib.load()
+    n0 = lib.tgsr_launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar_ms = 0.0
+    barrier()
+    s.record()
+    for _ in range(a.steps):
+        out = ts.step(LR, real, caps, lens, 18, time_allreduce=True)
+    e.record()
+    barrier()
+    ar_ms = ts.ev[0].elapsed_time(ts.ev[1])
+    t = torch.tensor([s.elapsed_time(e), ar_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / a.steps
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'generator training images/sec (G fwd train-BN + DAMSM + MSE + bwd + all-reduce + Adam)',
+            'value': world * B / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
+            'ms_per_step': ms, 'allreduce_ms_last_step': float(t[1]), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'configs[4]: x8 generator training step, batch %d per GPU, 32->256, 18-word captions, '
+                                   'gamma (4,5,10), Adam(2e-4,(0.5,0.999)), flat-bucket NCCL all-reduce of %d gradients'
+                                   % (B, ts.bucket.numel), 'batch_per_gpu': B,
+                       'image_encoder': 'frozen random-init Inception-v3 on torchvision/cuDNN (library, out of scope)'},
+            'gpu_launches': int(lib.tgsr_launch_count() - n0),
+            'loss': {k: float(v) for k, v in out.items()}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

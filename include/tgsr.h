@@ -261,6 +261,12 @@ int tgsr_mse_f32(const float* a, const float* b, float* loss, float* grad, size_
 /* grad = g[0] * 2 (a - b) / n  (g: device scalar, the upstream gradient of the mean). */
 int tgsr_mse_bwd_f32(const float* a, const float* b, const float* g, float* grad, size_t n, tgsr_stream_t stream);
 
+/* Fused Adam over a flat bucket (torch.optim.Adam semantics, no weight decay): g = grad*grad_scale; m = b1 m + (1-b1) g;
+ * v = b2 v + (1-b2) g^2; param -= (lr / bias_corr1) * m / (sqrt(v) / bias_corr2_sqrt + eps). */
+int tgsr_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                  float beta1, float beta2, float eps, float bias_corr1, float bias_corr2_sqrt, float grad_scale,
+                  tgsr_stream_t stream);
+
 /* Eval-flow edge: uint8 image quantisation of trainer_objective.py:153-155 on the device,
  * y[i] = uint8(round_half_even(clamp((x[i] + 1.0f) * 127.5f, 0, 255))), fp32 arithmetic as numpy does it.
  * x fp32 (16-byte aligned), y uint8 (4-byte aligned), n elements. */

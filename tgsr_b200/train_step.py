@@ -1,0 +1,150 @@
+"""Generator training step of BASELINE.json configs[4] (SURVEY.md 8d cfg 5):
+
+    G forward (train-mode BatchNorm) -> DAMSM word/sentence ranking loss on the final image (frozen image and text
+    encoders) + MSE against the real image pyramid -> backward -> gradient all-reduce (NCCL) -> Adam(2e-4, (0.5, 0.999)).
+
+The reference ships no SR training loop or optimiser; this composes its loss functions
+(miscc/losses.py:499-522, :779-784) with its published hyper-parameters.  Everything on the generator side runs on
+libtgsr_sm100 kernels (tgsr_b200/train.py, losses.py, csrc/optim.cu).  The frozen Inception-v3 image encoder
+(CNN_ENCODER, util.py:262-368) is out of the hot path's scope and runs on torchvision/cuDNN as in the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import losses
+from ._lib import call, ptr
+
+
+class FlatBucket:
+    """All trainable parameters of `modules` re-homed into ONE flat fp32 buffer, with a same-shaped flat gradient
+    buffer that autograd accumulates into directly (p.grad are views).  One all-reduce and one Adam launch per step."""
+
+    def __init__(self, modules: Sequence[nn.Module]):
+        self.params: List[nn.Parameter] = []
+        seen = set()
+        for m in modules:
+            for p in m.parameters():
+                if p.requires_grad and id(p) not in seen:
+                    seen.add(id(p)); self.params.append(p)
+        if not self.params:
+            raise ValueError('no trainable parameters')
+        dev = self.params[0].device
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n); n += (p.numel() + 3) // 4 * 4          # 16-byte aligned slices
+        self.numel = n
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        for p, o in zip(self.params, self.offsets):
+            self.flat[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + p.numel()].view(p.shape)
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+        for p, o in zip(self.params, self.offsets):                       # re-attach if something replaced .grad
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def all_reduce(self, group=None) -> None:
+        """Sum the flat gradient over the ranks (NCCL over NVLink on GPUs; gloo in the CPU tests).  The 1/world
+        average is folded into the optimiser's grad_scale."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+
+
+class FusedAdam:
+    """torch.optim.Adam semantics on a FlatBucket, one kernel per step (csrc/optim.cu)."""
+
+    def __init__(self, bucket: FlatBucket, lr: float = 2e-4, betas=(0.5, 0.999), eps: float = 1e-8):
+        self.b, self.lr, self.betas, self.eps, self.t = bucket, lr, betas, eps, 0
+        self.m = torch.zeros_like(bucket.flat); self.v = torch.zeros_like(bucket.flat)
+
+    def step(self, grad_scale: float = 1.0) -> None:
+        self.t += 1
+        bc1 = 1.0 - self.betas[0] ** self.t
+        bc2 = math.sqrt(1.0 - self.betas[1] ** self.t)
+        b = self.b
+        call('tgsr_adam_f32', b.flat.device, ptr(b.flat), ptr(b.grad), ptr(self.m), ptr(self.v), C.c_size_t(b.numel), self.lr,
+             self.betas[0], self.betas[1], self.eps, bc1, bc2, float(grad_scale))
+
+
+class FrozenImageEncoder(nn.Module):
+    """CNN_ENCODER (util.py:262-368) with random-init Inception-v3 weights (no network for the pretrained file), frozen,
+    eval mode.  Library code (torchvision + cuDNN) outside the hot path: only its input gradient is used."""
+
+    def __init__(self, nef: int = 256, seed: int = 100):
+        super().__init__()
+        from torchvision.models import inception_v3
+        g = torch.random.get_rng_state()
+        torch.manual_seed(seed)
+        m = inception_v3(weights=None, aux_logits=True, init_weights=True)
+        for n in ('Conv2d_1a_3x3', 'Conv2d_2a_3x3', 'Conv2d_2b_3x3', 'Conv2d_3b_1x1', 'Conv2d_4a_3x3', 'Mixed_5b', 'Mixed_5c',
+                  'Mixed_5d', 'Mixed_6a', 'Mixed_6b', 'Mixed_6c', 'Mixed_6d', 'Mixed_6e', 'Mixed_7a', 'Mixed_7b', 'Mixed_7c'):
+            setattr(self, n, getattr(m, n))
+        self.emb_features = nn.Conv2d(768, nef, 1, bias=False)
+        self.emb_cnn_code = nn.Linear(2048, nef)
+        self.emb_features.weight.data.uniform_(-0.1, 0.1); self.emb_cnn_code.weight.data.uniform_(-0.1, 0.1)
+        torch.random.set_rng_state(g)
+        for p in self.parameters():
+            p.requires_grad = False
+        self.eval()
+
+    def forward(self, x):
+        x = F.interpolate(x, size=(299, 299), mode='bilinear', align_corners=False)
+        x = self.Conv2d_2b_3x3(self.Conv2d_2a_3x3(self.Conv2d_1a_3x3(x)))
+        x = F.max_pool2d(x, kernel_size=3, stride=2)
+        x = self.Conv2d_4a_3x3(self.Conv2d_3b_1x1(x))
+        x = F.max_pool2d(x, kernel_size=3, stride=2)
+        x = self.Mixed_5d(self.Mixed_5c(self.Mixed_5b(x)))
+        x = self.Mixed_6e(self.Mixed_6d(self.Mixed_6c(self.Mixed_6b(self.Mixed_6a(x)))))
+        features = x
+        x = self.Mixed_7c(self.Mixed_7b(self.Mixed_7a(x)))
+        x = F.avg_pool2d(x, kernel_size=8).view(x.size(0), -1)
+        return self.emb_features(features), self.emb_cnn_code(x)
+
+
+class GeneratorTrainStep:
+    def __init__(self, netGL: nn.Module, netGH: nn.Module, text_encoder: nn.Module, image_encoder: nn.Module, lr: float = 2e-4,
+                 betas=(0.5, 0.999), group=None):
+        self.netGL, self.netGH, self.text_encoder, self.image_encoder = netGL, netGH, text_encoder, image_encoder
+        netGL.train(); netGH.train(); text_encoder.eval(); image_encoder.eval()
+        for p in netGL.ca_net.parameters():                                 # c_code is unused by the SR nets (model.py:51-52)
+            p.requires_grad = False
+        self.bucket = FlatBucket([netGL, netGH])
+        self.opt = FusedAdam(self.bucket, lr, betas)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.ev = None
+
+    def step(self, LR: torch.Tensor, real: Sequence[torch.Tensor], captions: torch.Tensor, cap_lens: torch.Tensor, tmax: int,
+             time_allreduce: bool = False) -> Dict[str, torch.Tensor]:
+        """LR [B,3,32,32]; real = [64x64, 128x128, 256x256] targets; captions int64 [B,18] sorted by length (desc)."""
+        B = LR.shape[0]
+        self.bucket.zero_grad()
+        with torch.no_grad():
+            words, sent = self.text_encoder._forward_tmax(captions, cap_lens, tmax)
+            mask = (captions == 0)[:, :tmax]
+        fake_imgL, _att, _mu, _logvar = self.netGL(LR, sent, words, mask)
+        fine, _a, _one = self.netGH(LR, fake_imgL, LR)
+        labels = torch.arange(B, device=LR.device)
+        errG, _ = losses.generator_lossor_wordsentOnly(self.image_encoder, fine, words, sent, labels, cap_lens, None)
+        mse = losses.MSE(list(fine) + list(fake_imgL), list(real) + list(real))
+        total = errG + mse
+        total.backward()
+        if time_allreduce:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+        self.bucket.all_reduce(self.group)
+        if time_allreduce:
+            e.record(); self.ev = (s, e)
+        self.opt.step(1.0 / self.world)
+        return {'total': total.detach(), 'damsm': errG.detach(), 'mse': mse.detach()}
