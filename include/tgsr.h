@@ -228,6 +228,19 @@ int tgsr_attn_bwd_f32(const float* input, const float* context, const float* w_c
                       const float* d_wctx, const float* d_attn, float* ws, float* d_input, float* d_w_ctx,
                       int B, int idf, int cdf, int Q, int T, tgsr_stream_t stream);
 
+/* TF32 tensor-core convolutions of the training step (fp32 tensors, TF32 operands, fp32 accumulate -- the precision
+ * PyTorch's cuDNN convs use by default).  tgsr_conv_prep_tf32 converts w [Cout,Cin,k,k] once per step into the K-major
+ * operand `wk` (Cout*Cin*k*k words): dgrad == 0 for the forward, dgrad == 1 for the data gradient (channels swapped, taps
+ * flipped).  tgsr_conv2d_tf32: y [B,N,Ho,Wo] = conv(x [B,Cin,H,W] (nearest x2 if up2x), wk), N = wk's output channels.
+ * tgsr_conv2d_wgrad_tf32: as tgsr_conv2d_wgrad_f32.  tgsr_conv_tf32_supported(Cin, Cout, k, wgrad) gives the envelope
+ * (output channels % 32 == 0; weight gradient: 3x3, both channel counts % 32 == 0). */
+int tgsr_conv_tf32_supported(int Cin, int Cout, int ksize, int wgrad);
+int tgsr_conv_prep_tf32(const float* w, void* wk, int Cout, int Cin, int ksize, int dgrad, tgsr_stream_t stream);
+int tgsr_conv2d_tf32(const float* x, const void* wk, float* y, int B, int Cin, int H, int W, int N, int ksize,
+                     int up2x, tgsr_stream_t stream);
+int tgsr_conv2d_wgrad_tf32(const float* x, const float* dy, float* dw, int B, int Cin, int H, int W, int Cout,
+                           int ksize, int up2x, tgsr_stream_t stream);
+
 /* ---- a2 / a14: DAMSM matching losses (miscc/losses.py:21-136; func_attention GlobalAttention.py:33-74), fp32 ----
  * One CTA per (image j, caption i) pair replaces the reference's Python loop over captions.
  * feats [n_img,256,S] (region features, S = 17*17), words [n_cap,256,T], cap_lens int64 [n_cap] or NULL (all T words).

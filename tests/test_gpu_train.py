@@ -222,3 +222,27 @@ def test_generator_train_step_runs_and_learns():
     assert all(torch.isfinite(torch.tensor(hist))), hist
     assert hist[-1] < hist[0], hist
     assert ts.bucket.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize('B,Cin,Cout,H,W,k,up', [(2, 64, 128, 32, 32, 3, False), (2, 64, 64, 16, 24, 3, True), (3, 32, 32, 20, 12, 3, False),
+                                                 (2, 32, 64, 8, 8, 3, True), (2, 3, 64, 32, 32, 3, False), (2, 32, 3, 16, 16, 5, False)])
+def test_tf32_convs_match_exact_kernels(B, Cin, Cout, H, W, k, up):
+    """TF32 tensor-core forward / data gradient / weight gradient against the exact fp32 kernels (themselves checked against
+    autograd above): operands rounded to 10-bit mantissas, fp32 accumulate -> 2e-3 of the output scale (PyTorch's own TF32
+    convs differ from fp32 by the same amount)."""
+    from tgsr_b200 import train
+    g = torch.Generator().manual_seed(Cin + Cout + H)
+    x = (torch.randn(B, Cin, H, W, generator=g) * 0.5).to(DEV)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) * (1.0 / (Cin * k * k) ** 0.5)).to(DEV)
+    Ho, Wo = (2 * H, 2 * W) if up else (H, W)
+    dy = (torch.randn(B, Cout, Ho, Wo, generator=g) * 0.5).to(DEV)
+    res = {}
+    for mode in ('fp32', 'tf32'):
+        train.set_conv_precision(mode)
+        try:
+            res[mode] = (train._conv_raw(x, w, up), train._conv_dgrad(dy, w, up), train._conv_wgrad(x, dy, w.shape, up))
+        finally:
+            train.set_conv_precision('fp32')
+    for a, b in zip(res['fp32'], res['tf32']):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= 2e-3 * max(1.0, float(a.abs().max())), (float((a - b).abs().max()), float(a.abs().max()))

@@ -14,6 +14,7 @@ int init_attention_mma(void);  // attention_mma.cu
 int init_attention_f32_mma(void);  // attention_f32_mma.cu
 int init_attention_bwd(void);      // attention_bwd.cu
 int init_damsm(void);              // damsm.cu
+int init_conv_tf32(void);          // conv_tf32.cu
 }  // namespace tgsr
 
 extern "C" {
@@ -54,6 +55,8 @@ int tgsr_init(int device) {
   s = tgsr::init_attention_bwd();
   if (s != TGSR_OK) return s;
   s = tgsr::init_damsm();
+  if (s != TGSR_OK) return s;
+  s = tgsr::init_conv_tf32();
   if (s != TGSR_OK) return s;
   return tgsr::init_lstm();
 }

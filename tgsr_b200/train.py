@@ -25,7 +25,38 @@ def _empty_like_shape(shape, ref: Tensor) -> Tensor:
 
 
 # ---------------------------------------------------------------- conv (raw, no BN / activation)
+_CONV_PRECISION = 'fp32'
+
+
+def set_conv_precision(mode: str) -> None:
+    """'fp32': exact CUDA-core convolutions (gradient-parity tests).  'tf32': TF32 tensor-core convolutions wherever the
+    kernels cover the shape (fp32 accumulate) -- the precision PyTorch's cuDNN convs use by default, i.e. what the
+    reference's own GPU training computes."""
+    global _CONV_PRECISION
+    if mode not in ('fp32', 'tf32'):
+        raise ValueError("conv precision must be 'fp32' or 'tf32'")
+    _CONV_PRECISION = mode
+
+
+def _tf32_ok(Cin: int, Cout: int, k: int, wgrad: bool) -> bool:
+    return _CONV_PRECISION == 'tf32' and bool(_lib.load().tgsr_conv_tf32_supported(Cin, Cout, k, int(wgrad)))
+
+
+def _conv_tf32(x: Tensor, w: Tensor, up2x: bool, dgrad: bool) -> Tensor:
+    Cout, Cin, k, _ = w.shape
+    wk = torch.empty(w.numel(), device=w.device, dtype=torch.int32)
+    call('tgsr_conv_prep_tf32', w.device, ptr(w), ptr(wk), Cout, Cin, k, int(dgrad))
+    B, Cx, H, W = x.shape
+    N = Cin if dgrad else Cout
+    Ho, Wo = (2 * H, 2 * W) if up2x else (H, W)
+    y = torch.empty((B, N, Ho, Wo), device=x.device, dtype=torch.float32)
+    call('tgsr_conv2d_tf32', x.device, ptr(x), ptr(wk), ptr(y), B, Cx, H, W, N, k, int(up2x))
+    return y
+
+
 def _conv_raw(x: Tensor, w: Tensor, up2x: bool) -> Tensor:
+    if _tf32_ok(w.shape[1], w.shape[0], w.shape[2], False):
+        return _conv_tf32(x, w, up2x, False)
     return ops.conv2d_fused(x, w, None, None, ACT_NONE, up2x=up2x)
 
 
@@ -33,9 +64,12 @@ def _conv_dgrad(dy: Tensor, w: Tensor, up2x: bool) -> Tensor:
     """Data gradient of conv(x [nearest x2 if up2x], w): the same conv kernel on dy with the transposed, flipped weights;
     the folded upsample becomes a 2x2 sum-pool."""
     Cout, Cin, k, _ = w.shape
-    wt = torch.empty((Cin, Cout, k, k), device=w.device, dtype=torch.float32)
-    call('tgsr_conv_weight_flip_f32', w.device, ptr(w), ptr(wt), Cout, Cin, k)
-    dx = ops.conv2d_fused(dy, wt, None, None, ACT_NONE)
+    if _tf32_ok(Cout, Cin, k, False):
+        dx = _conv_tf32(dy, w, False, True)
+    else:
+        wt = torch.empty((Cin, Cout, k, k), device=w.device, dtype=torch.float32)
+        call('tgsr_conv_weight_flip_f32', w.device, ptr(w), ptr(wt), Cout, Cin, k)
+        dx = ops.conv2d_fused(dy, wt, None, None, ACT_NONE)
     if up2x:
         B, _, Ho, Wo = dx.shape
         out = _empty_like_shape((B, Cin, Ho // 2, Wo // 2), dx)
@@ -48,7 +82,8 @@ def _conv_wgrad(x: Tensor, dy: Tensor, w_shape, up2x: bool) -> Tensor:
     Cout, Cin, k, _ = w_shape
     B, _, H, W = x.shape
     dw = _empty_like_shape(tuple(w_shape), x)
-    call('tgsr_conv2d_wgrad_f32', x.device, ptr(x), ptr(dy), ptr(dw), B, Cin, H, W, Cout, k, int(up2x))
+    name = 'tgsr_conv2d_wgrad_tf32' if _tf32_ok(Cin, Cout, k, True) else 'tgsr_conv2d_wgrad_f32'
+    call(name, x.device, ptr(x), ptr(dy), ptr(dw), B, Cin, H, W, Cout, k, int(up2x))
     return dw
 
 

@@ -114,7 +114,9 @@ class FrozenImageEncoder(nn.Module):
 
 class GeneratorTrainStep:
     def __init__(self, netGL: nn.Module, netGH: nn.Module, text_encoder: nn.Module, image_encoder: nn.Module, lr: float = 2e-4,
-                 betas=(0.5, 0.999), group=None):
+                 betas=(0.5, 0.999), group=None, conv_precision: str = 'tf32'):
+        from . import train
+        train.set_conv_precision(conv_precision)      # TF32 tensor-core convs by default, as PyTorch's cuDNN convs
         self.netGL, self.netGH, self.text_encoder, self.image_encoder = netGL, netGH, text_encoder, image_encoder
         netGL.train(); netGH.train(); text_encoder.eval(); image_encoder.eval()
         for p in netGL.ca_net.parameters():                                 # c_code is unused by the SR nets (model.py:51-52)
