@@ -280,6 +280,11 @@ int tgsr_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_av
                   float beta1, float beta2, float eps, float bias_corr1, float bias_corr2_sqrt, float grad_scale,
                   tgsr_stream_t stream);
 
+/* Same update with the 1-based step count read from device memory (CUDA-graph capturable training step). */
+int tgsr_adam_devstep_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                          float beta1, float beta2, float eps, const int* step, float grad_scale,
+                          tgsr_stream_t stream);
+
 /* Eval-flow edge: uint8 image quantisation of trainer_objective.py:153-155 on the device,
  * y[i] = uint8(round_half_even(clamp((x[i] + 1.0f) * 127.5f, 0, 255))), fp32 arithmetic as numpy does it.
  * x fp32 (16-byte aligned), y uint8 (4-byte aligned), n elements. */

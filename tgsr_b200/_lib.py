@@ -67,6 +67,7 @@ _SIGS = {
     'tgsr_conv_prep_tf32': ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p], C.c_int),
     'tgsr_conv2d_tf32': ([C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p], C.c_int),
     'tgsr_conv2d_wgrad_tf32': ([C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p], C.c_int),
+    'tgsr_adam_devstep_f32': ([C.c_void_p] * 4 + [C.c_size_t] + [C.c_float] * 4 + [C.c_void_p, C.c_float, C.c_void_p], C.c_int),
     'tgsr_quantize_u8': ([C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p], C.c_int),
     'tgsr_attn_sfrag_bytes': ([C.c_int], C.c_size_t),
     'tgsr_attn_project': ([C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p], C.c_int),

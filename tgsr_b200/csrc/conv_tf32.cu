@@ -46,7 +46,7 @@ __global__ void conv_prep_tf32_kernel(const float* __restrict__ w, uint32_t* __r
 // grid (tiles_x*tiles_y*B, N/NB); 256 threads: warp = (mw = warp&3: output rows 4mw..4mw+3, nw = warp>>2: NB/2 channels).
 // smem: xs [8 ch][TH][RS] tf32 (PLANE % 32 == 8) | ws [KK][8][NB+8] tf32.
 template <int K, int NB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv_tf32_kernel(const float* __restrict__ x, const uint32_t* __restrict__ wk, float* __restrict__ y, int Cin, int H, int W,
                  int N, int up2x) {
   constexpr int R = K / 2, KK = K * K, TH = 16 + K - 1, RS = (K == 3) ? 20 : 22, PLANE = TH * RS, LDW = NB + 8;

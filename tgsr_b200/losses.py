@@ -98,11 +98,32 @@ def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size)
     if labels is None:
         raise NotImplementedError('words_loss(labels=None) returns no losses in the reference; not needed here')
     loss0, loss1, attn = WordsLossFn.apply(img_features, words_emb, labels, cap_lens, cmask, sm.GAMMA1, sm.GAMMA2, sm.GAMMA3)
-    ih, iw = img_features.shape[2], img_features.shape[3]
-    lens = [int(v) for v in cap_lens.tolist()]
-    T = words_emb.shape[2]
-    att_maps: List[Tensor] = [attn[i * B + i, :min(lens[i], T)].reshape(1, -1, ih, iw) for i in range(B)]
-    return loss0, loss1, att_maps
+    return loss0, loss1, _AttMaps(attn, cap_lens, B, words_emb.shape[2], img_features.shape[2], img_features.shape[3])
+
+
+class _AttMaps(object):
+    """The att_maps list of words_loss (losses.py:93): element i = attention of caption i on its own image,
+    [1, cap_lens[i], 17, 17].  Built lazily: reading cap_lens is a device->host sync that the training step (which
+    discards the maps, losses.py:511) should not pay."""
+
+    def __init__(self, attn, cap_lens, B, T, ih, iw):
+        self._a, self._lens, self._B, self._T, self._ih, self._iw, self._list = attn, cap_lens, B, T, ih, iw, None
+
+    def _build(self):
+        if self._list is None:
+            lens = [int(v) for v in self._lens.tolist()]
+            B = self._B
+            self._list = [self._a[i * B + i, :min(lens[i], self._T)].reshape(1, -1, self._ih, self._iw) for i in range(B)]
+        return self._list
+
+    def __len__(self):
+        return self._B
+
+    def __getitem__(self, i):
+        return self._build()[i]
+
+    def __iter__(self):
+        return iter(self._build())
 
 
 class SentLossFn(torch.autograd.Function):

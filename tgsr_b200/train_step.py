@@ -67,14 +67,28 @@ class FusedAdam:
     def __init__(self, bucket: FlatBucket, lr: float = 2e-4, betas=(0.5, 0.999), eps: float = 1e-8):
         self.b, self.lr, self.betas, self.eps, self.t = bucket, lr, betas, eps, 0
         self.m = torch.zeros_like(bucket.flat); self.v = torch.zeros_like(bucket.flat)
+        self.step_t = None
 
     def step(self, grad_scale: float = 1.0) -> None:
         self.t += 1
         bc1 = 1.0 - self.betas[0] ** self.t
         bc2 = math.sqrt(1.0 - self.betas[1] ** self.t)
         b = self.b
+        if self.step_t is not None:
+            self.step_t.fill_(self.t)
         call('tgsr_adam_f32', b.flat.device, ptr(b.flat), ptr(b.grad), ptr(self.m), ptr(self.v), C.c_size_t(b.numel), self.lr,
              self.betas[0], self.betas[1], self.eps, bc1, bc2, float(grad_scale))
+
+    def step_capturable(self, grad_scale: float = 1.0) -> None:
+        """Same update with the step count kept on the device (no host-side constants change between steps), for a
+        training step captured in a CUDA graph."""
+        b = self.b
+        if self.step_t is None:
+            self.step_t = torch.full((1,), self.t, device=b.flat.device, dtype=torch.int32)
+        self.step_t += 1
+        self.t += 1
+        call('tgsr_adam_devstep_f32', b.flat.device, ptr(b.flat), ptr(b.grad), ptr(self.m), ptr(self.v), C.c_size_t(b.numel), self.lr,
+             self.betas[0], self.betas[1], self.eps, ptr(self.step_t), float(grad_scale))
 
 
 class FrozenImageEncoder(nn.Module):
@@ -126,10 +140,10 @@ class GeneratorTrainStep:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.ev = None
+        self._lab = None
+        self._graph = None
 
-    def step(self, LR: torch.Tensor, real: Sequence[torch.Tensor], captions: torch.Tensor, cap_lens: torch.Tensor, tmax: int,
-             time_allreduce: bool = False) -> Dict[str, torch.Tensor]:
-        """LR [B,3,32,32]; real = [64x64, 128x128, 256x256] targets; captions int64 [B,18] sorted by length (desc)."""
+    def _step_impl(self, LR, real, captions, cap_lens, tmax: int, capturable: bool, time_allreduce: bool = False):
         B = LR.shape[0]
         self.bucket.zero_grad()
         with torch.no_grad():
@@ -137,7 +151,7 @@ class GeneratorTrainStep:
             mask = (captions == 0)[:, :tmax]
         fake_imgL, _att, _mu, _logvar = self.netGL(LR, sent, words, mask)
         fine, _a, _one = self.netGH(LR, fake_imgL, LR)
-        labels = torch.arange(B, device=LR.device)
+        labels = self._labels(B, LR.device)
         errG, _ = losses.generator_lossor_wordsentOnly(self.image_encoder, fine, words, sent, labels, cap_lens, None)
         mse = losses.MSE(list(fine) + list(fake_imgL), list(real) + list(real))
         total = errG + mse
@@ -148,5 +162,47 @@ class GeneratorTrainStep:
         self.bucket.all_reduce(self.group)
         if time_allreduce:
             e.record(); self.ev = (s, e)
-        self.opt.step(1.0 / self.world)
+        if capturable:
+            self.opt.step_capturable(1.0 / self.world)
+        else:
+            self.opt.step(1.0 / self.world)
         return {'total': total.detach(), 'damsm': errG.detach(), 'mse': mse.detach()}
+
+    def _labels(self, B, dev):
+        if self._lab is None or self._lab.shape[0] != B:
+            self._lab = torch.arange(B, device=dev)
+        return self._lab
+
+    def step(self, LR: torch.Tensor, real: Sequence[torch.Tensor], captions: torch.Tensor, cap_lens: torch.Tensor, tmax: int,
+             time_allreduce: bool = False) -> Dict[str, torch.Tensor]:
+        """LR [B,3,32,32]; real = [64x64, 128x128, 256x256] targets; captions int64 [B,18] sorted by length (desc)."""
+        return self._step_impl(LR, real, captions, cap_lens, tmax, False, time_allreduce)
+
+    # ------------------------------------------------------------------ whole-step CUDA graph
+    def capture(self, LR, real, captions, cap_lens, tmax: int, warmup: int = 3) -> None:
+        """Capture forward + losses + backward + all-reduce + Adam of one step into a CUDA graph (static shapes).  The
+        ~1400 launches of a step are launch-bound from Python; replay removes that."""
+        if self.world > 1:
+            raise RuntimeError('GeneratorTrainStep.capture: the gradient all-reduce is not graph-captured; use step() with N > 1 ranks')
+        self._static = [LR.clone(), [r.clone() for r in real], captions.clone(), cap_lens.clone()]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_impl(self._static[0], self._static[1], self._static[2], self._static[3], tmax, True)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_out = self._step_impl(self._static[0], self._static[1], self._static[2], self._static[3], tmax, True)
+
+    def step_graph(self, LR, real, captions, cap_lens) -> Dict[str, torch.Tensor]:
+        st = self._static
+        if LR.data_ptr() != st[0].data_ptr():
+            st[0].copy_(LR, non_blocking=True)
+            for d, r in zip(st[1], real):
+                d.copy_(r, non_blocking=True)
+            st[2].copy_(captions, non_blocking=True); st[3].copy_(cap_lens, non_blocking=True)
+        self._graph.replay()
+        return self._graph_out
