@@ -64,6 +64,13 @@ def main():
         sfrag = fast.attention_project(st.att, ctx, cat.fmt) if a.what == 'attn' else None
         fn = lambda: fast.attention(cat.slice(0, 32), st.att, ctx, mask, out=cat.slice(32, 32), sfrag=sfrag)
         nbytes = B * S * S * (32 * 2 + 32 * 2 + 4 * 18) + B * 256 * 18 * 4 + 32 * 256 * 4 + B * 18
+    elif a.what == 'attnf32':                   # the module-API attention (fp32 NCHW I/O, 3xTF32 tensor-core kernel)
+        x = torch.randn(B, 32, S, S, device=dev) * 0.5
+        ctx = torch.randn(B, 256, 18, device=dev) * 0.3
+        tgsr_b200.set_precision('fp32')
+        st.att.applyMask(torch.zeros(B, 18, dtype=torch.uint8, device=dev))
+        fn = lambda: st.att(x, ctx)
+        nbytes = B * S * S * (32 * 4 + 32 * 4 + 4 * 18) + B * 256 * 18 * 4 + 32 * 256 * 4 + B * 18
     elif a.what == 'null':                      # calibration: a trivially small kernel in the same harness
         from tgsr_b200 import ops
         v = torch.ones(64, device=dev)

@@ -219,16 +219,22 @@ attn_f32_mma_kernel(const float* __restrict__ x, const float* __restrict__ S, co
         tf32_split(u.x, ah[0][2], al[0][2]); tf32_split(u.y, ah[0][3], al[0][3]);
         tf32_split(v.z, ah[1][0], al[1][0]); tf32_split(v.w, ah[1][1], al[1][1]);
         tf32_split(u.z, ah[1][2], al[1][2]); tf32_split(u.w, ah[1][3], al[1][3]);
+        uint4 bw[NT];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const uint4 bw = lds128u(sl_addr + (ks * NT + nt) * 512);
+        for (int nt = 0; nt < NT; ++nt) bw[nt] = lds128u(sl_addr + (ks * NT + nt) * 512);
+        // hi*hi, lo*hi, hi*lo -- product outermost, so consecutive MMAs hit different accumulators (no dependent chain)
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            mma_tf32(acc[mt][nt], ah[mt], bw.x, bw.y);
-            mma_tf32(acc[mt][nt], al[mt], bw.x, bw.y);
-            mma_tf32(acc[mt][nt], ah[mt], bw.z, bw.w);
-          }
-        }
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], ah[mt], bw[nt].x, bw[nt].y);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], al[mt], bw[nt].x, bw[nt].y);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], ah[mt], bw[nt].z, bw[nt].w);
       }
       // ---- caption mask (row r = b*Q+q uses caption r % B: GlobalAttention.py:109-116) + softmax over words
       // rows: [0] = px 4g (mt 0, row g), [1] = px 4g+1 (mt 0, row g+8), [2] = px 4g+2 (mt 1, g), [3] = px 4g+3
@@ -311,18 +317,21 @@ attn_f32_mma_kernel(const float* __restrict__ x, const float* __restrict__ S, co
             tf32_split(acc[mt][kt][0], ph[mt][0], pl[mt][0]); tf32_split(acc[mt][kt][2], ph[mt][1], pl[mt][1]);
             tf32_split(acc[mt][kt][1], ph[mt][2], pl[mt][2]); tf32_split(acc[mt][kt][3], ph[mt][3], pl[mt][3]);
           }
+          uint4 bo4[4];
 #pragma unroll
-          for (int cn = 0; cn < 4; ++cn) {
-            if (c4 + cn < K8) {
-              const uint4 bw = lds128u(so_addr + (kt * K8 + c4 + cn) * 512);
+          for (int cn = 0; cn < 4; ++cn) bo4[cn] = (c4 + cn < K8) ? lds128u(so_addr + (kt * K8 + c4 + cn) * 512) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-              for (int mt = 0; mt < 2; ++mt) {
-                mma_tf32(o[mt][cn], ph[mt], bw.x, bw.y);
-                mma_tf32(o[mt][cn], pl[mt], bw.x, bw.y);
-                mma_tf32(o[mt][cn], ph[mt], bw.z, bw.w);
-              }
-            }
-          }
+          for (int cn = 0; cn < 4; ++cn)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(o[mt][cn], ph[mt], bo4[cn].x, bo4[cn].y);
+#pragma unroll
+          for (int cn = 0; cn < 4; ++cn)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(o[mt][cn], pl[mt], bo4[cn].x, bo4[cn].y);
+#pragma unroll
+          for (int cn = 0; cn < 4; ++cn)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_tf32(o[mt][cn], ph[mt], bo4[cn].z, bo4[cn].w);
         }
         float* op = ob + (size_t)(8 * c4) * chQ + q0;
 #pragma unroll

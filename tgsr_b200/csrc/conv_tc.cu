@@ -266,6 +266,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     const int m = quad * 32 + lane;                  // accumulator row = pixel within the tile
     const int ty = m >> 3, tx = m & 7;
     const float4* sh4 = reinterpret_cast<const float4*>(sh_s);
+    uint4 rnext[4];                                  // skip-tensor planes of the next tile (conv mode with residual)
+    float adnext[2][3];                              // image-head addend of the next tile
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int acc = it % Cfg::NACC, aph = (it / Cfg::NACC) & 1;
@@ -294,8 +296,30 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           const int oy = (r / p.tiles_x) * Cfg::TH + (half * 2 + q) * 8 + hy;
           valid[q] = hx < Cfg::TWO && ox < p.W && oy < p.H;
           oi[q] = (size_t)b * 3 * hw + (size_t)oy * p.W + ox;
+        }
+        // the addend (SRb, fp32) of this tile was requested one tile ago: no DRAM round trip in the per-tile critical path
+        auto load_addend = [&](int tl, float (&dst)[2][3]) {
+          const int bb = tl / tiles_per_img, rr = tl % tiles_per_img;
+          const int xx = (rr % p.tiles_x) * Cfg::TWO + hx;
 #pragma unroll
-          for (int o = 0; o < 3; ++o) ad[q][o] = (valid[q] && p.addend) ? __ldg(p.addend + oi[q] + o * hw) : 0.f;
+          for (int q = 0; q < 2; ++q) {
+            const int yy = (rr / p.tiles_x) * Cfg::TH + (half * 2 + q) * 8 + hy;
+            const bool ok = hx < Cfg::TWO && xx < p.W && yy < p.H;
+            const size_t o0 = (size_t)bb * 3 * hw + (size_t)yy * p.W + xx;
+#pragma unroll
+            for (int o = 0; o < 3; ++o) dst[q][o] = ok ? __ldg(p.addend + o0 + o * hw) : 0.f;
+          }
+        };
+        if (p.addend) {
+          if (it == 0) load_addend(tile, adnext);
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int o = 0; o < 3; ++o) ad[q][o] = adnext[q][o];
+          if (tile + (int)gridDim.x < p.ntiles) load_addend(tile + (int)gridDim.x, adnext);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) ad[q][0] = ad[q][1] = ad[q][2] = 0.f;
         }
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
@@ -332,11 +356,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const size_t pix = ((size_t)gy * p.W + gx) * 8;
         const size_t plane_elems = (size_t)p.H * p.W * 8;
         h16* obase = p.out + ((size_t)b * p.yP + p.yp0 + c0 / 8) * plane_elems + pix;
+        // The skip tensor of this tile was requested one tile ago (rnext): in the HBM-bound ResBlock conv the epilogue
+        // would otherwise serialise on one DRAM round trip per tile.
         uint4 rres[CW / 8];
-        if (p.residual) {                                      // prefetch the skip tensor before the MMA wait
-          const h16* rbase = p.residual + ((size_t)b * p.rP + p.rp0 + c0 / 8) * plane_elems + pix;
+        if (p.residual) {
+          auto load_res = [&](int tl, uint4* dst) {
+            const int bb = tl / tiles_per_img, rr = tl % tiles_per_img;
+            const int yy = (rr / p.tiles_x) * TC_TH + ty, xx = (rr % p.tiles_x) * TC_TW + tx;
+            const h16* rbase = p.residual + ((size_t)bb * p.rP + p.rp0 + c0 / 8) * plane_elems + ((size_t)yy * p.W + xx) * 8;
 #pragma unroll
-          for (int j = 0; j < CW / 8; ++j) rres[j] = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)j * plane_elems));
+            for (int j = 0; j < CW / 8; ++j) dst[j] = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)j * plane_elems));
+          };
+          if (it == 0) load_res(tile, rnext);
+#pragma unroll
+          for (int j = 0; j < CW / 8; ++j) rres[j] = rnext[j];
+          if (tile + (int)gridDim.x < p.ntiles) load_res(tile + (int)gridDim.x, rnext);
         }
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();

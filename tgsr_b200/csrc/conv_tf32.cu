@@ -9,9 +9,10 @@
 //                      Used for the training forward and (with flipped/transposed weights) the data gradient.
 //   wgrad_tf32_kernel  dw[co][ci][tap] = sum_px dy[co][px] x[ci][px+tap]: M = COB output channels, N = 32 input
 //                      channels, K = the pixels of 16x16 tiles; the dy fragment of a K-step is reused by all taps.
-// Both use mma.sync m16n8k8 (measured on B200: one HMMA per 2.1 cycles per SM = 275 TFLOP/s TF32); operands are
-// converted to TF32 once, when they are staged in shared memory; shared-memory strides are chosen so that every
-// fragment load is bank-conflict free.
+// Both use mma.sync m16n8k8 (measured on B200: one HMMA per 2.1 cycles per SM = 275 TFLOP/s TF32).  Weights are rounded
+// to TF32 once per step (cvt.rna); activations and gradients are staged as raw fp32 bits -- the tensor core reads only the
+// TF32 part of an operand (truncation), and cvt.rna is a ~6-instruction integer emulation on sm_100 that would double the
+// instruction count of the staging loops.  Shared-memory strides make every fragment load bank-conflict free.
 #include "common.cuh"
 
 namespace tgsr {
@@ -80,7 +81,7 @@ conv_tf32_kernel(const float* __restrict__ x, const uint32_t* __restrict__ wk, f
         const int sy = up2x ? (gy >> 1) : gy, sx = up2x ? (gx >> 1) : gx;
         v = __ldg(x + (((size_t)b * Cin + c0 + c) * H + sy) * W + sx);
       }
-      xs[c * PLANE + yy * RS + xx] = to_tf32(v);
+      xs[c * PLANE + yy * RS + xx] = __float_as_uint(v);   // raw fp32 bits: the tensor core reads the TF32 part (truncation)
     }
     for (int idx = tid; idx < KK * 8 * NB; idx += 256) {
       const int n = idx % NB, c = (idx / NB) % 8, tp = idx / (NB * 8);
@@ -158,7 +159,7 @@ wgrad_tf32_kernel(const float* __restrict__ x, const float* __restrict__ dy, flo
       const int gy = ty0 + yy, gx = tx0 + xx;
       float v = 0.f;
       if (gy < Ho && gx < Wo) v = __ldg(dy + (((size_t)b * Cout + co0 + c) * Ho + gy) * Wo + gx);
-      ds[c * DP + r] = to_tf32(v);
+      ds[c * DP + r] = __float_as_uint(v);
     }
     for (int idx = tid; idx < 32 * TH * TH; idx += 256) {
       const int c = idx / (TH * TH), r = idx % (TH * TH), yy = r / TH, xx = r % TH;
@@ -168,7 +169,7 @@ wgrad_tf32_kernel(const float* __restrict__ x, const float* __restrict__ dy, flo
         const int sy = up2x ? (gy >> 1) : gy, sx = up2x ? (gx >> 1) : gx;
         v = __ldg(x + (((size_t)b * Cin + ci0 + c) * H + sy) * W + sx);
       }
-      xs[c * XP + r] = to_tf32(v);
+      xs[c * XP + r] = __float_as_uint(v);
     }
     __syncthreads();
     // K-steps: 8 consecutive pixels of one tile row
