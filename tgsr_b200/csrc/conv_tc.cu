@@ -266,7 +266,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     const int m = quad * 32 + lane;                  // accumulator row = pixel within the tile
     const int ty = m >> 3, tx = m & 7;
     const float4* sh4 = reinterpret_cast<const float4*>(sh_s);
-    uint4 rnext[4];                                  // skip-tensor planes of the next tile (conv mode with residual)
+    uint4 rnext[4], rnext2[4];                       // skip-tensor planes of the next two tiles (conv mode with residual)
     float adnext[2][3];                              // image-head addend of the next tile
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -356,7 +356,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const size_t pix = ((size_t)gy * p.W + gx) * 8;
         const size_t plane_elems = (size_t)p.H * p.W * 8;
         h16* obase = p.out + ((size_t)b * p.yP + p.yp0 + c0 / 8) * plane_elems + pix;
-        // The skip tensor of this tile was requested one tile ago (rnext): in the HBM-bound ResBlock conv the epilogue
+        // The skip tensor of this tile was requested two tiles ago (rnext2 -> rnext -> rres): in the HBM-bound ResBlock conv the epilogue
         // would otherwise serialise on one DRAM round trip per tile.
         uint4 rres[CW / 8];
         if (p.residual) {
@@ -367,10 +367,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 #pragma unroll
             for (int j = 0; j < CW / 8; ++j) dst[j] = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)j * plane_elems));
           };
-          if (it == 0) load_res(tile, rnext);
+          const int g2 = (int)gridDim.x;
+          if (it == 0) {
+            load_res(tile, rnext);
+            if (tile + g2 < p.ntiles) load_res(tile + g2, rnext2);
+          }
 #pragma unroll
-          for (int j = 0; j < CW / 8; ++j) rres[j] = rnext[j];
-          if (tile + (int)gridDim.x < p.ntiles) load_res(tile + (int)gridDim.x, rnext);
+          for (int j = 0; j < CW / 8; ++j) { rres[j] = rnext[j]; rnext[j] = rnext2[j]; }
+          if (tile + 2 * g2 < p.ntiles) load_res(tile + 2 * g2, rnext2);      // two tiles ahead: ~32 KB of reads in flight per SM
         }
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
@@ -413,26 +417,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const size_t plane_elems = (size_t)Ho * Wo * 8;
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
+        // both sub-pixel columns (phases 2*half, 2*half+1) of a plane are produced together: output pixels (oy, 2gx) and
+        // (oy, 2gx+1) are 32 contiguous bytes -> one 256-bit store per plane, full 32-byte sectors on every request
+        const int oy = 2 * gy + half, ox = 2 * gx;
+        h16* obase = p.out + ((size_t)b * p.yP + p.yp0) * plane_elems + ((size_t)oy * Wo + ox) * 8;
+        const uint32_t t0 = t_base + (half * 2) * NPRE, t1 = t0 + NPRE;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int ph = half * 2 + q;
-          uint32_t va[32], vg[32];
-          tmem_ld32(t_base + ph * NPRE, va);
-          tmem_ld32(t_base + ph * NPRE + COUT, vg);
+        for (int j = 0; j < 4; ++j) {
+          uint32_t a0[8], g0[8], a1[8], g1[8];
+          tmem_ld8(t0 + j * 8, a0); tmem_ld8(t0 + COUT + j * 8, g0);
+          tmem_ld8(t1 + j * 8, a1); tmem_ld8(t1 + COUT + j * 8, g1);
           tmem_ld_wait();
-          const int oy = 2 * gy + half, ox = 2 * gx + q;
-          h16* obase = p.out + ((size_t)b * p.yP + p.yp0) * plane_elems + ((size_t)oy * Wo + ox) * 8;
+          const float4 sa0 = sh4[j * 2], sa1 = sh4[j * 2 + 1], sg0 = sh4[(COUT + j * 8) / 4], sg1 = sh4[(COUT + j * 8) / 4 + 1];
+          const float sa[8] = {sa0.x, sa0.y, sa0.z, sa0.w, sa1.x, sa1.y, sa1.z, sa1.w};
+          const float sg[8] = {sg0.x, sg0.y, sg0.z, sg0.w, sg1.x, sg1.y, sg1.z, sg1.w};
+          float o0[8], o1[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 sa0 = sh4[j * 2], sa1 = sh4[j * 2 + 1], g0 = sh4[(COUT + j * 8) / 4], g1 = sh4[(COUT + j * 8) / 4 + 1];
-            const float sa[8] = {sa0.x, sa0.y, sa0.z, sa0.w, sa1.x, sa1.y, sa1.z, sa1.w};
-            const float sg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              o[e] = (__uint_as_float(va[j * 8 + e]) + sa[e]) * fast_sigmoid(__uint_as_float(vg[j * 8 + e]) + sg[e]);
-            *reinterpret_cast<uint4*>(obase + (size_t)j * plane_elems) = pack8_16<FMT>(o);
+          for (int e = 0; e < 8; ++e) {
+            o0[e] = (__uint_as_float(a0[e]) + sa[e]) * fast_sigmoid(__uint_as_float(g0[e]) + sg[e]);
+            o1[e] = (__uint_as_float(a1[e]) + sa[e]) * fast_sigmoid(__uint_as_float(g1[e]) + sg[e]);
           }
+          stg256(obase + (size_t)j * plane_elems, pack8_16<FMT>(o0), pack8_16<FMT>(o1));
         }
       }
       tc_fence_before();
