@@ -198,18 +198,19 @@ int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const void* sfrag, con
  * util.py:76, conv3x3/conv5x5 util.py:62-69, tanh head + `one*y + a*SRb` model.py:224,280, GlobalAttention.py:87-130). */
 
 /* BatchNorm2d train-mode statistics of x [B,C,HW]: mean[c], invstd[c] = 1/sqrt(biased var + eps); updates
- * running_mean / running_var (unbiased var, momentum) in place when not NULL. */
+ * running_mean / running_var (unbiased var, momentum) in place when not NULL.  ws: 2*C doubles of scratch (the channel
+ * sums of the multi-CTA reduction). */
 int tgsr_bn_stats_f32(const float* x, float* mean, float* invstd, float* running_mean, float* running_var,
-                      float momentum, float eps, int B, int C, int HW, tgsr_stream_t stream);
+                      float momentum, float eps, double* ws, int B, int C, int HW, tgsr_stream_t stream);
 /* y = act(gamma*(x-mean)*invstd + beta) (+ residual, shaped like y).  act NONE: y [B,C,HW]; act GLU: y [B,C/2,HW]. */
 int tgsr_bn_act_f32(const float* x, const float* mean, const float* invstd, const float* gamma,
                     const float* beta, const float* residual, float* y, int B, int C, int HW, int act,
                     tgsr_stream_t stream);
 /* Backward of tgsr_bn_act_f32 through the batch statistics: dx [B,C,HW], dgamma [C], dbeta [C] from dy (shape of y).
- * (The residual's gradient is dy itself.) */
+ * (The residual's gradient is dy itself.)  ws: 2*C doubles of scratch. */
 int tgsr_bn_act_bwd_f32(const float* x, const float* mean, const float* invstd, const float* gamma,
-                        const float* beta, const float* dy, float* dx, float* dgamma, float* dbeta, int B,
-                        int C, int HW, int act, tgsr_stream_t stream);
+                        const float* beta, const float* dy, float* dx, float* dgamma, float* dbeta, double* ws,
+                        int B, int C, int HW, int act, tgsr_stream_t stream);
 /* wt[ci][co][k-1-ky][k-1-kx] = w[co][ci][ky][kx]: tgsr_conv2d_f32(dy, wt) is the data gradient of conv(x, w). */
 int tgsr_conv_weight_flip_f32(const float* w, float* wt, int Cout, int Cin, int ksize, tgsr_stream_t stream);
 /* Backward of the nearest x2 upsample folded into a conv: y [BC,H,W] = 2x2 block sums of x [BC,2H,2W]. */

@@ -47,9 +47,9 @@ _SIGS = {
     'tgsr_img_head_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
                          + [C.c_int] * 7 + [C.c_void_p], C.c_int),
     'tgsr_conv_in_blocked': ([C.c_void_p] * 6 + [C.c_int] * 7 + [C.c_void_p], C.c_int),
-    'tgsr_bn_stats_f32': ([C.c_void_p] * 5 + [C.c_float, C.c_float] + [C.c_int] * 3 + [C.c_void_p], C.c_int),
+    'tgsr_bn_stats_f32': ([C.c_void_p] * 5 + [C.c_float, C.c_float, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p], C.c_int),
     'tgsr_bn_act_f32': ([C.c_void_p] * 7 + [C.c_int] * 4 + [C.c_void_p], C.c_int),
-    'tgsr_bn_act_bwd_f32': ([C.c_void_p] * 9 + [C.c_int] * 4 + [C.c_void_p], C.c_int),
+    'tgsr_bn_act_bwd_f32': ([C.c_void_p] * 10 + [C.c_int] * 4 + [C.c_void_p], C.c_int),
     'tgsr_conv_weight_flip_f32': ([C.c_void_p, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p], C.c_int),
     'tgsr_sumpool2x2_f32': ([C.c_void_p, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p], C.c_int),
     'tgsr_conv2d_wgrad_f32': ([C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p], C.c_int),

@@ -70,18 +70,30 @@ conv_tf32_kernel(const float* __restrict__ x, const uint32_t* __restrict__ wk, f
 #pragma unroll
     for (int n = 0; n < NT; ++n) { acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f; }
 
+  // halo-tile positions owned by this thread (the same for every channel and every chunk): source offset inside a
+  // channel plane, or -1 outside the image (zero padding)
+  constexpr int TW = 16 + K - 1, NPOS = (TH * TW + 255) / 256;
+  int src_off[NPOS], dst_off[NPOS];
+#pragma unroll
+  for (int k = 0; k < NPOS; ++k) {
+    const int r = tid + 256 * k, yy = r / TW, xx = r - yy * TW;
+    const int gy = ty0 + yy - R, gx = tx0 + xx - R;
+    const bool in = r < TH * TW && gy >= 0 && gy < Ho && gx >= 0 && gx < Wo;
+    src_off[k] = in ? (up2x ? (gy >> 1) * W + (gx >> 1) : gy * W + gx) : -1;
+    dst_off[k] = r < TH * TW ? yy * RS + xx : -1;
+  }
+  const size_t chan = (size_t)H * W;
+  const float* xb = x + (size_t)b * Cin * chan;
+
   for (int c0 = 0; c0 < Cin; c0 += 8) {
     __syncthreads();
-    for (int idx = tid; idx < 8 * TH * (16 + K - 1); idx += 256) {
-      const int TW = 16 + K - 1;
-      const int c = idx / (TH * TW), r = idx % (TH * TW), yy = r / TW, xx = r % TW;
-      const int gy = ty0 + yy - R, gx = tx0 + xx - R;
-      float v = 0.f;
-      if (c0 + c < Cin && gy >= 0 && gy < Ho && gx >= 0 && gx < Wo) {
-        const int sy = up2x ? (gy >> 1) : gy, sx = up2x ? (gx >> 1) : gx;
-        v = __ldg(x + (((size_t)b * Cin + c0 + c) * H + sy) * W + sx);
-      }
-      xs[c * PLANE + yy * RS + xx] = __float_as_uint(v);   // raw fp32 bits: the tensor core reads the TF32 part (truncation)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const bool cv = c0 + c < Cin;
+      const float* xc = xb + (size_t)(c0 + c) * chan;
+#pragma unroll
+      for (int k = 0; k < NPOS; ++k)
+        if (dst_off[k] >= 0) xs[c * PLANE + dst_off[k]] = (cv && src_off[k] >= 0) ? __float_as_uint(__ldg(xc + src_off[k])) : 0u;
     }
     for (int idx = tid; idx < KK * 8 * NB; idx += 256) {
       const int n = idx % NB, c = (idx / NB) % 8, tp = idx / (NB * 8);

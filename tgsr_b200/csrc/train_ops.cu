@@ -43,32 +43,37 @@ __device__ __forceinline__ void block_sum(double (&v)[N]) {
 }
 
 // ---------------------------------------------------------------- BatchNorm statistics (train forward)
-// One CTA per channel; fp32 loads, per-thread fp32 partials over short runs folded into double accumulators.
+// grid (C, SPLIT): CTA (c, s) sums channel c over images s, s+SPLIT, ... (fp32 partials per image folded into double
+// accumulators) and adds its two sums to ws[2c], ws[2c+1] (double atomics); bn_stats_final turns them into mean / invstd
+// and updates the running statistics.  One CTA per channel left most of the SMs idle and took ~1 ms per layer.
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ invstd,
-                float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps, int B,
-                int C, int HW) {
+bn_stats_partial_kernel(const float* __restrict__ x, double* __restrict__ ws, int B, int C, int HW) {
   const int c = blockIdx.x;
   double acc[2] = {0.0, 0.0};
-  for (int b = 0; b < B; ++b) {
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
     const float* p = x + ((size_t)b * C + c) * HW;
     float s = 0.f, q = 0.f;
     for (int i = threadIdx.x; i < HW; i += 256) { const float v = __ldg(p + i); s += v; q = fmaf(v, v, q); }
     acc[0] += s; acc[1] += q;
   }
   block_sum<2>(acc);
-  if (threadIdx.x == 0) {
-    const double n = (double)B * HW;
-    const double m = acc[0] / n;
-    double var = acc[1] / n - m * m;                  // biased variance (normalisation)
-    if (var < 0.0) var = 0.0;
-    mean[c] = (float)m;
-    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-    if (running_mean) {
-      const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
-      running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
-      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
-    }
+  if (threadIdx.x == 0) { atomicAdd(ws + 2 * c, acc[0]); atomicAdd(ws + 2 * c + 1, acc[1]); }
+}
+
+__global__ void bn_stats_final_kernel(const double* __restrict__ ws, float* __restrict__ mean, float* __restrict__ invstd,
+                                      float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                      float eps, int C, double n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = ws[2 * c] / n;
+  double var = ws[2 * c + 1] / n - m * m;                       // biased variance (normalisation)
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
   }
 }
 
@@ -102,13 +107,13 @@ template <bool GLU>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ dy,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int C, int HW) {
+                     double* __restrict__ ws, int B, int C, int HW) {
   const int Cf = GLU ? C / 2 : C;
   const int c = blockIdx.x, cg = c + Cf;
   const float m0 = mean[c], r0 = invstd[c], g0 = gamma[c], b0 = beta[c];
   const float m1 = GLU ? mean[cg] : 0.f, r1 = GLU ? invstd[cg] : 0.f, g1 = GLU ? gamma[cg] : 0.f, b1 = GLU ? beta[cg] : 0.f;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int b = 0; b < B; ++b) {
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {             // grid (Cf, SPLIT): images s, s+SPLIT, ...
     const float* xa = x + ((size_t)b * C + c) * HW;
     const float* xg = x + ((size_t)b * C + cg) * HW;
     const float* d = dy + ((size_t)b * Cf + c) * HW;
@@ -119,7 +124,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ mean
       if (GLU) {
         const float xhg = (__ldg(xg + i) - m1) * r1;
         const float za = fmaf(xh, g0, b0), zg = fmaf(xhg, g1, b1);
-        const float sg = 1.0f / (1.0f + expf(-zg));
+        const float sg = 1.0f / (1.0f + __expf(-zg));
         const float dzg = dz * za * sg * (1.0f - sg);
         dz *= sg;
         s1g += dzg; s2g = fmaf(dzg, xhg, s2g);
@@ -130,9 +135,16 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ mean
   }
   block_sum<4>(acc);
   if (threadIdx.x == 0) {
-    dbeta[c] = (float)acc[0]; dgamma[c] = (float)acc[1];
-    if (GLU) { dbeta[cg] = (float)acc[2]; dgamma[cg] = (float)acc[3]; }
+    atomicAdd(ws + 2 * c, acc[0]); atomicAdd(ws + 2 * c + 1, acc[1]);
+    if (GLU) { atomicAdd(ws + 2 * cg, acc[2]); atomicAdd(ws + 2 * cg + 1, acc[3]); }
   }
+}
+
+__global__ void bn_bwd_final_kernel(const double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dbeta[c] = (float)ws[2 * c];
+  dgamma[c] = (float)ws[2 * c + 1];
 }
 
 // ---------------------------------------------------------------- backward, stage 2: dx
@@ -155,7 +167,7 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
       const size_t xgi = xi + (size_t)Cf * HW;
       const float xhg = (__ldg(x + xgi) - mean[cg]) * invstd[cg];
       const float za = fmaf(xh, gamma[c], beta[c]), zg = fmaf(xhg, gamma[cg], beta[cg]);
-      const float sg = 1.0f / (1.0f + expf(-zg));
+      const float sg = 1.0f / (1.0f + __expf(-zg));
       const float dzg = dz * za * sg * (1.0f - sg);
       dz *= sg;
       dx[xgi] = gamma[cg] * invstd[cg] * (dzg - dbeta[cg] * inv_n - xhg * dgamma[cg] * inv_n);
@@ -282,13 +294,23 @@ static inline unsigned ew_blocks(size_t total) {
 
 using namespace tgsr;
 
+static inline int bn_split(int channels, int B) {
+  const int sms = g_sm_count > 0 ? g_sm_count : 148;
+  int s = ceil_div(4 * sms, channels);
+  return s < 1 ? 1 : (s > B ? B : s);
+}
+
 extern "C" int tgsr_bn_stats_f32(const float* x, float* mean, float* invstd, float* running_mean, float* running_var,
-                                 float momentum, float eps, int B, int C, int HW, tgsr_stream_t stream) {
-  TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(mean); TGSR_REQUIRE_PTR(invstd);
+                                 float momentum, float eps, double* ws, int B, int C, int HW, tgsr_stream_t stream) {
+  TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(mean); TGSR_REQUIRE_PTR(invstd); TGSR_REQUIRE_PTR(ws);
   TGSR_REQUIRE((running_mean == nullptr) == (running_var == nullptr), TGSR_ERR_NULL);
-  TGSR_REQUIRE(B > 0 && C > 0 && HW > 0, TGSR_ERR_BAD_SHAPE);
-  bn_stats_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(x, mean, invstd, running_mean, running_var, momentum, eps, B, C, HW);
-  return launch_status();
+  TGSR_REQUIRE(B > 0 && C > 0 && HW > 0 && C <= 65535, TGSR_ERR_BAD_SHAPE);
+  cudaStream_t st = (cudaStream_t)stream;
+  TGSR_CUDA(cudaMemsetAsync(ws, 0, (size_t)2 * C * sizeof(double), st));
+  bn_stats_partial_kernel<<<dim3(C, bn_split(C, B)), 256, 0, st>>>(x, ws, B, C, HW);
+  bn_stats_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, mean, invstd, running_mean, running_var, momentum, eps, C,
+                                                         (double)B * HW);
+  return launch_status(2);
 }
 
 extern "C" int tgsr_bn_act_f32(const float* x, const float* mean, const float* invstd, const float* gamma,
@@ -307,25 +329,29 @@ extern "C" int tgsr_bn_act_f32(const float* x, const float* mean, const float* i
 }
 
 extern "C" int tgsr_bn_act_bwd_f32(const float* x, const float* mean, const float* invstd, const float* gamma,
-                                   const float* beta, const float* dy, float* dx, float* dgamma, float* dbeta, int B,
-                                   int C, int HW, int act, tgsr_stream_t stream) {
+                                   const float* beta, const float* dy, float* dx, float* dgamma, float* dbeta, double* ws,
+                                   int B, int C, int HW, int act, tgsr_stream_t stream) {
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(mean); TGSR_REQUIRE_PTR(invstd); TGSR_REQUIRE_PTR(gamma); TGSR_REQUIRE_PTR(beta);
-  TGSR_REQUIRE_PTR(dy); TGSR_REQUIRE_PTR(dx); TGSR_REQUIRE_PTR(dgamma); TGSR_REQUIRE_PTR(dbeta);
-  TGSR_REQUIRE(B > 0 && C > 0 && HW > 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE_PTR(dy); TGSR_REQUIRE_PTR(dx); TGSR_REQUIRE_PTR(dgamma); TGSR_REQUIRE_PTR(dbeta); TGSR_REQUIRE_PTR(ws);
+  TGSR_REQUIRE(B > 0 && C > 0 && HW > 0 && C <= 65535, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE(act == TGSR_ACT_NONE || act == TGSR_ACT_GLU, TGSR_ERR_UNSUPPORTED);
   if (act == TGSR_ACT_GLU) TGSR_REQUIRE(C % 2 == 0, TGSR_ERR_BAD_SHAPE);
   const int Cf = act == TGSR_ACT_GLU ? C / 2 : C;
   const size_t total = (size_t)B * Cf * HW;
   const float inv_n = 1.0f / ((float)B * (float)HW);
   cudaStream_t st = (cudaStream_t)stream;
+  TGSR_CUDA(cudaMemsetAsync(ws, 0, (size_t)2 * C * sizeof(double), st));
+  const dim3 rgrid(Cf, bn_split(Cf, B));
   if (act == TGSR_ACT_GLU) {
-    bn_bwd_reduce_kernel<true><<<Cf, 256, 0, st>>>(x, mean, invstd, gamma, beta, dy, dgamma, dbeta, B, C, HW);
+    bn_bwd_reduce_kernel<true><<<rgrid, 256, 0, st>>>(x, mean, invstd, gamma, beta, dy, ws, B, C, HW);
+    bn_bwd_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, dgamma, dbeta, C);
     bn_bwd_apply_kernel<true><<<ew_blocks(total), 256, 0, st>>>(x, mean, invstd, gamma, beta, dy, dgamma, dbeta, dx, C, HW, total, inv_n);
   } else {
-    bn_bwd_reduce_kernel<false><<<Cf, 256, 0, st>>>(x, mean, invstd, gamma, beta, dy, dgamma, dbeta, B, C, HW);
+    bn_bwd_reduce_kernel<false><<<rgrid, 256, 0, st>>>(x, mean, invstd, gamma, beta, dy, ws, B, C, HW);
+    bn_bwd_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, dgamma, dbeta, C);
     bn_bwd_apply_kernel<false><<<ew_blocks(total), 256, 0, st>>>(x, mean, invstd, gamma, beta, dy, dgamma, dbeta, dx, C, HW, total, inv_n);
   }
-  return launch_status(2);
+  return launch_status(3);
 }
 
 extern "C" int tgsr_conv_weight_flip_f32(const float* w, float* wt, int Cout, int Cin, int ksize, tgsr_stream_t stream) {

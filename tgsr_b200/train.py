@@ -117,8 +117,9 @@ class BnActFn(torch.autograd.Function):
         mean = _empty_like_shape((Cc,), x); invstd = _empty_like_shape((Cc,), x)
         track = bn.track_running_stats and bn.running_mean is not None
         mom = 0.1 if bn.momentum is None else float(bn.momentum)
+        ws = torch.empty(2 * Cc, device=x.device, dtype=torch.float64)
         call('tgsr_bn_stats_f32', x.device, ptr(x), ptr(mean), ptr(invstd), ptr(bn.running_mean if track else None),
-             ptr(bn.running_var if track else None), mom, float(bn.eps), B, Cc, H * W)
+             ptr(bn.running_var if track else None), mom, float(bn.eps), ptr(ws), B, Cc, H * W)
         if track and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
         Cf = Cc // 2 if act == ACT_GLU else Cc
@@ -136,8 +137,9 @@ class BnActFn(torch.autograd.Function):
         dy = dy.contiguous()
         B, Cc, H, W = x.shape
         dx = torch.empty_like(x); dg = torch.empty_like(gamma); db = torch.empty_like(beta)
+        ws = torch.empty(2 * Cc, device=x.device, dtype=torch.float64)
         call('tgsr_bn_act_bwd_f32', x.device, ptr(x), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(dy), ptr(dx), ptr(dg), ptr(db),
-             B, Cc, H * W, ctx.act)
+             ptr(ws), B, Cc, H * W, ctx.act)
         return dx, dg, db, (dy if ctx.has_res else None), None, None
 
 
