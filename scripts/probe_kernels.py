@@ -71,6 +71,14 @@ def main():
         st.att.applyMask(torch.zeros(B, 18, dtype=torch.uint8, device=dev))
         fn = lambda: st.att(x, ctx)
         nbytes = B * S * S * (32 * 4 + 32 * 4 + 4 * 18) + B * 256 * 18 * 4 + 32 * 256 * 4 + B * 18
+    elif a.what in ('convtf32', 'wgradtf32'):   # training convs: TF32 tensor-core forward / weight gradient, 64 -> 128
+        from tgsr_b200 import train
+        train.set_conv_precision('tf32')
+        x = torch.randn(B, 64, S, S, device=dev) * 0.5
+        w = torch.randn(128, 64, 3, 3, device=dev) * 0.05
+        dy = torch.randn(B, 128, S, S, device=dev) * 0.5
+        fn = (lambda: train._conv_raw(x, w, False)) if a.what == 'convtf32' else (lambda: train._conv_wgrad(x, dy, w.shape, False))
+        flops = 2 * 9 * 64 * 128 * S * S * B
     elif a.what == 'null':                      # calibration: a trivially small kernel in the same harness
         from tgsr_b200 import ops
         v = torch.ones(64, device=dev)

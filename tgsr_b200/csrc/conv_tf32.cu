@@ -87,19 +87,38 @@ conv_tf32_kernel(const float* __restrict__ x, const uint32_t* __restrict__ wk, f
 
   for (int c0 = 0; c0 < Cin; c0 += 8) {
     __syncthreads();
+    // two phases -- all loads of the chunk into registers, then all shared-memory stores -- so the global-load latency
+    // is paid once per chunk, not once per element (a load->store chain per element serialised ~16 L2 round trips)
+    uint32_t xv[8][NPOS];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const bool cv = c0 + c < Cin;
-      const float* xc = xb + (size_t)(c0 + c) * chan;
+      const float* xc = xb + (size_t)(cv ? c0 + c : 0) * chan;
+#pragma unroll
+      for (int k = 0; k < NPOS; ++k) {
+        const float v = __ldg(xc + (src_off[k] >= 0 ? src_off[k] : 0));
+        xv[c][k] = (cv && src_off[k] >= 0) ? __float_as_uint(v) : 0u;
+      }
+    }
+    constexpr int NW = (KK * 8 * NB + 255) / 256;
+    uint32_t wv[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      const int idx = tid + 256 * k;
+      const int n = idx % NB, c = (idx / NB) % 8, tp = idx / (NB * 8);
+      const bool ok = idx < KK * 8 * NB && c0 + c < Cin && n0 + n < N;
+      const uint32_t v = __ldg(wk + (ok ? ((size_t)(c0 + c) * KK + tp) * N + n0 + n : 0));
+      wv[k] = ok ? v : 0u;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
 #pragma unroll
       for (int k = 0; k < NPOS; ++k)
-        if (dst_off[k] >= 0) xs[c * PLANE + dst_off[k]] = (cv && src_off[k] >= 0) ? __float_as_uint(__ldg(xc + src_off[k])) : 0u;
-    }
-    for (int idx = tid; idx < KK * 8 * NB; idx += 256) {
-      const int n = idx % NB, c = (idx / NB) % 8, tp = idx / (NB * 8);
-      uint32_t v = 0u;
-      if (c0 + c < Cin && n0 + n < N) v = __ldg(wk + ((size_t)(c0 + c) * KK + tp) * N + n0 + n);
-      ws[(tp * 8 + c) * LDW + n] = v;
+        if (dst_off[k] >= 0) xs[c * PLANE + dst_off[k]] = xv[c][k];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      const int idx = tid + 256 * k;
+      if (idx < KK * 8 * NB) ws[((idx / (NB * 8)) * 8 + (idx / NB) % 8) * LDW + idx % NB] = wv[k];
     }
     __syncthreads();
 #pragma unroll
@@ -166,22 +185,46 @@ wgrad_tf32_kernel(const float* __restrict__ x, const float* __restrict__ dy, flo
     const int b = wk / (tiles_x * tiles_y), t = wk % (tiles_x * tiles_y);
     const int ty0 = (t / tiles_x) * 16, tx0 = (t % tiles_x) * 16;
     __syncthreads();
-    for (int idx = tid; idx < COB * 256; idx += 256) {
-      const int c = idx >> 8, r = idx & 255, yy = r >> 4, xx = r & 15;
-      const int gy = ty0 + yy, gx = tx0 + xx;
-      float v = 0.f;
-      if (gy < Ho && gx < Wo) v = __ldg(dy + (((size_t)b * Cout + co0 + c) * Ho + gy) * Wo + gx);
-      ds[c * DP + r] = __float_as_uint(v);
-    }
-    for (int idx = tid; idx < 32 * TH * TH; idx += 256) {
-      const int c = idx / (TH * TH), r = idx % (TH * TH), yy = r / TH, xx = r % TH;
-      const int gy = ty0 + yy - R, gx = tx0 + xx - R;
-      float v = 0.f;
-      if (gy >= 0 && gy < Ho && gx >= 0 && gx < Wo) {
-        const int sy = up2x ? (gy >> 1) : gy, sx = up2x ? (gx >> 1) : gx;
-        v = __ldg(x + (((size_t)b * Cin + ci0 + c) * H + sy) * W + sx);
+    // staged in batches of 16 independent loads followed by 16 stores (one global-load latency per batch)
+    {
+      const int yy = tid >> 4, xx = tid & 15, gy = ty0 + yy, gx = tx0 + xx;
+      const bool in = gy < Ho && gx < Wo;
+      const float* dp = dy + (((size_t)b * Cout + co0) * Ho + (in ? gy : 0)) * Wo + (in ? gx : 0);
+      const size_t cs = (size_t)Ho * Wo;
+#pragma unroll
+      for (int c0 = 0; c0 < COB; c0 += 16) {
+        float v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = __ldg(dp + (size_t)(c0 + c) * cs);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) ds[(c0 + c) * DP + tid] = in ? __float_as_uint(v[c]) : 0u;
       }
-      xs[c * XP + r] = __float_as_uint(v);
+    }
+    {
+      constexpr int NPX = (TH * TH + 255) / 256;
+      int src[NPX], dst[NPX];
+#pragma unroll
+      for (int k = 0; k < NPX; ++k) {
+        const int r = tid + 256 * k, yy = r / TH, xx = r - yy * TH;
+        const int gy = ty0 + yy - R, gx = tx0 + xx - R;
+        const bool in = r < TH * TH && gy >= 0 && gy < Ho && gx >= 0 && gx < Wo;
+        src[k] = in ? (up2x ? (gy >> 1) * W + (gx >> 1) : gy * W + gx) : -1;
+        dst[k] = r < TH * TH ? r : -1;
+      }
+      const float* xb = x + ((size_t)b * Cin + ci0) * ((size_t)H * W);
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 8) {
+        float v[8][NPX];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int k = 0; k < NPX; ++k) v[c][k] = __ldg(xb + (size_t)(c0 + c) * H * W + (src[k] >= 0 ? src[k] : 0));
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int k = 0; k < NPX; ++k)
+            if (dst[k] >= 0) xs[(c0 + c) * XP + dst[k]] = src[k] >= 0 ? __float_as_uint(v[c][k]) : 0u;
+      }
     }
     __syncthreads();
     // K-steps: 8 consecutive pixels of one tile row
