@@ -36,14 +36,13 @@ conv_in_kernel(const float* __restrict__ x, const float* __restrict__ xsub, cons
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
+          // branch-free: clamped address + select, so the 27 (54) loads are independent and in flight together
           const int yy = py + ky - 1, xx = px + kx - 1;
-          float v = 0.f;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-            const size_t o = (((size_t)b * 3 + c) * H + yy) * W + xx;
-            v = __ldg(x + o);
-            if (xsub) v -= __ldg(xsub + o);
-          }
-          in[c * 9 + ky * 3 + kx] = v;
+          const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+          const size_t o = (((size_t)b * 3 + c) * H + (ok ? yy : py)) * W + (ok ? xx : px);
+          float v = __ldg(x + o);
+          if (xsub) v -= __ldg(xsub + o);
+          in[c * 9 + ky * 3 + kx] = ok ? v : 0.f;
         }
     float o8[8];
 #pragma unroll

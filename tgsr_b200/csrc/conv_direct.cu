@@ -45,20 +45,20 @@ conv2d_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
     for (int idx = tid; idx < CD_CCH * TS * TS; idx += CD_TILE * CD_TILE) {
       const int c = idx / (TS * TS), r = idx % (TS * TS), yy = r / TS, xx = r % TS;
       const int gy = ty0 + yy - R, gx = tx0 + xx - R;
-      float v = 0.f;
-      if (c0 + c < Cin && gy >= 0 && gy < Ho && gx >= 0 && gx < Wo) {
-        const int sy = up2x ? (gy >> 1) : gy, sx = up2x ? (gx >> 1) : gx;
-        v = __ldg(x + (((size_t)b * Cin + c0 + c) * H + sy) * W + sx);
-      }
-      tile[c][yy][xx] = v;
+      // branch-free (clamped address + select): the loads of the staging loop stay independent and overlap
+      const bool ok = c0 + c < Cin && gy >= 0 && gy < Ho && gx >= 0 && gx < Wo;
+      const int cy = ok ? gy : 0, cx = ok ? gx : 0, cc = ok ? c0 + c : 0;
+      const int sy = up2x ? (cy >> 1) : cy, sx = up2x ? (cx >> 1) : cx;
+      const float v = __ldg(x + (((size_t)b * Cin + cc) * H + sy) * W + sx);
+      tile[c][yy][xx] = ok ? v : 0.f;
     }
     for (int idx = tid; idx < NH * CD_COB * CD_CCH * K * K; idx += CD_TILE * CD_TILE) {
       const int kk = idx % (K * K), c = (idx / (K * K)) % CD_CCH, o = (idx / (K * K * CD_CCH)) % CD_COB,
                 h = idx / (K * K * CD_CCH * CD_COB);
       const int co = co0 + o + h * Cf;
-      float v = 0.f;
-      if (co0 + o < Cf && c0 + c < Cin) v = __ldg(w + ((size_t)co * Cin + c0 + c) * K * K + kk);
-      wsm[h][o][c][kk] = v;
+      const bool okw = co0 + o < Cf && c0 + c < Cin;
+      const float v = __ldg(w + (okw ? ((size_t)co * Cin + c0 + c) * K * K + kk : 0));
+      wsm[h][o][c][kk] = okw ? v : 0.f;
     }
     __syncthreads();
 #pragma unroll 2
