@@ -188,7 +188,7 @@ def run_ours(args):
     import tgsr_b200
     from tgsr_b200 import _lib
     from tgsr_b200.pipeline import SRPipeline
-    from oracle import tgsr_oracle as O           # synthetic-input generators only (checker code, not timed)
+    from tgsr_b200 import synth as O              # synthetic-input generators
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))

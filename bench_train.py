@@ -34,7 +34,7 @@ def main():
     from tgsr_b200 import _lib, nets
     from tgsr_b200.text_encoder import RNN_ENCODER
     from tgsr_b200.train_step import FrozenImageEncoder, GeneratorTrainStep
-    from oracle import tgsr_oracle as O                    # synthetic-input generators only
+    from tgsr_b200 import synth as O                       # synthetic-input generators
 
     world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0')); local = int(os.environ.get('LOCAL_RANK', '0'))
     if not torch.cuda.is_available():

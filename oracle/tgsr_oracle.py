@@ -356,28 +356,7 @@ def rnn_encoder(sd: SD, captions: Tensor, cap_lens: Tensor) -> Tuple[Tensor, Ten
 # --------------------------------------------------------------------------
 # Synthetic inputs and image metrics
 # --------------------------------------------------------------------------
-def synth_lr(batch: int, size: int, seed: int, kind: str = 'smooth') -> Tensor:
-    """'smooth': U(-1,1) at 4x4, bicubic to size, clamp; 'noise': iid U(-1,1)."""
-    g = torch.Generator().manual_seed(seed)
-    if kind == 'noise':
-        return torch.rand(batch, 3, size, size, generator=g) * 2 - 1
-    base = torch.rand(batch, 3, 4, 4, generator=g) * 2 - 1
-    return F.interpolate(base, size=(size, size), mode='bicubic', align_corners=False).clamp(-1, 1)
-
-
-def synth_captions(batch: int, ntoken: int, seed: int, words_num: int = 18, ragged: bool = False):
-    """iid tokens in [1,ntoken); lengths all words_num, or sorted-descending ragged 18..5."""
-    g = torch.Generator().manual_seed(seed)
-    caps = torch.randint(1, ntoken, (batch, words_num), generator=g)
-    if ragged:
-        lens = torch.randint(5, words_num + 1, (batch,), generator=g)
-        lens[0] = words_num
-        lens = torch.sort(lens, descending=True).values
-    else:
-        lens = torch.full((batch,), words_num, dtype=torch.int64)
-    for b in range(batch):
-        caps[b, int(lens[b]):] = 0
-    return caps, lens
+from tgsr_b200.synth import synth_captions, synth_lr  # noqa: E402,F401  (shared synthetic-input generators)
 
 
 def to_uint8(img: Tensor) -> Tensor:
