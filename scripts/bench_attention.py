@@ -91,7 +91,7 @@ def main():
             fn = lambda: ops.func_attention_fwd(q, c, 4.0)
             ms = cold_time_ms(fn, flush, iters=10)
             nbytes = B * (256 * 289 + 2 * 256 * T + T * 289) * 4
-            r = {'op': 'func_attention', 'variant': 'fp32', 'kernel': 'func_attn_fwd_kernel', 'B': B, 'Q': 289, 'T': T, 'idf': 256, 'cdf': 256,
+            r = {'op': 'func_attention', 'variant': 'fp32', 'kernel': 'damsm_pair_fwd_kernel (diagonal pairs)', 'B': B, 'Q': 289, 'T': T, 'idf': 256, 'cdf': 256,
                  'bytes': nbytes, 'us': ms * 1e3, 'GBps': nbytes / ms / 1e6, 'frac_of_hbm_peak': nbytes / ms / 1e6 / peak, 'peak_GBps': peak,
                  'peak_source': src}
             rows.append(r)

@@ -54,14 +54,19 @@ def attention_fwd(inp: Tensor, context: Tensor, w_ctx: Tensor, mask: Optional[Te
 
 # ------------------------------------------------------------------ a2
 def func_attention_fwd(query: Tensor, context: Tensor, gamma1: float) -> Tuple[Tensor, Tensor]:
-    """func_attention (GlobalAttention.py:33-74), forward only."""
+    """func_attention (GlobalAttention.py:33-74), forward only.  At the DAMSM shape (ndf 256, <= 24 words) it runs as
+    the diagonal of the fused pair kernel of the matching losses (csrc/damsm.cu); other shapes keep the generic kernel."""
     query = _f32c(query, 'query'); context = _f32c(context, 'context')
     B, ndf, Tq = query.shape
     ih, iw = context.shape[2], context.shape[3]
     wctx = torch.empty_like(query)
     attn = torch.empty((B, Tq, ih, iw), device=query.device, dtype=torch.float32)
-    call('tgsr_func_attn_fwd_f32', query.device, ptr(query), ptr(context), float(gamma1), ptr(wctx), ptr(attn),
-         B, ndf, Tq, ih * iw)
+    if ndf == 256 and Tq <= 24 and ih * iw <= 1024 and B <= 65535:
+        call('tgsr_damsm_pairs_fwd_f32', query.device, ptr(context), ptr(query), None, float(gamma1), 0.0, 1e-8, None, ptr(attn),
+             None, ptr(wctx), B, B, ndf, ih * iw, Tq, 1)
+    else:
+        call('tgsr_func_attn_fwd_f32', query.device, ptr(query), ptr(context), float(gamma1), ptr(wctx), ptr(attn),
+             B, ndf, Tq, ih * iw)
     return wctx, attn
 
 
