@@ -170,7 +170,7 @@ def run_reference(args):
     total = sum(times)
     value = steps * n_img / total
     sample = '%d steps of %d images per step (bounded sample of the batch-%d workload)' % (steps, n_img, BATCH_PER_GPU)
-    print(json.dumps({
+    line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
         'warmup': warm, 'ms_per_step': 1e3 * total / steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -178,7 +178,60 @@ def run_reference(args):
                                'CPU oracle (PyTorch fp32 port of the reference modules) on host cores'},
         'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0}))
+        'gpu_launches': 0}
+    # Informational (SURVEY.md 8d "library comparison"): the same reference arithmetic run by torch eager on the B200
+    # (ATen/cuDNN/cuBLAS), fp32 with PyTorch's default TF32 convs and under bf16 autocast, batch 32, device-resident.
+    if torch.cuda.is_available():
+        try:
+            line['torch_eager_b200'] = torch_eager_gpu(O, sdE, sdL, sdH)
+        except Exception as e:                       # noqa: BLE001  (never let the extra leg break the reference arm)
+            line['torch_eager_b200'] = {'error': repr(e)[:200]}
+    print(json.dumps(line))
+
+
+def torch_eager_gpu(O, sdE, sdL, sdH, B=BATCH_PER_GPU, iters=10):
+    import torch
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    mv = lambda sd: {k: v.to(dev) for k, v in sd.items()}
+    sdE, sdL, sdH = mv(sdE), mv(sdL), mv(sdH)
+    LR = O.synth_lr(B, 32, seed=101).to(dev)
+    caps, lens = O.synth_captions(B, NTOKEN, seed=102, words_num=WORDS)
+    caps_d = caps.to(dev)
+    # the text encoder as the reference runs it on a GPU: nn.Embedding + cuDNN nn.LSTM over a packed sequence (util.py:233-260)
+    H = sdE['rnn.weight_hh_l0'].shape[1]
+    emb = torch.nn.Embedding(sdE['encoder.weight'].shape[0], sdE['encoder.weight'].shape[1]).to(dev)
+    rnn = torch.nn.LSTM(sdE['encoder.weight'].shape[1], H, 1, batch_first=True, bidirectional=True).to(dev)
+    emb.load_state_dict({'weight': sdE['encoder.weight']})
+    rnn.load_state_dict({k[4:]: v for k, v in sdE.items() if k.startswith('rnn.')})
+    emb.eval(); rnn.eval()
+
+    def text(caps_d, lens):
+        packed = torch.nn.utils.rnn.pack_padded_sequence(emb(caps_d), lens.tolist(), batch_first=True)
+        o, (h, _c) = rnn(packed)
+        words = torch.nn.utils.rnn.pad_packed_sequence(o, batch_first=True)[0].transpose(1, 2)
+        return words, h.transpose(0, 1).contiguous().view(-1, 2 * H)
+    out = {}
+    for name, ctx in (('fp32_tf32_convs', None), ('bf16_autocast', torch.autocast('cuda', dtype=torch.bfloat16))):
+        def one():
+            with torch.no_grad():
+                words, sent = text(caps_d, lens)
+                mask = (caps_d == 0)[:, :words.shape[2]]
+                if ctx is None:
+                    imgs, atts, mu, lv, _ = O.g_sr_net_low(sdL, LR, sent, words, mask)
+                    return O.netg_high(sdH, LR, imgs, LR, low='lr')
+                with ctx:
+                    imgs, atts, mu, lv, _ = O.g_sr_net_low(sdL, LR, sent, words, mask)
+                    return O.netg_high(sdH, LR, imgs, LR, low='lr')
+        for _ in range(3):
+            one()
+        torch.cuda.synchronize(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            one()
+        e.record(); e.synchronize()
+        out[name] = {'value': B * iters / (s.elapsed_time(e) * 1e-3), 'unit': 'images/s', 'batch': B}
+    return out
 
 
 # ----------------------------------------------------------------------------- our arm
