@@ -84,11 +84,27 @@ def main():
         out = one(True)
     e.record()
     barrier()
+    launches = ts.graph_kernels * a.steps if use_graph else int(lib.tgsr_launch_count() - n0)   # replays bypass the counter
     ar_ms = ts.ev[0].elapsed_time(ts.ev[1]) if ts.ev is not None and not use_graph else float('nan')
     t = torch.tensor([s.elapsed_time(e), ar_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0]) / a.steps
+    roof = None
+    if rank == 0:
+        # dominant library kernel of the step: the TF32 implicit-GEMM conv (64 -> 128 at 128x128), timed alone, L2-cold
+        from tgsr_b200 import train
+        from tgsr_b200.timing import cold_time_ms, make_flush
+        xq = torch.randn(B, 64, 128, 128, device=dev) * 0.5
+        wq = torch.randn(128, 64, 3, 3, device=dev) * 0.05
+        cms = cold_time_ms(lambda: train._conv_raw(xq, wq, False), make_flush(dev), iters=5)
+        fl = 2.0 * 9 * 64 * 128 * 128 * 128 * B
+        ach = fl / (cms * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'achieved': ach, 'peak': 275.0, 'unit': 'TFLOP/s', 'frac': ach / 275.0, 'traffic': None,
+                'kernel': 'conv_prep_tf32_kernel + conv_tf32_kernel<3,64> (mma.sync m16n8k8 TF32, fp32 accumulate)', 'ms_per_launch': cms,
+                'flops_per_launch': fl, 'peak_source': 'measured HMMA TF32 issue rate on B200 (scripts/micro/hmma_rate.cu, profiles/r1_hmma_rate.md); '
+                                                       'the tcgen05 bf16 peak (1675 TFLOP/s) is the round-2 target for these convs'}
+        del xq, wq
     if rank == 0:
         print(json.dumps({
             'metric': 'generator training images/sec (G fwd train-BN + DAMSM + MSE + bwd + all-reduce + Adam)',
@@ -99,7 +115,7 @@ def main():
                                    'gamma (4,5,10), Adam(2e-4,(0.5,0.999)), flat-bucket NCCL all-reduce of %d gradients'
                                    % (B, ts.bucket.numel), 'batch_per_gpu': B, 'launch': 'CUDA-graph replay of the whole step' if use_graph else 'per-kernel launches from Python',
                        'image_encoder': 'frozen random-init Inception-v3 on torchvision/cuDNN (library, out of scope)'},
-            'gpu_launches': int(lib.tgsr_launch_count() - n0),
+            'gpu_launches': launches, 'roofline': roof,
             'loss': {k: float(v) for k, v in out.items()}}))
     if world > 1:
         dist.destroy_process_group()

@@ -193,9 +193,13 @@ class GeneratorTrainStep:
                 self._step_impl(self._static[0], self._static[1], self._static[2], self._static[3], tmax, True)
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        from . import _lib
+        lib = _lib.load()
+        n0 = lib.tgsr_launch_count()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._graph_out = self._step_impl(self._static[0], self._static[1], self._static[2], self._static[3], tmax, True)
+        self.graph_kernels = int(lib.tgsr_launch_count() - n0)      # libtgsr kernels inside one replay
 
     def step_graph(self, LR, real, captions, cap_lens) -> Dict[str, torch.Tensor]:
         st = self._static
