@@ -220,8 +220,10 @@ attn_blocked_kernel(const h16* __restrict__ xin, int xP, int xp0, const uint32_t
   const int t_begin = (int)(((long long)blockIdx.x * n_tiles) / gridDim.x);
   const int t_end = (int)(((long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
 
-  // ---- TMA ring: one elected lane requests the four 512-byte plane rows of a tile.  Each warp owns its
-  // barriers, so the first requests go out before anything else in the kernel.
+  // Programmatic dependent launch: the next kernel of the stream may start its prologue on SMs this grid has left.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // ---- TMA ring: one elected lane requests the four 512-byte plane rows of a tile.  Each warp owns its barriers.
   uint64_t* my_bars = bars + warp * AM_DEPTH;
   if (lane == 0) {
 #pragma unroll
@@ -246,9 +248,9 @@ attn_blocked_kernel(const h16* __restrict__ xin, int xP, int xp0, const uint32_t
     rtile += AM_WARPS; rt += AM_WARPS;
     while (rt >= tiles_img) { rt -= tiles_img; ++rb; }
   };
-#pragma unroll
-  for (int d = 0; d < AM_DEPTH; ++d) request(d);
 
+  // operand words and caption mask words come from kernels that finished long before the predecessor: they are read
+  // while the predecessor (the conv that produces x) may still be draining on other SMs
   uint32_t fr[AM_NFRAG];                                         // operand words of the current caption
   auto load_operands = [&](int bb) {
     const uint4* sf = reinterpret_cast<const uint4*>(sfrag) + (size_t)bb * (AM_NFRAG / 4) * 32 + lane;
@@ -271,6 +273,9 @@ attn_blocked_kernel(const h16* __restrict__ xin, int xP, int xp0, const uint32_t
     }
     __syncthreads();
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");             // x (and the output planes) belong to the predecessor until here
+#pragma unroll
+  for (int d = 0; d < AM_DEPTH; ++d) request(d);
 
   // ldmatrix row address of this lane: matrices 0..3 = (plane 2s, px 0-7), (plane 2s, px 8-15), (plane 2s+1, px 0-7),
   // (plane 2s+1, px 8-15); lanes 8j..8j+7 address the rows of matrix j
@@ -482,9 +487,18 @@ extern "C" int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const void*
   auto xi = reinterpret_cast<const h16*>(x);
   auto yo = reinterpret_cast<h16*>(y);
   auto sf = reinterpret_cast<const uint32_t*>(sfrag);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(AM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  static const int use_pdl = [] { const char* e = getenv("TGSR_PDL"); return e ? atoi(e) : 1; }();
+  cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
+  cudaError_t e;
   if (fmt == TGSR_FMT_F16)
-    attn_blocked_kernel<TGSR_FMT_F16><<<grid, AM_THREADS, smem, st>>>(xi, xP, xp0, sf, mask, yo, yP, yp0, attn, B, Q, T, tiles_img, n_tiles);
+    e = cudaLaunchKernelEx(&cfg, attn_blocked_kernel<TGSR_FMT_F16>, xi, xP, xp0, sf, mask, yo, yP, yp0, attn, B, Q, T, tiles_img, n_tiles);
   else
-    attn_blocked_kernel<TGSR_FMT_BF16><<<grid, AM_THREADS, smem, st>>>(xi, xP, xp0, sf, mask, yo, yP, yp0, attn, B, Q, T, tiles_img, n_tiles);
+    e = cudaLaunchKernelEx(&cfg, attn_blocked_kernel<TGSR_FMT_BF16>, xi, xP, xp0, sf, mask, yo, yP, yp0, attn, B, Q, T, tiles_img, n_tiles);
+  if (e != cudaSuccess) return cuda_fail(e);
   return launch_status();
 }

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x, const float* __restrict__ xsub, const float* __restrict__ w,
                const float* __restrict__ scale, const float* __restrict__ shift, h16* __restrict__ y,
                int B, int H, int W, int C, int yP, int yp0) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the attention kernel that follows starts its prologue early
   __shared__ float ws[2 * CI_MAXC * 27];
   __shared__ float sc[2 * CI_MAXC], sh[2 * CI_MAXC];
   for (int i = threadIdx.x; i < 2 * C * 27; i += blockDim.x) ws[i] = w[i];

@@ -168,6 +168,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // Programmatic dependent launch: let the next kernel of the stream start its own prologue (barrier init, TMEM
+  // allocation, weight TMA) on every SM this grid has left, instead of after the whole grid has drained.  Everything
+  // below that touches activations produced by earlier kernels sits behind griddepcontrol.wait.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(wbar, 1);
@@ -197,6 +202,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       }
     }
     __syncwarp();
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // weights are not produced by the predecessor; patches are
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
@@ -261,6 +267,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     // Two warps per TMEM lane quadrant: `half` selects which half of the output channels (or which
     // sub-pixel phases / RGB outputs) this warp produces, so two warps per SM sub-partition work on
     // every tile and the per-tile epilogue latency halves.
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // skip tensor / addend reads and all output writes follow
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;                // 0: warps 2..5, 1: warps 6..9
     const int m = quad * 32 + lane;                  // accumulator row = pixel within the tile
@@ -604,11 +611,20 @@ static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, i
 
 template <int CIN, int NPRE, int MODE, bool GLU>
 static int launch_tc(const CUtensorMap& tmap, const TcParams& p, int fmt, cudaStream_t st) {
-  const int grid = p.ntiles < g_sm_count ? p.ntiles : g_sm_count;
-  if (fmt == TGSR_FMT_F16)
-    conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_F16><<<grid, TC_THREADS, TcCfg<CIN, NPRE, MODE>::SMEM, st>>>(tmap, p);
-  else
-    conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_BF16><<<grid, TC_THREADS, TcCfg<CIN, NPRE, MODE>::SMEM, st>>>(tmap, p);
+  static const int use_pdl = [] { const char* e = getenv("TGSR_PDL"); return e ? atoi(e) : 1; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.ntiles < g_sm_count ? p.ntiles : g_sm_count);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TcCfg<CIN, NPRE, MODE>::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
+  cudaError_t e;
+  if (fmt == TGSR_FMT_F16) e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_F16>, tmap, p);
+  else e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_BF16>, tmap, p);
+  if (e != cudaSuccess) return cuda_fail(e);
   return launch_status();
 }
 
