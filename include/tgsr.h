@@ -188,6 +188,11 @@ int tgsr_conv_in_blocked(const float* x, const float* x_sub, const float* w, con
 size_t tgsr_attn_sfrag_bytes(int B);
 int tgsr_attn_project(const float* context, const float* w_ctx, void* sfrag, int B, int idf, int cdf, int T,
                       int fmt, tgsr_stream_t stream);
+/* n (1..3) projections of the same captions with different conv_context weights in ONE launch (a forward computes the
+ * operand images of all generator stages up front). */
+int tgsr_attn_project_multi(const float* context, const float* w0, const float* w1, const float* w2, void* sfrag0,
+                            void* sfrag1, void* sfrag2, int n, int B, int idf, int cdf, int T, int fmt,
+                            tgsr_stream_t stream);
 int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const void* sfrag, const uint8_t* mask, void* y,
                           int yP, int yp0, float* attn, int B, int idf, int Q, int T, int fmt,
                           tgsr_stream_t stream);

@@ -123,11 +123,15 @@ constexpr int AP_KS = 16;
 
 template <int FMT>
 __global__ void __launch_bounds__(AP_THREADS)
-attn_project_kernel(const float* __restrict__ context, const float* __restrict__ w_ctx, uint32_t* __restrict__ sfrag,
-                    int cdf, int T) {
+attn_project_kernel(const float* __restrict__ context, const float* __restrict__ w_ctx0, const float* __restrict__ w_ctx1,
+                    const float* __restrict__ w_ctx2, uint32_t* __restrict__ sfrag0, uint32_t* __restrict__ sfrag1,
+                    uint32_t* __restrict__ sfrag2, int cdf, int T) {
   __shared__ float part[AP_KS][AP_ROWS][AM_TP];
   __shared__ float Srow[AP_ROWS][AM_TP + 1];
   const int tid = threadIdx.x, b = blockIdx.x, r = blockIdx.y;
+  // blockIdx.z: which projection weight (the three generator stages share the captions: one launch for all of them)
+  const float* __restrict__ w_ctx = blockIdx.z == 0 ? w_ctx0 : (blockIdx.z == 1 ? w_ctx1 : w_ctx2);
+  uint32_t* __restrict__ sfrag = blockIdx.z == 0 ? sfrag0 : (blockIdx.z == 1 ? sfrag1 : sfrag2);
   {
     const int tq = tid & 7, ig = (tid >> 3) & 1, ks = tid >> 4;
     const int nquad = cdf >> 2;
@@ -450,6 +454,18 @@ int init_attention_mma() {
 
 extern "C" size_t tgsr_attn_sfrag_bytes(int B) { return (size_t)B * tgsr::AM_NFRAG * 32 * 4; }
 
+static int attn_project_launch(const float* context, const float* const w[3], void* const sf[3], int n, int B, int idf, int cdf,
+                               int T, int fmt, cudaStream_t st) {
+  using namespace tgsr;
+  dim3 grid(B, AM_IDF / AP_ROWS, n);
+  auto s0 = reinterpret_cast<uint32_t*>(sf[0]); auto s1 = reinterpret_cast<uint32_t*>(sf[1]); auto s2 = reinterpret_cast<uint32_t*>(sf[2]);
+  if (fmt == TGSR_FMT_F16)
+    attn_project_kernel<TGSR_FMT_F16><<<grid, AP_THREADS, 0, st>>>(context, w[0], w[1], w[2], s0, s1, s2, cdf, T);
+  else
+    attn_project_kernel<TGSR_FMT_BF16><<<grid, AP_THREADS, 0, st>>>(context, w[0], w[1], w[2], s0, s1, s2, cdf, T);
+  return launch_status();
+}
+
 extern "C" int tgsr_attn_project(const float* context, const float* w_ctx, void* sfrag, int B, int idf, int cdf, int T,
                                  int fmt, tgsr_stream_t stream) {
   using namespace tgsr;
@@ -457,13 +473,26 @@ extern "C" int tgsr_attn_project(const float* context, const float* w_ctx, void*
   TGSR_REQUIRE_PTR(context); TGSR_REQUIRE_PTR(w_ctx); TGSR_REQUIRE_PTR(sfrag);
   TGSR_REQUIRE(B > 0 && idf > 0 && cdf > 0 && T > 0, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE(idf == AM_IDF && T <= AM_TP && cdf % 4 == 0 && B <= 65535, TGSR_ERR_UNSUPPORTED);
-  dim3 grid(B, AM_IDF / AP_ROWS);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (fmt == TGSR_FMT_F16)
-    attn_project_kernel<TGSR_FMT_F16><<<grid, AP_THREADS, 0, st>>>(context, w_ctx, reinterpret_cast<uint32_t*>(sfrag), cdf, T);
-  else
-    attn_project_kernel<TGSR_FMT_BF16><<<grid, AP_THREADS, 0, st>>>(context, w_ctx, reinterpret_cast<uint32_t*>(sfrag), cdf, T);
-  return launch_status();
+  const float* w[3] = {w_ctx, w_ctx, w_ctx};
+  void* sf[3] = {sfrag, sfrag, sfrag};
+  return attn_project_launch(context, w, sf, 1, B, idf, cdf, T, fmt, (cudaStream_t)stream);
+}
+
+/* Up to three projections of the same captions (the generator stages' conv_context weights) in one launch. */
+extern "C" int tgsr_attn_project_multi(const float* context, const float* w0, const float* w1, const float* w2, void* sfrag0,
+                                       void* sfrag1, void* sfrag2, int n, int B, int idf, int cdf, int T, int fmt,
+                                       tgsr_stream_t stream) {
+  using namespace tgsr;
+  TGSR_REQUIRE(fmt == TGSR_FMT_BF16 || fmt == TGSR_FMT_F16, TGSR_ERR_UNSUPPORTED);
+  TGSR_REQUIRE(n >= 1 && n <= 3, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE_PTR(context); TGSR_REQUIRE_PTR(w0); TGSR_REQUIRE_PTR(sfrag0);
+  if (n > 1) { TGSR_REQUIRE_PTR(w1); TGSR_REQUIRE_PTR(sfrag1); }
+  if (n > 2) { TGSR_REQUIRE_PTR(w2); TGSR_REQUIRE_PTR(sfrag2); }
+  TGSR_REQUIRE(B > 0 && idf > 0 && cdf > 0 && T > 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE(idf == AM_IDF && T <= AM_TP && cdf % 4 == 0 && B <= 65535, TGSR_ERR_UNSUPPORTED);
+  const float* w[3] = {w0, n > 1 ? w1 : w0, n > 2 ? w2 : w0};
+  void* sf[3] = {sfrag0, n > 1 ? sfrag1 : sfrag0, n > 2 ? sfrag2 : sfrag0};
+  return attn_project_launch(context, w, sf, n, B, idf, cdf, T, fmt, (cudaStream_t)stream);
 }
 
 extern "C" int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const void* sfrag, const uint8_t* mask, void* y,

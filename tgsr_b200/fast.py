@@ -110,6 +110,18 @@ def attention_project(att, words: Tensor, fmt: int) -> Tensor:
     return sfrag
 
 
+def attention_project_multi(atts, words: Tensor, fmt: int):
+    """Operand images of up to three attention modules for the same captions, one launch."""
+    B, cdf, T = words.shape
+    ws = [a.conv_context.weight.detach().contiguous() for a in atts]
+    sf = [torch.empty(B * 48 * 32, device=words.device, dtype=torch.int32) for _ in atts]
+    n = len(atts)
+    p = lambda lst, k: ptr(lst[k]) if k < n else None
+    call('tgsr_attn_project_multi', words.device, ptr(words.contiguous()), p(ws, 0), p(ws, 1), p(ws, 2), p(sf, 0), p(sf, 1), p(sf, 2),
+         n, B, ws[0].shape[0], cdf, T, fmt)
+    return sf
+
+
 def attention_blocked_supported(idf: int, T: int, Q: int) -> bool:
     return idf == 32 and T <= 24 and Q % 32 == 0
 
@@ -161,16 +173,12 @@ def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, hea
     imgs: List[Tensor] = []
     atts: List[Tensor] = []
     feats: List[Blocked] = []
-    c_code, mu, logvar = net.ca_net(sent)
     if mask is not None and mask.dtype != torch.uint8:       # one conversion per forward, not one per stage
         mask = mask.to(device=LR.device, dtype=torch.uint8).contiguous()
+    c_code, mu, logvar = net.ca_net(sent)
+    sfrags = text_side_work(stages, words, LR.shape[2] * LR.shape[3], fmt)
     h = None
     n = len(stages)
-    # the word projections depend on the captions only: all stages' operand images first
-    size = LR.shape[2] * LR.shape[3]
-    sfrags = [attention_project(st.att, words, fmt)
-              if attention_blocked_supported(st.att.conv_context.weight.shape[0], words.shape[2], size * 4 ** i) else None
-              for i, st in enumerate(stages)]
     for i, (st, hd) in enumerate(zip(stages, heads)):
         planes = 8 if i + 1 < n else 4                     # leave room for the next stage's c_code
         h, att = stage(st, h, LR if i == 0 else None, words, mask, planes, fmt, sfrags[i])
@@ -180,6 +188,19 @@ def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, hea
     if outmiddle:
         return imgs, atts, mu, logvar, [tc.to_nchw(f) for f in feats]
     return imgs, atts, mu, logvar
+
+
+def text_side_work(stages, words: Tensor, lr_pixels: int, fmt: int):
+    """The word projections depend on the captions only: the operand images of all stages in one launch."""
+    ok = [attention_blocked_supported(st.att.conv_context.weight.shape[0], words.shape[2], lr_pixels * 4 ** i)
+          for i, st in enumerate(stages)]
+    sfrags = [None] * len(stages)
+    idx = [i for i, o in enumerate(ok) if o]
+    for k in range(0, len(idx), 3):
+        grp = idx[k:k + 3]
+        for i, sf in zip(grp, attention_project_multi([stages[i].att for i in grp], words, fmt)):
+            sfrags[i] = sf
+    return sfrags
 
 
 def netg_high_trunk(net, x: Tensor, x_sub: Optional[Tensor], fmt: int = 0) -> Blocked:
