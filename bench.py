@@ -27,8 +27,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-    os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the single JSON line (the launcher's default prints the NCCL version there)
+if os.environ.get('NCCL_DEBUG', 'VERSION').upper() in ('VERSION', 'WARN'):
+    os.environ['NCCL_DEBUG'] = 'NONE'      # keep stdout to the single JSON line (NCCL prints its version there from VERSION up)
 
 BATCH_PER_GPU = 32
 NTOKEN = 5450
