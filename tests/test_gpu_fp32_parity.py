@@ -214,3 +214,36 @@ def test_conv_properties_full_size():
     torch.testing.assert_close(y12, y1 + y2, rtol=1e-4, atol=1e-4)
     xu = x1.repeat_interleave(2, 2).repeat_interleave(2, 3).contiguous()
     torch.testing.assert_close(ops.conv2d_fused(xu, w, None, None, 0), y1, rtol=0, atol=0)
+
+
+def test_attention_all_masked_caption_is_nan_like_torch():
+    """A caption whose words are all masked gives NaN rows in the reference (softmax over -inf only); the kernels keep
+    that behaviour at exactly the same pixels (row-order quirk included) and stay finite elsewhere."""
+    from tgsr_b200 import fast, ops, tc
+    g = torch.Generator().manual_seed(123)
+    B, idf, cdf, ih, iw, T = 3, 32, 256, 16, 8, 6
+    inp = torch.randn(B, idf, ih, iw, generator=g) * 0.5
+    ctx = torch.randn(B, cdf, T, generator=g) * 0.5
+    w = torch.randn(idf, cdf, 1, 1, generator=g) * 0.1
+    mask = torch.zeros(B, T, dtype=torch.bool); mask[1, :] = True; mask[2, 3:] = True
+    ref_w, ref_a = O.global_attention(inp, ctx, w, mask)
+    assert torch.isnan(ref_a).any() and not torch.isnan(ref_a).all()
+    for tcores in (True, False):
+        wctx, attn = ops.attention_fwd(inp.to(DEV), ctx.to(DEV), w.to(DEV), mask.to(DEV), tensor_cores=tcores)
+        assert torch.equal(torch.isnan(attn.cpu()), torch.isnan(ref_a)) and torch.equal(torch.isnan(wctx.cpu()), torch.isnan(ref_w))
+        ok = ~torch.isnan(ref_a)
+        close(attn.cpu()[ok], ref_a[ok], rtol=1e-5, atol=1e-7)
+    # blocked 16-bit path
+    tgsr_b200.set_precision('mixed16')
+    try:
+        att = tgsr_b200.GlobalAttentionGeneral(idf, cdf).to(DEV); att.conv_context.weight.data.copy_(w)
+        xb = inp.to(torch.bfloat16).float()
+        rw, ra = O.global_attention(xb, ctx, w, mask)
+        cat = tc.Blocked.empty(B, 64, ih, iw, DEV)
+        h = tc.to_blocked(xb.to(DEV), out=cat.slice(0, 32))
+        a16 = fast.attention(h, att, ctx.to(DEV), mask.to(DEV), out=cat.slice(32, 32)).cpu()
+        assert torch.equal(torch.isnan(a16), torch.isnan(ra))
+        ok = ~torch.isnan(ra)
+        torch.testing.assert_close(a16[ok], ra[ok], rtol=5e-5, atol=1e-7)
+    finally:
+        tgsr_b200.set_precision('fp32')
