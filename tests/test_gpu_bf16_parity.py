@@ -213,3 +213,9 @@ def test_quantize_u8_and_pipelined_host_api():
     assert torch.equal(pipe.result(t1), blocking)
     u8 = np.round(np.maximum(0, np.minimum(255, (blocking.numpy() + 1.0) * 127.5))).astype(np.uint8)
     assert np.array_equal(pipe.result(t2).numpy(), u8) and np.array_equal(pipe.result(t3).numpy(), u8)
+    # the same batch built inside one pinned buffer crosses PCIe as a single copy
+    packed = torch.empty(SRPipeline.packed_nbytes(B, 18, 32), dtype=torch.uint8).pin_memory()
+    vLR, vc, vl = SRPipeline.packed_views(packed, B, 18, 32)
+    vLR.copy_(LR); vc.copy_(caps); vl.copy_(lens)
+    t4 = pipe.submit(vLR, vc, vl, out='uint8', packed=packed)
+    assert np.array_equal(pipe.result(t4).numpy(), u8)
