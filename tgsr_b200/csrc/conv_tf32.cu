@@ -10,7 +10,7 @@
 //   wgrad_tf32_kernel  dw[co][ci][tap] = sum_px dy[co][px] x[ci][px+tap]: M = COB output channels, N = 32 input
 //                      channels, K = the pixels of 16x16 tiles; the dy fragment of a K-step is reused by all taps.
 // Both use mma.sync m16n8k8 (measured on B200: one HMMA per 2.1 cycles per SM = 275 TFLOP/s TF32).  Weights are rounded
-// to TF32 once per step (cvt.rna); activations and gradients are staged as raw fp32 bits -- the tensor core reads only the
+// to TF32 once per step (cvt.rna); activations and gradients are staged (cp.async double buffer in the conv kernel) as raw fp32 bits -- the tensor core reads only the
 // TF32 part of an operand (truncation), and cvt.rna is a ~6-instruction integer emulation on sm_100 that would double the
 // instruction count of the staging loops.  Shared-memory strides make every fragment load bank-conflict free.
 #include "common.cuh"
@@ -53,9 +53,7 @@ conv_tf32_kernel(const float* __restrict__ x, const uint32_t* __restrict__ wk, f
   constexpr int R = K / 2, KK = K * K, TH = 16 + K - 1, RS = (K == 3) ? 20 : 22, PLANE = TH * RS, LDW = NB + 8;
   constexpr int NT = NB / 16;                                   // n-tiles (8 channels) per warp
   static_assert(PLANE % 32 == 8 || PLANE % 32 == 24, "conflict-free A fragments");
-  extern __shared__ __align__(16) uint32_t csm[];
-  uint32_t* xs = csm;
-  uint32_t* ws = xs + 8 * PLANE;
+  extern __shared__ __align__(16) uint32_t csm[];               // two buffers of { xs [8][PLANE] | ws [KK][8][LDW] }
   const int Ho = up2x ? 2 * H : H, Wo = up2x ? 2 * W : W;
   const int tiles_x = ceil_div(Wo, 16), tiles_y = ceil_div(Ho, 16);
   const int b = blockIdx.x / (tiles_x * tiles_y), t = blockIdx.x % (tiles_x * tiles_y);
@@ -85,42 +83,55 @@ conv_tf32_kernel(const float* __restrict__ x, const uint32_t* __restrict__ wk, f
   const size_t chan = (size_t)H * W;
   const float* xb = x + (size_t)b * Cin * chan;
 
-  for (int c0 = 0; c0 < Cin; c0 += 8) {
-    __syncthreads();
-    // two phases -- all loads of the chunk into registers, then all shared-memory stores -- so the global-load latency
-    // is paid once per chunk, not once per element (a load->store chain per element serialised ~16 L2 round trips)
-    uint32_t xv[8][NPOS];
+  // cp.async double buffer over 8-channel chunks: chunk c+1 streams global -> shared memory (no registers: 4-byte copies
+  // with zero fill for the halo / padding, 16-byte copies for the weight rows) while the tensor cores work on chunk c.
+  constexpr int XS_WORDS = 8 * PLANE, WS_WORDS = KK * 8 * LDW, BUF_WORDS = XS_WORDS + WS_WORDS;
+  constexpr int NW16 = (KK * 8 * (NB / 4) + 255) / 256;          // 16-byte weight copies per thread
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(csm);
+  auto issue_chunk = [&](int c0, int bufi) {
+    const uint32_t xs_a = smem0 + (uint32_t)(bufi * BUF_WORDS) * 4u, ws_a = xs_a + XS_WORDS * 4u;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const bool cv = c0 + c < Cin;
       const float* xc = xb + (size_t)(cv ? c0 + c : 0) * chan;
 #pragma unroll
       for (int k = 0; k < NPOS; ++k) {
-        const float v = __ldg(xc + (src_off[k] >= 0 ? src_off[k] : 0));
-        xv[c][k] = (cv && src_off[k] >= 0) ? __float_as_uint(v) : 0u;
+        if (dst_off[k] >= 0) {
+          const bool ok = cv && src_off[k] >= 0;
+          const float* src = xc + (ok ? src_off[k] : 0);
+          const int nbytes = ok ? 4 : 0;                           // 0 source bytes: the 4 destination bytes are zero-filled
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(xs_a + (uint32_t)(c * PLANE + dst_off[k]) * 4u), "l"(src),
+                       "r"(nbytes) : "memory");
+        }
       }
     }
-    constexpr int NW = (KK * 8 * NB + 255) / 256;
-    uint32_t wv[NW];
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      const int idx = tid + 256 * k;
-      const int n = idx % NB, c = (idx / NB) % 8, tp = idx / (NB * 8);
-      const bool ok = idx < KK * 8 * NB && c0 + c < Cin && n0 + n < N;
-      const uint32_t v = __ldg(wk + (ok ? ((size_t)(c0 + c) * KK + tp) * N + n0 + n : 0));
-      wv[k] = ok ? v : 0u;
+    for (int k = 0; k < NW16; ++k) {
+      const int idx = tid + 256 * k;                              // (tap, channel, group of 4 output channels)
+      if (idx < KK * 8 * (NB / 4)) {
+        const int n4 = idx % (NB / 4), c = (idx / (NB / 4)) % 8, tp = idx / ((NB / 4) * 8);
+        const bool ok = c0 + c < Cin && n0 + 4 * n4 < N;          // N % 32 == 0: a group is valid as a whole
+        const uint32_t* src = wk + (ok ? ((size_t)(c0 + c) * KK + tp) * N + n0 + 4 * n4 : 0);
+        const int nbytes = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ws_a + (uint32_t)((tp * 8 + c) * LDW + 4 * n4) * 4u), "l"(src),
+                     "r"(nbytes) : "memory");
+      }
     }
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-#pragma unroll
-      for (int k = 0; k < NPOS; ++k)
-        if (dst_off[k] >= 0) xs[c * PLANE + dst_off[k]] = xv[c][k];
-#pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      const int idx = tid + 256 * k;
-      if (idx < KK * 8 * NB) ws[((idx / (NB * 8)) * 8 + (idx / NB) % 8) * LDW + idx % NB] = wv[k];
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue_chunk(0, 0);
+  int buf = 0;
+  for (int c0 = 0; c0 < Cin; c0 += 8) {
+    const bool more = c0 + 8 < Cin;
+    if (more) {
+      issue_chunk(c0 + 8, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    __syncthreads();
+    __syncthreads();                                              // chunk c0 has landed for every thread
+    const uint32_t* xs = csm + buf * BUF_WORDS;
+    const uint32_t* ws = xs + XS_WORDS;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky)
 #pragma unroll
@@ -137,6 +148,8 @@ conv_tf32_kernel(const float* __restrict__ x, const uint32_t* __restrict__ wk, f
           for (int n = 0; n < NT; ++n) mma_tf32_16x8x8(acc[m][n], a0, a1, a2, a3, bf[n][0], bf[n][1]);
         }
       }
+    __syncthreads();                                              // all warps done with this buffer before it is refilled
+    buf ^= 1;
   }
   // epilogue: D (row g -> pixel x = g / g+8, cols 2tig, 2tig+1 -> channel)
 #pragma unroll
@@ -264,7 +277,7 @@ wgrad_tf32_kernel(const float* __restrict__ x, const float* __restrict__ dy, flo
 
 template <int K, int NB> static size_t conv_tf32_smem() {
   constexpr int TH = 16 + K - 1, RS = (K == 3) ? 20 : 22;
-  return (size_t)(8 * TH * RS + K * K * 8 * (NB + 8)) * 4;
+  return (size_t)2 * (8 * TH * RS + K * K * 8 * (NB + 8)) * 4;       // double-buffered
 }
 template <int K, int COB> static size_t wgrad_tf32_smem() {
   constexpr int XP = (K == 3) ? 18 * 18 : 20 * 20 + 4;
