@@ -249,9 +249,52 @@ def gen_losses(ns):
     torch.save(cases, os.path.join(OUT, 'losses.pt'))
 
 
+def gen_train(ns):
+    """The UNMODIFIED reference generator modules in train() mode (batch-statistics BatchNorm) on a small batch: outputs,
+    an MSE loss over all six images and autograd gradients.  Pins the oracle's train_mode() and, on the GPU, the explicit
+    backward kernels.  Weights are regenerated from the seed by the tests (state dicts are not stored)."""
+    torch.manual_seed(4242)
+    netGL = ns.model.G_SR_NET_low().train()
+    with ref_loader.cuda_noop():
+        netGH = ns.model.NetG_highweight(weightmap=False, low='lr')
+    netGH.train()
+    g = torch.Generator().manual_seed(4243)
+    for m in list(netGL.modules()) + list(netGH.modules()):
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.copy_(1 + 0.2 * torch.randn(m.weight.shape, generator=g)); m.bias.data.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+    for net in (netGL, netGH):                     # fp16-exact weights: the fixture stores them as halves
+        for p_ in net.parameters():
+            p_.data.copy_(p_.data.half().float())
+    half = lambda sd: {k: (v.half() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    sdL = half(netGL.state_dict()); sdH = half(netGH.state_dict())
+    B, T = 2, 18
+    LR = O.synth_lr(B, 16, seed=4244)
+    words = torch.randn(B, 256, T, generator=g) * 0.5; sent = torch.randn(B, 256, generator=g) * 0.5
+    mask = torch.zeros(B, T, dtype=torch.bool); mask[1, 11:] = True
+    targets = [torch.randn(B, 3, 16 * 2 ** (k + 1), 16 * 2 ** (k + 1), generator=g) * 0.5 for k in range(3)]
+    imgs, atts, mu, lv = netGL(LR, sent, words, mask)
+    fine, a, one = netGH(LR, imgs, LR)
+    loss = sum(torch.nn.functional.mse_loss(f, t) for f, t in zip(fine, targets)) + sum(torch.nn.functional.mse_loss(f, t) for f, t in zip(imgs, targets))
+    loss.backward()
+    pick = lambda net, names: {n: dict(net.named_parameters())[n].grad.clone() for n in names}
+    gl_names = ['h_net1.im2f.0.weight', 'h_net1.im2f.1.weight', 'h_net1.att.conv_context.weight', 'h_net2.residual.1.block.3.weight',
+                'h_net3.upsample.1.weight', 'h_net3.upsample.2.bias', 'img_net2.img.0.weight']
+    gh_names = ['convin.0.weight', 'residual.3.block.0.weight', 'residual.5.block.4.weight', 'upscale4x.1.weight', 'residual48.1.bias',
+                'conv_output.0.weight']
+    torch.save(dict(sdL=sdL, sdH=sdH, LR=LR, words=words, sent=sent, mask=mask, targets=[t.half() for t in targets],
+                    loss=loss.detach(), img0=imgs[0].detach().clone(), fine0=fine[0].detach().clone(),
+                    fine2_sub4=fine[2].detach()[:, :, ::4, ::4].clone(), gradL=pick(netGL, gl_names), gradH=pick(netGH, gh_names),
+                    run_mean=netGL.h_net1.im2f[1].running_mean.clone(), run_var=netGL.h_net1.im2f[1].running_var.clone()),
+               os.path.join(OUT, 'train_step.pt'))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == 'train':
+        gen_train(ns)
+        print('train_step.pt', os.path.getsize(os.path.join(OUT, 'train_step.pt')))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'losses':
         gen_losses(ns)
         print('losses.pt', os.path.getsize(os.path.join(OUT, 'losses.pt')))
@@ -263,6 +306,7 @@ def main():
     gen_face_x8(ns)
     gen_x16(ns)
     gen_losses(ns)
+    gen_train(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -252,3 +252,33 @@ def test_tf32_convs_match_exact_kernels(B, Cin, Cout, H, W, k, up):
     for a, b in zip(res['fp32'], res['tf32']):
         assert a.shape == b.shape
         assert float((a - b).abs().max()) <= 2e-3 * max(1.0, float(a.abs().max())), (float((a - b).abs().max()), float(a.abs().max()))
+
+
+def test_generator_train_grads_vs_reference_modules(golden):
+    """The explicit backward kernels against gradients of the UNMODIFIED reference modules in train() mode
+    (tests/golden/train_step.pt): loss, outputs, BatchNorm running statistics and a spread of parameter gradients."""
+    from tgsr_b200 import nets
+    c = golden('train_step.pt')
+    f32 = lambda sd: {k: (v.float() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    gl = nets.G_SR_NET_low(); gh = nets.NetG_highweight(low='lr')
+    gl.load_state_dict(f32(c['sdL']), strict=True); gh.load_state_dict(f32(c['sdH']), strict=True)
+    # the stored state is the one AFTER the reference's step (running statistics updated once): reset them
+    for m in list(gl.modules()) + list(gh.modules()):
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.reset_running_stats()
+    gl.to(DEV).train(); gh.to(DEV).train()
+    targets = [t.float().to(DEV) for t in c['targets']]
+    imgs, atts, mu, lv = gl(c['LR'].to(DEV), c['sent'].to(DEV), c['words'].to(DEV), c['mask'].to(DEV))
+    fine, a, one = gh(c['LR'].to(DEV), imgs, c['LR'].to(DEV))
+    loss = sum(F.mse_loss(f, t) for f, t in zip(fine, targets)) + sum(F.mse_loss(f, t) for f, t in zip(imgs, targets))
+    loss.backward()
+    close(loss, c['loss'], rtol=1e-4, atol=1e-6)
+    close(imgs[0], c['img0'], rtol=1e-3, atol=1e-4); close(fine[0], c['fine0'], rtol=1e-3, atol=1e-4)
+    close(fine[2][:, :, ::4, ::4], c['fine2_sub4'], rtol=1e-3, atol=1e-4)
+    close(gl.h_net1.im2f[1].running_mean, c['run_mean'], rtol=1e-4, atol=1e-6)
+    close(gl.h_net1.im2f[1].running_var, c['run_var'], rtol=1e-4, atol=1e-6)
+    for net, grads in ((gl, c['gradL']), (gh, c['gradH'])):
+        params = dict(net.named_parameters())
+        for name, g in grads.items():
+            torch.testing.assert_close(params[name].grad.cpu(), g, rtol=5e-3, atol=1e-6 + 2e-4 * float(g.abs().max()),
+                                       msg=lambda m, name=name: name + ': ' + m)

@@ -136,3 +136,33 @@ def test_losses_oracle_matches_reference(golden):
         (c['gw'][0] * w0 + c['gw'][1] * w1 + c['gs'][0] * s0 + c['gs'][1] * s1).backward()
         torch.testing.assert_close(feats.grad, c['d_feats'], rtol=1e-4, atol=1e-7)
         torch.testing.assert_close(cnn.grad, c['d_cnn'], rtol=1e-4, atol=1e-7)
+
+
+def _train_case(golden):
+    c = golden('train_step.pt')
+    f32 = lambda sd: {k: (v.float() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    return c, f32(c['sdL']), f32(c['sdH'])
+
+
+def test_train_mode_oracle_matches_reference(golden):
+    """oracle.train_mode() (batch-statistics BatchNorm) + autograd against the UNMODIFIED reference modules in train():
+    outputs, the 6-image MSE loss and parameter gradients (tests/golden/train_step.pt, oracle/make_golden.py gen_train)."""
+    import torch.nn.functional as F
+    c, sdL, sdH = _train_case(golden)
+    for sd in (sdL, sdH):
+        for k, v in sd.items():
+            if v.is_floating_point():
+                v.requires_grad_(True)
+    targets = [t.float() for t in c['targets']]
+    with O.train_mode():
+        imgs, atts, mu, lv, _ = O.g_sr_net_low(sdL, c['LR'], c['sent'], c['words'], c['mask'])
+        fine = O.netg_high(sdH, c['LR'], imgs, c['LR'], low='lr')
+    loss = sum(F.mse_loss(f, t) for f, t in zip(fine, targets)) + sum(F.mse_loss(f, t) for f, t in zip(imgs, targets))
+    loss.backward()
+    torch.testing.assert_close(loss.detach(), c['loss'], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(imgs[0].detach(), c['img0'], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(fine[0].detach(), c['fine0'], rtol=1e-4, atol=1e-5)
+    for name, g in c['gradL'].items():
+        torch.testing.assert_close(sdL[name].grad, g, rtol=2e-3, atol=1e-6 + 1e-4 * float(g.abs().max()))
+    for name, g in c['gradH'].items():
+        torch.testing.assert_close(sdH[name].grad, g, rtol=2e-3, atol=1e-6 + 1e-4 * float(g.abs().max()))
