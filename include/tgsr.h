@@ -296,6 +296,31 @@ int tgsr_adam_devstep_f32(float* param, const float* grad, float* exp_avg, float
  * x fp32 (16-byte aligned), y uint8 (4-byte aligned), n elements. */
 int tgsr_quantize_u8(const float* x, uint8_t* y, size_t n, tgsr_stream_t stream);
 
+/* Input pyramid on the device (replaces the per-image PIL work of datasets.py:151-196 get_imgs_blur / :112-148 get_imgs
+ * done in the DataLoader workers).  Byte-exact with Pillow: Image.resize(BILINEAR) (antialiased triangle filter, 8-bit fixed
+ * point, horizontal then vertical pass), ImageFilter.GaussianBlur (3 extended box blurs per axis, edge replication) and
+ * ToTensor()+Normalize(.5,.5) (datasets.py:1563).  Images are uint8 [B, H, W, C] (decoded, HWC as PIL holds them);
+ * normalised outputs are fp32 [B, C, H, W].
+ *   tgsr_resize_u8        : transforms.Resize([oh, ow])(img) for a batch; ws >= tgsr_resize_u8_ws_bytes(...).
+ *   tgsr_gaussian_blur_u8 : img.filter(GaussianBlur(radius)) with `passes` box blurs per axis (PIL uses 3); tmp = B*H*W*C bytes.
+ *   tgsr_normalize_u8_f32 : ToTensor()+Normalize.
+ *   tgsr_pyramid_levels_u8: up to 4 levels of one source in ONE launch; per level i the source is resized to (oh[i], ow[i])
+ *                           (or taken as is when the size matches) and any of out[i] (normalised), out_blur[i] (normalised
+ *                           GaussianBlur(blur_radius) of the resized image) and out_u8[i] (the resized bytes, [B,oh,ow,C]) that
+ *                           is non-NULL is written.  out / out_blur / out_u8 are HOST arrays of device pointers (or NULL).
+ *                           Envelope (tgsr_pyramid_supported): ow % 4 == 0, plane fits shared memory (all sizes up to 256x256
+ *                           from sources up to 256 rows), blur_radius == 2. */
+size_t tgsr_resize_u8_ws_bytes(int B, int ih, int iw, int oh, int ow, int C);
+int tgsr_resize_u8(const uint8_t* src, uint8_t* dst, void* ws, int B, int ih, int iw, int oh, int ow, int C,
+                   tgsr_stream_t stream);
+int tgsr_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, uint8_t* tmp, int B, int H, int W, int C, float radius,
+                          int passes, tgsr_stream_t stream);
+int tgsr_normalize_u8_f32(const uint8_t* src, float* dst, int B, int H, int W, int C, tgsr_stream_t stream);
+int tgsr_pyramid_supported(int ih, int iw, int oh, int ow, int blur);
+int tgsr_pyramid_levels_u8(const uint8_t* src, int B, int ih, int iw, int C, int nlevels, const int* oh, const int* ow,
+                           float* const* out, float* const* out_blur, uint8_t* const* out_u8, float blur_radius,
+                           tgsr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

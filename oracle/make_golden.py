@@ -288,9 +288,44 @@ def gen_train(ns):
                os.path.join(OUT, 'train_step.pt'))
 
 
+def gen_pyramid(ns):
+    """The reference's own `get_imgs_blur` (datasets.py:151-196), unmodified, on data/face/000155.png with the eval
+    transform (Resize(288) -> CenterCrop(256), datasets.py:1558-1561) and norm (:1563); imsize = [32, 64, 128, 256]
+    (BASE_SIZE 32, BRANCH_NUM 4).  datasets.py imports nltk at module scope for its caption tokenizer, which the image
+    lacks; an empty stand-in module satisfies the import and is never called on this path.  The branch-0 tensors are
+    stored as fp32 (pins ToTensor/Normalize); the larger ones as the uint8 they were computed from."""
+    import types
+    from torchvision import transforms
+    if 'nltk' not in sys.modules:
+        nltk = types.ModuleType('nltk'); tok = types.ModuleType('nltk.tokenize')
+        tok.RegexpTokenizer = object; nltk.tokenize = tok
+        sys.modules['nltk'] = nltk; sys.modules['nltk.tokenize'] = tok
+    import datasets as D
+    path = os.path.join(ref_loader.REF_ROOT, 'data/face/000155.png')
+    transform = transforms.Compose([transforms.Resize(int(256 * 72 / 64)), transforms.CenterCrop(256)])
+    norm = transforms.Compose([transforms.ToTensor(), transforms.Normalize((0.5,) * 3, (0.5,) * 3)])
+    imsize = [32, 64, 128, 256]
+    ret, bic, retb, bicb = D.get_imgs_blur(path, imsize, None, transform, normalize=norm, cfg=ns.cfg)
+    from PIL import Image
+    hr = np.asarray(transform(Image.open(path).convert('RGB')))
+
+    def u8(t):
+        return np.round((t.numpy().transpose(1, 2, 0) * 0.5 + 0.5) * 255.0).astype(np.uint8)
+    out = dict(hr=hr, imsize=np.asarray(imsize))
+    for name, lst in (('ret', ret), ('bic', bic), ('retb', retb), ('bicb', bicb)):
+        out[name + '0_f32'] = lst[0].numpy()
+        for i in range(1, 4):
+            out['%s%d_u8' % (name, i)] = u8(lst[i])
+    np.savez_compressed(os.path.join(OUT, 'pyramid.npz'), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == 'pyramid':
+        gen_pyramid(ns)
+        print('pyramid.npz', os.path.getsize(os.path.join(OUT, 'pyramid.npz')))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'train':
         gen_train(ns)
         print('train_step.pt', os.path.getsize(os.path.join(OUT, 'train_step.pt')))
@@ -307,6 +342,7 @@ def main():
     gen_x16(ns)
     gen_losses(ns)
     gen_train(ns)
+    gen_pyramid(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
