@@ -321,6 +321,15 @@ int tgsr_pyramid_levels_u8(const uint8_t* src, int B, int ih, int iw, int C, int
                            float* const* out, float* const* out_blur, uint8_t* const* out_u8, float blur_radius,
                            tgsr_stream_t stream);
 
+/* Word-axis reductions of the attention maps (miscc/utils.py:122-125 attn.max(dim=1); :389-392 conf_score; the max-map also
+ * weighs weight_MSE, miscc/losses.py:796).  attn fp32 [B, T, Q] (Q % 4 == 0, T <= 255) ->
+ *   maxv   fp32  [B, Q]     max over the T words,
+ *   argmax uint8 [B, Q]     first word index attaining it,
+ *   conf   fp64  [B, T+1]   replicas * sum over pixels of v * (v > 2*thresh): column 0 for the max-map, column 1+t for
+ *                           word t (the reference sums a 3-channel replica of each map: replicas = 3). */
+int tgsr_attn_word_stats_f32(const float* attn, float* maxv, uint8_t* argmax, double* conf, int B, int T, int Q, float thresh,
+                             int replicas, tgsr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -369,3 +369,22 @@ def psnr_u8(a: Tensor, b: Tensor) -> float:
     diff = a.to(torch.float64) - b.to(torch.float64)
     rmse = math.sqrt(float((diff ** 2).mean()))
     return float('inf') if rmse == 0 else 20 * math.log10(255.0 / rmse)
+
+
+def attention_word_stats(attn, thresh=0.0):
+    """Word-axis reductions of attention maps [B,T,ih,iw] as the reference's visualisation computes them on the host:
+    miscc/utils.py:122-125 `attn.max(dim=1, keepdim=True)` (values, indices) and :389-392
+    `conf_score[j] = np.sum(one_map * (one_map > 2*thresh))` over the 3-channel replica of [max-map, word maps...].
+    (miscc/utils.py imports skimage, absent from the image, so this restatement is not pinned by executing the reference;
+    it is three numpy/torch calls.)"""
+    import numpy as np
+    mx, am = attn.max(dim=1, keepdim=True)
+    maps = torch.cat([mx, attn], 1)                                   # utils.py:125
+    B, T1 = maps.shape[:2]
+    conf = np.zeros((B, T1), np.float64)
+    for b in range(B):
+        rep = maps[b].view(-1, 1, *attn.shape[2:]).repeat(1, 3, 1, 1).numpy().transpose(0, 2, 3, 1)   # utils.py:127-130
+        for j in range(T1):
+            one_map = rep[j]
+            conf[b, j] = np.sum(one_map * (one_map > (2. * thresh)))
+    return mx, am, torch.from_numpy(conf)

@@ -247,3 +247,17 @@ def test_attention_all_masked_caption_is_nan_like_torch():
         torch.testing.assert_close(a16[ok], ra[ok], rtol=5e-5, atol=1e-7)
     finally:
         tgsr_b200.set_precision('fp32')
+
+
+def test_attention_word_stats():
+    """Per-pixel max / arg-max over words and thresholded confidence sums (miscc/utils.py:122-125, 389-392) against the oracle."""
+    from tgsr_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for (B, T, s, thresh) in [(3, 18, 32, 0.02), (2, 7, 64, 0.0), (4, 18, 128, 1.0 / 18), (1, 48, 6, 0.01)]:
+        attn = torch.softmax(torch.randn((B, T, s, s), generator=g) * 2.0, dim=1)
+        attn[0, :, 0, 0] = 1.0 / T                              # exact ties: first index wins
+        mx, am, conf = O.attention_word_stats(attn, thresh)
+        gmx, gam, gconf = ops.attention_word_stats(attn.cuda(), thresh)
+        assert torch.equal(gmx.cpu(), mx)
+        assert torch.equal(gam.cpu(), am)
+        torch.testing.assert_close(gconf.cpu(), conf, rtol=1e-5, atol=1e-6)

@@ -12,8 +12,8 @@
 //
 // Two sets of kernels:
 //   * generic one-thread-per-output kernels for any size / channel count (resize, box-blur pass, normalise);
-//   * pyramid_plane_kernel: one CTA per (image, channel, level) plane that keeps the plane in shared memory from the first
-//     resample tap to the last blur pass: source bytes are read once per level, and every output byte is written once.
+//   * pyramid_plane_kernel: one CTA per (image, channel, level, row band) that keeps its rows in shared memory from the
+//     first resample tap to the last blur pass: every output byte is written once, nothing intermediate reaches HBM.
 #include "common.cuh"
 #include <math.h>
 #include <string.h>
@@ -22,8 +22,12 @@ namespace tgsr {
 namespace {
 
 constexpr int PREC_BITS = 22;              // 32 - 8 - 2: fraction bits of the 8-bit resample path
-constexpr int PYR_THREADS = 512;
+constexpr int PYR_THREADS = 256;
 constexpr int PYR_MAX_JOBS = 4;
+constexpr int PYR_BANDS_PER_JOB = 4;
+constexpr int PYR_MAX_BANDS = PYR_MAX_JOBS * PYR_BANDS_PER_JOB;
+constexpr int PYR_BAND_ROWS = 64;
+constexpr int PYR_HALO = 6;                // three vertical box passes, each reaching 2 rows (radius 1 + the fractional tap)
 constexpr int PYR_MAX_SMEM = 200 * 1024;
 
 __host__ __device__ inline int resample_ksize(int in_size, int out_size) {
@@ -147,6 +151,11 @@ normalize_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_
 }
 
 // ----------------------------------------------------------------------------------------------- fused plane kernel
+//
+// One CTA per (image, channel, level, row band).  A band is up to a quarter of the level's rows; with the blur it carries a
+// 6-row halo on each interior side (three vertical passes, each reaching 2 rows), so the rows it finally stores are exact
+// while every band stays small enough for several CTAs per SM.  At the real image edges the halo is absent and the passes
+// replicate the edge row, which is the filter's own boundary rule.
 
 struct PyrJob {
   const uint8_t* src;      // [B, ih, iw, C]
@@ -159,6 +168,8 @@ struct PyrJobs {
   PyrJob j[PYR_MAX_JOBS];
   int C;
   uint32_t ww, fw;
+  uint8_t band_job[PYR_MAX_BANDS];
+  short band_r0[PYR_MAX_BANDS], band_r1[PYR_MAX_BANDS];
 };
 
 __device__ __forceinline__ uint32_t blur_lane(uint32_t far0, uint32_t a, uint32_t b, uint32_t c, uint32_t far1, uint32_t ww,
@@ -187,7 +198,7 @@ __device__ __forceinline__ void plane_blur_x(const uint8_t* __restrict__ s, uint
   }
 }
 
-// Same along y.
+// Same along y (rows clamp to the band's buffer: exact at image edges, absorbed by the halo elsewhere).
 __device__ __forceinline__ void plane_blur_y(const uint8_t* __restrict__ s, uint8_t* __restrict__ d, int h, int w, uint32_t ww,
                                              uint32_t fw) {
   const int nw = w >> 2;
@@ -216,17 +227,29 @@ __device__ __forceinline__ void plane_store_norm(const uint8_t* __restrict__ s, 
 }
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
+__host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
 
-// Shared-memory layout of one job (host and device agree through this function).
+// Rows [e0, e1) of the level that a band holding output rows [r0, r1) keeps in shared memory.
+__host__ __device__ inline void band_extent(int r0, int r1, int oh, bool blur, int* e0, int* e1) {
+  const int halo = blur ? PYR_HALO : 0;
+  *e0 = imax(r0 - halo, 0);
+  *e1 = imin(r1 + halo, oh);
+}
+
+// Shared-memory layout of one band (host and device agree through this function).  ns is an upper bound of the source rows
+// the band's vertical taps touch.
 struct PyrLayout { size_t tx, ty, T, A, Bp, total; };
-__host__ __device__ inline PyrLayout pyr_layout(const PyrJob& J, bool blur) {
+__host__ __device__ inline PyrLayout pyr_layout(const PyrJob& J, bool blur, int ne) {
   PyrLayout L;
+  const bool vpass = J.ih != J.oh;
+  const int ns = vpass ? imin(J.ih, (ne * J.ih + J.oh - 1) / J.oh + J.ksy + 2) : ne;
   size_t off = 256 * sizeof(float);                                  // normalisation table
   L.tx = off; off += align16(J.iw != J.ow ? (size_t)J.ow * (J.ksx + 2) * 4 : 0);
-  L.ty = off; off += align16(J.ih != J.oh ? (size_t)J.oh * (J.ksy + 2) * 4 : 0);
-  L.T = off; off += align16((size_t)J.ih * J.ow);
-  if (J.ih != J.oh) { L.A = off; off += align16((size_t)J.oh * J.ow); } else L.A = L.T;
-  L.Bp = off; off += align16(blur ? (size_t)J.oh * J.ow : 0);
+  L.ty = off; off += align16(vpass ? (size_t)ne * (J.ksy + 2) * 4 : 0);
+  L.T = off; off += align16((size_t)ns * J.ow);
+  if (vpass) { L.A = off; off += align16((size_t)ne * J.ow); } else L.A = L.T;
+  L.Bp = off; off += align16(blur ? (size_t)ne * J.ow : 0);
   L.total = off;
   return L;
 }
@@ -234,30 +257,38 @@ __host__ __device__ inline PyrLayout pyr_layout(const PyrJob& J, bool blur) {
 __global__ void __launch_bounds__(PYR_THREADS)
 pyramid_plane_kernel(const __grid_constant__ PyrJobs jobs) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const PyrJob& J = jobs.j[blockIdx.y];
+  const PyrJob& J = jobs.j[jobs.band_job[blockIdx.y]];
+  const int r0 = jobs.band_r0[blockIdx.y], r1 = jobs.band_r1[blockIdx.y];
   const int C = jobs.C;
   const int b = blockIdx.x / C, c = blockIdx.x - b * C;
   const int ih = J.ih, iw = J.iw, oh = J.oh, ow = J.ow;
   const bool hpass = iw != ow, vpass = ih != oh, blur = J.out_blur != nullptr;
-  const PyrLayout L = pyr_layout(J, blur);
+  int e0, e1;
+  band_extent(r0, r1, oh, blur, &e0, &e1);
+  const int ne = e1 - e0;
+  const PyrLayout L = pyr_layout(J, blur, ne);
   float* lut = reinterpret_cast<float*>(smem);
   int* txb = reinterpret_cast<int*>(smem + L.tx);       // [ow][2] bounds, then [ow][ksx] weights
   int* txk = txb + 2 * ow;
-  int* tyb = reinterpret_cast<int*>(smem + L.ty);
-  int* tyk = tyb + 2 * oh;
+  int* tyb = reinterpret_cast<int*>(smem + L.ty);       // [ne][2] bounds, then [ne][ksy] weights (rows e0..e1-1)
+  int* tyk = tyb + 2 * ne;
   uint8_t* T = smem + L.T;
   uint8_t* A = smem + L.A;
   uint8_t* Bp = smem + L.Bp;
 
   if (threadIdx.x < 256) lut[threadIdx.x] = norm_u8(threadIdx.x);
   if (hpass) for (int x = threadIdx.x; x < ow; x += PYR_THREADS) resample_taps(iw, ow, J.ksx, x, txk + x * J.ksx, txb + 2 * x);
-  if (vpass) for (int y = threadIdx.x; y < oh; y += PYR_THREADS) resample_taps(ih, oh, J.ksy, y, tyk + y * J.ksy, tyb + 2 * y);
+  if (vpass) for (int y = threadIdx.x; y < ne; y += PYR_THREADS) resample_taps(ih, oh, J.ksy, e0 + y, tyk + y * J.ksy, tyb + 2 * y);
   __syncthreads();
+  // source rows [s0, s1) feed this band
+  const int s0 = vpass ? tyb[0] : e0;
+  const int s1 = vpass ? tyb[2 * (ne - 1)] + tyb[2 * (ne - 1) + 1] : e1;
+  const int ns = s1 - s0;
 
-  // stage 1: T[ih][ow] = horizontally resampled (or copied) channel plane
-  const uint8_t* sp = J.src + (size_t)b * ih * iw * C + c;
+  // stage 1: T[ns][ow] = horizontally resampled (or copied) rows of the channel plane
+  const uint8_t* sp = J.src + ((size_t)b * ih + s0) * iw * C + c;
   if (hpass) {
-    for (int i = threadIdx.x; i < ih * ow; i += PYR_THREADS) {
+    for (int i = threadIdx.x; i < ns * ow; i += PYR_THREADS) {
       const int y = i / ow, x = i - y * ow;
       const int x0 = txb[2 * x], n = txb[2 * x + 1];
       const uint8_t* p = sp + ((size_t)y * iw + x0) * C;
@@ -267,14 +298,14 @@ pyramid_plane_kernel(const __grid_constant__ PyrJobs jobs) {
       T[i] = clip8(acc);
     }
   } else {
-    for (int i = threadIdx.x; i < ih * ow; i += PYR_THREADS) T[i] = __ldg(sp + (size_t)i * C);
+    for (int i = threadIdx.x; i < ns * ow; i += PYR_THREADS) T[i] = __ldg(sp + (size_t)i * C);
   }
   __syncthreads();
-  // stage 2: A[oh][ow] = vertically resampled plane (A aliases T when the height is unchanged)
+  // stage 2: A[ne][ow] = vertically resampled rows e0..e1-1 (A aliases T when the height is unchanged)
   if (vpass) {
-    for (int i = threadIdx.x; i < oh * ow; i += PYR_THREADS) {
+    for (int i = threadIdx.x; i < ne * ow; i += PYR_THREADS) {
       const int y = i / ow, x = i - y * ow;
-      const int y0 = tyb[2 * y], n = tyb[2 * y + 1];
+      const int y0 = tyb[2 * y] - s0, n = tyb[2 * y + 1];
       const uint8_t* p = T + y0 * ow + x;
       const int* k = tyk + y * J.ksy;
       int acc = 1 << (PREC_BITS - 1);
@@ -283,20 +314,22 @@ pyramid_plane_kernel(const __grid_constant__ PyrJobs jobs) {
     }
     __syncthreads();
   }
-  const size_t plane = ((size_t)b * C + c) * oh * ow;
-  if (J.out != nullptr) plane_store_norm(A, J.out + plane, (oh * ow) >> 2, lut);
+  const size_t plane = ((size_t)b * C + c) * oh * ow + (size_t)r0 * ow;
+  const uint8_t* Aout = A + (r0 - e0) * ow;
+  const int nout = (r1 - r0) * ow;
+  if (J.out != nullptr) plane_store_norm(Aout, J.out + plane, nout >> 2, lut);
   if (J.out_u8 != nullptr) {
-    uint8_t* g = J.out_u8 + (size_t)b * oh * ow * C + c;
-    for (int i = threadIdx.x; i < oh * ow; i += PYR_THREADS) g[(size_t)i * C] = A[i];
+    uint8_t* g = J.out_u8 + ((size_t)b * oh + r0) * ow * C + c;
+    for (int i = threadIdx.x; i < nout; i += PYR_THREADS) g[(size_t)i * C] = Aout[i];
   }
   if (!blur) return;
-  plane_blur_x(A, Bp, oh, ow, jobs.ww, jobs.fw); __syncthreads();
-  plane_blur_x(Bp, A, oh, ow, jobs.ww, jobs.fw); __syncthreads();
-  plane_blur_x(A, Bp, oh, ow, jobs.ww, jobs.fw); __syncthreads();
-  plane_blur_y(Bp, A, oh, ow, jobs.ww, jobs.fw); __syncthreads();
-  plane_blur_y(A, Bp, oh, ow, jobs.ww, jobs.fw); __syncthreads();
-  plane_blur_y(Bp, A, oh, ow, jobs.ww, jobs.fw); __syncthreads();
-  plane_store_norm(A, J.out_blur + plane, (oh * ow) >> 2, lut);
+  plane_blur_x(A, Bp, ne, ow, jobs.ww, jobs.fw); __syncthreads();
+  plane_blur_x(Bp, A, ne, ow, jobs.ww, jobs.fw); __syncthreads();
+  plane_blur_x(A, Bp, ne, ow, jobs.ww, jobs.fw); __syncthreads();
+  plane_blur_y(Bp, A, ne, ow, jobs.ww, jobs.fw); __syncthreads();
+  plane_blur_y(A, Bp, ne, ow, jobs.ww, jobs.fw); __syncthreads();
+  plane_blur_y(Bp, A, ne, ow, jobs.ww, jobs.fw); __syncthreads();
+  plane_store_norm(Aout, J.out_blur + plane, nout >> 2, lut);
 }
 
 // BoxBlur.c _gaussian_blur_radius + the 8.24 weights of ImagingHorizontalBoxBlur, float arithmetic as the host library.
@@ -400,9 +433,30 @@ extern "C" int tgsr_normalize_u8_f32(const uint8_t* src, float* dst, int B, int 
   return launch_status();
 }
 
+// Row bands of one level: at most PYR_BANDS_PER_JOB, about PYR_BAND_ROWS rows each.
+static int pyr_bands(int oh, int* rows) {
+  int nb = ceil_div(oh, PYR_BAND_ROWS);
+  if (nb > PYR_BANDS_PER_JOB) nb = PYR_BANDS_PER_JOB;
+  *rows = ceil_div(oh, nb);
+  return ceil_div(oh, *rows);
+}
+
+static size_t pyr_job_smem(const PyrJob& J, bool blur) {
+  int rows;
+  const int nb = pyr_bands(J.oh, &rows);
+  size_t smem = 0;
+  for (int k = 0; k < nb; ++k) {
+    int e0, e1;
+    band_extent(k * rows, imin((k + 1) * rows, J.oh), J.oh, blur, &e0, &e1);
+    const size_t s = pyr_layout(J, blur, e1 - e0).total;
+    smem = s > smem ? s : smem;
+  }
+  return smem;
+}
+
 static bool pyr_job_ok(const PyrJob& J, bool blur) {
-  if (J.ow % 4 != 0 || J.oh < 1 || J.ow < 4) return false;
-  return pyr_layout(J, blur).total <= (size_t)PYR_MAX_SMEM;
+  if (J.ow % 4 != 0 || J.oh < 1 || J.ow < 4 || J.oh > 32767) return false;
+  return pyr_job_smem(J, blur) <= (size_t)PYR_MAX_SMEM;
 }
 
 extern "C" int tgsr_pyramid_supported(int ih, int iw, int oh, int ow, int blur) {
@@ -429,6 +483,7 @@ extern "C" int tgsr_pyramid_levels_u8(const uint8_t* src, int B, int ih, int iw,
     TGSR_REQUIRE(r == 1, TGSR_ERR_UNSUPPORTED);          // GaussianBlur(radius=2), the one the reference uses
   }
   size_t smem = 0;
+  int nbands = 0;
   for (int i = 0; i < nlevels; ++i) {
     PyrJob& J = jobs.j[i];
     J.src = src; J.ih = ih; J.iw = iw; J.oh = oh[i]; J.ow = ow[i];
@@ -438,12 +493,21 @@ extern "C" int tgsr_pyramid_levels_u8(const uint8_t* src, int B, int ih, int iw,
     J.out_blur = out_blur != nullptr ? out_blur[i] : nullptr;
     J.out_u8 = out_u8 != nullptr ? out_u8[i] : nullptr;
     TGSR_REQUIRE(J.out != nullptr || J.out_blur != nullptr || J.out_u8 != nullptr, TGSR_ERR_NULL);
-    TGSR_REQUIRE(pyr_job_ok(J, J.out_blur != nullptr), TGSR_ERR_UNSUPPORTED);
+    const bool blur = J.out_blur != nullptr;
+    TGSR_REQUIRE(pyr_job_ok(J, blur), TGSR_ERR_UNSUPPORTED);
     TGSR_REQUIRE((reinterpret_cast<uintptr_t>(J.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(J.out_blur) & 15) == 0,
                  TGSR_ERR_BAD_SHAPE);
-    const size_t s = pyr_layout(J, J.out_blur != nullptr).total;
+    const size_t s = pyr_job_smem(J, blur);
     smem = s > smem ? s : smem;
+    int rows;
+    const int nb = pyr_bands(J.oh, &rows);
+    for (int k = 0; k < nb; ++k) {
+      jobs.band_job[nbands] = (uint8_t)i;
+      jobs.band_r0[nbands] = (short)(k * rows);
+      jobs.band_r1[nbands] = (short)imin((k + 1) * rows, J.oh);
+      ++nbands;
+    }
   }
-  pyramid_plane_kernel<<<dim3((unsigned)(B * C), (unsigned)nlevels), PYR_THREADS, smem, (cudaStream_t)stream>>>(jobs);
+  pyramid_plane_kernel<<<dim3((unsigned)(B * C), (unsigned)nbands), PYR_THREADS, smem, (cudaStream_t)stream>>>(jobs);
   return launch_status();
 }

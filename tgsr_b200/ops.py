@@ -174,3 +174,24 @@ def quantize_u8(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     import ctypes as C
     call('tgsr_quantize_u8', x.device, ptr(x), ptr(out), C.c_size_t(x.numel()))
     return out
+
+
+def attention_word_stats(attn: Tensor, thresh: float = 0.0) -> Tuple[Tensor, Tensor, Tensor]:
+    """Word-axis reductions of attention maps `attn` [B, T, ih, iw] in one pass on the device:
+    (attn_max [B,1,ih,iw], attn_argmax int64 [B,1,ih,iw]) = attn.max(dim=1, keepdim=True) (miscc/utils.py:122-125; the same
+    max-map weighs weight_MSE, miscc/losses.py:796) and conf [B, T+1] fp64 = the thresholded confidence sums of
+    miscc/utils.py:389-392 (`np.sum(one_map * (one_map > 2*thresh))` over the 3-channel replica of the max-map, column 0,
+    and of each word map, columns 1..T)."""
+    attn = _f32c(attn, 'attn')
+    if attn.dim() != 4:
+        raise ValueError('expected attn [B,T,ih,iw]')
+    B, T, ih, iw = attn.shape
+    Q = ih * iw
+    if Q % 4 != 0 or T > 255:
+        raise ValueError('attention_word_stats needs ih*iw %% 4 == 0 and T <= 255, got %s' % (tuple(attn.shape),))
+    maxv = torch.empty((B, 1, ih, iw), device=attn.device, dtype=torch.float32)
+    arg = torch.empty((B, 1, ih, iw), device=attn.device, dtype=torch.uint8)
+    conf = torch.empty((B, T + 1), device=attn.device, dtype=torch.float64)
+    import ctypes as C
+    call('tgsr_attn_word_stats_f32', attn.device, ptr(attn), ptr(maxv), ptr(arg), ptr(conf), B, T, Q, C.c_float(thresh), 3)
+    return maxv, arg.long(), conf
