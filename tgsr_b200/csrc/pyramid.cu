@@ -172,29 +172,49 @@ struct PyrJobs {
   short band_r0[PYR_MAX_BANDS], band_r1[PYR_MAX_BANDS];
 };
 
-__device__ __forceinline__ uint32_t blur_lane(uint32_t far0, uint32_t a, uint32_t b, uint32_t c, uint32_t far1, uint32_t ww,
-                                              uint32_t fw) {
-  return ((a + b + c) * ww + (far0 + far1) * fw + (1u << 23)) >> 24;
-}
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 
-// Box blur (integer radius 1) along x of an [h][w] byte plane, four pixels per thread.
+// Division by a loop-invariant width: a shift when it is a power of two (every production size), a real division otherwise.
+struct FastDiv { int d, shift; };
+__device__ __forceinline__ FastDiv fast_div(int d) { return FastDiv{d, (d & (d - 1)) == 0 ? __ffs(d) - 1 : -1}; }
+__device__ __forceinline__ void divmod(int i, const FastDiv& f, int& q, int& r) {
+  if (f.shift >= 0) { q = i >> f.shift; r = i & (f.d - 1); }
+  else { q = i / f.d; r = i - q * f.d; }
+}
+
+// One extended box blur step (integer radius 1) on four byte lanes at once.  f0,a,b,c,f1 hold, per byte lane, the far-left,
+// left, centre, right and far-right sample: out = (ww*(a+b+c) + fw*(f0+f1) + 2^23) >> 24.  The sums run two pixels per
+// register in 16-bit lanes (max 765, no carry between lanes); the products are per pixel; the four top bytes are gathered
+// with byte permutes.
+__device__ __forceinline__ uint32_t blur_word(uint32_t f0, uint32_t a, uint32_t b, uint32_t c, uint32_t f1, uint32_t ww,
+                                              uint32_t fw) {
+  const uint32_t se = __byte_perm(a, 0, 0x4240) + __byte_perm(b, 0, 0x4240) + __byte_perm(c, 0, 0x4240);   // pixels 0, 2
+  const uint32_t so = __byte_perm(a, 0, 0x4341) + __byte_perm(b, 0, 0x4341) + __byte_perm(c, 0, 0x4341);   // pixels 1, 3
+  const uint32_t fe = __byte_perm(f0, 0, 0x4240) + __byte_perm(f1, 0, 0x4240);
+  const uint32_t fo = __byte_perm(f0, 0, 0x4341) + __byte_perm(f1, 0, 0x4341);
+  const uint32_t r0 = (se & 0xffffu) * ww + ((fe & 0xffffu) * fw + (1u << 23));
+  const uint32_t r1 = (so & 0xffffu) * ww + ((fo & 0xffffu) * fw + (1u << 23));
+  const uint32_t r2 = (se >> 16) * ww + ((fe >> 16) * fw + (1u << 23));
+  const uint32_t r3 = (so >> 16) * ww + ((fo >> 16) * fw + (1u << 23));
+  return __byte_perm(__byte_perm(r0, r1, 0x0073), __byte_perm(r2, r3, 0x0073), 0x5410);
+}
+
+// Box blur along x of an [h][w] byte plane, four pixels per thread: the shifted neighbourhoods are funnel shifts of the
+// three words around the output word; the row ends replicate the edge pixel.
 __device__ __forceinline__ void plane_blur_x(const uint8_t* __restrict__ s, uint8_t* __restrict__ d, int h, int w, uint32_t ww,
                                              uint32_t fw) {
   const int nw = w >> 2;
+  const FastDiv dn = fast_div(nw);
   const uint32_t* s32 = reinterpret_cast<const uint32_t*>(s);
   uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
   for (int i = threadIdx.x; i < h * nw; i += PYR_THREADS) {
-    const int j = i % nw;
+    int y, j;
+    divmod(i, dn, y, j);
     const uint32_t w1 = s32[i];
     const uint32_t w0 = j > 0 ? s32[i - 1] : (w1 & 0xffu) * 0x01010101u;
     const uint32_t w2 = j < nw - 1 ? s32[i + 1] : (w1 >> 24) * 0x01010101u;
-    uint32_t p[8] = {byte_of(w0, 2), byte_of(w0, 3), byte_of(w1, 0), byte_of(w1, 1),
-                     byte_of(w1, 2), byte_of(w1, 3), byte_of(w2, 0), byte_of(w2, 1)};
-    uint32_t o = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) o |= blur_lane(p[k], p[k + 1], p[k + 2], p[k + 3], p[k + 4], ww, fw) << (8 * k);
-    d32[i] = o;
+    d32[i] = blur_word(__funnelshift_r(w0, w1, 16), __funnelshift_r(w0, w1, 24), w1, __funnelshift_r(w1, w2, 8),
+                       __funnelshift_r(w1, w2, 16), ww, fw);
   }
 }
 
@@ -202,17 +222,39 @@ __device__ __forceinline__ void plane_blur_x(const uint8_t* __restrict__ s, uint
 __device__ __forceinline__ void plane_blur_y(const uint8_t* __restrict__ s, uint8_t* __restrict__ d, int h, int w, uint32_t ww,
                                              uint32_t fw) {
   const int nw = w >> 2;
+  const FastDiv dn = fast_div(nw);
   const uint32_t* s32 = reinterpret_cast<const uint32_t*>(s);
   uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
   for (int i = threadIdx.x; i < h * nw; i += PYR_THREADS) {
-    const int y = i / nw, j = i - y * nw;
-    const int y0 = max(y - 2, 0), y1 = max(y - 1, 0), y3 = min(y + 1, h - 1), y4 = min(y + 2, h - 1);
-    const uint32_t a = s32[y0 * nw + j], b = s32[y1 * nw + j], c = s32[i], e = s32[y3 * nw + j], f = s32[y4 * nw + j];
-    uint32_t o = 0;
+    int y, j;
+    divmod(i, dn, y, j);
+    const int up1 = y > 0 ? nw : 0, up2 = y > 1 ? nw : 0;             // row steps, zero where the edge row replicates
+    const int dn1 = y < h - 1 ? nw : 0, dn2 = y < h - 2 ? nw : 0;
+    d32[i] = blur_word(s32[i - up1 - up2], s32[i - up1], s32[i], s32[i + dn1], s32[i + dn1 + dn2], ww, fw);
+  }
+}
+
+// Horizontal resample of rows [0, ns) of one channel with the KS taps of a column held in registers: a thread owns one
+// output column (ow a power of two <= PYR_THREADS) and walks down the rows, so the per-tap work is one byte load and one
+// multiply-add.  Columns whose tap window would run past the row end are shifted left with their weights.
+template <int KS, int CC>
+__device__ __forceinline__ void hpass_columns(const uint8_t* __restrict__ sp, uint8_t* __restrict__ T, int ns, int iw, int ow,
+                                              int ow_shift, const int* __restrict__ txb, const int* __restrict__ txk) {
+  const int x = threadIdx.x & (ow - 1);
+  const int ystep = PYR_THREADS >> ow_shift;
+  int x0 = txb[2 * x];
+  const int shift = max(x0 - (iw - KS), 0);
+  x0 -= shift;
+  int kreg[KS];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      o |= blur_lane(byte_of(a, k), byte_of(b, k), byte_of(c, k), byte_of(e, k), byte_of(f, k), ww, fw) << (8 * k);
-    d32[i] = o;
+  for (int t = 0; t < KS; ++t) kreg[t] = (t >= shift) ? txk[x * KS + t - shift] : 0;
+  const uint8_t* p = sp + (size_t)x0 * CC;
+  for (int y = threadIdx.x >> ow_shift; y < ns; y += ystep) {
+    const uint8_t* q = p + (size_t)y * iw * CC;
+    int acc = 1 << (PREC_BITS - 1);
+#pragma unroll
+    for (int t = 0; t < KS; ++t) acc += (int)__ldg(q + t * CC) * kreg[t];
+    T[y * ow + x] = clip8(acc);
   }
 }
 
@@ -287,9 +329,20 @@ pyramid_plane_kernel(const __grid_constant__ PyrJobs jobs) {
 
   // stage 1: T[ns][ow] = horizontally resampled (or copied) rows of the channel plane
   const uint8_t* sp = J.src + ((size_t)b * ih + s0) * iw * C + c;
-  if (hpass) {
+  const FastDiv dow = fast_div(ow);
+  const bool columns = hpass && C == 3 && dow.shift >= 0 && ow <= PYR_THREADS && iw >= J.ksx &&
+                       (J.ksx == 3 || J.ksx == 5 || J.ksx == 9 || J.ksx == 17);
+  if (columns) {
+    switch (J.ksx) {
+      case 3: hpass_columns<3, 3>(sp, T, ns, iw, ow, dow.shift, txb, txk); break;
+      case 5: hpass_columns<5, 3>(sp, T, ns, iw, ow, dow.shift, txb, txk); break;
+      case 9: hpass_columns<9, 3>(sp, T, ns, iw, ow, dow.shift, txb, txk); break;
+      default: hpass_columns<17, 3>(sp, T, ns, iw, ow, dow.shift, txb, txk); break;
+    }
+  } else if (hpass) {
     for (int i = threadIdx.x; i < ns * ow; i += PYR_THREADS) {
-      const int y = i / ow, x = i - y * ow;
+      int y, x;
+      divmod(i, dow, y, x);
       const int x0 = txb[2 * x], n = txb[2 * x + 1];
       const uint8_t* p = sp + ((size_t)y * iw + x0) * C;
       const int* k = txk + x * J.ksx;
@@ -304,7 +357,8 @@ pyramid_plane_kernel(const __grid_constant__ PyrJobs jobs) {
   // stage 2: A[ne][ow] = vertically resampled rows e0..e1-1 (A aliases T when the height is unchanged)
   if (vpass) {
     for (int i = threadIdx.x; i < ne * ow; i += PYR_THREADS) {
-      const int y = i / ow, x = i - y * ow;
+      int y, x;
+      divmod(i, dow, y, x);
       const int y0 = tyb[2 * y] - s0, n = tyb[2 * y + 1];
       const uint8_t* p = T + y0 * ow + x;
       const int* k = tyk + y * J.ksy;
