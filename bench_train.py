@@ -92,6 +92,37 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0]) / a.steps
+    # ---- end to end from decoded images: per step the H2D copy of a pinned uint8 [B,256,256,3] batch + captions, the input
+    # pyramid on the device (the reference's per-sample PIL work, datasets.py:112-148), the step, and the D2H of the loss.
+    hr = torch.nn.functional.interpolate(O.synth_lr(B, 32, seed=201 + rank), size=(256, 256), mode='bicubic').clamp(-1, 1)
+    hr_h = ((hr + 1.0) * 127.5).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory()
+    caps_h, lens_h = caps.cpu().pin_memory(), lens.cpu().pin_memory()
+    loss_h = torch.empty(1, dtype=torch.float32).pin_memory()
+    hr_d = torch.empty_like(hr_h, device=dev)
+    caps_d, lens_d = torch.empty_like(caps), torch.empty_like(lens)
+    if use_graph:
+        hr_d.copy_(hr_h); caps_d.copy_(caps_h); lens_d.copy_(lens_h)
+        ts.capture_from_images(hr_d, caps_d, lens_d, 18)
+
+    def one_e2e():
+        hr_d.copy_(hr_h, non_blocking=True); caps_d.copy_(caps_h, non_blocking=True); lens_d.copy_(lens_h, non_blocking=True)
+        o = ts.step_graph_from_images(hr_d, caps_d, lens_d) if use_graph else ts.step_from_images(hr_d, caps_d, lens_d, 18)
+        loss_h.copy_(o['total'].reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()                      # the host reads the loss every step
+        return float(loss_h[0])
+    for _ in range(3):
+        one_e2e()
+    barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for _ in range(a.steps):
+        last_loss = one_e2e()
+    e2.record()
+    barrier()
+    t2 = torch.tensor([s2.elapsed_time(e2)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2[0]) / a.steps
     roof = None
     if rank == 0:
         # dominant library kernel of the step: the TF32 implicit-GEMM conv (64 -> 128 at 128x128), timed alone, L2-cold
@@ -117,6 +148,10 @@ def main():
                                    'gamma (4,5,10), Adam(2e-4,(0.5,0.999)), flat-bucket NCCL all-reduce of %d gradients'
                                    % (B, ts.bucket.numel), 'batch_per_gpu': B, 'launch': 'CUDA-graph replay of the whole step' if use_graph else 'per-kernel launches from Python',
                        'image_encoder': 'frozen random-init Inception-v3 on torchvision/cuDNN (library, out of scope)'},
+            'e2e': {'value': world * B / (e2e_ms * 1e-3), 'unit': 'images/s', 'ms_per_step': e2e_ms,
+                    'h2d_bytes_per_step': hr_h.numel() + caps_h.numel() * 8 + lens_h.numel() * 8, 'd2h_bytes_per_step': 4,
+                    'input': 'pinned uint8 [B,256,256,3] decoded images + int64 captions; input pyramid (PIL-exact resize, '
+                             'normalise) on the device inside the step', 'loss': last_loss},
             'gpu_launches': launches, 'roofline': roof,
             'loss': {k: float(v) for k, v in out.items()}}))
     if world > 1:

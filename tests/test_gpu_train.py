@@ -230,6 +230,38 @@ def test_generator_train_step_runs_and_learns():
     assert float(o2[-1]['mse']) < mse[0] and torch.isfinite(o2[-1]['total'])
 
 
+def test_train_step_from_images_matches_explicit_inputs():
+    """step_from_images(uint8 batch) == step(LR, real) when LR / real come from the PIL-exact oracle pyramid
+    (datasets.py:112-148): the device pyramid feeds the step bit-identical inputs, so the first-step losses agree."""
+    from oracle import pil_pyramid as P
+    from tgsr_b200 import nets
+    from tgsr_b200.text_encoder import RNN_ENCODER
+    from tgsr_b200.train_step import FrozenImageEncoder, GeneratorTrainStep
+    B = 3
+    hr = torch.nn.functional.interpolate(O.synth_lr(B, 32, seed=41), size=(256, 256), mode='bicubic').clamp(-1, 1)
+    hr_u8 = ((hr + 1.0) * 127.5).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    ret, _, _, _ = P.get_imgs_blur(hr_u8.numpy(), [32, 64, 128, 256])
+    caps, lens = O.synth_captions(B, 200, seed=42, words_num=18)
+    caps, lens = caps.to(DEV), lens.to(DEV)
+    losses = []
+    for mode in ('explicit', 'images', 'graph'):
+        torch.manual_seed(31)
+        gl = nets.G_SR_NET_low().to(DEV); gh = nets.NetG_highweight(low='lr').to(DEV)
+        enc = RNN_ENCODER(200, nhidden=256).to(DEV).eval()
+        img = FrozenImageEncoder().to(DEV)
+        ts = GeneratorTrainStep(gl, gh, enc, img, conv_precision='fp32')
+        if mode == 'explicit':
+            o = ts.step(torch.from_numpy(ret[0]).to(DEV), [torch.from_numpy(r).to(DEV) for r in ret[1:]], caps, lens, 18)
+        elif mode == 'images':
+            o = ts.step_from_images(hr_u8.to(DEV), caps, lens, 18)
+        else:
+            ts.capture_from_images(hr_u8.to(DEV), caps, lens, 18, warmup=1)
+            assert ts.graph_img_kernels > 0
+            continue
+        losses.append({k: float(v) for k, v in o.items()})
+    assert losses[0] == pytest.approx(losses[1], rel=1e-5), losses
+
+
 @pytest.mark.parametrize('B,Cin,Cout,H,W,k,up', [(2, 64, 128, 32, 32, 3, False), (2, 64, 64, 16, 24, 3, True), (3, 32, 32, 20, 12, 3, False),
                                                  (2, 32, 64, 8, 8, 3, True), (2, 3, 64, 32, 32, 3, False), (2, 32, 3, 16, 16, 5, False)])
 def test_tf32_convs_match_exact_kernels(B, Cin, Cout, H, W, k, up):

@@ -178,6 +178,58 @@ class GeneratorTrainStep:
         """LR [B,3,32,32]; real = [64x64, 128x128, 256x256] targets; captions int64 [B,18] sorted by length (desc)."""
         return self._step_impl(LR, real, captions, cap_lens, tmax, False, time_allreduce)
 
+    # ------------------------------------------------------------------ steps fed with decoded images
+    IMSIZE = (32, 64, 128, 256)        # cfg.TREE.BASE_SIZE * 2**i, BRANCH_NUM 4 (datasets.py:1575-1578)
+
+    def _inputs_from_images(self, hr_u8: torch.Tensor, imsize=None):
+        """uint8 [B, S, S, 3] decoded + cropped HR batch on the device -> (LR, real pyramid) with the reference's PIL
+        arithmetic (datasets.py:112-148 `get_imgs`: ret[0] is the LR input, ret[1:] the MSE targets), csrc/pyramid.cu."""
+        from . import pyramid
+        ret, _bic = pyramid.get_imgs(hr_u8, list(imsize or self.IMSIZE))
+        return ret[0], ret[1:]
+
+    def step_from_images(self, hr_u8: torch.Tensor, captions: torch.Tensor, cap_lens: torch.Tensor, tmax: int,
+                         time_allreduce: bool = False) -> Dict[str, torch.Tensor]:
+        """One step from decoded images: the input pyramid the reference builds per sample on the host (PIL, DataLoader
+        workers) runs on the device in front of the step."""
+        LR, real = self._inputs_from_images(hr_u8)
+        return self._step_impl(LR, real, captions, cap_lens, tmax, False, time_allreduce)
+
+    def capture_from_images(self, hr_u8, captions, cap_lens, tmax: int, warmup: int = 3) -> None:
+        """As capture(), with the input pyramid inside the graph: the static inputs are the uint8 batch and the captions."""
+        if self.world > 1:
+            raise RuntimeError('GeneratorTrainStep.capture_from_images: the gradient all-reduce is not graph-captured; use '
+                               'step_from_images() with N > 1 ranks')
+        self._static_img = [hr_u8.clone(), captions.clone(), cap_lens.clone()]
+        st = self._static_img
+
+        def body():
+            LR, real = self._inputs_from_images(st[0])
+            return self._step_impl(LR, real, st[1], st[2], tmax, True)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _lib
+        lib = _lib.load()
+        n0 = lib.tgsr_launch_count()
+        self._graph_img = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_img):
+            self._graph_img_out = body()
+        self.graph_img_kernels = int(lib.tgsr_launch_count() - n0)
+
+    def step_graph_from_images(self, hr_u8, captions, cap_lens) -> Dict[str, torch.Tensor]:
+        st = self._static_img
+        if hr_u8.data_ptr() != st[0].data_ptr():
+            st[0].copy_(hr_u8, non_blocking=True)
+            st[1].copy_(captions, non_blocking=True); st[2].copy_(cap_lens, non_blocking=True)
+        self._graph_img.replay()
+        return self._graph_img_out
+
     # ------------------------------------------------------------------ whole-step CUDA graph
     def capture(self, LR, real, captions, cap_lens, tmax: int, warmup: int = 3) -> None:
         """Capture forward + losses + backward + all-reduce + Adam of one step into a CUDA graph (static shapes).  The
