@@ -356,15 +356,25 @@ pyramid_plane_kernel(const __grid_constant__ PyrJobs jobs) {
   __syncthreads();
   // stage 2: A[ne][ow] = vertically resampled rows e0..e1-1 (A aliases T when the height is unchanged)
   if (vpass) {
-    for (int i = threadIdx.x; i < ne * ow; i += PYR_THREADS) {
-      int y, x;
-      divmod(i, dow, y, x);
+    // four adjacent columns per thread: one word load and one weight load per tap
+    const int nw = ow >> 2;
+    const FastDiv dnw = fast_div(nw);
+    const uint32_t* T32 = reinterpret_cast<const uint32_t*>(T);
+    uint32_t* A32 = reinterpret_cast<uint32_t*>(A);
+    for (int i = threadIdx.x; i < ne * nw; i += PYR_THREADS) {
+      int y, j;
+      divmod(i, dnw, y, j);
       const int y0 = tyb[2 * y] - s0, n = tyb[2 * y + 1];
-      const uint8_t* p = T + y0 * ow + x;
+      const uint32_t* p = T32 + y0 * nw + j;
       const int* k = tyk + y * J.ksy;
-      int acc = 1 << (PREC_BITS - 1);
-      for (int t = 0; t < n; ++t) acc += (int)p[t * ow] * k[t];
-      A[i] = clip8(acc);
+      int a0 = 1 << (PREC_BITS - 1), a1 = a0, a2 = a0, a3 = a0;
+      for (int t = 0; t < n; ++t) {
+        const uint32_t w = p[t * nw];
+        const int kt = k[t];
+        a0 += (int)byte_of(w, 0) * kt; a1 += (int)byte_of(w, 1) * kt;
+        a2 += (int)byte_of(w, 2) * kt; a3 += (int)byte_of(w, 3) * kt;
+      }
+      A32[i] = (uint32_t)clip8(a0) | ((uint32_t)clip8(a1) << 8) | ((uint32_t)clip8(a2) << 16) | ((uint32_t)clip8(a3) << 24);
     }
     __syncthreads();
   }
