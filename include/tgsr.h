@@ -330,6 +330,20 @@ int tgsr_pyramid_levels_u8(const uint8_t* src, int B, int ih, int iw, int C, int
 int tgsr_attn_word_stats_f32(const float* attn, float* maxv, uint8_t* argmax, double* conf, int B, int T, int Q, float thresh,
                              int replicas, tgsr_stream_t stream);
 
+/* Stand-alone losses of miscc/losses.py.
+ *   KL_loss (losses.py:806-810): out[0] = -0.5 * mean(1 + logvar - mu^2 - exp(logvar)) over n elements; the backward takes
+ *   the upstream scalar gradient g[0] (device) and writes d_mu, d_logvar.
+ *   cosine_similarity (losses.py:12-18) along the middle axis of an [outer, D, inner] view:
+ *   out[o,i] = sum_d x1*x2 / max(|x1|*|x2|, eps); stats (nullable; 3 floats per output: dot, |x1|, |x2|) feeds the backward,
+ *   which writes d1, d2 (same shape as the inputs) from the upstream gradient g [outer, inner]. */
+int tgsr_kl_loss_f32(const float* mu, const float* logvar, float* out, size_t n, tgsr_stream_t stream);
+int tgsr_kl_loss_bwd_f32(const float* mu, const float* logvar, const float* g, float* d_mu, float* d_logvar, size_t n,
+                         tgsr_stream_t stream);
+int tgsr_cosine_similarity_f32(const float* x1, const float* x2, float* out, float* stats, size_t outer, int D, int inner,
+                               float eps, tgsr_stream_t stream);
+int tgsr_cosine_similarity_bwd_f32(const float* x1, const float* x2, const float* stats, const float* g, float* d1, float* d2,
+                                   size_t outer, int D, int inner, float eps, tgsr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -288,6 +288,31 @@ def gen_train(ns):
                os.path.join(OUT, 'train_step.pt'))
 
 
+def gen_misc_losses(ns):
+    """KL_loss and cosine_similarity of the UNMODIFIED miscc/losses.py (:806-810, :12-18) with autograd gradients."""
+    from miscc import losses as L
+    g = torch.Generator().manual_seed(1203)
+    cases = []
+    for shape, dim in [((4, 100), 1), ((3, 256, 7), 1), ((2, 5, 64), 2), ((6, 256), 1)]:
+        x1 = torch.randn(shape, generator=g).requires_grad_(True)
+        x2 = torch.randn(shape, generator=g).requires_grad_(True)
+        if len(shape) == 2 and shape[0] == 6:
+            x1.data[0] = 0.0                                   # zero vector: the eps clamp decides the value and the gradient
+        c = L.cosine_similarity(x1, x2, dim)
+        gc = torch.randn(c.shape, generator=g)
+        (c * gc).sum().backward()
+        cases.append(dict(kind='cos', x1=x1.detach().clone(), x2=x2.detach().clone(), dim=dim, out=c.detach().clone(), g=gc,
+                          d1=x1.grad.clone(), d2=x2.grad.clone()))
+    for shape in [(4, 100), (32, 100)]:
+        mu = (torch.randn(shape, generator=g) * 0.7).requires_grad_(True)
+        lv = (torch.randn(shape, generator=g) * 0.5).requires_grad_(True)
+        k = L.KL_loss(mu, lv)
+        (2.5 * k).backward()
+        cases.append(dict(kind='kl', mu=mu.detach().clone(), logvar=lv.detach().clone(), out=k.detach().clone(), gscale=2.5,
+                          d_mu=mu.grad.clone(), d_logvar=lv.grad.clone()))
+    torch.save(cases, os.path.join(OUT, 'misc_losses.pt'))
+
+
 def gen_pyramid(ns):
     """The reference's own `get_imgs_blur` (datasets.py:151-196), unmodified, on data/face/000155.png with the eval
     transform (Resize(288) -> CenterCrop(256), datasets.py:1558-1561) and norm (:1563); imsize = [32, 64, 128, 256]
@@ -322,6 +347,10 @@ def gen_pyramid(ns):
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == 'misc':
+        gen_misc_losses(ns)
+        print('misc_losses.pt', os.path.getsize(os.path.join(OUT, 'misc_losses.pt')))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'pyramid':
         gen_pyramid(ns)
         print('pyramid.npz', os.path.getsize(os.path.join(OUT, 'pyramid.npz')))
@@ -343,6 +372,7 @@ def main():
     gen_losses(ns)
     gen_train(ns)
     gen_pyramid(ns)
+    gen_misc_losses(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

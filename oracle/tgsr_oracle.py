@@ -258,6 +258,12 @@ def cosine_similarity(x1: Tensor, x2: Tensor, dim: int = 1, eps: float = 1e-8) -
     return (w12 / (w1 * w2).clamp(min=eps)).squeeze()
 
 
+def KL_loss(mu: Tensor, logvar: Tensor) -> Tensor:
+    """miscc/losses.py:806-810."""
+    KLD_element = mu.pow(2).add(logvar.exp()).mul(-1).add(1).add(logvar)
+    return torch.mean(KLD_element).mul(-0.5)
+
+
 def _class_masks(class_ids, B: int) -> Optional[Tensor]:
     """miscc/losses.py:24-34 / :73-77, :117-120."""
     if class_ids is None:

@@ -65,3 +65,24 @@ def test_words_loss_batch32_vs_oracle():
     torch.testing.assert_close(fg.grad.cpu(), fr.grad, rtol=5e-3, atol=1e-7)
     for a, b in zip(att, ratt):
         torch.testing.assert_close(a.detach().cpu(), b.detach(), rtol=1e-4, atol=1e-7)
+
+
+def test_kl_and_cosine_golden(golden):
+    """KL_loss / cosine_similarity (csrc/loss_misc.cu) forward and backward against the reference's own outputs and
+    autograd gradients (tests/golden/misc_losses.pt), including a zero vector where the eps clamp is active."""
+    for c in golden('misc_losses.pt'):
+        if c['kind'] == 'cos':
+            x1 = c['x1'].to(DEV).requires_grad_(True); x2 = c['x2'].to(DEV).requires_grad_(True)
+            out = L.cosine_similarity(x1, x2, c['dim'])
+            assert out.shape == c['out'].shape
+            torch.testing.assert_close(out.detach().cpu(), c['out'], rtol=1e-5, atol=1e-6)
+            (out * c['g'].to(DEV)).sum().backward()
+            torch.testing.assert_close(x1.grad.cpu(), c['d1'], rtol=1e-4, atol=1e-6)
+            torch.testing.assert_close(x2.grad.cpu(), c['d2'], rtol=1e-4, atol=1e-6)
+        else:
+            mu = c['mu'].to(DEV).requires_grad_(True); lv = c['logvar'].to(DEV).requires_grad_(True)
+            k = L.KL_loss(mu, lv)
+            torch.testing.assert_close(k.detach().cpu(), c['out'], rtol=1e-5, atol=1e-6)
+            (c['gscale'] * k).backward()
+            torch.testing.assert_close(mu.grad.cpu(), c['d_mu'], rtol=1e-5, atol=1e-7)
+            torch.testing.assert_close(lv.grad.cpu(), c['d_logvar'], rtol=1e-5, atol=1e-7)

@@ -166,3 +166,12 @@ def test_train_mode_oracle_matches_reference(golden):
         torch.testing.assert_close(sdL[name].grad, g, rtol=2e-3, atol=1e-6 + 1e-4 * float(g.abs().max()))
     for name, g in c['gradH'].items():
         torch.testing.assert_close(sdH[name].grad, g, rtol=2e-3, atol=1e-6 + 1e-4 * float(g.abs().max()))
+
+
+def test_misc_losses_oracle_matches_reference(golden):
+    """KL_loss / cosine_similarity restatements against the unmodified miscc/losses.py outputs (tests/golden/misc_losses.pt)."""
+    for c in golden('misc_losses.pt'):
+        if c['kind'] == 'cos':
+            close(O.cosine_similarity(c['x1'], c['x2'], c['dim']), c['out'], rtol=1e-6, atol=1e-7)
+        else:
+            close(O.KL_loss(c['mu'], c['logvar']), c['out'], rtol=1e-6, atol=1e-7)

@@ -70,6 +70,10 @@ _SIGS = {
     'tgsr_adam_devstep_f32': ([C.c_void_p] * 4 + [C.c_size_t] + [C.c_float] * 4 + [C.c_void_p, C.c_float, C.c_void_p], C.c_int),
     'tgsr_quantize_u8': ([C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p], C.c_int),
     'tgsr_attn_word_stats_f32': ([C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_float, C.c_int, C.c_void_p], C.c_int),
+    'tgsr_kl_loss_f32': ([C.c_void_p] * 3 + [C.c_size_t, C.c_void_p], C.c_int),
+    'tgsr_kl_loss_bwd_f32': ([C.c_void_p] * 5 + [C.c_size_t, C.c_void_p], C.c_int),
+    'tgsr_cosine_similarity_f32': ([C.c_void_p] * 4 + [C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_void_p], C.c_int),
+    'tgsr_cosine_similarity_bwd_f32': ([C.c_void_p] * 6 + [C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_void_p], C.c_int),
     'tgsr_resize_u8_ws_bytes': ([C.c_int] * 6, C.c_size_t),
     'tgsr_resize_u8': ([C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p], C.c_int),
     'tgsr_gaussian_blur_u8': ([C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_float, C.c_int, C.c_void_p], C.c_int),

@@ -194,6 +194,70 @@ def MSE(fake, label):
     return MseFn.apply(len(fake), *fake, *label)
 
 
+class KlLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar):
+        mu = _f32(mu); logvar = _f32(logvar)
+        if mu.shape != logvar.shape:
+            raise ValueError('KL_loss: shape mismatch %s vs %s' % (tuple(mu.shape), tuple(logvar.shape)))
+        out = torch.empty(1, device=mu.device, dtype=torch.float32)
+        call('tgsr_kl_loss_f32', mu.device, ptr(mu), ptr(logvar), ptr(out), C.c_size_t(mu.numel()))
+        ctx.save_for_backward(mu, logvar)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        mu, logvar = ctx.saved_tensors
+        g = g.to(torch.float32).reshape(1).contiguous()
+        d_mu, d_lv = torch.empty_like(mu), torch.empty_like(logvar)
+        call('tgsr_kl_loss_bwd_f32', mu.device, ptr(mu), ptr(logvar), ptr(g), ptr(d_mu), ptr(d_lv), C.c_size_t(mu.numel()))
+        return d_mu, d_lv
+
+
+def KL_loss(mu, logvar):
+    """losses.py:806-810: -0.5 * mean(1 + logvar - mu^2 - exp(logvar))."""
+    return KlLossFn.apply(mu, logvar)
+
+
+class CosineFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, dim, eps):
+        x1 = _f32(x1); x2 = _f32(x2)
+        if x1.shape != x2.shape:
+            raise ValueError('cosine_similarity: shape mismatch %s vs %s' % (tuple(x1.shape), tuple(x2.shape)))
+        dim = dim % x1.dim()
+        outer = 1
+        for s in x1.shape[:dim]:
+            outer *= s
+        inner = 1
+        for s in x1.shape[dim + 1:]:
+            inner *= s
+        D = x1.shape[dim]
+        oshape = tuple(x1.shape[:dim]) + tuple(x1.shape[dim + 1:])
+        out = torch.empty(oshape, device=x1.device, dtype=torch.float32)
+        stats = torch.empty((max(out.numel(), 1), 3), device=x1.device, dtype=torch.float32)
+        call('tgsr_cosine_similarity_f32', x1.device, ptr(x1), ptr(x2), ptr(out), ptr(stats), C.c_size_t(outer), D, inner,
+             C.c_float(eps))
+        ctx.save_for_backward(x1, x2, stats)
+        ctx.geom = (outer, D, inner, eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x1, x2, stats = ctx.saved_tensors
+        outer, D, inner, eps = ctx.geom
+        g = g.to(torch.float32).contiguous()
+        d1, d2 = torch.empty_like(x1), torch.empty_like(x2)
+        call('tgsr_cosine_similarity_bwd_f32', x1.device, ptr(x1), ptr(x2), ptr(stats), ptr(g), ptr(d1), ptr(d2),
+             C.c_size_t(outer), D, inner, C.c_float(eps))
+        return d1, d2, None, None
+
+
+def cosine_similarity(x1, x2, dim=1, eps=1e-8):
+    """losses.py:12-18: cosine similarity along `dim`, squeezed like the reference's."""
+    return CosineFn.apply(x1, x2, dim, eps).squeeze()
+
+
 def generator_lossor_wordsentOnly(image_encoder, fake_imgs, words_embs, sent_emb, match_labels, cap_lens, class_ids, w=1, s=1):
     """losses.py:499-522: ranking losses on the last generated image through the (frozen) image encoder."""
     batch_size = fake_imgs[0].size(0)
