@@ -148,14 +148,25 @@ lstm_recurrence_kernel(const int64_t* __restrict__ cap_lens, const float* __rest
 // direction for all time steps.  CTA `rank` owns hidden units [64*rank, 64*rank+64): thread r holds
 // gate row (g = r/64, u = 64*rank + r%64) of W_hh ENTIRELY IN REGISTERS (128 floats), so the
 // recurrent GEMV reads no weights from memory after the prologue.  The input projection is a
-// gather from the precomputed table xtab[token][dir][4H] = E.W_ih^T + b_ih + b_hh.  Each step the
-// new h of a CTA's 64 units is written to both CTAs' shared memory (DSMEM) and one cluster barrier
-// publishes it.
-constexpr int LC_BT = 4;
+// gather from the precomputed table xtab[token][dir][4H] = E.W_ih^T + b_ih + b_hh; the values of
+// step s+1 are fetched into registers while step s computes, so the serial loop never waits for
+// global memory.  Every thread applies its own gate's nonlinearity (the five transcendental
+// evaluations of a cell run in parallel on four threads instead of in sequence on one).  Each step
+// the new h of a CTA's 64 units is written to both CTAs' shared memory (DSMEM) and one cluster
+// barrier publishes it.  Two captions per cluster: the step time is latency (barrier, DSMEM,
+// transcendental chains), so more, smaller clusters finish sooner than fewer, wider ones.
+constexpr int LC_BT = 2;
 constexpr int LC_H = 128;
 
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  cluster_arrive();
+  cluster_wait();
 }
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -174,8 +185,9 @@ lstm_cluster_kernel(const int64_t* __restrict__ captions, const int64_t* __restr
                     const float* __restrict__ xtab, const float* __restrict__ w_hh, float* __restrict__ words,
                     float* __restrict__ sent, int B, int Tcap, int Tmax, int ntoken) {
   constexpr int H = LC_H, G = 4 * H;
+  static_assert(LC_BT == 2, "the hidden state is read as float2 (two captions per unit)");
   __shared__ __align__(16) float h_s[2][H][LC_BT];      // double-buffered hidden state, [unit][caption]
-  __shared__ float g_s[4][64][LC_BT];                   // this CTA's gate pre-activations
+  __shared__ float g_s[4][64][LC_BT];                   // this CTA's activated gates
   __shared__ int len_s[LC_BT];
   __shared__ int tok_s[LC_BT * 64];                     // token ids of this cluster's captions (Tcap <= 64)
   const uint32_t rank = cluster_rank();
@@ -191,6 +203,11 @@ lstm_cluster_kernel(const int64_t* __restrict__ captions, const int64_t* __restr
     len_s[r] = L;
   }
   for (int i = r; i < H * LC_BT; i += 256) (&h_s[0][0][0])[i] = 0.f;
+  for (int i = r; i < LC_BT * Tcap; i += 256) {
+    const int bb = i / Tcap, t = i % Tcap;
+    long long id = (b0 + bb < B) ? captions[(size_t)(b0 + bb) * Tcap + t] : 0;
+    tok_s[i] = (int)(id < 0 ? 0 : (id >= ntoken ? ntoken - 1 : id));
+  }
   float w[H];                                           // W_hh[d][row][:] in registers
   {
     const float4* wr = reinterpret_cast<const float4*>(w_hh + ((size_t)d * G + row) * H);
@@ -201,75 +218,66 @@ lstm_cluster_kernel(const int64_t* __restrict__ captions, const int64_t* __restr
     }
   }
   __syncthreads();
+  int len[LC_BT];
   int maxlen = 0;
 #pragma unroll
-  for (int bb = 0; bb < LC_BT; ++bb) maxlen = max(maxlen, len_s[bb]);
-  cluster_sync_all();                                   // both CTAs initialised before any remote store
-
-  float c_reg = 0.f;                                    // cell (unit ul, caption g): 64 x 4 cells = 256 threads
-  const int cb = g;                                     // caption handled by this thread in the cell update
-  // Input projections of ALL steps for this CTA's 256 gate rows: gathered from the table into shared
-  // memory up front (independent loads, full memory-level parallelism), so the serial step loop below
-  // touches no global memory except its outputs.
-  extern __shared__ float xs[];                         // [maxlen][LC_BT][256]
-  for (int i = r; i < LC_BT * Tcap; i += 256) {
-    const int bb = i / Tcap, t = i % Tcap;
-    long long id = (b0 + bb < B) ? captions[(size_t)(b0 + bb) * Tcap + t] : 0;
-    tok_s[i] = (int)(id < 0 ? 0 : (id >= ntoken ? ntoken - 1 : id));
-  }
-  __syncthreads();
-#pragma unroll 6
-  for (int s = 0; s < maxlen; ++s) {
+  for (int bb = 0; bb < LC_BT; ++bb) { len[bb] = len_s[bb]; maxlen = max(maxlen, len[bb]); }
+  // input projection of this thread's gate row at step s, one value per caption (zero once a caption has ended)
+  auto fetch_x = [&](int s, float (&x)[LC_BT]) {
 #pragma unroll
     for (int bb = 0; bb < LC_BT; ++bb) {
-      const int L = len_s[bb];
-      float v = 0.f;
-      if (s < L) {
-        const int t = d == 0 ? s : L - 1 - s;
-        v = __ldg(xtab + ((size_t)tok_s[bb * Tcap + t] * 2 + d) * G + row);
+      x[bb] = 0.f;
+      if (s < len[bb]) {
+        const int t = d == 0 ? s : len[bb] - 1 - s;
+        x[bb] = __ldg(xtab + ((size_t)tok_s[bb * Tcap + t] * 2 + d) * G + row);
       }
-      xs[(s * LC_BT + bb) * 256 + r] = v;
     }
-  }
+  };
+  float xc[LC_BT], xn[LC_BT];
+  fetch_x(0, xc);
+  cluster_sync_all();                                   // both CTAs initialised before any remote store
+
+  float c_reg = 0.f;                                    // cell (unit cu, caption cb) lives in thread cb*64 + cu
+  const int cb = r >> 6, cu = r & 63, cunit = (int)rank * 64 + cu;
+  const bool cell_thread = r < 64 * LC_BT;
+  const int cL = cell_thread ? len_s[cb] : 0;
   for (int s = 0; s < maxlen; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
+    fetch_x(s + 1, xn);                                 // lands while the recurrent product below runs
     float acc[LC_BT];
 #pragma unroll
-    for (int bb = 0; bb < LC_BT; ++bb) acc[bb] = xs[(s * LC_BT + bb) * 256 + r];
-    const float4* h4 = reinterpret_cast<const float4*>(&h_s[cur][0][0]);
+    for (int bb = 0; bb < LC_BT; ++bb) acc[bb] = xc[bb];
+    const float2* h2 = reinterpret_cast<const float2*>(&h_s[cur][0][0]);
 #pragma unroll
     for (int k = 0; k < H; ++k) {
-      const float4 hv = h4[k];                          // broadcast: h[k] of the 4 captions
+      const float2 hv = h2[k];                          // broadcast: h[k] of the 2 captions
       acc[0] = fmaf(w[k], hv.x, acc[0]); acc[1] = fmaf(w[k], hv.y, acc[1]);
-      acc[2] = fmaf(w[k], hv.z, acc[2]); acc[3] = fmaf(w[k], hv.w, acc[3]);
     }
 #pragma unroll
-    for (int bb = 0; bb < LC_BT; ++bb) g_s[g][ul][bb] = acc[bb];
+    for (int bb = 0; bb < LC_BT; ++bb)                  // gate order i, f, g, o: g is tanh, the rest sigmoid
+      g_s[g][ul][bb] = g == 2 ? tanhf(acc[bb]) : 1.0f / (1.0f + expf(-acc[bb]));
     __syncthreads();
-    {
-      const int L = len_s[cb];
-      if (s < L) {
-        const float ig = 1.0f / (1.0f + expf(-g_s[0][ul][cb]));
-        const float fg = 1.0f / (1.0f + expf(-g_s[1][ul][cb]));
-        const float gg = tanhf(g_s[2][ul][cb]);
-        const float og = 1.0f / (1.0f + expf(-g_s[3][ul][cb]));
-        c_reg = fmaf(fg, c_reg, ig * gg);
-        const float h = og * tanhf(c_reg);
-        h_s[nxt][u][cb] = h;
-        st_remote_f32(&h_s[nxt][u][cb], rank ^ 1u, h);
-        const int t = d == 0 ? s : L - 1 - s;
-        if (t < Tmax) words[((size_t)(b0 + cb) * 2 * H + d * H + u) * Tmax + t] = h;
-        if (s == L - 1) sent[(size_t)(b0 + cb) * 2 * H + d * H + u] = h;
-      }
+    if (cell_thread && s < cL) {
+      c_reg = fmaf(g_s[1][cu][cb], c_reg, g_s[0][cu][cb] * g_s[2][cu][cb]);
+      const float h = g_s[3][cu][cb] * tanhf(c_reg);
+      h_s[nxt][cunit][cb] = h;
+      st_remote_f32(&h_s[nxt][cunit][cb], rank ^ 1u, h);
     }
-    cluster_sync_all();
+    cluster_arrive();
+    if (cell_thread && s < cL) {                        // outputs leave while the barrier completes
+      const float h = h_s[nxt][cunit][cb];
+      const int t = d == 0 ? s : cL - 1 - s;
+      if (t < Tmax) words[((size_t)(b0 + cb) * 2 * H + d * H + cunit) * Tmax + t] = h;
+      if (s == cL - 1) sent[(size_t)(b0 + cb) * 2 * H + d * H + cunit] = h;
+    }
+#pragma unroll
+    for (int bb = 0; bb < LC_BT; ++bb) xc[bb] = xn[bb];
+    cluster_wait();
   }
 }
 
 int init_lstm() {
-  cudaError_t e = cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       48 * LC_BT * 256 * 4);
-  return e == cudaSuccess ? TGSR_OK : cuda_fail(e);
+  return TGSR_OK;
 }
 
 }  // namespace tgsr
@@ -296,8 +304,7 @@ extern "C" int tgsr_lstm_bidir_fwd_tab_f32(const int64_t* captions, const int64_
   cudaStream_t st = (cudaStream_t)stream;
   TGSR_CUDA(cudaMemsetAsync(words, 0, (size_t)B * 2 * H * Tmax * sizeof(float), st));
   TGSR_CUDA(cudaMemsetAsync(sent, 0, (size_t)B * 2 * H * sizeof(float), st));
-  const size_t xs_bytes = (size_t)Tcap * LC_BT * 256 * sizeof(float);
-  lstm_cluster_kernel<<<dim3(2, 2, ceil_div(B, LC_BT)), 256, xs_bytes, st>>>(captions, cap_lens, xtab, w_hh, words, sent,
+  lstm_cluster_kernel<<<dim3(2, 2, ceil_div(B, LC_BT)), 256, 0, st>>>(captions, cap_lens, xtab, w_hh, words, sent,
                                                                              B, Tcap, Tmax, ntoken);
   return launch_status();
 }
