@@ -64,13 +64,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_graph = not a.no_graph and world == 1      # the NCCL all-reduce is not captured: multi-GPU steps launch from Python
+    use_graph = not a.no_graph      # N > 1: two graphs per step with the (uncaptured) NCCL all-reduce between them
     if use_graph:
         ts.capture(LR, real, caps, lens, 18)
 
     def one(timed=False):
         if use_graph:
-            return ts.step_graph(ts._static[0], ts._static[1], ts._static[2], ts._static[3])
+            return ts.step_graph(ts._static[0], ts._static[1], ts._static[2], ts._static[3], time_allreduce=timed)
         return ts.step(LR, real, caps, lens, 18, time_allreduce=timed)
 
     for _ in range(max(a.warmup, 3)):
@@ -87,7 +87,7 @@ def main():
     e.record()
     barrier()
     launches = ts.graph_kernels * a.steps if use_graph else int(lib.tgsr_launch_count() - n0)   # replays bypass the counter
-    ar_ms = ts.ev[0].elapsed_time(ts.ev[1]) if ts.ev is not None and not use_graph else float('nan')
+    ar_ms = ts.ev[0].elapsed_time(ts.ev[1]) if ts.ev is not None and world > 1 else float('nan')
     t = torch.tensor([s.elapsed_time(e), ar_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -146,7 +146,7 @@ def main():
             'dtype': 'tf32 tensor-core convs (fp32 accumulate), fp32 elsewhere', 'data': 'synthetic',
             'config': {'workload': 'configs[4]: x8 generator training step, batch %d per GPU, 32->256, 18-word captions, '
                                    'gamma (4,5,10), Adam(2e-4,(0.5,0.999)), flat-bucket NCCL all-reduce of %d gradients'
-                                   % (B, ts.bucket.numel), 'batch_per_gpu': B, 'launch': 'CUDA-graph replay of the whole step' if use_graph else 'per-kernel launches from Python',
+                                   % (B, ts.bucket.numel), 'batch_per_gpu': B, 'launch': ('CUDA-graph replay of the whole step' if world == 1 else 'two CUDA graphs per step (fwd+bwd, Adam) around the eager NCCL all-reduce') if use_graph else 'per-kernel launches from Python',
                        'image_encoder': 'frozen random-init Inception-v3 on torchvision/cuDNN (library, out of scope)'},
             'e2e': {'value': world * B / (e2e_ms * 1e-3), 'unit': 'images/s', 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': hr_h.numel() + caps_h.numel() * 8 + lens_h.numel() * 8, 'd2h_bytes_per_step': 4,

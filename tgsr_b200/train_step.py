@@ -143,7 +143,8 @@ class GeneratorTrainStep:
         self._lab = None
         self._graph = None
 
-    def _step_impl(self, LR, real, captions, cap_lens, tmax: int, capturable: bool, time_allreduce: bool = False):
+    def _fwd_bwd(self, LR, real, captions, cap_lens, tmax: int):
+        """Zero the flat gradient, forward (train-mode BN), losses, backward: everything before the exchange step."""
         B = LR.shape[0]
         self.bucket.zero_grad()
         with torch.no_grad():
@@ -156,17 +157,27 @@ class GeneratorTrainStep:
         mse = losses.MSE(list(fine) + list(fake_imgL), list(real) + list(real))
         total = errG + mse
         total.backward()
+        return {'total': total.detach(), 'damsm': errG.detach(), 'mse': mse.detach()}
+
+    def _exchange(self, time_allreduce: bool = False) -> None:
         if time_allreduce:
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
         self.bucket.all_reduce(self.group)
         if time_allreduce:
             e.record(); self.ev = (s, e)
+
+    def _update(self, capturable: bool) -> None:
         if capturable:
             self.opt.step_capturable(1.0 / self.world)
         else:
             self.opt.step(1.0 / self.world)
-        return {'total': total.detach(), 'damsm': errG.detach(), 'mse': mse.detach()}
+
+    def _step_impl(self, LR, real, captions, cap_lens, tmax: int, capturable: bool, time_allreduce: bool = False):
+        out = self._fwd_bwd(LR, real, captions, cap_lens, tmax)
+        self._exchange(time_allreduce)
+        self._update(capturable)
+        return out
 
     def _labels(self, B, dev):
         if self._lab is None or self._lab.shape[0] != B:
@@ -197,68 +208,74 @@ class GeneratorTrainStep:
 
     def capture_from_images(self, hr_u8, captions, cap_lens, tmax: int, warmup: int = 3) -> None:
         """As capture(), with the input pyramid inside the graph: the static inputs are the uint8 batch and the captions."""
-        if self.world > 1:
-            raise RuntimeError('GeneratorTrainStep.capture_from_images: the gradient all-reduce is not graph-captured; use '
-                               'step_from_images() with N > 1 ranks')
         self._static_img = [hr_u8.clone(), captions.clone(), cap_lens.clone()]
         st = self._static_img
 
-        def body():
+        def inputs():
             LR, real = self._inputs_from_images(st[0])
-            return self._step_impl(LR, real, st[1], st[2], tmax, True)
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                body()
-        cur.wait_stream(side)
-        torch.cuda.synchronize()
-        from . import _lib
-        lib = _lib.load()
-        n0 = lib.tgsr_launch_count()
-        self._graph_img = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph_img):
-            self._graph_img_out = body()
-        self.graph_img_kernels = int(lib.tgsr_launch_count() - n0)
+            return LR, real, st[1], st[2]
+        self._graph_img, self._graph_img_b, self._graph_img_out, self.graph_img_kernels = self._capture_graphs(inputs, tmax, warmup)
 
-    def step_graph_from_images(self, hr_u8, captions, cap_lens) -> Dict[str, torch.Tensor]:
+    def step_graph_from_images(self, hr_u8, captions, cap_lens, time_allreduce: bool = False) -> Dict[str, torch.Tensor]:
         st = self._static_img
         if hr_u8.data_ptr() != st[0].data_ptr():
             st[0].copy_(hr_u8, non_blocking=True)
             st[1].copy_(captions, non_blocking=True); st[2].copy_(cap_lens, non_blocking=True)
-        self._graph_img.replay()
+        self._replay(self._graph_img, self._graph_img_b, time_allreduce)
         return self._graph_img_out
 
     # ------------------------------------------------------------------ whole-step CUDA graph
-    def capture(self, LR, real, captions, cap_lens, tmax: int, warmup: int = 3) -> None:
-        """Capture forward + losses + backward + all-reduce + Adam of one step into a CUDA graph (static shapes).  The
-        ~1400 launches of a step are launch-bound from Python; replay removes that."""
-        if self.world > 1:
-            raise RuntimeError('GeneratorTrainStep.capture: the gradient all-reduce is not graph-captured; use step() with N > 1 ranks')
-        self._static = [LR.clone(), [r.clone() for r in real], captions.clone(), cap_lens.clone()]
+    def _capture_graphs(self, body_inputs, tmax: int, warmup: int):
+        """Capture one step.  On one GPU the whole step is ONE graph; with N > 1 ranks the NCCL all-reduce stays outside:
+        graph A = zero-grad + forward + losses + backward, the eager all-reduce of the flat bucket, graph B = fused Adam
+        (capturing the collective itself hung the ranks in round 1, so it is not attempted)."""
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._step_impl(self._static[0], self._static[1], self._static[2], self._static[3], tmax, True)
+                self._fwd_bwd(*body_inputs(), tmax)
+                self._exchange()
+                self._update(True)
         cur.wait_stream(side)
         torch.cuda.synchronize()
         from . import _lib
         lib = _lib.load()
         n0 = lib.tgsr_launch_count()
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._graph_out = self._step_impl(self._static[0], self._static[1], self._static[2], self._static[3], tmax, True)
-        self.graph_kernels = int(lib.tgsr_launch_count() - n0)      # libtgsr kernels inside one replay
+        g_a = torch.cuda.CUDAGraph()
+        g_b = None
+        if self.world == 1:
+            with torch.cuda.graph(g_a):
+                out = self._fwd_bwd(*body_inputs(), tmax)
+                self._update(True)
+        else:
+            with torch.cuda.graph(g_a):
+                out = self._fwd_bwd(*body_inputs(), tmax)
+            g_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_b, pool=g_a.pool()):
+                self._update(True)
+        return g_a, g_b, out, int(lib.tgsr_launch_count() - n0)
 
-    def step_graph(self, LR, real, captions, cap_lens) -> Dict[str, torch.Tensor]:
+    def _replay(self, g_a, g_b, time_allreduce: bool = False) -> None:
+        g_a.replay()
+        if g_b is not None:
+            self._exchange(time_allreduce)
+            g_b.replay()
+
+    def capture(self, LR, real, captions, cap_lens, tmax: int, warmup: int = 3) -> None:
+        """Capture forward + losses + backward (+ Adam) of one step into CUDA graphs (static shapes).  The ~1400 launches
+        of a step are launch-bound from Python; replay removes that."""
+        self._static = [LR.clone(), [r.clone() for r in real], captions.clone(), cap_lens.clone()]
+        st = self._static
+        self._graph, self._graph_b, self._graph_out, self.graph_kernels = self._capture_graphs(
+            lambda: (st[0], st[1], st[2], st[3]), tmax, warmup)
+
+    def step_graph(self, LR, real, captions, cap_lens, time_allreduce: bool = False) -> Dict[str, torch.Tensor]:
         st = self._static
         if LR.data_ptr() != st[0].data_ptr():
             st[0].copy_(LR, non_blocking=True)
             for d, r in zip(st[1], real):
                 d.copy_(r, non_blocking=True)
             st[2].copy_(captions, non_blocking=True); st[3].copy_(cap_lens, non_blocking=True)
-        self._graph.replay()
+        self._replay(self._graph, self._graph_b, time_allreduce)
         return self._graph_out
