@@ -83,3 +83,34 @@ def test_glu_odd_channels_error():
         pytest.skip('checked on the GPU path')
     with pytest.raises(RuntimeError):
         ops.conv2d_fused(torch.zeros(1, 3, 4, 4), torch.zeros(5, 3, 3, 3), None, None, 1)
+
+
+def test_pyramid_host_logic_and_argument_errors():
+    """Host-only parts of the input-pyramid entry points: the fused kernel's envelope, the resize workspace size, and
+    argument validation that returns before any CUDA call (so it runs without a GPU)."""
+    lib = _lib.load()
+    # every x8 / x16 branch from a 256-row source fits the fused kernel, with and without blur
+    for (ih, oh) in [(256, 256), (256, 128), (256, 64), (256, 32), (32, 256), (32, 128), (32, 64), (128, 128), (16, 128)]:
+        assert lib.tgsr_pyramid_supported(ih, ih, oh, oh, 1) == 1 and lib.tgsr_pyramid_supported(ih, ih, oh, oh, 0) == 1
+    assert lib.tgsr_pyramid_supported(100, 100, 50, 50, 1) == 0          # width not a multiple of 4 -> generic kernels
+    assert lib.tgsr_pyramid_supported(0, 256, 32, 32, 1) == 0
+    # workspace: two tap tables (ksize + 2 ints per output sample) + the horizontally resized intermediate
+    assert lib.tgsr_resize_u8_ws_bytes(2, 256, 256, 32, 32, 3) >= 2 * 32 * (17 + 2) * 4 + 2 * 256 * 32 * 3
+    assert lib.tgsr_resize_u8_ws_bytes(0, 256, 256, 32, 32, 3) == 0
+    err_null, err_shape = -3, -1
+    assert lib.tgsr_error_string(err_null) and lib.tgsr_error_string(err_shape)
+    assert lib.tgsr_resize_u8(None, None, None, 1, 8, 8, 4, 4, 3, None) != 0
+    assert lib.tgsr_gaussian_blur_u8(None, None, None, 1, 8, 8, 3, 2.0, 3, None) != 0
+    assert lib.tgsr_normalize_u8_f32(None, None, 1, 8, 8, 3, None) != 0
+    assert lib.tgsr_attn_word_stats_f32(None, None, None, None, 1, 4, 16, 0.1, 3, None) != 0
+    assert lib.tgsr_kl_loss_f32(None, None, None, 4, None) != 0
+
+
+def test_pyramid_module_has_no_cpu_path():
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from tgsr_b200 import pyramid
+    with pytest.raises(RuntimeError, match='CUDA'):
+        pyramid.get_imgs_blur(torch.zeros(1, 64, 64, 3, dtype=torch.uint8), [16, 32, 64])
+    with pytest.raises(RuntimeError, match='CUDA'):
+        pyramid.resize(torch.zeros(1, 64, 64, 3, dtype=torch.uint8), 32)
