@@ -632,6 +632,11 @@ static int launch_tc(const CUtensorMap& tmap, const TcParams& p, int fmt, cudaSt
 
 #define TGSR_CHECK_FMT(fmt) TGSR_REQUIRE((fmt) == TGSR_FMT_BF16 || (fmt) == TGSR_FMT_F16, TGSR_ERR_UNSUPPORTED)
 
+namespace tgsr {
+int img_head_mma(const void* x, int xP, int xp0, const void* wpacked, const float* addend, float out_scale, float addend_scale,
+                 float* y, int B, int H, int W, int ksize, int act_tanh, int fmt, cudaStream_t st);   // head_mma.cu
+}
+
 extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const float* shift,
                                const void* residual, int rP, int rp0, void* y, int yP, int yp0, int B, int Cin,
                                int H, int W, int Cout, int up2x, int act, int fmt, tgsr_stream_t stream) {
@@ -718,6 +723,12 @@ extern "C" int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpac
   TGSR_REQUIRE(act == TGSR_ACT_NONE || act == TGSR_ACT_TANH, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(xp0 >= 0 && xp0 + Cin / 8 <= xP, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE((long long)B * xP < (1LL << 31), TGSR_ERR_UNSUPPORTED);
+  // TGSR_HEAD_IMPL=mma selects the warp-level tensor-core head (head_mma.cu): parity-tested, but measured slower than the
+  // tcgen05 head below (72.6 vs 48.9 us for the 3x3 head at 256x256, batch 32), so it is not the default.
+  static const bool use_mma = [] { const char* e = getenv("TGSR_HEAD_IMPL"); return e != nullptr && e[0] == 'm'; }();
+  if (use_mma)
+    return img_head_mma(x, xP, xp0, wpacked, addend, out_scale, addend_scale, y, B, H, W, ksize, act == TGSR_ACT_TANH, fmt,
+                        (cudaStream_t)stream);
   CUtensorMap tmap;
   int s = make_patch_tmap(&tmap, x, B, xP, H, W, Cin / 8, fmt, ksize / 2, 1);
   if (s != TGSR_OK) return s;
