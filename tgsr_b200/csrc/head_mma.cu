@@ -44,6 +44,7 @@ struct HmParams {
   float* y;                 // [B,3,H,W]
   float out_scale, addend_scale;
   int xP, xp0, B, H, W, tiles_x, tiles_y, act_tanh;
+  int debug;                // TGSR_TC_DEBUG stage skipping (1 MMA loop, 2 epilogue, 4 copies): timing experiments only
 };
 
 template <int FMT>
@@ -148,13 +149,13 @@ head_mma_kernel(const HmParams p) {
 
   asm volatile("griddepcontrol.wait;" ::: "memory");          // the activations (and addend) come from predecessors
   int tile = blockIdx.x;
-  if (tile < ntiles) hm_issue_tile<K>(p, tile, hm_smem, reinterpret_cast<float*>(hm_smem + 2 * Cfg::PATCH + Cfg::WFRAG));
+  if (tile < ntiles && !(p.debug & 4)) hm_issue_tile<K>(p, tile, hm_smem, reinterpret_cast<float*>(hm_smem + 2 * Cfg::PATCH + Cfg::WFRAG));
   for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
     unsigned char* patch = hm_smem + buf * Cfg::PATCH;
     const float* adt = reinterpret_cast<const float*>(hm_smem + 2 * Cfg::PATCH + Cfg::WFRAG + buf * Cfg::ADDEND);
     const int next = tile + gridDim.x;
-    if (next < ntiles) {
+    if (next < ntiles && !(p.debug & 4)) {
       hm_issue_tile<K>(p, next, hm_smem + (buf ^ 1) * Cfg::PATCH,
                        reinterpret_cast<float*>(hm_smem + 2 * Cfg::PATCH + Cfg::WFRAG + (buf ^ 1) * Cfg::ADDEND));
       asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -168,7 +169,7 @@ head_mma_kernel(const HmParams p) {
     for (int o = 0; o < HM_ROWS; ++o) { acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0.f; }
     const uint32_t patch_a = (uint32_t)__cvta_generic_to_shared(patch) + lane_off;
 #pragma unroll 1
-    for (int t2 = 0; t2 < K * 2; ++t2) {
+    for (int t2 = 0; t2 < ((p.debug & 1) ? 0 : K * 2); ++t2) {
       const int dx = t2 >> 1, ks = t2 & 1;
       uint2 bf[K];
 #pragma unroll
@@ -188,7 +189,7 @@ head_mma_kernel(const HmParams p) {
     }
 
     // epilogue: accumulator registers c0,c1 = pixel g, channels 2q,2q+1; c2,c3 = pixel g+8
-    if (q < 2) {
+    if (q < 2 && !(p.debug & 2)) {
       const int b = tile / tiles_per_img, rt = tile - b * tiles_per_img;
       const int ty = rt / p.tiles_x, tx = rt - ty * p.tiles_x;
       const int y0 = ty * HM_TH, x0 = tx * HM_TW;
@@ -255,6 +256,8 @@ int img_head_mma(const void* x, int xP, int xp0, const void* wpacked, const floa
   p.addend = addend; p.y = y; p.out_scale = out_scale; p.addend_scale = addend_scale;
   p.xP = xP; p.xp0 = xp0; p.B = B; p.H = H; p.W = W;
   p.tiles_x = ceil_div(W, HM_TW); p.tiles_y = ceil_div(H, HM_TH); p.act_tanh = act_tanh;
+  static const int dbg = [] { const char* e = getenv("TGSR_TC_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = dbg;
   if ((long long)B * p.tiles_x * p.tiles_y >= (1LL << 31)) return TGSR_ERR_UNSUPPORTED;
   if (ksize == 3) return fmt == TGSR_FMT_F16 ? launch_head_mma<3, TGSR_FMT_F16>(p, st) : launch_head_mma<3, TGSR_FMT_BF16>(p, st);
   return fmt == TGSR_FMT_F16 ? launch_head_mma<5, TGSR_FMT_F16>(p, st) : launch_head_mma<5, TGSR_FMT_BF16>(p, st);
