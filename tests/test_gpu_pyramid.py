@@ -55,6 +55,8 @@ def test_fused_pyramid_vs_oracle(imsize):
         ret, bic = Y.get_imgs(hr.to(DEV), imsize)
         for w, g in zip(want[0] + want[1], ret + bic):
             assert np.array_equal(w, g.cpu().numpy())
+        for w, g in zip(want[0], Y.real_pyramid(hr.to(DEV), imsize)):
+            assert np.array_equal(w, g.cpu().numpy())
 
 
 def test_generic_path_odd_sizes():

@@ -92,7 +92,7 @@ def _levels(src: Tensor, sizes: Sequence[Tuple[int, int]], want_out: Sequence[bo
     return outs, blurs, u8s
 
 
-def _pyramid(img: Tensor, imsize: Sequence[int], blur: bool, radius: float):
+def _pyramid(img: Tensor, imsize: Sequence[int], blur: bool, radius: float, want_bic: bool = True):
     img = _u8(img)
     B, H, W, Cn = img.shape
     sizes = [_size2(int(s), H, W) for s in imsize]
@@ -112,18 +112,24 @@ def _pyramid(img: Tensor, imsize: Sequence[int], blur: bool, radius: float):
         ret, bic, retb, bicb = [], [], [], []
         for i, s in enumerate(sizes):
             re_img = resize(img, s) if i < n - 1 else img
-            bicim = resize(lr, s)
-            ret.append(normalize(re_img)); bic.append(normalize(bicim))
+            ret.append(normalize(re_img))
             if blur:
-                retb.append(normalize(gaussian_blur(re_img, radius))); bicb.append(normalize(gaussian_blur(bicim, radius)))
+                retb.append(normalize(gaussian_blur(re_img, radius)))
+            if want_bic:
+                bicim = resize(lr, s)
+                bic.append(normalize(bicim))
+                if blur:
+                    bicb.append(normalize(gaussian_blur(bicim, radius)))
         return ret, bic, retb, bicb
     # launch 1: every branch of the HR image, largest plane first; branch 0 also leaves the LR bytes for launch 2
     order = list(range(n - 1, -1, -1))
-    outs, blurs, u8s = _levels(img, [sizes[i] for i in order], [True] * n, [blur] * n, [i == 0 for i in order], radius)
+    outs, blurs, u8s = _levels(img, [sizes[i] for i in order], [True] * n, [blur] * n, [want_bic and i == 0 for i in order], radius)
     ret = [None] * n
     retb = [None] * n
     for k, i in enumerate(order):
         ret[i], retb[i] = outs[k], blurs[k]
+    if not want_bic:
+        return ret, [], (retb if blur else []), []
     lr = u8s[order.index(0)]
     # launch 2: the LR image resized to branches 1.. ("bic"); branch 0 of bic is the LR image itself
     bic = [ret[0]] + [None] * (n - 1)
@@ -144,6 +150,11 @@ def get_imgs_blur(img: Tensor, imsize: Sequence[int], radius: float = 2.0
        bic[i]  = Resize(imsize[i])(Resize(imsize[0])(img)),                    bicb[i] = GaussianBlur(2) of it.
     bic[0] / bicb[0] are the same tensors as ret[0] / retb[0] (Resize to the same size returns a copy of the image)."""
     return _pyramid(img, imsize, True, radius)
+
+
+def real_pyramid(img: Tensor, imsize: Sequence[int]) -> List[Tensor]:
+    """Only `ret` of get_imgs (the LR input and the MSE targets of a training step): one launch, no "bic" branch."""
+    return _pyramid(img, imsize, False, 2.0, want_bic=False)[0]
 
 
 def get_imgs(img: Tensor, imsize: Sequence[int]) -> Tuple[List[Tensor], List[Tensor]]:

@@ -196,7 +196,7 @@ class GeneratorTrainStep:
         """uint8 [B, S, S, 3] decoded + cropped HR batch on the device -> (LR, real pyramid) with the reference's PIL
         arithmetic (datasets.py:112-148 `get_imgs`: ret[0] is the LR input, ret[1:] the MSE targets), csrc/pyramid.cu."""
         from . import pyramid
-        ret, _bic = pyramid.get_imgs(hr_u8, list(imsize or self.IMSIZE))
+        ret = pyramid.real_pyramid(hr_u8, list(imsize or self.IMSIZE))
         return ret[0], ret[1:]
 
     def step_from_images(self, hr_u8: torch.Tensor, captions: torch.Tensor, cap_lens: torch.Tensor, tmax: int,
