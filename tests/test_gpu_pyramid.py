@@ -42,7 +42,7 @@ def test_golden_reference_pyramid():
             assert np.array_equal(_u8(lst[i][0].cpu().numpy()), g['%s%d_u8' % (name, i)]), (name, i)
 
 
-@pytest.mark.parametrize('imsize', [[32, 64, 128, 256], [16, 32, 64, 128], [64, 128], [128]])
+@pytest.mark.parametrize('imsize', [[32, 64, 128, 256], [16, 32, 64, 128], [64, 128], [128], [12, 24, 48, 96], [40, 80, 160]])
 def test_fused_pyramid_vs_oracle(imsize):
     for smooth in (False, True):
         hr = _rand(5, imsize[-1], imsize[-1], seed=3 + len(imsize), smooth=smooth)
