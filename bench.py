@@ -392,7 +392,8 @@ def run_ours(args):
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'result': 'final SR image as uint8 [B,3,256,256] (device-side quantisation of trainer_objective.py:153-155); '
-                              'D2H of step i overlaps compute of step i+1; every result waited for on the host',
+                              'the packed H2D copy of step i+1 (own stream, two staging buffers) and the D2H of step i overlap the compute of the '
+                              'neighbouring steps; every result waited for on the host',
                     'fp32_result': {'value': e2e_fp32, 'unit': 'images/s', 'd2h_bytes_per_step': d2h_fp32}},
             'gpu_launches': int(launches),
             'roofline': roof, 'roofline_attention': attn_roof,
