@@ -319,8 +319,9 @@ def run_ours(args):
 
     # ---- end-to-end timing through the public API with host buffers: SRPipeline.submit / result.
     # Every step copies its inputs from pinned host memory (H2D), runs the whole forward, quantises the SR image to
-    # the saved-image format (uint8, trainer_objective.py:153-155) and copies it to pinned host memory (D2H); the D2H
-    # of step i overlaps the compute of step i+1 (two output slots, copy stream).  Every result is waited for on the
+    # the saved-image format (uint8, trainer_objective.py:153-155) and copies it to pinned host memory (D2H); the H2D
+    # of step i+1 (own stream, two staging buffers) and the D2H of step i (two output slots, copy stream) overlap the
+    # compute of the neighbouring steps.  Every result is waited for on the
     # host inside the timed region.  No explicit L2 flush here: one step streams ~1.3 GB through the 126 MB L2.
     def e2e_loop(n, out):
         prev = None
