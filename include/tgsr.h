@@ -138,24 +138,32 @@ int tgsr_nchw_to_blocked(const float* x, void* y, int B, int C, int H, int W, in
 int tgsr_blocked_to_nchw(const void* x, float* y, int B, int C, int H, int W, int xP, int xp0, int fmt,
                          tgsr_stream_t stream);
 
-/* Weight prep: conv3x3 weight [Cout,Cin,3,3] fp32 -> packed 16-bit UMMA operand image.
- * up2x == 0: 9 taps, Cout*Cin*9 elements.  up2x == 1: the nearest-x2 upsample of util.py:76 is
- * folded into the weights as four 2x2 sub-pixel phases (pre-summed in fp32, rounded once),
- * Cout*Cin*16 elements.  scale [Cout] (the folded BatchNorm scale, or NULL) is multiplied into the
- * weights in fp32 before the single rounding, so the conv epilogue only adds the BN shift. */
-int tgsr_pack_conv3x3(const float* w, const float* scale, void* packed, int Cout, int Cin, int up2x,
-                      int fmt, tgsr_stream_t stream);
+/* Weight prep: conv3x3 weight [Cout,Cin,3,3] fp32 + folded BatchNorm (scale, shift) -> packed 16-bit UMMA operand
+ * image of tgsr_packed_conv3x3_elems(Cout,Cin,up2x) elements: [tap weight blocks | shift block | ones block].
+ * up2x == 0: 9 taps.  up2x == 1: the nearest-x2 upsample of util.py:76 is folded into the weights as four 2x2
+ * sub-pixel phases (pre-summed in fp32, rounded once), 16 blocks.  scale [Cout] (or NULL = 1) is multiplied into the
+ * weights in fp32 before the single rounding; shift [Cout] (or NULL = 0) is applied by one extra MMA per tile
+ * (ones x shift, the shift split into three 16-bit terms, exact to 2^-24), so the conv epilogue adds nothing.
+ * act: TGSR_ACT_NONE or TGSR_ACT_GLU as in the conv call (bf16 GLU layers carry an exact factor 1/2 in weights and
+ * shift: z*sigmoid(g) = z/2 + z/2*tanh(g/2)). */
+size_t tgsr_packed_conv3x3_elems(int Cout, int Cin, int up2x);
+int tgsr_pack_conv3x3(const float* w, const float* scale, const float* shift, void* packed, int Cout, int Cin,
+                      int up2x, int act, int fmt, tgsr_stream_t stream);
 
-/* a3/a4/a5: conv3x3 (+ folded BN: scale in the packed weights, shift [Cout] here) (+GLU) (+residual) on tcgen05,
+/* a3/a4/a5: conv3x3 (+ folded BN, both parts inside wpacked) (+GLU) (+residual) on tcgen05,
  * 16-bit operands, fp32 accumulation in TMEM; util.py:62-65, :45-53, :110-130, :74-80.
  * x view (xP,xp0) of Cin channels at HxW; y view (yP,yp0) of Cout (or Cout/2 with GLU) channels at
  * HxW, or at 2Hx2W when up2x (wpacked must then come from tgsr_pack_conv3x3(up2x=1)).
  * residual view (rP,rp0) or NULL (only with act NONE, no up2x).  Supported (Cin,Cout,act,up2x):
  * (64,128,GLU,0) (64,64,NONE,0) (32,64,GLU,0) (32,32,NONE,0) (64,64,GLU,1) (32,64,GLU,1);
- * H % 16 == 0, W % 8 == 0. */
-int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const float* shift,
-                    const void* residual, int rP, int rp0, void* y, int yP, int yp0, int B, int Cin, int H,
-                    int W, int Cout, int up2x, int act, int fmt, tgsr_stream_t stream);
+ * H % 16 == 0, W % 8 == 0.
+ * flags: TGSR_CONV_REVERSE walks the output tiles from the last one backwards.  Results are identical; a kernel that
+ * consumes what its predecessor just wrote in forward order finds the most recently written (still L2-resident) part
+ * of its input first, which matters when a layer's tensors exceed the 126 MB L2 (64 channels at 128x128, batch 32). */
+#define TGSR_CONV_REVERSE 1
+int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const void* residual, int rP, int rp0,
+                    void* y, int yP, int yp0, int B, int Cin, int H, int W, int Cout, int up2x, int act, int fmt,
+                    int flags, tgsr_stream_t stream);
 
 /* a8 image heads on tensor cores: GET_IMAGE_G / GET_IMAGE_G_noAct (conv3x3 32->3, util.py:894-919) and
  * conv_output (conv5x5 32->3 + Tanh, model.py:223-226) with the fused `one*y + a*SRb` of model.py:280.

@@ -56,12 +56,21 @@ CASES = [  # Cin, Cout, glu, up2x, residual, B, H, W
     (64, 64, True, True, False, 2, 16, 16),
     (32, 64, True, True, False, 1, 32, 8),
     (64, 128, True, False, False, 5, 64, 64),     # more tiles than SMs -> pipeline wrap-around
+    (64, 64, False, False, True, 5, 64, 64),      # skip-tile ring wrap-around
+    (64, 128, True, False, False, 2, 128, 128),   # production resolutions of h_net3 / residual48 (per-kernel, 128x128)
+    (64, 64, False, False, True, 2, 128, 128),
+    (64, 64, True, True, False, 2, 128, 128),     # -> 256x256 output
+    (32, 64, True, False, False, 2, 128, 128),
+    (32, 32, False, False, True, 2, 128, 128),
+    (32, 64, True, True, False, 2, 128, 128),
+    (64, 64, False, False, True, 1, 48, 24),      # tile grid that is not a power of two (3 x 3 tiles)
 ]
 
 
+@pytest.mark.parametrize('reverse', [False, True], ids=['fwd', 'rev'])
 @pytest.mark.parametrize('fmt', [0, 1], ids=['bf16', 'fp16'])
 @pytest.mark.parametrize('Cin,Cout,glu,up2x,use_res,B,H,W', CASES)
-def test_conv_tc_matches_16bit_emulation(Cin, Cout, glu, up2x, use_res, B, H, W, fmt):
+def test_conv_tc_matches_16bit_emulation(Cin, Cout, glu, up2x, use_res, B, H, W, fmt, reverse):
     from tgsr_b200 import tc
     from tgsr_b200._lib import ACT_GLU, ACT_NONE
     g = torch.Generator().manual_seed(Cin * 7 + Cout + H)
@@ -77,7 +86,8 @@ def test_conv_tc_matches_16bit_emulation(Cin, Cout, glu, up2x, use_res, B, H, W,
     conv.weight.data.copy_(w)
     xb = tc.to_blocked(x.to(DEV), fmt=fmt)
     rb = tc.to_blocked(res.to(DEV), fmt=fmt) if use_res else None
-    yb = tc.conv3x3_tc(xb, conv, scale.to(DEV), shift.to(DEV), ACT_GLU if glu else ACT_NONE, residual=rb, up2x=up2x)
+    yb = tc.conv3x3_tc(xb, conv, scale.to(DEV), shift.to(DEV), ACT_GLU if glu else ACT_NONE, residual=rb, up2x=up2x,
+                       reverse=reverse)
     y = tc.to_nchw(yb).cpu()
     assert y.shape == ref.shape
     err = (y - ref).abs().max().item()

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libtgsr_sm100.so')
 
 ACT_NONE, ACT_GLU, ACT_TANH = 0, 1, 2
 FMT_BF16, FMT_F16 = 0, 1
+CONV_REVERSE = 1
 
 _lib = None
 _lock = threading.Lock()
@@ -40,9 +41,10 @@ _SIGS = {
     'tgsr_ca_reparam_f32': ([C.c_void_p] * 3 + [C.c_int] * 2 + [C.c_void_p], C.c_int),
     'tgsr_nchw_to_blocked': ([C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p], C.c_int),
     'tgsr_blocked_to_nchw': ([C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p], C.c_int),
-    'tgsr_pack_conv3x3': ([C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p], C.c_int),
-    'tgsr_conv3x3_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                         C.c_void_p, C.c_int, C.c_int] + [C.c_int] * 8 + [C.c_void_p], C.c_int),
+    'tgsr_packed_conv3x3_elems': ([C.c_int] * 3, C.c_size_t),
+    'tgsr_pack_conv3x3': ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p], C.c_int),
+    'tgsr_conv3x3_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                         C.c_void_p, C.c_int, C.c_int] + [C.c_int] * 9 + [C.c_void_p], C.c_int),
     'tgsr_pack_head': ([C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     'tgsr_img_head_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
                          + [C.c_int] * 7 + [C.c_void_p], C.c_int),
@@ -137,6 +139,27 @@ def check(status: int, what: str) -> None:
 
 def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+# ---------------------------------------------------------------- derived-parameter cache keys
+# The kernels write parameters and BatchNorm running statistics through raw pointers (fused Adam, bn_stats), which
+# bumps neither data_ptr nor tensor._version.  Every such writer calls bump_weights_epoch(); every derived-parameter
+# cache (folded BN, packed 16-bit operands, LSTM tables, captured eval graphs) keys on tensor_key(), which includes
+# the epoch, so an eval after training steps refolds / repacks instead of replaying stale weights.
+_weights_epoch = 0
+
+
+def weights_epoch() -> int:
+    return _weights_epoch
+
+
+def bump_weights_epoch() -> None:
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def tensor_key(t):
+    return None if t is None else (t.data_ptr(), t._version, str(t.device), _weights_epoch)
 
 
 def stream_ptr():

@@ -19,7 +19,7 @@ from . import ops
 from .attention import GlobalAttentionGeneral as ATT_NET
 from .attention import conv1x1  # noqa: F401  (re-export, util.py:56)
 from .config import cfg
-from ._lib import ACT_GLU, ACT_NONE, ACT_TANH
+from ._lib import ACT_GLU, ACT_NONE, ACT_TANH, tensor_key
 
 
 # ---------------------------------------------------------------- derived-parameter cache
@@ -30,7 +30,7 @@ def _folded_bn(bn: Optional[nn.Module]):
     if bn.training:
         raise RuntimeError('tgsr_b200: training-mode BatchNorm is not implemented on the CUDA path; call .eval()')
     src = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
-    key = tuple((t.data_ptr(), t._version, str(t.device)) for t in src)
+    key = tuple(tensor_key(t) for t in src)
     cached = bn.__dict__.get('_tgsr_fold')
     if cached is None or cached[0] != key:
         scale, shift = ops.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)

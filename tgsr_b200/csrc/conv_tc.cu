@@ -47,7 +47,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode_tiled = nullptr;
-static int g_tc_debug = 0;
 
 // ------------------------------------------------------------------------------------------
 // MMA op tables.  An op = one filter tap (or one tap x phase group of the 4-phase upsample):
@@ -83,7 +82,7 @@ template <> struct OpTable<MODE_UP> {
   }
 };
 
-template <int CIN, int NPRE, int MODE>
+template <int CIN, int NPRE, int MODE, bool GLU>
 struct TcCfg {
   static constexpr bool UP = MODE == MODE_UP;
   static constexpr bool HEAD = MODE == MODE_HEAD3 || MODE == MODE_HEAD5;
@@ -100,71 +99,137 @@ struct TcCfg {
   static constexpr int TH = HEAD ? 8 * MB : TC_TH;             // output rows per tile
   static constexpr int PH = TH + 2 * R;
   static constexpr int SBO_A = HEAD ? 128 : PW * 16;
-  static constexpr int NACC = 2;                               // TMEM accumulator stages
   static constexpr int PLANE_BYTES = PH * PW * 16;             // one 8-channel plane of the halo patch
   static constexpr int NPL = CIN / 8;                          // input planes
   static constexpr int KSTEPS = CIN / 16;                      // UMMA K = 16
   static constexpr int PATCH_BYTES = NPL * PLANE_BYTES;
-  static constexpr int ACC_COLS = UP ? 4 * NPRE : (HEAD ? 32 * (HEAD ? 4 : 1) : NPRE);   // fp32 accumulator columns per stage
+  static constexpr int ACC_COLS = UP ? 4 * NPRE : (HEAD ? 32 * MB : NPRE);   // fp32 accumulator columns per stage
+  // TMEM accumulator stages: the epilogue frees a stage as soon as its values are in registers, so two stages already
+  // decouple it from the MMA issuer; the rest of the 512 columns is used when the tile is narrow.
+  static constexpr int NACC = 512 / ACC_COLS > 4 ? 4 : 512 / ACC_COLS;
   static constexpr int TMEM_COLS = NACC * ACC_COLS;            // power of two >= 32
   static constexpr int NTAPB = UP ? 16 : OpTable<MODE>::NOPS;  // number of [NPRE x CIN] weight blocks
-  static constexpr int WBYTES = NTAPB * CIN * NPRE * 2;
-  static constexpr int NSCALE = NPRE;
+  static constexpr int WBYTES_TAPS = NTAPB * CIN * NPRE * 2;
+  // Folded-BatchNorm shift: applied by ONE extra MMA per tile, D = ones[128 x 16] * shift[N x 16]^T, issued first with
+  // accumulate = 0, so the epilogue starts from shifted accumulators (no per-element add, no shift table in shared
+  // memory).  The shift is split into three 16-bit terms (k = 0,1,2 against three ones), exact to 2^-24.
+  static constexpr bool BIAS = !HEAD;
+  static constexpr int NBIAS = UP ? 4 * NPRE : NPRE;           // bias-block rows = accumulator columns
+  static constexpr int BIAS_BYTES = BIAS ? NBIAS * 32 : 0;     // [N x 16] 16-bit, K-major core matrices
+  static constexpr int ONES_BYTES = BIAS ? 4096 : 0;           // [128 x 16] 16-bit
+  static constexpr int WBYTES = WBYTES_TAPS + BIAS_BYTES + ONES_BYTES;
+  static constexpr int WB_PAD = ((WBYTES + 1023) / 1024) * 1024;
+  // Skip-tensor ring (ResBlock second conv): the producer warp fetches the skip tile with TMA RSTAGE tiles ahead, so
+  // the epilogue never waits for a DRAM round trip of its own.
+  static constexpr bool RES = MODE == MODE_CONV && !GLU;
+  static constexpr int RSTAGE = RES ? 3 : 0;
+  static constexpr int RES_BYTES = RES ? TC_TH * TC_TW * NPRE * 2 : 0;
   // Patch-ring depth: as many stages as fit next to the resident weights (TMA latency ~1-2 us must be
   // covered by stages in flight: small-channel layers and heads spend < 0.5 us of MMA time per tile).
-  static constexpr int WB_PAD_ = ((WBYTES + 1023) / 1024) * 1024;
-  static constexpr int STAGE_ROOM = (232448 - 1024 - WB_PAD_ - 2 * NSCALE * 4 - 512) / PATCH_BYTES;
+  static constexpr int STAGE_ROOM = (232448 - 1024 - WB_PAD - RSTAGE * RES_BYTES - 512) / PATCH_BYTES;
   static constexpr int NSTAGE = STAGE_ROOM > 12 ? 12 : STAGE_ROOM;
   static_assert(NSTAGE >= 2, "not enough shared memory for a double-buffered patch ring");
-  static constexpr int PBUF_BYTES = 0;
-  static constexpr size_t SMEM = 1024 /*align slack*/ + ((WBYTES + 1023) / 1024) * 1024 + NSTAGE * PATCH_BYTES +
-                                 2 * NSCALE * 4 + 512 + PBUF_BYTES;
+  static constexpr size_t SMEM = 1024 /*align slack*/ + WB_PAD + NSTAGE * PATCH_BYTES + RSTAGE * RES_BYTES + 512;
 };
 
 struct TcParams {
-  const void* wpacked;
-  const float* scale;      // [NPRE] or null
-  const float* shift;
-  const h16* residual;   // blocked, or null
+  const void* wpacked;   // [tap weight blocks | shift block | ones block] (tgsr_pack_conv3x3 / tgsr_pack_head)
   h16* out;              // blocked
+  int has_res;                     // conv mode: add the skip tile fetched through `rmap`
   int rP, rp0, yP, yp0;            // planes per image / first plane of the residual and output views
   int xP, xp0;                     // input view (for the TMA plane coordinate)
   int B, H, W;                     // INPUT spatial size
   int tiles_x, tiles_y, ntiles;
+  int step_x, step_y, step_b;      // gridDim.x decomposed in (tile x, tile y, image) units: the per-CTA tile stride
+  int reverse;                     // walk the tiles from the last one backwards (see tgsr_conv3x3_tc flags)
   // image-head epilogue (MODE_HEAD*): y = out_scale * act(conv) + addend_scale * addend, fp32 NCHW [B,3,H,W]
   float* out_f32;
   const float* addend;
   float out_scale, addend_scale;
   int act_tanh;
-  int debug;   // profiling aid (TGSR_TC_DEBUG env): 1 skip MMAs, 2 skip epilogue work, 4 skip TMA patch loads
+};
+
+// Tile walk of a persistent CTA: tile index t = (b * tiles_y + ty) * tiles_x + tx, advanced by gridDim.x with carries
+// instead of two integer divisions per tile and role.
+struct TileIter {
+  int b, ty, tx;
+  // k-th tile of this CTA = blockIdx.x + k * gridDim.x, counted from the last tile backwards when p.reverse is set.
+  __device__ __forceinline__ void init(int first, const TcParams& p) {
+    const int tile = p.reverse ? p.ntiles - 1 - first : first;
+    tx = tile % p.tiles_x;
+    const int q = tile / p.tiles_x;
+    ty = q % p.tiles_y;
+    b = q / p.tiles_y;
+  }
+  __device__ __forceinline__ void next(const TcParams& p) {
+    if (!p.reverse) {
+      tx += p.step_x;
+      if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+      ty += p.step_y;
+      if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
+      b += p.step_b;
+    } else {
+      tx -= p.step_x;
+      if (tx < 0) { tx += p.tiles_x; --ty; }
+      ty -= p.step_y;
+      if (ty < 0) { ty += p.tiles_y; --b; }
+      b -= p.step_b;
+    }
+  }
 };
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// GLU of one (value, gate) accumulator pair.  bf16 layers: the packed weights and shift of BOTH halves carry a factor
+// 1/2 (exact), so z * sigmoid(g) = z/2 + z/2 * tanh(g/2): one MUFU + one FMA per output.  The approximation error of
+// tanh.approx (2^-11 relative) is below the bf16 rounding of the result.  fp16 layers keep exp + reciprocal.
+template <int FMT>
+__device__ __forceinline__ float glu_pair(uint32_t a, uint32_t g) {
+  if constexpr (FMT == TGSR_FMT_BF16) {
+    const float zh = __uint_as_float(a);
+    return fmaf(zh, tanh_approx(__uint_as_float(g)), zh);
+  } else {
+    return __uint_as_float(a) * fast_sigmoid(__uint_as_float(g));
+  }
+}
+__host__ __device__ constexpr float glu_prescale(bool glu, int fmt) { return (glu && fmt == TGSR_FMT_BF16) ? 0.5f : 1.0f; }
+
+__device__ __forceinline__ uint4 lds128(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
 
 template <int CIN, int NPRE, int MODE, bool GLU, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
-  using Cfg = TcCfg<CIN, NPRE, MODE>;
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap rmap, const TcParams p) {
+  using Cfg = TcCfg<CIN, NPRE, MODE, GLU>;
   using Ops = OpTable<MODE>;
   constexpr bool UP = Cfg::UP;
   constexpr bool HEAD = Cfg::HEAD;
   constexpr int TC_PW = Cfg::PW;
   constexpr int TC_PLANE_BYTES = Cfg::PLANE_BYTES;
-  constexpr int WB_PAD = ((Cfg::WBYTES + 1023) / 1024) * 1024;
   constexpr int TC_NSTAGE = Cfg::NSTAGE;
+  constexpr int RSTAGE = Cfg::RSTAGE;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char* w_s = base;
-  unsigned char* patch_s = w_s + WB_PAD;
-  float* sc_s = reinterpret_cast<float*>(patch_s + TC_NSTAGE * Cfg::PATCH_BYTES);
-  float* sh_s = sc_s + Cfg::NSCALE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sh_s + Cfg::NSCALE);
-  uint64_t* full = bars;                       // [NSTAGE]
-  uint64_t* empty = bars + TC_NSTAGE;          // [NSTAGE]
-  uint64_t* wbar = bars + 2 * TC_NSTAGE;       // [1]
-  uint64_t* tfull = wbar + 1;                  // [NACC <= 4]
-  uint64_t* tempty = tfull + 4;                // [NACC <= 4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
+  unsigned char* patch_s = w_s + Cfg::WB_PAD;
+  unsigned char* res_s = patch_s + TC_NSTAGE * Cfg::PATCH_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(res_s + RSTAGE * Cfg::RES_BYTES);
+  uint64_t* full = bars;                       // [NSTAGE <= 12]
+  uint64_t* empty = bars + 12;                 // [NSTAGE <= 12]
+  uint64_t* wbar = bars + 42;                  // [NOPS + 1 <= 12]: weight block of op o; [NOPS]: shift + ones blocks
+  uint64_t* tfull = bars + 25;                 // [NACC <= 4]
+  uint64_t* tempty = bars + 29;                // [NACC <= 4]
+  uint64_t* rfull = bars + 33;                 // [RSTAGE <= 4]
+  uint64_t* rempty = bars + 37;                // [RSTAGE <= 4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 41);
+  static_assert(Ops::NOPS + 1 <= 12, "weight barriers");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -175,52 +240,74 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(wbar, 1);
+    for (int o = 0; o <= Ops::NOPS; ++o) mbar_init(&wbar[o], 1);
     for (int a = 0; a < Cfg::NACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    for (int s = 0; s < RSTAGE; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 8); }
     fence_barrier_init();
     prefetch_tensormap(&tmap);
+    if constexpr (Cfg::RES) prefetch_tensormap(&rmap);
   }
-  for (int i = threadIdx.x; i < Cfg::NSCALE; i += TC_THREADS) sh_s[i] = p.shift ? p.shift[i] : 0.0f;
-  (void)sc_s;   // the BN scale is folded into the packed weights (tgsr_pack_conv3x3)
   if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
-
   if (warp == 0) {
     // ================================ TMA producer ================================
     // The whole warp runs the loop (uniform control flow); one elected lane issues.
+    // Weights arrive block by block (shift + ones first, then the taps in issue order), each on its own barrier, so the
+    // first tile's MMAs start after ~1/10 of the packed image has landed instead of all of it.
     if (elect_one()) {
-      mbar_arrive_expect_tx(wbar, Cfg::WBYTES);
-      constexpr int CH = 32768;
-      for (int off = 0; off < Cfg::WBYTES; off += CH) {
-        const int n = Cfg::WBYTES - off < CH ? Cfg::WBYTES - off : CH;
-        bulk_g2s(w_s + off, reinterpret_cast<const unsigned char*>(p.wpacked) + off, n, wbar);
+      auto fetch = [&](uint64_t* bar, int off, int bytes) {
+        mbar_arrive_expect_tx(bar, bytes);
+        constexpr int CH = 32768;
+        for (int o2 = 0; o2 < bytes; o2 += CH)
+          bulk_g2s(w_s + off + o2, reinterpret_cast<const unsigned char*>(p.wpacked) + off + o2, bytes - o2 < CH ? bytes - o2 : CH, bar);
+      };
+      if constexpr (Cfg::BIAS) fetch(&wbar[Ops::NOPS], Cfg::WBYTES_TAPS, Cfg::BIAS_BYTES + Cfg::ONES_BYTES);
+      int off = 0;
+#pragma unroll
+      for (int o = 0; o < Ops::NOPS; ++o) {
+        const int bytes = CIN * Ops::op(o).n_mul * NPRE * 2;
+        fetch(&wbar[o], off, bytes);
+        off += bytes;
       }
     }
     __syncwarp();
     asm volatile("griddepcontrol.wait;" ::: "memory");      // weights are not produced by the predecessor; patches are
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
-      mbar_wait(&empty[s], ph ^ 1);
-      const int b = tile / tiles_per_img, r = tile % tiles_per_img;
-      const int y0 = (r / p.tiles_x) * Cfg::TH, x0 = (r % p.tiles_x) * Cfg::TWO;
-      if (p.debug & 4) {
-        if (elect_one()) mbar_arrive(&full[s]);
-      } else if (elect_one()) {
-        mbar_arrive_expect_tx(&full[s], Cfg::PATCH_BYTES);
-        tma_load_3d(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], (x0 - Cfg::R) * 8, y0 - Cfg::R, b * p.xP + p.xp0);
+    TileIter t; t.init(blockIdx.x, p);
+    TileIter tr = t;                                         // skip tiles trail the patches by RLAG tiles
+    constexpr int RLAG = 1;
+    auto fetch_res = [&](int k) {
+      const int rs = k % (RSTAGE > 0 ? RSTAGE : 1), rph = (k / (RSTAGE > 0 ? RSTAGE : 1)) & 1;
+      mbar_wait(&rempty[rs], rph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&rfull[rs], Cfg::RES_BYTES);
+        tma_load_3d(res_s + rs * Cfg::RES_BYTES, &rmap, &rfull[rs], tr.tx * Cfg::TWO * 8, tr.ty * Cfg::TH, tr.b * p.rP + p.rp0);
       }
       __syncwarp();
+      tr.next(p);
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it, t.next(p)) {
+      const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
+      const int y0 = t.ty * Cfg::TH, x0 = t.tx * Cfg::TWO;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[s], Cfg::PATCH_BYTES);
+        tma_load_3d(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], (x0 - Cfg::R) * 8, y0 - Cfg::R, t.b * p.xP + p.xp0);
+      }
+      __syncwarp();
+      // The skip tile of tile k is only needed by the epilogue, after the MMAs of tile k: it is requested RLAG patches
+      // later, so a full skip ring never holds back the patch stream that feeds the tensor core.
+      if constexpr (Cfg::RES) { if (p.has_res && it >= RLAG) fetch_res(it - RLAG); }
+    }
+    if constexpr (Cfg::RES) {
+      if (p.has_res) for (int k = it > RLAG ? it - RLAG : 0; k < it; ++k) fetch_res(k);
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    mbar_wait(wbar, 0);
-    tc_fence_after();
     const uint32_t w_addr = smem_u32(w_s);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -229,9 +316,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       mbar_wait(&tempty[acc], aph ^ 1);            // epilogue has drained this accumulator stage
       mbar_wait(&full[s], ph);                     // patch landed
       tc_fence_after();
-      if (p.debug & 1) {
-        if (elect_one()) { mbar_arrive(&empty[s]); mbar_arrive(&tfull[acc]); }
-      } else if (elect_one()) {
+      const bool first = it == 0;                  // weight blocks land in issue order; later tiles find them resident
+      if (elect_one()) {
         // Descriptors are "per-tile base + compile-time constant": only the 14-bit start-address field of
         // the low word changes between MMAs, so each one costs a single 32-bit add on the issuing thread.
         const uint32_t a_lo0 = (smem_u32(patch_s + s * Cfg::PATCH_BYTES) >> 4) | ((uint32_t)(TC_PLANE_BYTES >> 4) << 16);
@@ -239,6 +325,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
         const uint32_t b_lo0 = w_addr >> 4;
         const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
+        if constexpr (Cfg::BIAS) {
+          // accumulators start at the folded-BN shift: ones[128 x 16] (8-row groups 128 B apart, K chunks 2 KB apart)
+          // times the shift block [NBIAS x 16]
+          constexpr int NB = Cfg::NBIAS;
+          if (first) { mbar_wait(&wbar[Ops::NOPS], 0); tc_fence_after(); }
+          const uint32_t one_lo = b_lo0 + (uint32_t)((Cfg::WBYTES_TAPS + Cfg::BIAS_BYTES) >> 4) + ((uint32_t)(2048 >> 4) << 16);
+          const uint32_t bias_lo = b_lo0 + (uint32_t)(Cfg::WBYTES_TAPS >> 4) + ((uint32_t)((NB * 16) >> 4) << 16);
+          umma_f16(d_base, make_desc64(one_lo, b_hi), make_desc64(bias_lo, b_hi),
+                   make_idesc_f16(128, NB, Fmt16<FMT>::kUmmaFormat), 0u);
+        }
 #pragma unroll
         for (int j = 0; j < Cfg::MB; ++j) {         // heads: 4 M-blocks of 8 patch rows each per tile
           uint32_t b_off = 0;                       // compile-time after unrolling
@@ -247,12 +343,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             const TcOp op = Ops::op(o);
             const int N = op.n_mul * NPRE;
             const uint32_t idesc = make_idesc_f16(128, N, Fmt16<FMT>::kUmmaFormat);
+            if (first && j == 0) { mbar_wait(&wbar[o], 0); tc_fence_after(); }
 #pragma unroll
             for (int k = 0; k < Cfg::KSTEPS; ++k) {
               const uint32_t a_lo = a_lo0 + (uint32_t)((((j * 8 + op.tap_r) * TC_PW + op.tap_c) * 16 + k * 2 * TC_PLANE_BYTES) >> 4);
               const uint32_t b_lo = b_lo0 + (uint32_t)((b_off + k * (N * 32)) >> 4) + ((uint32_t)((N * 16) >> 4) << 16);
               umma_f16(d_base + op.dcol_mul * NPRE + j * 32, make_desc64(a_lo, a_hi), make_desc64(b_lo, b_hi), idesc,
-                       (o | k) != 0 ? 1u : 0u);
+                       (Cfg::BIAS || (o | k) != 0) ? 1u : 0u);
             }
             b_off += CIN * N * 2;
           }
@@ -266,27 +363,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     // ================================ epilogue (warps 2..9) ========================
     // Two warps per TMEM lane quadrant: `half` selects which half of the output channels (or which
     // sub-pixel phases / RGB outputs) this warp produces, so two warps per SM sub-partition work on
-    // every tile and the per-tile epilogue latency halves.
+    // every tile.  A TMEM stage is handed back to the MMA issuer as soon as its values sit in registers.
     asm volatile("griddepcontrol.wait;" ::: "memory");      // skip tensor / addend reads and all output writes follow
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;                // 0: warps 2..5, 1: warps 6..9
     const int m = quad * 32 + lane;                  // accumulator row = pixel within the tile
     const int ty = m >> 3, tx = m & 7;
-    const float4* sh4 = reinterpret_cast<const float4*>(sh_s);
-    uint4 rnext[4], rnext2[4];                       // skip-tensor planes of the next two tiles (conv mode with residual)
     float adnext[2][3];                              // image-head addend of the next tile
+    TileIter t; t.init(blockIdx.x, p);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it, t.next(p)) {
       const int acc = it % Cfg::NACC, aph = (it / Cfg::NACC) & 1;
-      const int b = tile / tiles_per_img, r = tile % tiles_per_img;
-      const int gy = (r / p.tiles_x) * TC_TH + ty, gx = (r % p.tiles_x) * TC_TW + tx;
+      const int b = t.b;
+      const int gy = t.ty * TC_TH + ty, gx = t.tx * TC_TW + tx;
       const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + ((uint32_t)(quad * 32) << 16);
-      if (p.debug & 2) {
-        mbar_wait(&tfull[acc], aph);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-        continue;
-      }
 
       if constexpr (HEAD) {
         // Image head.  A tile is MB=4 accumulator blocks (columns j*32..) of 8 patch rows each; accumulator row
@@ -295,35 +385,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         // Warp group `half` produces blocks 2*half and 2*half+1.
         constexpr int K = Cfg::KS;
         const int hy = m >> 4, hx = m & 15;
-        const int ox = (r % p.tiles_x) * Cfg::TWO + hx;
+        const int ox = t.tx * Cfg::TWO + hx;
         const size_t hw = (size_t)p.H * p.W;
         bool valid[2]; size_t oi[2]; float ad[2][3];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const int oy = (r / p.tiles_x) * Cfg::TH + (half * 2 + q) * 8 + hy;
+          const int oy = t.ty * Cfg::TH + (half * 2 + q) * 8 + hy;
           valid[q] = hx < Cfg::TWO && ox < p.W && oy < p.H;
           oi[q] = (size_t)b * 3 * hw + (size_t)oy * p.W + ox;
         }
         // the addend (SRb, fp32) of this tile was requested one tile ago: no DRAM round trip in the per-tile critical path
-        auto load_addend = [&](int tl, float (&dst)[2][3]) {
-          const int bb = tl / tiles_per_img, rr = tl % tiles_per_img;
-          const int xx = (rr % p.tiles_x) * Cfg::TWO + hx;
+        auto load_addend = [&](const TileIter& tt, float (&dst)[2][3]) {
+          const int xx = tt.tx * Cfg::TWO + hx;
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const int yy = (rr / p.tiles_x) * Cfg::TH + (half * 2 + q) * 8 + hy;
+            const int yy = tt.ty * Cfg::TH + (half * 2 + q) * 8 + hy;
             const bool ok = hx < Cfg::TWO && xx < p.W && yy < p.H;
-            const size_t o0 = (size_t)bb * 3 * hw + (size_t)yy * p.W + xx;
+            const size_t o0 = (size_t)tt.b * 3 * hw + (size_t)yy * p.W + xx;
 #pragma unroll
             for (int o = 0; o < 3; ++o) dst[q][o] = ok ? __ldg(p.addend + o0 + o * hw) : 0.f;
           }
         };
         if (p.addend) {
-          if (it == 0) load_addend(tile, adnext);
+          if (it == 0) load_addend(t, adnext);
 #pragma unroll
           for (int q = 0; q < 2; ++q)
 #pragma unroll
             for (int o = 0; o < 3; ++o) ad[q][o] = adnext[q][o];
-          if (tile + (int)gridDim.x < p.ntiles) load_addend(tile + (int)gridDim.x, adnext);
+          if (tile + (int)gridDim.x < p.ntiles) { TileIter tn = t; tn.next(p); load_addend(tn, adnext); }
         } else {
 #pragma unroll
           for (int q = 0; q < 2; ++q) ad[q][0] = ad[q][1] = ad[q][2] = 0.f;
@@ -349,13 +438,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           if (valid[q]) {
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
-              float t = z[o];
-              if (p.act_tanh) t = tanhf(t);
-              __stcs(p.out_f32 + oi[q] + o * hw, fmaf(p.addend_scale, ad[q][o], t * p.out_scale));
+              float tv = z[o];
+              if (p.act_tanh) tv = tanhf(tv);
+              __stcs(p.out_f32 + oi[q] + o * hw, fmaf(p.addend_scale, ad[q][o], tv * p.out_scale));
             }
           }
         }
-        continue;                                               // (tempty already signalled)
       } else if constexpr (!UP) {
         constexpr int COUT = GLU ? NPRE / 2 : NPRE;            // channels written
         constexpr int CW = COUT / 2;                           // channels per epilogue warp (32 or 16)
@@ -363,29 +451,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const size_t pix = ((size_t)gy * p.W + gx) * 8;
         const size_t plane_elems = (size_t)p.H * p.W * 8;
         h16* obase = p.out + ((size_t)b * p.yP + p.yp0 + c0 / 8) * plane_elems + pix;
-        // The skip tensor of this tile was requested two tiles ago (rnext2 -> rnext -> rres): in the HBM-bound ResBlock conv the epilogue
-        // would otherwise serialise on one DRAM round trip per tile.
-        uint4 rres[CW / 8];
-        if (p.residual) {
-          auto load_res = [&](int tl, uint4* dst) {
-            const int bb = tl / tiles_per_img, rr = tl % tiles_per_img;
-            const int yy = (rr / p.tiles_x) * TC_TH + ty, xx = (rr % p.tiles_x) * TC_TW + tx;
-            const h16* rbase = p.residual + ((size_t)bb * p.rP + p.rp0 + c0 / 8) * plane_elems + ((size_t)yy * p.W + xx) * 8;
-#pragma unroll
-            for (int j = 0; j < CW / 8; ++j) dst[j] = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)j * plane_elems));
-          };
-          const int g2 = (int)gridDim.x;
-          if (it == 0) {
-            load_res(tile, rnext);
-            if (tile + g2 < p.ntiles) load_res(tile + g2, rnext2);
-          }
-#pragma unroll
-          for (int j = 0; j < CW / 8; ++j) { rres[j] = rnext[j]; rnext[j] = rnext2[j]; }
-          if (tile + 2 * g2 < p.ntiles) load_res(tile + 2 * g2, rnext2);      // two tiles ahead: ~32 KB of reads in flight per SM
-        }
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
-        uint32_t va[CW], vg[CW];
+        uint32_t va[CW], vg[GLU ? CW : 1];
         if constexpr (CW == 32) {
           tmem_ld32(t_base + c0, va);
           if constexpr (GLU) tmem_ld32(t_base + COUT + c0, vg);
@@ -393,24 +461,40 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           tmem_ld16(t_base + c0, va);
           if constexpr (GLU) tmem_ld16(t_base + COUT + c0, vg);
         }
+        uint4 rres[CW / 8];
+        bool has_res = false;
+        if constexpr (Cfg::RES) {
+          has_res = p.has_res != 0;
+          if (has_res) {                                        // skip tile: [plane][16 x 8 pixels][8 ch], landed by TMA
+            const int rs = it % RSTAGE, rph = (it / RSTAGE) & 1;
+            mbar_wait(&rfull[rs], rph);
+            const unsigned char* rp = res_s + rs * Cfg::RES_BYTES + (c0 / 8) * (TC_TH * TC_TW * 16) + m * 16;
+#pragma unroll
+            for (int j = 0; j < CW / 8; ++j) rres[j] = lds128(rp + j * (TC_TH * TC_TW * 16));
+          }
+        }
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&tempty[acc]);                            // accumulators are in registers: stage free
+          if constexpr (Cfg::RES) { if (has_res) mbar_arrive(&rempty[it % RSTAGE]); }
+        }
 #pragma unroll
         for (int j = 0; j < CW / 8; ++j) {                      // planes of 8 channels
-          float o[8], res[8];
-          if (p.residual) unpack8_16<FMT>(rres[j], res);
-          const float4 sa0 = sh4[(c0 + j * 8) / 4], sa1 = sh4[(c0 + j * 8) / 4 + 1];
-          const float sa[8] = {sa0.x, sa0.y, sa0.z, sa0.w, sa1.x, sa1.y, sa1.z, sa1.w};
-          float sg[8];
-          if constexpr (GLU) {
-            const float4 g0 = sh4[(COUT + c0 + j * 8) / 4], g1 = sh4[(COUT + c0 + j * 8) / 4 + 1];
-            sg[0] = g0.x; sg[1] = g0.y; sg[2] = g0.z; sg[3] = g0.w; sg[4] = g1.x; sg[5] = g1.y; sg[6] = g1.z; sg[7] = g1.w;
-          }
+          float o[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float z = __uint_as_float(va[j * 8 + e]) + sa[e];
-            if constexpr (GLU) z *= fast_sigmoid(__uint_as_float(vg[j * 8 + e]) + sg[e]);
-            if (p.residual) z += res[e];
-            o[e] = z;
+            if constexpr (GLU) o[e] = glu_pair<FMT>(va[j * 8 + e], vg[j * 8 + e]);
+            else o[e] = __uint_as_float(va[j * 8 + e]);
+          }
+          if constexpr (Cfg::RES) {
+            if (has_res) {
+              float res[8];
+              unpack8_16<FMT>(rres[j], res);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] += res[e];
+            }
           }
           *reinterpret_cast<uint4*>(obase + (size_t)j * plane_elems) = pack8_16<FMT>(o);
         }
@@ -418,7 +502,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         // 4-phase upsample: accumulator columns [ph*NPRE, (ph+1)*NPRE) hold output pixel
         // (2*gy + ph/2, 2*gx + ph%2); GLU halves inside each phase block.  half h -> phases 2h, 2h+1
         // (= output row 2*gy + h, both columns: one 32-byte run per plane).
-        static_assert(GLU && NPRE == 64, "upsample path is conv(C -> 64) + GLU -> 32 channels");
+        static_assert(!UP || (GLU && NPRE == 64), "upsample path is conv(C -> 64) + GLU -> 32 channels");
         constexpr int COUT = NPRE / 2;                          // 32
         const int Ho = 2 * p.H, Wo = 2 * p.W;
         const size_t plane_elems = (size_t)Ho * Wo * 8;
@@ -429,27 +513,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const int oy = 2 * gy + half, ox = 2 * gx;
         h16* obase = p.out + ((size_t)b * p.yP + p.yp0) * plane_elems + ((size_t)oy * Wo + ox) * 8;
         const uint32_t t0 = t_base + (half * 2) * NPRE, t1 = t0 + NPRE;
+        // software pipeline over the four output planes: the TMEM loads of plane j+1 are in flight while plane j is
+        // evaluated and stored
+        uint32_t a0[2][8], g0[2][8], a1[2][8], g1[2][8];
+        tmem_ld8(t0, a0[0]); tmem_ld8(t0 + COUT, g0[0]); tmem_ld8(t1, a1[0]); tmem_ld8(t1 + COUT, g1[0]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint32_t a0[8], g0[8], a1[8], g1[8];
-          tmem_ld8(t0 + j * 8, a0); tmem_ld8(t0 + COUT + j * 8, g0);
-          tmem_ld8(t1 + j * 8, a1); tmem_ld8(t1 + COUT + j * 8, g1);
+          const int cur = j & 1, nxt = cur ^ 1;
           tmem_ld_wait();
-          const float4 sa0 = sh4[j * 2], sa1 = sh4[j * 2 + 1], sg0 = sh4[(COUT + j * 8) / 4], sg1 = sh4[(COUT + j * 8) / 4 + 1];
-          const float sa[8] = {sa0.x, sa0.y, sa0.z, sa0.w, sa1.x, sa1.y, sa1.z, sa1.w};
-          const float sg[8] = {sg0.x, sg0.y, sg0.z, sg0.w, sg1.x, sg1.y, sg1.z, sg1.w};
+          if (j < 3) {
+            tmem_ld8(t0 + (j + 1) * 8, a0[nxt]); tmem_ld8(t0 + COUT + (j + 1) * 8, g0[nxt]);
+            tmem_ld8(t1 + (j + 1) * 8, a1[nxt]); tmem_ld8(t1 + COUT + (j + 1) * 8, g1[nxt]);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);           // last plane is in registers: stage free
+          }
           float o0[8], o1[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            o0[e] = (__uint_as_float(a0[e]) + sa[e]) * fast_sigmoid(__uint_as_float(g0[e]) + sg[e]);
-            o1[e] = (__uint_as_float(a1[e]) + sa[e]) * fast_sigmoid(__uint_as_float(g1[e]) + sg[e]);
+            o0[e] = glu_pair<FMT>(a0[cur][e], g0[cur][e]);
+            o1[e] = glu_pair<FMT>(a1[cur][e], g1[cur][e]);
           }
           stg256(obase + (size_t)j * plane_elems, pack8_16<FMT>(o0), pack8_16<FMT>(o1));
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
     }
   }
 
@@ -464,13 +552,37 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 //   byte offset(op, n, c) = op_base + (c/8)*(N_op*16) + (n/8)*128 + (n%8)*16 + (c%8)*2
 template <int FMT>
 __global__ void pack_conv3x3_kernel(const float* __restrict__ w, const float* __restrict__ scale, h16* __restrict__ out,
-                                    int Cout, int Cin) {
+                                    int Cout, int Cin, float pre) {
   const int total = 9 * Cout * Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % Cin, n = (i / Cin) % Cout, t = i / (Cin * Cout);
-    const float v = w[((size_t)n * Cin + c) * 9 + t] * (scale ? scale[n] : 1.0f);   // BN scale folded, fp32
+    const float v = w[((size_t)n * Cin + c) * 9 + t] * (scale ? scale[n] : 1.0f) * pre;   // BN scale folded, fp32
     const size_t off = (size_t)t * Cin * Cout + (size_t)(c / 8) * (Cout * 8) + (size_t)(n / 8) * 64 + (n % 8) * 8 + (c % 8);
     out[off] = Fmt16<FMT>::cvt(v);
+  }
+}
+
+// Shift block [NB x 16] (row nn -> shift[nn % Cout], split into three 16-bit terms at k = 0,1,2) followed by the
+// ones block [128 x 16] (k = 0,1,2 set): the operands of the per-tile bias MMA (see TcCfg::BIAS).
+template <int FMT>
+__global__ void pack_bias_kernel(const float* __restrict__ shift, h16* __restrict__ out, int Cout, int NB, float pre) {
+  const int total = NB * 16 + 128 * 16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < NB * 16) {
+      const int c = i % 16, nn = i / 16;
+      float v = 0.f;
+      if (c < 3 && shift != nullptr) {
+        const float sft = shift[nn % Cout] * pre;
+        const float hi = Fmt16<FMT>::cvtf(sft);
+        const float mid = Fmt16<FMT>::cvtf(sft - hi);
+        v = c == 0 ? hi : (c == 1 ? mid : Fmt16<FMT>::cvtf(sft - hi - mid));
+      }
+      out[(size_t)(c / 8) * (NB * 8) + (size_t)(nn / 8) * 64 + (nn % 8) * 8 + (c % 8)] = Fmt16<FMT>::cvt(v);
+    } else {
+      const int j = i - NB * 16, c = j % 16, r = j / 16;
+      out[(size_t)NB * 16 + (size_t)(c / 8) * 1024 + (size_t)(r / 8) * 64 + (r % 8) * 8 + (c % 8)] =
+          Fmt16<FMT>::cvt(c < 3 ? 1.0f : 0.0f);
+    }
   }
 }
 
@@ -501,7 +613,7 @@ __device__ __forceinline__ int up_taps(int parity, int r, int (&ks)[2]) {
 
 template <int FMT>
 __global__ void pack_up2x_kernel(const float* __restrict__ w, const float* __restrict__ scale, h16* __restrict__ out,
-                                 int Cout, int Cin) {
+                                 int Cout, int Cin, float pre) {
   // 11 ops; op o covers phases {ph = dcol_mul .. dcol_mul + n_mul - 1}; rows of op = [phase][Cout]
   using Ops = OpTable<MODE_UP>;
   int op_base = 0;
@@ -519,6 +631,7 @@ __global__ void pack_up2x_kernel(const float* __restrict__ w, const float* __res
       for (int a = 0; a < ny; ++a)
         for (int bq = 0; bq < nx; ++bq) v += w[((size_t)n * Cin + c) * 9 + kys[a] * 3 + kxs[bq]];
       if (scale) v *= scale[n];
+      v *= pre;
       const size_t off = (size_t)op_base + (size_t)(c / 8) * (N * 8) + (size_t)(nn / 8) * 64 + (nn % 8) * 8 + (c % 8);
       out[off] = Fmt16<FMT>::cvt(v);
     }
@@ -563,10 +676,10 @@ __global__ void blocked_to_nchw_kernel(const h16* __restrict__ x, float* __restr
 template <int CIN, int NPRE, int MODE, bool GLU>
 static int set_tc_attr() {
   cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_BF16>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<CIN, NPRE, MODE>::SMEM);
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<CIN, NPRE, MODE, GLU>::SMEM);
   if (e != cudaSuccess) return cuda_fail(e);
   e = cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_F16>,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<CIN, NPRE, MODE>::SMEM);
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<CIN, NPRE, MODE, GLU>::SMEM);
   return e == cudaSuccess ? TGSR_OK : cuda_fail(e);
 }
 
@@ -577,7 +690,6 @@ int init_conv_tc() {
   if (e != cudaSuccess) return cuda_fail(e);
   if (q != cudaDriverEntryPointSuccess || fn == nullptr) return TGSR_ERR_UNSUPPORTED;
   g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
-  if (const char* d = getenv("TGSR_TC_DEBUG")) g_tc_debug = atoi(d);
   int s;
   if ((s = set_tc_attr<64, 128, MODE_CONV, true>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<64, 64, MODE_CONV, false>()) != TGSR_OK) return s;
@@ -590,16 +702,13 @@ int init_conv_tc() {
   return TGSR_OK;
 }
 
-static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl, int fmt, int R = 1,
-                           int head = 0) {
-  const int TC_PW = head ? 16 : TC_TW + 2 * R;
-  const int TC_PH = (head ? 32 : TC_TH) + 2 * R;
-  // A pixel row of one plane is W*8 contiguous 16-bit elements, so (x, c%8) is described as ONE inner
-  // dimension: the box's inner run is PW*16 bytes (160/192 B) instead of 16 B, which is what the TMA
-  // engine's per-row cost wants; the bytes landing in shared memory are identical to a [8,PW,PH,planes] box.
+// Box [box_w pixels x 8 ch, box_h rows, npl planes] of a blocked view.  A pixel row of one plane is W*8 contiguous 16-bit
+// elements, so (x, c%8) is described as ONE inner dimension: the box's inner run is box_w*16 bytes instead of 16 B, which is
+// what the TMA engine's per-row cost wants; the bytes landing in shared memory are identical to a [8,box_w,box_h,planes] box.
+static int make_box_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl, int fmt, int box_w, int box_h) {
   cuuint64_t gdim[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)B * P};
   cuuint64_t gstr[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-  cuuint32_t box[3] = {(cuuint32_t)TC_PW * 8, (cuuint32_t)TC_PH, (cuuint32_t)npl};
+  cuuint32_t box[3] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_h, (cuuint32_t)npl};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode_tiled(m, fmt == TGSR_FMT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                               const_cast<void*>(x), gdim, gstr, box, estr,
@@ -609,37 +718,50 @@ static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, i
   return TGSR_OK;
 }
 
+static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl, int fmt, int R = 1,
+                           int head = 0) {
+  return make_box_tmap(m, x, B, P, H, W, npl, fmt, head ? 16 : TC_TW + 2 * R, (head ? 32 : TC_TH) + 2 * R);
+}
+
 template <int CIN, int NPRE, int MODE, bool GLU>
-static int launch_tc(const CUtensorMap& tmap, const TcParams& p, int fmt, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& tmap, const CUtensorMap& rmap, TcParams& p, int fmt, cudaStream_t st) {
   static const int use_pdl = [] { const char* e = getenv("TGSR_PDL"); return e ? atoi(e) : 1; }();
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(p.ntiles < g_sm_count ? p.ntiles : g_sm_count);
+  const int grid = p.ntiles < g_sm_count ? p.ntiles : g_sm_count;
+  p.step_x = grid % p.tiles_x;
+  p.step_y = (grid / p.tiles_x) % p.tiles_y;
+  p.step_b = grid / (p.tiles_x * p.tiles_y);
+  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = TcCfg<CIN, NPRE, MODE>::SMEM;
+  cfg.dynamicSmemBytes = TcCfg<CIN, NPRE, MODE, GLU>::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
   cudaError_t e;
-  if (fmt == TGSR_FMT_F16) e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_F16>, tmap, p);
-  else e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_BF16>, tmap, p);
+  if (fmt == TGSR_FMT_F16) e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_F16>, tmap, rmap, p);
+  else e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<CIN, NPRE, MODE, GLU, TGSR_FMT_BF16>, tmap, rmap, p);
   if (e != cudaSuccess) return cuda_fail(e);
   return launch_status();
 }
+
+template <int CIN, int NPRE, int MODE, bool GLU>
+static constexpr size_t packed_elems() { return TcCfg<CIN, NPRE, MODE, GLU>::WBYTES / 2; }
 
 }  // namespace tgsr
 
 #define TGSR_CHECK_FMT(fmt) TGSR_REQUIRE((fmt) == TGSR_FMT_BF16 || (fmt) == TGSR_FMT_F16, TGSR_ERR_UNSUPPORTED)
 
-namespace tgsr {
-int img_head_mma(const void* x, int xP, int xp0, const void* wpacked, const float* addend, float out_scale, float addend_scale,
-                 float* y, int B, int H, int W, int ksize, int act_tanh, int fmt, cudaStream_t st);   // head_mma.cu
+extern "C" size_t tgsr_packed_conv3x3_elems(int Cout, int Cin, int up2x) {
+  if (Cout <= 0 || Cin <= 0) return 0;
+  const size_t nb = (size_t)(up2x ? 4 : 1) * Cout;
+  return (size_t)(up2x ? 16 : 9) * Cout * Cin + nb * 16 + 128 * 16;
 }
 
-extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const float* shift,
-                               const void* residual, int rP, int rp0, void* y, int yP, int yp0, int B, int Cin,
-                               int H, int W, int Cout, int up2x, int act, int fmt, tgsr_stream_t stream) {
+extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const void* residual, int rP, int rp0,
+                               void* y, int yP, int yp0, int B, int Cin, int H, int W, int Cout, int up2x, int act, int fmt,
+                               int flags, tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(wpacked); TGSR_REQUIRE_PTR(y);
   TGSR_CHECK_FMT(fmt);
@@ -652,51 +774,64 @@ extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpack
   TGSR_REQUIRE(xp0 >= 0 && xp0 + npl <= xP && yp0 >= 0 && yp0 + cout_planes <= yP, TGSR_ERR_BAD_SHAPE);
   if (residual) TGSR_REQUIRE(rp0 >= 0 && rp0 + cout_planes <= rP && !up2x && act == TGSR_ACT_NONE, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-               (reinterpret_cast<uintptr_t>(wpacked) & 15) == 0, TGSR_ERR_BAD_SHAPE);
-  TGSR_REQUIRE((long long)B * xP < (1LL << 31), TGSR_ERR_UNSUPPORTED);
+               (reinterpret_cast<uintptr_t>(wpacked) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+               TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE((long long)B * xP < (1LL << 31) && (long long)B * (residual ? rP : 1) < (1LL << 31), TGSR_ERR_UNSUPPORTED);
 
-  CUtensorMap tmap;
+  CUtensorMap tmap, rmap;
   int s = make_patch_tmap(&tmap, x, B, xP, H, W, npl, fmt);
   if (s != TGSR_OK) return s;
-  TcParams p;
-  p.wpacked = wpacked; p.scale = nullptr; p.shift = shift;
-  p.residual = reinterpret_cast<const h16*>(residual);
+  if (residual) {
+    s = make_box_tmap(&rmap, residual, B, rP, H, W, cout_planes, fmt, TC_TW, TC_TH);
+    if (s != TGSR_OK) return s;
+  } else {
+    rmap = tmap;
+  }
+  TcParams p = {};
+  p.wpacked = wpacked;
   p.out = reinterpret_cast<h16*>(y);
+  p.has_res = residual != nullptr;
+  p.reverse = (flags & TGSR_CONV_REVERSE) != 0;
   p.rP = rP; p.rp0 = rp0; p.yP = yP; p.yp0 = yp0; p.xP = xP; p.xp0 = xp0;
   p.B = B; p.H = H; p.W = W;
   p.tiles_x = W / TC_TW; p.tiles_y = H / TC_TH; p.ntiles = B * p.tiles_x * p.tiles_y;
   p.out_f32 = nullptr; p.addend = nullptr; p.out_scale = 1.f; p.addend_scale = 0.f; p.act_tanh = 0;
-  p.debug = g_tc_debug;
   cudaStream_t st = (cudaStream_t)stream;
   const bool glu = act == TGSR_ACT_GLU;
   if (!up2x) {
-    if (Cin == 64 && Cout == 128 && glu) return launch_tc<64, 128, MODE_CONV, true>(tmap, p, fmt, st);
-    if (Cin == 64 && Cout == 64 && !glu) return launch_tc<64, 64, MODE_CONV, false>(tmap, p, fmt, st);
-    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, MODE_CONV, true>(tmap, p, fmt, st);
-    if (Cin == 32 && Cout == 32 && !glu) return launch_tc<32, 32, MODE_CONV, false>(tmap, p, fmt, st);
+    if (Cin == 64 && Cout == 128 && glu) return launch_tc<64, 128, MODE_CONV, true>(tmap, rmap, p, fmt, st);
+    if (Cin == 64 && Cout == 64 && !glu) return launch_tc<64, 64, MODE_CONV, false>(tmap, rmap, p, fmt, st);
+    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, MODE_CONV, true>(tmap, rmap, p, fmt, st);
+    if (Cin == 32 && Cout == 32 && !glu) return launch_tc<32, 32, MODE_CONV, false>(tmap, rmap, p, fmt, st);
   } else {
-    if (Cin == 64 && Cout == 64 && glu) return launch_tc<64, 64, MODE_UP, true>(tmap, p, fmt, st);
-    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, MODE_UP, true>(tmap, p, fmt, st);
+    if (Cin == 64 && Cout == 64 && glu) return launch_tc<64, 64, MODE_UP, true>(tmap, rmap, p, fmt, st);
+    if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, MODE_UP, true>(tmap, rmap, p, fmt, st);
   }
   return TGSR_ERR_UNSUPPORTED;
 }
 
-extern "C" int tgsr_pack_conv3x3(const float* w, const float* scale, void* packed, int Cout, int Cin, int up2x,
-                                 int fmt, tgsr_stream_t stream) {
+extern "C" int tgsr_pack_conv3x3(const float* w, const float* scale, const float* shift, void* packed, int Cout, int Cin,
+                                 int up2x, int act, int fmt, tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(w); TGSR_REQUIRE_PTR(packed);
   TGSR_CHECK_FMT(fmt);
   TGSR_REQUIRE(Cout > 0 && Cin > 0 && Cout % 8 == 0 && Cin % 8 == 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE(act == TGSR_ACT_NONE || act == TGSR_ACT_GLU, TGSR_ERR_UNSUPPORTED);
   cudaStream_t st = (cudaStream_t)stream;
   h16* o = reinterpret_cast<h16*>(packed);
+  const float pre = glu_prescale(act == TGSR_ACT_GLU, fmt);
+  const int nb = (up2x ? 4 : 1) * Cout;
+  h16* ob = o + (size_t)(up2x ? 16 : 9) * Cout * Cin;
   if (fmt == TGSR_FMT_F16) {
-    if (up2x) pack_up2x_kernel<TGSR_FMT_F16><<<64, 256, 0, st>>>(w, scale, o, Cout, Cin);
-    else pack_conv3x3_kernel<TGSR_FMT_F16><<<64, 256, 0, st>>>(w, scale, o, Cout, Cin);
+    if (up2x) pack_up2x_kernel<TGSR_FMT_F16><<<64, 256, 0, st>>>(w, scale, o, Cout, Cin, pre);
+    else pack_conv3x3_kernel<TGSR_FMT_F16><<<64, 256, 0, st>>>(w, scale, o, Cout, Cin, pre);
+    pack_bias_kernel<TGSR_FMT_F16><<<16, 256, 0, st>>>(shift, ob, Cout, nb, pre);
   } else {
-    if (up2x) pack_up2x_kernel<TGSR_FMT_BF16><<<64, 256, 0, st>>>(w, scale, o, Cout, Cin);
-    else pack_conv3x3_kernel<TGSR_FMT_BF16><<<64, 256, 0, st>>>(w, scale, o, Cout, Cin);
+    if (up2x) pack_up2x_kernel<TGSR_FMT_BF16><<<64, 256, 0, st>>>(w, scale, o, Cout, Cin, pre);
+    else pack_conv3x3_kernel<TGSR_FMT_BF16><<<64, 256, 0, st>>>(w, scale, o, Cout, Cin, pre);
+    pack_bias_kernel<TGSR_FMT_BF16><<<16, 256, 0, st>>>(shift, ob, Cout, nb, pre);
   }
-  return launch_status();
+  return launch_status(2);
 }
 
 extern "C" int tgsr_pack_head(const float* w, void* packed, int Cin, int ksize, int fmt, tgsr_stream_t stream) {
@@ -723,28 +858,20 @@ extern "C" int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpac
   TGSR_REQUIRE(act == TGSR_ACT_NONE || act == TGSR_ACT_TANH, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(xp0 >= 0 && xp0 + Cin / 8 <= xP, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE((long long)B * xP < (1LL << 31), TGSR_ERR_UNSUPPORTED);
-  // TGSR_HEAD_IMPL=mma selects the warp-level tensor-core head (head_mma.cu): parity-tested, but measured slower than the
-  // tcgen05 head below (72.6 vs 48.9 us for the 3x3 head at 256x256, batch 32), so it is not the default.
-  static const bool use_mma = [] { const char* e = getenv("TGSR_HEAD_IMPL"); return e != nullptr && e[0] == 'm'; }();
-  if (use_mma)
-    return img_head_mma(x, xP, xp0, wpacked, addend, out_scale, addend_scale, y, B, H, W, ksize, act == TGSR_ACT_TANH, fmt,
-                        (cudaStream_t)stream);
   CUtensorMap tmap;
   int s = make_patch_tmap(&tmap, x, B, xP, H, W, Cin / 8, fmt, ksize / 2, 1);
   if (s != TGSR_OK) return s;
-  TcParams p;
-  p.wpacked = wpacked; p.scale = nullptr; p.shift = nullptr; p.residual = nullptr; p.out = nullptr;
+  TcParams p = {};
+  p.wpacked = wpacked; p.out = nullptr; p.has_res = 0;
   p.rP = p.rp0 = p.yP = p.yp0 = 0; p.xP = xP; p.xp0 = xp0;
   p.B = B; p.H = H; p.W = W;
-  p.tiles_x = W / TC_TW; p.tiles_y = H / TC_TH; p.ntiles = B * p.tiles_x * p.tiles_y;
   const int two = 16 - 2 * (ksize / 2);                      // output columns per head tile (32 rows x two cols)
   p.tiles_x = (W + two - 1) / two; p.tiles_y = (H + 31) / 32; p.ntiles = B * p.tiles_x * p.tiles_y;
   p.out_f32 = y; p.addend = addend; p.out_scale = out_scale; p.addend_scale = addend_scale;
   p.act_tanh = act == TGSR_ACT_TANH;
-  p.debug = g_tc_debug;
   cudaStream_t st = (cudaStream_t)stream;
-  if (ksize == 3) return launch_tc<32, 16, MODE_HEAD3, false>(tmap, p, fmt, st);
-  return launch_tc<32, 16, MODE_HEAD5, false>(tmap, p, fmt, st);
+  if (ksize == 3) return launch_tc<32, 16, MODE_HEAD3, false>(tmap, tmap, p, fmt, st);
+  return launch_tc<32, 16, MODE_HEAD5, false>(tmap, tmap, p, fmt, st);
 }
 
 extern "C" int tgsr_nchw_to_blocked(const float* x, void* y, int B, int C, int H, int W, int yP, int yp0, int fmt,

@@ -23,6 +23,7 @@ template <> struct Fmt16<TGSR_FMT_BF16> {
     __nv_bfloat16 h = __float2bfloat16_rn(a);
     return *reinterpret_cast<uint16_t*>(&h);
   }
+  __device__ __forceinline__ static float cvtf(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
 };
 
 template <> struct Fmt16<TGSR_FMT_F16> {
@@ -38,6 +39,7 @@ template <> struct Fmt16<TGSR_FMT_F16> {
     __half h = __float2half_rn(a);
     return *reinterpret_cast<uint16_t*>(&h);
   }
+  __device__ __forceinline__ static float cvtf(float a) { return __half2float(__float2half_rn(a)); }
 };
 
 template <int FMT>

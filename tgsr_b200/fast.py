@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import ops, tc
-from ._lib import ACT_GLU, ACT_NONE, ACT_TANH, call, ptr
+from ._lib import ACT_GLU, ACT_NONE, ACT_TANH, call, ptr, tensor_key
 from .tc import Blocked
 
 Tensor = torch.Tensor
@@ -27,9 +27,9 @@ def _fold(bn):
 
 # ---------------------------------------------------------------- single layers
 def conv_bn_act(x: Blocked, conv: nn.Conv2d, bn, act: int, residual: Optional[Blocked] = None, up2x: bool = False,
-                out: Optional[Blocked] = None) -> Blocked:
+                out: Optional[Blocked] = None, reverse: bool = False) -> Blocked:
     scale, shift = _fold(bn)
-    return tc.conv3x3_tc(x, conv, scale, shift, act, residual=residual, up2x=up2x, out=out)
+    return tc.conv3x3_tc(x, conv, scale, shift, act, residual=residual, up2x=up2x, out=out, reverse=reverse)
 
 
 def conv_in(seq, x: Tensor, out: Blocked, x_sub: Optional[Tensor] = None) -> Blocked:
@@ -50,13 +50,15 @@ def conv_in(seq, x: Tensor, out: Blocked, x_sub: Optional[Tensor] = None) -> Blo
 def res_block(x: Blocked, rb) -> Blocked:
     """ResBlock (util.py:110-130): two tcgen05 kernels, the skip add fused into the second."""
     blk = rb.block
-    y = conv_bn_act(x, blk[0], blk[1], ACT_GLU)
+    # Tile order alternates along the chain (see TGSR_CONV_REVERSE): the first conv walks backwards, so the second one,
+    # walking forwards, starts where the intermediate tensor and the skip tensor were touched last.
+    y = conv_bn_act(x, blk[0], blk[1], ACT_GLU, reverse=True)
     return conv_bn_act(y, blk[3], blk[4], ACT_NONE, residual=x)
 
 
 def body_noskip(x: Blocked, seq) -> Blocked:
     """residual24 / residual48 (model.py:229-232): conv-BN-GLU-conv-BN without skip."""
-    y = conv_bn_act(x, seq[0], seq[1], ACT_GLU)
+    y = conv_bn_act(x, seq[0], seq[1], ACT_GLU, reverse=True)
     return conv_bn_act(y, seq[3], seq[4], ACT_NONE)
 
 
@@ -66,12 +68,12 @@ def up_block(x: Blocked, seq, out_planes: Optional[int] = None) -> Blocked:
     conv, bn = seq[1], seq[2]
     C = conv.weight.shape[0] // 2
     out = Blocked.empty(x.B, C, 2 * x.H, 2 * x.W, x.device, planes=out_planes, fmt=x.fmt)
-    return conv_bn_act(x, conv, bn, ACT_GLU, up2x=True, out=out)
+    return conv_bn_act(x, conv, bn, ACT_GLU, up2x=True, out=out, reverse=True)
 
 
 def _packed_head(conv: nn.Conv2d, fmt: int) -> Tensor:
     w = conv.weight
-    key = (w.data_ptr(), w._version, str(w.device), fmt)
+    key = (tensor_key(w), fmt)
     name = '_tgsr_packed_head_%d' % fmt
     cached = conv.__dict__.get(name)
     if cached is None or cached[0] != key:

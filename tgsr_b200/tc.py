@@ -7,7 +7,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from ._lib import ACT_GLU, ACT_NONE, FMT_BF16, FMT_F16, call, ptr
+from ._lib import ACT_GLU, ACT_NONE, FMT_BF16, FMT_F16, call, ptr, tensor_key
 
 Tensor = torch.Tensor
 
@@ -65,18 +65,24 @@ def to_nchw(xb: Blocked) -> Tensor:
     return y
 
 
-def packed_weights(conv: nn.Conv2d, up2x: bool, fmt: int, scale: Optional[Tensor] = None) -> Tensor:
-    """16-bit UMMA operand image of a conv3x3 weight with the folded BN scale multiplied in (fp32, one
-    rounding); cached per weight / BN version (not in state_dict)."""
+def packed_weights(conv: nn.Conv2d, up2x: bool, fmt: int, scale: Optional[Tensor] = None, shift: Optional[Tensor] = None,
+                   act: int = ACT_NONE) -> Tensor:
+    """16-bit UMMA operand image of a conv3x3 weight with the folded BatchNorm inside: the scale is multiplied into
+    the weights (fp32, one rounding), the shift becomes the operand of the per-tile bias MMA; cached per weight / BN
+    version (not in state_dict)."""
     w = conv.weight
-    key = (w.data_ptr(), w._version, str(w.device), bool(up2x), fmt, None if scale is None else scale.data_ptr())
-    name = '_tgsr_packed_%d_%d' % (int(up2x), fmt)
+    key = (tensor_key(w), bool(up2x), fmt, act, None if scale is None else scale.data_ptr(),
+           None if shift is None else shift.data_ptr())
+    name = '_tgsr_packed_%d_%d_%d' % (int(up2x), fmt, act)
     cached = conv.__dict__.get(name)
     if cached is None or cached[0] != key:
         Cout, Cin = w.shape[0], w.shape[1]
-        packed = torch.empty(Cout * Cin * (16 if up2x else 9), device=w.device, dtype=_DTYPES[fmt])
-        call('tgsr_pack_conv3x3', w.device, ptr(w.detach().contiguous()), ptr(scale), ptr(packed), Cout, Cin, int(up2x), fmt)
-        cached = (key, packed, scale)      # keep `scale` alive so its data_ptr stays unique
+        from . import _lib
+        n = _lib.load().tgsr_packed_conv3x3_elems(Cout, Cin, int(up2x))
+        packed = torch.empty(n, device=w.device, dtype=_DTYPES[fmt])
+        call('tgsr_pack_conv3x3', w.device, ptr(w.detach().contiguous()), ptr(scale), ptr(shift), ptr(packed), Cout, Cin,
+             int(up2x), act, fmt)
+        cached = (key, packed, scale, shift)      # keep scale / shift alive so their data_ptr stays unique
         conv.__dict__[name] = cached
     return cached[1]
 
@@ -90,7 +96,8 @@ def tc_supported(Cin: int, Cout: int, act: int, up2x: bool, H: int, W: int) -> b
 
 
 def conv3x3_tc(xb: Blocked, conv: nn.Conv2d, scale: Optional[Tensor], shift: Optional[Tensor], act: int,
-               residual: Optional[Blocked] = None, up2x: bool = False, out: Optional[Blocked] = None) -> Blocked:
+               residual: Optional[Blocked] = None, up2x: bool = False, out: Optional[Blocked] = None,
+               reverse: bool = False) -> Blocked:
     Cout, Cin = conv.weight.shape[0], conv.weight.shape[1]
     assert Cin == xb.C, (Cin, xb.C)
     Cf = Cout // 2 if act == ACT_GLU else Cout
@@ -98,10 +105,10 @@ def conv3x3_tc(xb: Blocked, conv: nn.Conv2d, scale: Optional[Tensor], shift: Opt
     if out is None:
         out = Blocked.empty(xb.B, Cf, Ho, Wo, xb.device, fmt=xb.fmt)
     assert out.fmt == xb.fmt and out.C == Cf and out.H == Ho and out.W == Wo and out.B == xb.B
-    wp = packed_weights(conv, up2x, xb.fmt, scale)
+    wp = packed_weights(conv, up2x, xb.fmt, scale, shift, act)
     rbuf, rP, rp0 = (residual.buf, residual.P, residual.p0) if residual is not None else (None, 0, 0)
     if residual is not None:
         assert residual.C == Cf and residual.H == Ho and residual.W == Wo and residual.fmt == xb.fmt
-    call('tgsr_conv3x3_tc', xb.device, ptr(xb.buf), xb.P, xb.p0, ptr(wp), ptr(shift), ptr(rbuf), rP, rp0,
-         ptr(out.buf), out.P, out.p0, xb.B, Cin, xb.H, xb.W, Cout, int(up2x), act, xb.fmt)
+    call('tgsr_conv3x3_tc', xb.device, ptr(xb.buf), xb.P, xb.p0, ptr(wp), ptr(rbuf), rP, rp0,
+         ptr(out.buf), out.P, out.p0, xb.B, Cin, xb.H, xb.W, Cout, int(up2x), act, xb.fmt, int(reverse))
     return out

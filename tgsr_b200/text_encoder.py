@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from ._lib import tensor_key
 from .config import cfg
 
 
@@ -56,32 +57,39 @@ class RNN_ENCODER(nn.Module):
         r = self.rnn
         src = (r.weight_ih_l0, r.weight_ih_l0_reverse, r.weight_hh_l0, r.weight_hh_l0_reverse,
                r.bias_ih_l0, r.bias_ih_l0_reverse, r.bias_hh_l0, r.bias_hh_l0_reverse)
-        key = tuple((t.data_ptr(), t._version, str(t.device)) for t in src)
+        key = tuple(tensor_key(t) for t in src)
         cached = self.__dict__.get('_tgsr_stacked')
         if cached is None or cached[0] != key:
             d = [t.detach() for t in src]
             cached = [key, torch.stack((d[0], d[1])).contiguous(), torch.stack((d[2], d[3])).contiguous(),
                       torch.stack((d[4], d[5])).contiguous(), torch.stack((d[6], d[7])).contiguous(), None, None]
             self.__dict__['_tgsr_stacked'] = cached
-        ek = (self.encoder.weight.data_ptr(), self.encoder.weight._version)
+        ek = tensor_key(self.encoder.weight)
         if self.nhidden == 128 and cached[1].is_cuda and (cached[5] is None or cached[6] != ek):
             # weight prep (derived, not in state_dict): input-projection lookup table
             cached[5] = ops.lstm_prepare(self.encoder.weight.detach(), cached[1], cached[3], cached[4])
             cached[6] = ek
         return cached[1:6]
 
-    def forward(self, captions, cap_lens, hidden, mask=None):
+    def forward(self, captions, cap_lens, hidden, mask=None, tmax=None):
         """captions int64 [B, n_steps]; cap_lens [B]; hidden = init_hidden(B) (zeros, as in every
         reference call site; non-zero initial state is not supported).  Returns
-        words_emb [B, nhidden*2, max(cap_lens)], sent_emb [B, nhidden*2]."""
+        words_emb [B, nhidden*2, max(cap_lens)], sent_emb [B, nhidden*2].
+
+        The OUTPUT SHAPE depends on max(cap_lens), so the host must know it.  Pass `tmax` (extension of the reference
+        signature), host lengths (list / CPU tensor), or sorted-descending lengths as every reference call site does:
+        none of those reads the device.  Only unsorted device lengths without `tmax` cost the one device->host read the
+        reference's own `cap_lens.data.tolist()` (util.py:239) always pays."""
         if self.training and self.drop_prob > 0:
             raise RuntimeError('tgsr_b200: RNN_ENCODER CUDA path is eval-only (dropout); call .eval()')
-        if torch.is_tensor(cap_lens):
-            tmax = int(cap_lens.max())           # one host read when cap_lens lives on the GPU (util.py:239 does the same)
-        else:
-            tmax = int(max(cap_lens))
+        if tmax is None:
+            if torch.is_tensor(cap_lens):
+                tmax = int(cap_lens.max())
+            else:
+                tmax = int(max(cap_lens))
+        if not torch.is_tensor(cap_lens):
             cap_lens = torch.as_tensor(cap_lens, dtype=torch.int64)
-        return self._forward_tmax(captions, cap_lens, tmax)
+        return self._forward_tmax(captions, cap_lens, int(tmax))
 
     def _forward_tmax(self, captions, cap_lens, tmax: int):
         """Same as forward() when max(cap_lens) is already known on the host (no device read)."""
