@@ -126,7 +126,14 @@ struct TcCfg {
   static constexpr int RES_BYTES = RES ? TC_TH * TC_TW * NPRE * 2 : 0;
   // Patch-ring depth: as many stages as fit next to the resident weights (TMA latency ~1-2 us must be
   // covered by stages in flight: small-channel layers and heads spend < 0.5 us of MMA time per tile).
-  static constexpr int STAGE_ROOM = (232448 - 1024 - WB_PAD - RSTAGE * RES_BYTES - 512) / PATCH_BYTES;
+  // Kernels with small weights (Cin = 32, heads) stay below half of an SM's shared memory and TMEM: the CTA of the next
+  // kernel in the stream (programmatic dependent launch) then becomes resident while this one still runs and has its
+  // barriers, TMEM and weights ready when the grid dependency resolves -- these layers are launch-latency bound.
+  static constexpr int HALF_SM = 113 * 1024;
+  static constexpr bool SMALL = WB_PAD + RSTAGE * RES_BYTES + 4 * PATCH_BYTES + 1536 <= HALF_SM;
+  static constexpr int BUDGET = SMALL ? HALF_SM : 232448;
+  static_assert(!SMALL || TMEM_COLS <= 256, "a co-resident pair of small kernels must fit the 512 TMEM columns");
+  static constexpr int STAGE_ROOM = (BUDGET - 1024 - WB_PAD - RSTAGE * RES_BYTES - 512) / PATCH_BYTES;
   static constexpr int NSTAGE = STAGE_ROOM > 12 ? 12 : STAGE_ROOM;
   static_assert(NSTAGE >= 2, "not enough shared memory for a double-buffered patch ring");
   static constexpr size_t SMEM = 1024 /*align slack*/ + WB_PAD + NSTAGE * PATCH_BYTES + RSTAGE * RES_BYTES + 512;
@@ -184,19 +191,25 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// GLU of one (value, gate) accumulator pair.  bf16 layers: the packed weights and shift of BOTH halves carry a factor
-// 1/2 (exact), so z * sigmoid(g) = z/2 + z/2 * tanh(g/2): one MUFU + one FMA per output.  The approximation error of
-// tanh.approx (2^-11 relative) is below the bf16 rounding of the result.  fp16 layers keep exp + reciprocal.
+// GLU of one (value, gate) accumulator pair.  The packed weights and shift of BOTH halves carry a factor 1/2 (exact),
+// so z * sigmoid(g) = z/2 + z/2 * tanh(g/2): one MUFU + one FMA per output instead of exp + reciprocal (the 4-phase
+// up-block kernels evaluate 16384 gates per tile and were bound by the MUFU pipe).  tanh.approx has a relative error of
+// 2^-11: below the bf16 rounding of the result and at the fp16 rounding of it.  -DTGSR_GLU_EXACT keeps exp + reciprocal.
+#ifdef TGSR_GLU_EXACT
+constexpr bool kGluTanh = false;
+#else
+constexpr bool kGluTanh = true;
+#endif
 template <int FMT>
 __device__ __forceinline__ float glu_pair(uint32_t a, uint32_t g) {
-  if constexpr (FMT == TGSR_FMT_BF16) {
+  if constexpr (kGluTanh) {
     const float zh = __uint_as_float(a);
     return fmaf(zh, tanh_approx(__uint_as_float(g)), zh);
   } else {
     return __uint_as_float(a) * fast_sigmoid(__uint_as_float(g));
   }
 }
-__host__ __device__ constexpr float glu_prescale(bool glu, int fmt) { return (glu && fmt == TGSR_FMT_BF16) ? 0.5f : 1.0f; }
+__host__ __device__ constexpr float glu_prescale(bool glu, int fmt) { return (glu && kGluTanh) ? 0.5f : 1.0f; }
 
 __device__ __forceinline__ uint4 lds128(const void* p) {
   uint4 v;

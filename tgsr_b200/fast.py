@@ -148,15 +148,22 @@ def attention(h: Blocked, att, words: Tensor, mask: Optional[Tensor], out: Block
 
 
 # ---------------------------------------------------------------- stages and nets
+def stage_im2f(st, LR: Tensor, fmt: int = 0) -> Blocked:
+    """im2f of INIT_STAGE_GImgup (util.py:741-744, :769) into the first half of a concat-sized buffer.  It needs nothing
+    from the text encoder, so the eval pipeline runs it on its own stream next to the LSTM."""
+    B, _, H, W = LR.shape
+    cat = Blocked.empty(B, 2 * st.gf_dim, H, W, LR.device, fmt=fmt)
+    return conv_in(st.im2f, LR, cat.slice(0, st.gf_dim))
+
+
 def stage(st, h: Optional[Blocked], LR: Optional[Tensor], words: Tensor, mask, out_planes: Optional[int],
           fmt: int = 0, sfrag: Optional[Tensor] = None):
     """INIT_STAGE_GImgup (LR given) / NEXT_STAGE_G (h given); util.py:763-777 / :807-823.
     `h` must be the first 32-channel view of a 64-channel buffer: c_code is appended in place."""
     ngf = st.gf_dim
     if h is None:
-        B, _, H, W = LR.shape
-        cat = Blocked.empty(B, 2 * ngf, H, W, LR.device, fmt=fmt)
-        h = conv_in(st.im2f, LR, cat.slice(0, ngf))
+        h = stage_im2f(st, LR, fmt)
+        cat = Blocked(h.buf, 0, 2 * ngf)
     else:
         assert h.p0 == 0 and h.P * 8 >= 2 * ngf, 'h_code must live in a concat-sized buffer'
         cat = Blocked(h.buf, 0, 2 * ngf)
@@ -171,19 +178,23 @@ def stage_supported(st, H: int, W: int) -> bool:
     return st.gf_dim == 32 and H % 16 == 0 and W % 8 == 0 and getattr(st, 'batchnorm', True)
 
 
-def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, heads, outmiddle: bool, fmt: int = 0):
+def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, heads, outmiddle: bool, fmt: int = 0,
+                 h0: Optional[Blocked] = None, ca=None):
+    """G_SR_NET_low.forward (model.py:48-78) on blocked activations.  `h0`: stage_im2f(stages[0], LR) computed ahead;
+    `ca`: callable returning ca_net(sent) = (c_code, mu, logvar), for callers that evaluate it off the critical path
+    (c_code is unused by the SR nets, model.py:51-52)."""
     imgs: List[Tensor] = []
     atts: List[Tensor] = []
     feats: List[Blocked] = []
     if mask is not None and mask.dtype != torch.uint8:       # one conversion per forward, not one per stage
         mask = mask.to(device=LR.device, dtype=torch.uint8).contiguous()
-    c_code, mu, logvar = net.ca_net(sent)
     sfrags = text_side_work(stages, words, LR.shape[2] * LR.shape[3], fmt)
-    h = None
+    c_code, mu, logvar = net.ca_net(sent) if ca is None else ca()
+    h = h0
     n = len(stages)
     for i, (st, hd) in enumerate(zip(stages, heads)):
         planes = 8 if i + 1 < n else 4                     # leave room for the next stage's c_code
-        h, att = stage(st, h, LR if i == 0 else None, words, mask, planes, fmt, sfrags[i])
+        h, att = stage(st, h, LR if (i == 0 and h0 is None) else None, words, mask, planes, fmt, sfrags[i])
         imgs.append(image_head(h, hd.img))
         atts.append(att)
         feats.append(h)

@@ -60,26 +60,51 @@ class SRPipeline:
         small grids) runs on a second stream next to the text encoder (a latency-bound cluster kernel) and the
         first G_SR_NET_low stage; the streams join before the first high-frequency image head."""
         from . import fast, fmt_for, is_16bit
-        gh = self.netGH
+        gh, gl = self.netGH, self.netGL
         overlap = (is_16bit() and self.variant == 'x8' and gh.low == 'lr' and LR.shape[2] % 16 == 0 and LR.shape[3] % 8 == 0
-                   and gh.convin[0].weight.shape[0] == 64)
-        if overlap:
-            cur = torch.cuda.current_stream(self.device)
-            if self._side is None:
-                self._side = torch.cuda.Stream(self.device)
-            self._side.wait_stream(cur)
-            with torch.cuda.stream(self._side):
-                h_high = fast.netg_high_trunk(gh, LR, None, fmt_for('high'))
-        words_embs, sent_emb = self.text_encoder._forward_tmax(captions, cap_lens, tmax)
-        mask = (captions == 0)[:, :tmax]
-        fake_imgL, attention_maps, mu, logvar = self.netGL(LR, sent_emb, words_embs, mask)
-        if overlap:
-            cur.wait_stream(self._side)
-            h_high.buf.record_stream(cur)
-            fine_im = fast.netg_high_finish(gh, h_high, fake_imgL, 0.5, 1.0,
-                                            [(gh.residual24, gh.upscale4x), (gh.residual48, gh.upscale8x)])
-        else:
+                   and gh.convin[0].weight.shape[0] == 64 and fast.stage_supported(gl.h_net1, LR.shape[2], LR.shape[3]))
+        if not overlap:
+            words_embs, sent_emb = self.text_encoder._forward_tmax(captions, cap_lens, tmax)
+            mask = (captions == 0)[:, :tmax]
+            fake_imgL, attention_maps, mu, logvar = gl(LR, sent_emb, words_embs, mask)
             fine_im, a, one = gh(LR, fake_imgL, LR)
+            return fine_im, fake_imgL, attention_maps
+        # Three independent chains start a step: the text encoder (a latency-bound cluster kernel; everything word-related
+        # hangs off it), im2f of the first stage, and the whole 32x32 trunk of NetG_highweight.  Only the first is on the
+        # critical path, so the other two run on their own streams and join where their results are consumed.
+        cur = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        s_trunk, s_im2f = self._side
+        s_trunk.wait_stream(cur); s_im2f.wait_stream(cur)                    # fork before anything of this step is enqueued
+        words_embs, sent_emb = self.text_encoder._forward_tmax(captions, cap_lens, tmax)   # critical chain first
+        with torch.cuda.stream(s_im2f):
+            mask = (captions == 0)[:, :tmax].to(torch.uint8).contiguous()     # trainer_objective.py:136-140
+            h0 = fast.stage_im2f(gl.h_net1, LR, fmt_for('low'))
+            ev_h0 = torch.cuda.Event()
+            ev_h0.record(s_im2f)
+        with torch.cuda.stream(s_trunk):
+            h_high = fast.netg_high_trunk(gh, LR, None, fmt_for('high'))
+        stages = [gl.h_net1, gl.h_net2, gl.h_net3]
+        for st in stages:
+            st.att.applyMask(mask)                                       # keep the modules' stateful contract
+
+        def ca():                                                        # mu / logvar are only returned: off the critical path
+            s_im2f.wait_stream(cur)
+            with torch.cuda.stream(s_im2f):
+                out = gl.ca_net(sent_emb)
+            return out
+        cur.wait_event(ev_h0)
+        h0.buf.record_stream(cur); mask.record_stream(cur)
+        fake_imgL, attention_maps, mu, logvar = fast.g_sr_net_low(gl, LR, sent_emb, words_embs, mask, stages,
+                                                                  [gl.img_net1, gl.img_net2, gl.img_net3], False,
+                                                                  fmt_for('low'), h0=h0, ca=ca)
+        cur.wait_stream(s_im2f)
+        mu.record_stream(cur); logvar.record_stream(cur)
+        cur.wait_stream(s_trunk)
+        h_high.buf.record_stream(cur)
+        fine_im = fast.netg_high_finish(gh, h_high, fake_imgL, 0.5, 1.0,
+                                        [(gh.residual24, gh.upscale4x), (gh.residual48, gh.upscale8x)])
         return fine_im, fake_imgL, attention_maps
 
     # ------------------------------------------------------------------ CUDA-graph replay
