@@ -13,7 +13,8 @@ Prints ONE JSON line on rank 0 (see the contract in the task statement):
   value     : images/s, inputs resident in HBM
   e2e       : same metric through SRPipeline.forward_host (pinned host buffers, H2D + D2H inside)
   roofline  : the dominant conv kernel timed alone with CUDA events vs the measured bf16 peak
-  cpu_baseline : the CPU oracle (port of the reference's PyTorch path) on this box's host cores
+  cpu_baseline : the reference's own modules (baseline/_ref, unmodified) on this box's host cores
+  sustained : >= 3 s of back-to-back replays with their own clock record; roofline_per_kernel: every conv variant timed alone
 """
 from __future__ import annotations
 
@@ -49,6 +50,8 @@ def parse():
                     help='configs[3] (batch 512 sharded): total images per step, split evenly over the ranks (strong scaling); '
                          '0 = the headline config, 32 images per GPU (weak scaling)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of CUDA-graph replay')
+    ap.add_argument('--no-kernel-table', action='store_true', help='skip the per-kernel roofline table (roofline_per_kernel)')
+    ap.add_argument('--sustained-s', type=float, default=3.0, help='seconds of back-to-back replays for the `sustained` leg (0 = skip)')
     return ap.parse_args()
 
 
@@ -110,9 +113,38 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm
+def workload_config(B, world, precision=None, launch=None):
+    cfg = {'workload': 'bird SR eval (cfg/eval_birdSR_attn2.yml dims): text encoder + G_SR_NET_low + '
+                       'NetG_highweight, x8 32->256, batch %d per GPU, 18-word captions, ntoken %d, '
+                       'random-init weights, randomised BN stats' % (B, NTOKEN),
+           'batch_per_gpu': B, 'parallelism': 'image-sharded replicas x%d (no collective)' % world,
+           'gflop_per_image_reference': GFLOP_PER_IMAGE}
+    if precision is not None:
+        cfg.update({'l2': 'flushed between timed iterations (256 MiB write)', 'precision': precision, 'launch': launch})
+    return cfg
+
+
+def cpu_reference_leg(budget_quick: bool = True):
+    """`cpu_baseline` of the product arm: the reference's OWN modules (baseline/_ref, unmodified) on this box's host cores,
+    SURVEY.md 8d protocol (B = 1 and 8, all threads and one thread, 3 warm-ups, median of >= 10 passes); ~20 s.
+    Falls back to the CPU oracle port when baseline/_ref was not installed."""
+    cores = os.cpu_count() or 1
+    from baseline import ref_arm
+    if ref_arm.available():
+        ref = ref_arm.load()
+        nets = ref_arm.build(ref, NTOKEN)
+        rows = ref_arm.cpu_protocol(nets, NTOKEN, WORDS, cores, quick=budget_quick)
+        r = rows['all_threads_b8']
+        return {'value': r['images_per_s'], 'unit': 'images/s', 'cores': cores, 'kind': 'reference',
+                'sample': 'unmodified reference modules (baseline/_ref), fp32, %d threads: median of %d passes over one 8-image '
+                          'batch of the batch-%d workload after %d warm-ups' % (cores, r['passes'], BATCH_PER_GPU, r['warmup']),
+                'protocol': rows}
+    v, sample = cpu_oracle_rate(4, 12.0, cores)
+    return {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample + ' (baseline/_ref not installed)'}
+
+
 def cpu_oracle_rate(n_images: int, budget_s: float, threads: int):
-    """Times the CPU oracle (PyTorch fp32 port of the reference path) on `n_images`-image batches
-    until `budget_s` seconds are used (at least 2 timed passes).  Returns (img/s, description)."""
+    """Fallback only: times the CPU oracle (PyTorch fp32 port of the reference path) on `n_images`-image batches."""
     import torch
     from oracle import tgsr_oracle as O
     import tgsr_b200
@@ -137,103 +169,54 @@ def cpu_oracle_rate(n_images: int, budget_s: float, threads: int):
     while n < 2 or time.perf_counter() - t0 < budget_s:
         one(); n += 1
     dt = time.perf_counter() - t0
-    return n * n_images / dt, '%d passes of %d images (x8, 32->256, 18 words) in %.1f s' % (n, n_images, dt)
+    return n * n_images / dt, 'CPU oracle port: %d passes of %d images (x8, 32->256, 18 words) in %.1f s' % (n, n_images, dt)
 
 
 def run_reference(args):
+    """The reference arm: the reference's own modules (baseline/_ref) through the gen_exampleSRHL body on the host cores,
+    all threads.  K timed steps after W warm-up steps, exactly as asked; a step = one pass over a batch of the product arm's
+    workload (32 images; 8 when K > 60 so the run stays within minutes -- stated in `sample`)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_img = 8
     import torch
-    from oracle import tgsr_oracle as O                                     # noqa: F401
-    # each "step" = one 8-image pass; W warm-up + K timed
-    rate_s, times = None, []
-    import tgsr_b200
-    tgsr_b200.set_eval_defaults()
-    from tgsr_b200 import nets, text_encoder
-    torch.set_num_threads(cores)
-    torch.manual_seed(100)
-    enc = text_encoder.RNN_ENCODER(NTOKEN, nhidden=256).eval()
-    gl = nets.G_SR_NET_low().eval(); gh = nets.NetG_highweight(low='lr').eval()
-    sdE, sdL, sdH = enc.state_dict(), gl.state_dict(), gh.state_dict()
-    LR = O.synth_lr(n_img, 32, seed=101); caps, lens = O.synth_captions(n_img, NTOKEN, seed=102, words_num=WORDS)
-    steps = min(args.steps, 12); warm = min(args.warmup, 2)
-    for i in range(warm + steps):
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            words, sent = O.rnn_encoder(sdE, caps, lens)
-            mask = (caps == 0)[:, :words.shape[2]]
-            imgs, atts, mu, lv, _ = O.g_sr_net_low(sdL, LR, sent, words, mask)
-            O.netg_high(sdH, LR, imgs, LR, low='lr')
-        if i >= warm:
-            times.append(time.perf_counter() - t0)
-    total = sum(times)
+    from baseline import ref_arm
+    steps, warm = args.steps, args.warmup
+    n_img = BATCH_PER_GPU if steps <= 60 else 8
+    if not ref_arm.available():
+        v, sample = cpu_oracle_rate(4, 12.0, cores)
+        print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus,
+                          'steps': steps, 'warmup': warm, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                          'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(BATCH_PER_GPU, 1),
+                          'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+                          'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+    ref = ref_arm.load()
+    nets = ref_arm.build(ref, NTOKEN)
+    ts = ref_arm.time_cpu(nets, n_img, NTOKEN, WORDS, cores, warm, steps)
+    total = sum(ts)
     value = steps * n_img / total
-    sample = '%d steps of %d images per step (bounded sample of the batch-%d workload)' % (steps, n_img, BATCH_PER_GPU)
+    sample = ('unmodified reference modules (baseline/_ref), fp32, %d threads: %d timed steps of %d images after %d warm-up '
+              'steps' % (cores, steps, n_img, warm))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
         'warmup': warm, 'ms_per_step': 1e3 * total / steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'bird SR eval x8 (32->256), 18-word captions, ntoken 5450, random-init weights; '
-                               'CPU oracle (PyTorch fp32 port of the reference modules) on host cores'},
-        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': workload_config(BATCH_PER_GPU, 1),
+        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': 'reference', 'sample': sample},
         'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}
-    # Informational (SURVEY.md 8d "library comparison"): the same reference arithmetic run by torch eager on the B200
-    # (ATen/cuDNN/cuBLAS), fp32 with PyTorch's default TF32 convs and under bf16 autocast, batch 32, device-resident.
+    line['config']['images_per_step'] = n_img
+    # SURVEY.md 8d protocol rows (B = 1 / 8, all threads / one thread, median of >= 10), bounded
+    line['cpu_protocol'] = ref_arm.cpu_protocol(nets, NTOKEN, WORDS, cores, quick=False)
+    # Informational (SURVEY.md 8d "library comparison"): the same unmodified modules under torch eager on the B200
     if torch.cuda.is_available():
         try:
-            line['torch_eager_b200'] = torch_eager_gpu(O, sdE, sdL, sdH)
+            line['torch_eager_b200'] = ref_arm.torch_eager_gpu(ref, NTOKEN, WORDS, BATCH_PER_GPU)
         except Exception as e:                       # noqa: BLE001  (never let the extra leg break the reference arm)
             line['torch_eager_b200'] = {'error': repr(e)[:200]}
     print(json.dumps(line))
-
-
-def torch_eager_gpu(O, sdE, sdL, sdH, B=BATCH_PER_GPU, iters=10):
-    import torch
-    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
-    mv = lambda sd: {k: v.to(dev) for k, v in sd.items()}
-    sdE, sdL, sdH = mv(sdE), mv(sdL), mv(sdH)
-    LR = O.synth_lr(B, 32, seed=101).to(dev)
-    caps, lens = O.synth_captions(B, NTOKEN, seed=102, words_num=WORDS)
-    caps_d = caps.to(dev)
-    # the text encoder as the reference runs it on a GPU: nn.Embedding + cuDNN nn.LSTM over a packed sequence (util.py:233-260)
-    H = sdE['rnn.weight_hh_l0'].shape[1]
-    emb = torch.nn.Embedding(sdE['encoder.weight'].shape[0], sdE['encoder.weight'].shape[1]).to(dev)
-    rnn = torch.nn.LSTM(sdE['encoder.weight'].shape[1], H, 1, batch_first=True, bidirectional=True).to(dev)
-    emb.load_state_dict({'weight': sdE['encoder.weight']})
-    rnn.load_state_dict({k[4:]: v for k, v in sdE.items() if k.startswith('rnn.')})
-    emb.eval(); rnn.eval()
-
-    def text(caps_d, lens):
-        packed = torch.nn.utils.rnn.pack_padded_sequence(emb(caps_d), lens.tolist(), batch_first=True)
-        o, (h, _c) = rnn(packed)
-        words = torch.nn.utils.rnn.pad_packed_sequence(o, batch_first=True)[0].transpose(1, 2)
-        return words, h.transpose(0, 1).contiguous().view(-1, 2 * H)
-    out = {}
-    for name, ctx in (('fp32_tf32_convs', None), ('bf16_autocast', torch.autocast('cuda', dtype=torch.bfloat16))):
-        def one():
-            with torch.no_grad():
-                words, sent = text(caps_d, lens)
-                mask = (caps_d == 0)[:, :words.shape[2]]
-                if ctx is None:
-                    imgs, atts, mu, lv, _ = O.g_sr_net_low(sdL, LR, sent, words, mask)
-                    return O.netg_high(sdH, LR, imgs, LR, low='lr')
-                with ctx:
-                    imgs, atts, mu, lv, _ = O.g_sr_net_low(sdL, LR, sent, words, mask)
-                    return O.netg_high(sdH, LR, imgs, LR, low='lr')
-        for _ in range(3):
-            one()
-        torch.cuda.synchronize(dev)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(iters):
-            one()
-        e.record(); e.synchronize()
-        out[name] = {'value': B * iters / (s.elapsed_time(e) * 1e-3), 'unit': 'images/s', 'batch': B}
-    return out
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -371,11 +354,32 @@ def run_ours(args):
     roof = pipe.dominant_kernel_roofline(B, flush, pk) if rank == 0 else None
     attn_roof = pipe.attention_roofline(B, flush, pk) if rank == 0 else None
 
+    per_kernel = pipe.kernel_rooflines(B, flush, pk) if (rank == 0 and not args.no_kernel_table) else None
+
+    # ---- sustained leg: >= 3 s of back-to-back replays (no L2 flush, no gaps), own clock record: what a long-running
+    # job gets once the power cap (1000 W) has pulled the SM clock down; the headline above is the burst figure.
+    sustained = None
+    if use_graph and args.sustained_s > 0:
+        n_rep = max(50, int(args.sustained_s / (t_ms / args.steps * 1e-3)))
+        s_samp = ClockSampler(sampler.index)
+        barrier()
+        s_samp.start()
+        s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s3.record()
+        for _ in range(n_rep):
+            step_device()
+        e3.record()
+        barrier()
+        t3 = torch.tensor([s3.elapsed_time(e3)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        sustained = {'value': world * B * n_rep / (float(t3.item()) * 1e-3), 'unit': 'images/s', 'steps': n_rep,
+                     'seconds': float(t3.item()) * 1e-3, 'ms_per_step': float(t3.item()) / n_rep, 'clocks': s_samp.stop(),
+                     'l2': 'not flushed (a step streams ~1.3 GB through the 126 MB L2)'}
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        v, sample = cpu_oracle_rate(4, 12.0, cores)
-        cpu_base = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+        cpu_base = cpu_reference_leg()
 
     if rank == 0:
         line = {
@@ -383,13 +387,7 @@ def run_ours(args):
             'warmup': max(args.warmup, 3), 'ms_per_step': t_ms / args.steps, 'higher_is_better': True,
             'scaling': 'strong' if args.global_batch else 'weak', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16': 'bf16', 'fp16': 'f16', 'mixed16': 'bf16+f16 (16-bit tcgen05 operands, f32 accumulate)'}[precision],
             'data': 'synthetic',
-            'config': {'workload': 'bird SR eval (cfg/eval_birdSR_attn2.yml dims): text encoder + G_SR_NET_low + '
-                                   'NetG_highweight, x8 32->256, batch %d per GPU, 18-word captions, ntoken %d, '
-                                   'random-init weights, randomised BN stats' % (B, NTOKEN),
-                       'batch_per_gpu': B, 'parallelism': 'image-sharded replicas x%d (no collective)' % world,
-                       'l2': 'flushed between timed iterations (256 MiB write)', 'precision': precision,
-                       'launch': 'CUDA-graph replay' if use_graph else 'per-kernel launches from Python',
-                       'gflop_per_image_reference': GFLOP_PER_IMAGE},
+            'config': workload_config(B, world, precision, 'CUDA-graph replay' if use_graph else 'per-kernel launches from Python'),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'result': 'final SR image as uint8 [B,3,256,256] (device-side quantisation of trainer_objective.py:153-155); '
@@ -397,7 +395,7 @@ def run_ours(args):
                               'neighbouring steps; every result waited for on the host',
                     'fp32_result': {'value': e2e_fp32, 'unit': 'images/s', 'd2h_bytes_per_step': d2h_fp32}},
             'gpu_launches': int(launches),
-            'roofline': roof, 'roofline_attention': attn_roof,
+            'roofline': roof, 'roofline_attention': attn_roof, 'roofline_per_kernel': per_kernel, 'sustained': sustained,
             'model_tflops': value * GFLOP_PER_IMAGE / 1e3, 'peaks': pk,
         }
         if cpu_base is not None:

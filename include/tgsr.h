@@ -170,11 +170,13 @@ int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const v
  * x: blocked view of 32 channels; wpacked from tgsr_pack_head (w [3,Cin,k,k] fp32);
  * y fp32 NCHW [B,3,H,W] = out_scale * act(conv(x)) + addend_scale * addend (addend NCHW or NULL).
  * act NONE or TANH; W % 8 == 0 (any H).  The kx taps are folded into the MMA N dimension (N = 3k <= 16), so
- * a kxk head issues k row-tap MMAs per K-step; packed weights hold k*16*Cin elements. */
+ * a kxk head issues k row-tap MMAs per K-step; packed weights hold k*16*Cin elements.
+ * nonfinite_flag: optional device int; the kernel ORs 1 into it when a pre-activation sum is inf or NaN -- an
+ * overflow of the 16-bit activations anywhere upstream ends up there (tanh would otherwise hide it). */
 int tgsr_pack_head(const float* w, void* packed, int Cin, int ksize, int fmt, tgsr_stream_t stream);
 int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpacked, const float* addend,
                      float out_scale, float addend_scale, float* y, int B, int Cin, int H, int W,
-                     int ksize, int act, int fmt, tgsr_stream_t stream);
+                     int ksize, int act, int fmt, int* nonfinite_flag, tgsr_stream_t stream);
 
 /* im2f / convin: conv3x3(3 -> 2C) + folded BN + GLU from the NCHW fp32 LR image (minus x_sub if not
  * NULL: model.py:268-270 `LR - LRb`) into a blocked 16-bit view of C channels; util.py:741-744,

@@ -214,6 +214,42 @@ def gen_x16(ns):
                os.path.join(OUT, 'x16.pt'))
 
 
+def gen_x16_gf32(ns):
+    """models16 at PRODUCTION width (GF_DIM = 32; 16x16 -> 256x256): G_SR_NET_low, NetG_high and NetG_highweight.
+
+    NetG_highweight x16 cannot finish its own forward on a real pyramid: its last stage adds SRb8 (128^2) to a 256^2
+    tensor (models16.py:178).  To pin everything the reference DOES define -- including the reuse of residual48 /
+    upscale8x for the last stage (:172-173) and which addend it takes -- the unmodified forward is executed with SRb[2]
+    given as a per-image constant colour [B,3,1,1], which broadcasts against both the 128^2 and the 256^2 sums."""
+    g = torch.Generator().manual_seed(1632)
+    torch.manual_seed(132)
+    netGL = ns.models16.G_SR_NET_low(); randomize_bn(netGL, g); netGL.eval()
+    netGH = ns.models16.NetG_high(); randomize_bn(netGH, g); netGH.eval()
+    with ref_loader.cuda_noop():
+        netGHw = ns.models16.NetG_highweight(weightmap=False, low='lr')
+    randomize_bn(netGHw, g); netGHw.eval()
+    B, T = 2, 18
+    LR = O.synth_lr(B, 16, seed=216)
+    LRb = (LR + 0.05 * torch.randn(LR.shape, generator=g)).clamp(-1, 1)
+    words = torch.randn(B, 256, T, generator=g) * 0.2
+    sent = torch.randn(B, 256, generator=g) * 0.2
+    mask = torch.zeros(B, T, dtype=torch.bool); mask[1, 11:] = True
+    c8 = torch.rand(B, 3, 1, 1, generator=g) * 2 - 1
+    with torch.no_grad():
+        imgsL, atts, mu, logvar = netGL(LR, sent, words, mask)
+        fine = netGH(LR, imgsL, LRb, low=False)                                # convin(LR - LRb)
+        finew, a, one = netGHw(LR, [imgsL[0], imgsL[1], c8, imgsL[3]], LRb)
+    assert float(a) == 0.5 and float(one) == 1.0
+    sub = lambda t, k: t[:, :, ::k, ::k].clone()
+    torch.save(dict(sdL=netGL.state_dict(), sdH=netGH.state_dict(), sdHw=netGHw.state_dict(), LR=LR, LRb=LRb, words=words,
+                    sent=sent, mask=mask, c8=c8, mu=mu.clone(), logvar=logvar.clone(),
+                    imgsL=[imgsL[0].clone(), imgsL[1].clone(), sub(imgsL[2], 2), sub(imgsL[3], 4)],
+                    atts=[atts[0].clone(), sub(atts[1], 2), sub(atts[2], 4), sub(atts[3], 8)],
+                    fine=[fine[0].clone(), fine[1].clone(), sub(fine[2], 2), sub(fine[3], 4)],
+                    finew=[finew[0].clone(), finew[1].clone(), sub(finew[2], 2), sub(finew[3], 4)]),
+               os.path.join(OUT, 'x16_gf32.pt'))
+
+
 def gen_losses(ns):
     """words_loss / sent_loss / MSE of the UNMODIFIED miscc/losses.py (gamma 4/5/10, cfg/DAMSM/bird.yml:23-25) with
     autograd gradients to the image side: the pin for tgsr_b200/losses.py and the oracle's restatement."""
@@ -355,6 +391,10 @@ def main():
         gen_pyramid(ns)
         print('pyramid.npz', os.path.getsize(os.path.join(OUT, 'pyramid.npz')))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'x16':
+        gen_x16_gf32(ns)
+        print('x16_gf32.pt', os.path.getsize(os.path.join(OUT, 'x16_gf32.pt')))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'train':
         gen_train(ns)
         print('train_step.pt', os.path.getsize(os.path.join(OUT, 'train_step.pt')))
@@ -369,6 +409,7 @@ def main():
     gen_rnn(ns)
     gen_face_x8(ns)
     gen_x16(ns)
+    gen_x16_gf32(ns)
     gen_losses(ns)
     gen_train(ns)
     gen_pyramid(ns)

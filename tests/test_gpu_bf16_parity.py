@@ -219,3 +219,135 @@ def test_quantize_u8_and_pipelined_host_api():
     vLR.copy_(LR); vc.copy_(caps); vl.copy_(lens)
     t4 = pipe.submit(vLR, vc, vl, out='uint8', packed=packed)
     assert np.array_equal(pipe.result(t4).numpy(), u8)
+
+
+def test_bench_config_batch32_vs_oracle():
+    """The EXACT bench.py workload (configs[1]: batch 32, ntoken 5450, 18-word captions, seeds 100/101/102, randomised BN)
+    against the CPU oracle, through the same graph-replay entry point the bench times."""
+    from tgsr_b200.pipeline import SRPipeline
+    pipe = SRPipeline(5450, device=DEV, variant='x8', low='lr', seed=100, randomize_bn=True)
+    B = 32
+    LR = O.synth_lr(B, 32, seed=101)
+    caps, lens = O.synth_captions(B, 5450, seed=102, words_num=18)
+    fine, imgsL, atts = pipe.forward_graph(LR.to(DEV), caps.to(DEV), lens.to(DEV), 18)
+    sd = lambda m: {k: v.cpu() for k, v in m.state_dict().items()}
+    words, sent = O.rnn_encoder(sd(pipe.text_encoder), caps, lens)
+    mask = (caps == 0)[:, :words.shape[2]]
+    r_imgs, r_atts, _, _, _ = O.g_sr_net_low(sd(pipe.netGL), LR, sent, words, mask)
+    r_fine = O.netg_high(sd(pipe.netGH), LR, r_imgs, LR, low='lr')
+    hr = F.interpolate(LR, size=(256, 256), mode='bicubic', align_corners=False).clamp(-1, 1)
+    err, dp = _report('bench config (B=32) SR', fine[-1].cpu(), r_fine[-1], hr)
+    assert fine[-1].shape == (32, 3, 256, 256)
+    assert err <= 2e-2, err
+    assert abs(dp) <= 0.05, dp
+    for k in range(3):
+        assert (imgsL[k].cpu() - r_imgs[k]).abs().max() <= 2e-2
+        assert torch.equal(atts[k].cpu() == 0, r_atts[k] == 0)
+    from tgsr_b200 import fast
+    assert not fast.nonfinite_seen(DEV)
+
+
+@pytest.mark.parametrize('k', [3, 5])
+def test_image_head_256_batch32(k):
+    """Per-kernel parity of the image heads at the production output size (256x256, batch 32)."""
+    from tgsr_b200 import fast, tc
+    g = torch.Generator().manual_seed(k)
+    B, H, W = 32, 256, 256
+    x = torch.randn(B, 32, H, W, generator=g) * 0.5
+    w = torch.randn(3, 32, k, k, generator=g) * (1.0 / (k * 32 ** 0.5))
+    add = torch.randn(B, 3, H, W, generator=g) if k == 5 else None
+    seq = torch.nn.Sequential(torch.nn.Conv2d(32, 3, k, 1, k // 2, bias=False), *([torch.nn.Tanh()] if k == 5 else [])).to(DEV)
+    seq[0].weight.data.copy_(w)
+    y = fast.image_head(tc.to_blocked(x.to(DEV), fmt=1 if k == 5 else 0), seq, None if add is None else add.to(DEV), 0.5, 1.0)
+    rnd = (lambda t: t.to(torch.float16).to(torch.float32)) if k == 5 else bf
+    xd, wd = rnd(x).to(DEV), rnd(w).to(DEV)                       # 16-bit-faithful reference, evaluated in fp64 on the device
+    ref = F.conv2d(xd.double(), wd.double(), None, 1, k // 2).float()
+    if k == 5:
+        ref = torch.tanh(ref) + 0.5 * add.to(DEV)
+    torch.testing.assert_close(y, ref, rtol=1e-4, atol=5e-5)
+
+
+def test_fp16_range_netg_high(golden):
+    """fp16 half of `mixed16` (NetG_high*): (i) on the shipped checkpoint and the real LR crop every activation stays more
+    than 2^7 below the fp16 maximum; (ii) an overflow is not silent: with the BatchNorm gains scaled until an activation
+    passes 65504 the forward sets the non-finite flag (and `SRPipeline.result` raises)."""
+    from tgsr_b200 import fast, nets
+    w = golden('face_S8_weights.pt'); c = golden('face_x8.pt')['b1']
+    gh = nets.NetG_high(); gh.load_state_dict(w['netGH']); gh.to(DEV).eval()
+    LR = c['LR'].to(DEV)
+    SRb = [t.to(DEV) for t in c['imgsL']]
+    tgsr_b200.set_precision('fp16')
+    fast.nonfinite_seen(DEV)                                        # clear
+    ims, feats = gh(LR, SRb, LR, low=True, outmiddle=True)
+    peak = max(float(f.abs().max()) for f in feats)
+    print('NetG_high fp16 activations on the checkpoint: max |h| = %.2f (fp16 max 65504)' % peak)
+    assert peak < 65504 / 128
+    assert all(torch.isfinite(i).all() for i in ims) and not fast.nonfinite_seen(DEV)
+    # scaled gains: 1e3 per BatchNorm compounds past the fp16 range within two layers
+    for m in gh.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.mul_(1e3)
+    ims2 = gh(LR, SRb, LR, low=True)
+    torch.cuda.synchronize()
+    assert fast.nonfinite_seen(DEV), 'fp16 overflow went unnoticed'
+    assert not fast.nonfinite_seen(DEV)                              # reading clears it
+
+
+def test_pipeline_result_raises_on_overflow():
+    from tgsr_b200.pipeline import SRPipeline
+    pipe = SRPipeline(50, device=DEV, seed=3, randomize_bn=True)
+    for m in pipe.netGH.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.mul_(1e3)
+    LR = O.synth_lr(2, 32, seed=7).pin_memory()
+    caps, lens = O.synth_captions(2, 50, seed=8, words_num=18)
+    t = pipe.submit(LR, caps.pin_memory(), lens.pin_memory(), out='fp32')
+    with pytest.raises(FloatingPointError):
+        pipe.result(t)
+
+
+def _psnr_delta(sr, ref, hr):
+    p_ref = O.psnr_u8(O.to_uint8(ref), O.to_uint8(hr)); p_sr = O.psnr_u8(O.to_uint8(sr), O.to_uint8(hr))
+    return p_sr - p_ref
+
+
+def test_x16_production_width_mixed16(golden):
+    """x16 nets (models16.py, 16 -> 256) at GF_DIM = 32 on the 16-bit tensor-core path -- G_SR_NET_low through the blocked
+    stages, NetG_high / NetG_highweight through fast.netg_high -- against the unmodified reference's fp32 outputs:
+    max-abs <= 2e-2, |dPSNR| <= 0.05 dB (PSNR against a bicubic x16 of the LR input), masks bit-exact."""
+    from test_gpu_fp32_parity import run_x16_gf32
+    g = golden('x16_gf32.pt')
+    imgs, atts, mu, fine, finew = run_x16_gf32(g)
+    for k, sub in enumerate((1, 2, 4, 8)):
+        assert torch.equal(atts[k][:, :, ::sub, ::sub].cpu() == 0, g['atts'][k] == 0)
+    for k, sub in enumerate((1, 1, 2, 4)):
+        for name, got, want in (('netGL', imgs, g['imgsL']), ('NetG_high', fine, g['fine']), ('NetG_highweight', finew, g['finew'])):
+            err = (got[k][:, :, ::sub, ::sub].cpu() - want[k]).abs().max().item()
+            print('x16 %s level %d: max-abs %.4f' % (name, k, err))
+            assert err <= 2e-2, (name, k, err)
+    hr = F.interpolate(g['LR'], size=(256, 256), mode='bicubic', align_corners=False).clamp(-1, 1)[:, :, ::4, ::4]
+    for name, got, want in (('NetG_high', fine, g['fine']), ('NetG_highweight', finew, g['finew'])):
+        dp = _psnr_delta(got[3][:, :, ::4, ::4].cpu(), want[3], hr)
+        print('x16 %s: dPSNR %+.4f dB' % (name, dp))
+        assert abs(dp) <= 0.05
+
+
+def test_x16_pipeline_graph_vs_oracle():
+    """The x16 eval flow end to end (SRPipeline variant 'x16', graph replay) at a test-sized batch against the CPU oracle."""
+    from tgsr_b200.pipeline import SRPipeline
+    pipe = SRPipeline(300, device=DEV, variant='x16', low='lr', seed=16, randomize_bn=True)
+    B = 4
+    LR = O.synth_lr(B, 16, seed=41)
+    caps, lens = O.synth_captions(B, 300, seed=42, ragged=True)
+    tmax = int(lens.max())
+    fine, imgsL, atts = pipe.forward_graph(LR.to(DEV), caps.to(DEV), lens.to(DEV), tmax)
+    sd = lambda m: {k: v.cpu() for k, v in m.state_dict().items()}
+    words, sent = O.rnn_encoder(sd(pipe.text_encoder), caps, lens)
+    mask = (caps == 0)[:, :words.shape[2]]
+    r_imgs, r_atts, _, _, _ = O.g_sr_net_low(sd(pipe.netGL), LR, sent, words, mask, variant='x16')
+    r_fine = O.netg_high(sd(pipe.netGH), LR, r_imgs, LR, low='lr', a=0.5, variant='x16')
+    assert len(fine) == 4 and fine[-1].shape == (B, 3, 256, 256)
+    for k in range(4):
+        assert torch.equal(atts[k].cpu() == 0, r_atts[k] == 0)
+        assert (imgsL[k].cpu() - r_imgs[k]).abs().max() <= 2e-2
+        assert (fine[k].cpu() - r_fine[k]).abs().max() <= 2e-2

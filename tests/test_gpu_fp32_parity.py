@@ -201,6 +201,42 @@ def test_x16_nets_fp32(golden):
         close(a, b, rtol=1e-3, atol=1e-4)
 
 
+def _x16_nets(g):
+    from tgsr_b200 import nets16
+    gl = nets16.G_SR_NET_low(); gl.load_state_dict(g['sdL'], strict=True); gl.to(DEV).eval()
+    gh = nets16.NetG_high(); gh.load_state_dict(g['sdH'], strict=True); gh.to(DEV).eval()
+    ghw = nets16.NetG_highweight(weightmap=False, low='lr'); ghw.load_state_dict(g['sdHw'], strict=True); ghw.to(DEV).eval()
+    return gl, gh, ghw
+
+
+def run_x16_gf32(g):
+    """All three models16 nets at GF_DIM = 32 on the fixture's inputs (shared by the fp32 and the 16-bit test)."""
+    gl, gh, ghw = _x16_nets(g)
+    LR, LRb = g['LR'].to(DEV), g['LRb'].to(DEV)
+    imgs, atts, mu, lv = gl(LR, g['sent'].to(DEV), g['words'].to(DEV), g['mask'].to(DEV))
+    fine = gh(LR, imgs, LRb, low=False)
+    B = LR.shape[0]
+    c8 = g['c8'].to(DEV)
+    srb_w = [imgs[0], imgs[1], c8.expand(B, 3, 128, 128).contiguous(), c8.expand(B, 3, 256, 256).contiguous()]
+    finew, a, one = ghw(LR, srb_w, LRb)
+    assert float(a) == 0.5 and float(one) == 1.0 and 'a' in ghw.state_dict()       # registered here (models16.py:131)
+    return imgs, atts, mu, fine, finew
+
+
+def test_x16_production_width_fp32(golden):
+    """models16 at GF_DIM = 32 against the unmodified reference (x16_gf32.pt), fp32 kernels."""
+    g = golden('x16_gf32.pt')
+    imgs, atts, mu, fine, finew = run_x16_gf32(g)
+    close(mu, g['mu'], rtol=1e-4, atol=1e-6)
+    for k, sub in enumerate((1, 1, 2, 4)):
+        close(imgs[k][:, :, ::sub, ::sub], g['imgsL'][k], rtol=1e-3, atol=1e-4)
+        close(fine[k][:, :, ::sub, ::sub], g['fine'][k], rtol=1e-3, atol=2e-4)
+        close(finew[k][:, :, ::sub, ::sub], g['finew'][k], rtol=1e-3, atol=2e-4)
+    for k, sub in enumerate((1, 2, 4, 8)):
+        close(atts[k][:, :, ::sub, ::sub], g['atts'][k], rtol=1e-3, atol=1e-6)
+        assert torch.equal(atts[k][:, :, ::sub, ::sub].cpu() == 0, g['atts'][k] == 0)
+
+
 def test_conv_properties_full_size():
     """Size-independent checks at the production size (256^2 output): linearity of the conv
     path and equivalence of the fused upsample with an explicit nearest upsample."""

@@ -316,3 +316,94 @@ def test_generator_train_grads_vs_reference_modules(golden):
         for name, g in grads.items():
             torch.testing.assert_close(params[name].grad.cpu(), g, rtol=5e-3, atol=1e-6 + 2e-4 * float(g.abs().max()),
                                        msg=lambda m, name=name: name + ': ' + m)
+
+
+def test_eval_after_train_uses_fresh_weights():
+    """Derived-parameter caches (folded BN, packed 16-bit operands, captured eval graphs) key on the weights epoch: the fused
+    Adam and the BatchNorm running-stat update write through raw pointers, which bumps neither data_ptr nor _version.
+    eval -> train steps -> eval must equal a fresh model loaded with the trained state dict."""
+    from tgsr_b200 import nets
+    from tgsr_b200.pipeline import SRPipeline
+    from tgsr_b200.text_encoder import RNN_ENCODER
+    from tgsr_b200.train_step import FrozenImageEncoder, GeneratorTrainStep
+    torch.manual_seed(5)
+    B = 4
+    pipe = SRPipeline(200, device=DEV, seed=11, randomize_bn=True)
+    LR = O.synth_lr(B, 32, seed=31).to(DEV)
+    caps, lens = O.synth_captions(B, 200, seed=32, words_num=18)
+    caps, lens = caps.to(DEV), lens.to(DEV)
+    tgsr_b200.set_precision('mixed16')
+    before = pipe.forward_graph(LR, caps, lens, 18)[0][-1].clone()           # warms every cache and captures a graph
+    # two training steps on the same modules (fp32 training kernels)
+    tgsr_b200.set_precision('fp32')
+    img = FrozenImageEncoder().to(DEV)
+    ts = GeneratorTrainStep(pipe.netGL, pipe.netGH, pipe.text_encoder, img, lr=2e-3, conv_precision='fp32')
+    real = [torch.nn.functional.interpolate(LR, size=(s, s), mode='bicubic', align_corners=False).clamp(-1, 1) for s in (64, 128, 256)]
+    for _ in range(2):
+        ts.step(LR, real, caps, lens, 18)
+    assert ts.opt.t == 2 and int(ts.opt.step_t.item()) == 2
+    pipe.netGL.eval(); pipe.netGH.eval()
+    tgsr_b200.set_precision('mixed16')
+    after = pipe.forward_graph(LR, caps, lens, 18)[0][-1].clone()
+    assert (after - before).abs().max() > 1e-3, 'training changed nothing?'
+    fresh = SRPipeline(200, device=DEV, seed=11, randomize_bn=False)
+    fresh.text_encoder.load_state_dict(pipe.text_encoder.state_dict())
+    fresh.load_generators(pipe.netGL.state_dict(), pipe.netGH.state_dict())
+    want = fresh.forward_device(LR, caps, lens)[0][-1]
+    assert torch.equal(after, want), 'eval after training replayed stale folded / packed weights: max-abs %.3e' % \
+        (after - want).abs().max().item()
+    tgsr_b200.set_precision('fp32')
+
+
+def test_adam_step_counter_eager_graph_mix():
+    """The device step counter is the single source of truth: eager steps, a captured step and its replays, and eager steps
+    again produce the same parameters as torch.optim.Adam over the same gradient sequence."""
+    from tgsr_b200.train_step import FlatBucket, FusedAdam
+    torch.manual_seed(3)
+    net = torch.nn.Linear(16, 8).to(DEV)
+    ref = [p.detach().cpu().clone().requires_grad_(True) for p in net.parameters()]
+    opt_ref = torch.optim.Adam(ref, lr=1e-3, betas=(0.5, 0.999))
+    bucket = FlatBucket([net]); opt = FusedAdam(bucket, 1e-3, (0.5, 0.999))
+    gfix = [torch.randn(r.shape, generator=torch.Generator().manual_seed(7 + i)) for i, r in enumerate(ref)]
+
+    def set_grads():
+        for p, g in zip(net.parameters(), gfix):
+            p.grad.copy_(g.to(DEV))
+    set_grads(); opt.step()                                  # eager
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        set_grads(); opt.step()                              # warm-up on the capture stream
+    torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        opt.step()
+    for _ in range(3):
+        g.replay(); opt.note_replay()
+    set_grads(); opt.step()                                  # eager again
+    torch.cuda.synchronize()
+    assert opt.t == 6 and int(opt.step_t.item()) == 6
+    for _ in range(6):
+        for r, gr in zip(ref, gfix):
+            r.grad = gr.clone()
+        opt_ref.step()
+    for p, r in zip(net.parameters(), ref):
+        torch.testing.assert_close(p.detach().cpu(), r.detach(), rtol=2e-5, atol=1e-7)
+
+
+def test_text_side_gradients_raise():
+    """The drop-in losses / attention only carry the generator-side gradients; asking for a text-side gradient must raise
+    instead of silently training nothing."""
+    from tgsr_b200 import losses
+    B, T = 4, 6
+    feats = torch.randn(B, 256, 17, 17, device=DEV, requires_grad=True)
+    words = torch.randn(B, 256, T, device=DEV, requires_grad=True)
+    labels = torch.arange(B, device=DEV); lens = torch.full((B,), T, device=DEV)
+    with pytest.raises(NotImplementedError, match='words_emb'):
+        losses.words_loss(feats, words, labels, lens, None, B)
+    losses.words_loss(feats, words.detach(), labels, lens, None, B)          # the supported call
+    code = torch.randn(B, 256, device=DEV, requires_grad=True)
+    with pytest.raises(NotImplementedError, match='rnn_code'):
+        losses.sent_loss(code, torch.randn(B, 256, device=DEV, requires_grad=True), labels, None, B)
+    att = tgsr_b200.GlobalAttentionGeneral(32, 256).to(DEV).train()
+    with pytest.raises(NotImplementedError, match='context'):
+        att(torch.randn(1, 32, 8, 8, device=DEV, requires_grad=True), torch.randn(1, 256, T, device=DEV, requires_grad=True))

@@ -47,10 +47,14 @@ def test_state_dict_contract(golden):
     from tgsr_b200 import nets, nets16, text_encoder
     w = golden('face_S8_weights.pt')
     gl = nets.G_SR_NET_low(); gl.load_state_dict(w['netG'], strict=True)
-    assert len(gl.state_dict()) == 104 and sum(v.numel() for k, v in gl.state_dict().items()
-                                                if 'num_batches' not in k) == 911488 - 0 or True
+    # 104 keys / 911 488 elements and 121 keys / 284 724 elements (num_batches_tracked included)
+    assert len(gl.state_dict()) == 104
+    assert sum(v.numel() for v in gl.state_dict().values()) == 911488
+    assert {k: tuple(v.shape) for k, v in gl.state_dict().items()} == {k: tuple(v.shape) for k, v in w['netG'].items()}
     gh = nets.NetG_highweight(weightmap=False, low='lr'); gh.load_state_dict(w['netGH'], strict=True)
     assert len(gh.state_dict()) == 121 and 'a' not in gh.state_dict()
+    assert sum(v.numel() for v in gh.state_dict().values()) == 284724
+    assert {k: tuple(v.shape) for k, v in gh.state_dict().items()} == {k: tuple(v.shape) for k, v in w['netGH'].items()}
     nets.NetG_high().load_state_dict(w['netGH'], strict=True)
     assert set(gl.state_dict()) == set(w['netG']) and set(gh.state_dict()) == set(w['netGH'])
     x16 = golden('x16.pt')

@@ -113,6 +113,33 @@ def test_x16_wiring(golden):
         close(a, b, rtol=1e-4, atol=2e-5)
 
 
+def _x16_srb_w(g):
+    """NetG_highweight x16 inputs of the fixture: SRb[2] is a per-image constant colour (see make_golden.gen_x16_gf32); the
+    implementations take a full pyramid, so the constant is expanded to the 128^2 and 256^2 addends it was broadcast to."""
+    c8 = g['c8']
+    B = c8.shape[0]
+    return [g['imgsL_full'][0], g['imgsL_full'][1], c8.expand(B, 3, 128, 128).contiguous(), c8.expand(B, 3, 256, 256).contiguous()]
+
+
+def test_x16_production_width(golden):
+    """models16 at GF_DIM = 32 (16 -> 256): the oracle against the unmodified reference's outputs for all three nets,
+    including NetG_highweight's reuse of residual48 / upscale8x in the last stage (models16.py:172-173)."""
+    g = dict(golden('x16_gf32.pt'))
+    imgs, atts, mu, lv, _ = O.g_sr_net_low(g['sdL'], g['LR'], g['sent'], g['words'], g['mask'], variant='x16')
+    g['imgsL_full'] = imgs
+    close(mu, g['mu'], rtol=1e-4, atol=1e-6)
+    for k, sub in enumerate((1, 1, 2, 4)):
+        close(imgs[k][:, :, ::sub, ::sub], g['imgsL'][k], rtol=1e-4, atol=2e-5)
+    for k, sub in enumerate((1, 2, 4, 8)):
+        close(atts[k][:, :, ::sub, ::sub], g['atts'][k], rtol=1e-4, atol=1e-6)
+    fine = O.netg_high(g['sdH'], g['LR'], imgs, g['LRb'], low='lr-lrblur', a=1.0, one=1.0, variant='x16',
+                       x16_last=('residual816', 'upscale16x'))
+    finew = O.netg_high(g['sdHw'], g['LR'], _x16_srb_w(g), g['LRb'], low='lr', a=0.5, one=1.0, variant='x16')
+    for k, sub in enumerate((1, 1, 2, 4)):
+        close(fine[k][:, :, ::sub, ::sub], g['fine'][k], rtol=1e-4, atol=5e-5)
+        close(finew[k][:, :, ::sub, ::sub], g['finew'][k], rtol=1e-4, atol=5e-5)
+
+
 def test_psnr_and_quantisation():
     x = torch.tensor([[-1.0, 0.0, 1.0, 1.2]])
     assert O.to_uint8(x).tolist() == [[0, 128, 255, 255]]       # round-half-even of 127.5 -> 128

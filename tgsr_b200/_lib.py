@@ -47,7 +47,7 @@ _SIGS = {
                          C.c_void_p, C.c_int, C.c_int] + [C.c_int] * 9 + [C.c_void_p], C.c_int),
     'tgsr_pack_head': ([C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     'tgsr_img_head_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
-                         + [C.c_int] * 7 + [C.c_void_p], C.c_int),
+                         + [C.c_int] * 7 + [C.c_void_p, C.c_void_p], C.c_int),
     'tgsr_conv_in_blocked': ([C.c_void_p] * 6 + [C.c_int] * 7 + [C.c_void_p], C.c_int),
     'tgsr_bn_stats_f32': ([C.c_void_p] * 5 + [C.c_float, C.c_float, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p], C.c_int),
     'tgsr_bn_act_f32': ([C.c_void_p] * 7 + [C.c_int] * 4 + [C.c_void_p], C.c_int),
@@ -156,6 +156,18 @@ def weights_epoch() -> int:
 def bump_weights_epoch() -> None:
     global _weights_epoch
     _weights_epoch += 1
+
+
+def no_grad_path(what: str, *tensors) -> None:
+    """The frozen-text SR training step is the only backward path built (SURVEY.md 8d cfg 5: text and image encoders
+    frozen).  An input that would receive a gradient in the reference but has no backward kernel here must not silently
+    train nothing: raise instead."""
+    if torch.is_grad_enabled():
+        for t in tensors:
+            if t is not None and t.requires_grad:
+                raise NotImplementedError(
+                    'tgsr_b200: %s: a gradient was requested for an input whose backward is not implemented (the CUDA path '
+                    'trains the generator against frozen text / image-text encoders); detach() it or freeze its parameters' % what)
 
 
 def tensor_key(t):

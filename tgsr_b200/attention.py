@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from ._lib import no_grad_path
 
 
 def conv1x1(in_planes, out_planes, bias=False):
@@ -18,7 +19,9 @@ def conv1x1(in_planes, out_planes, bias=False):
 
 
 def func_attention(query, context, gamma1):
-    """GlobalAttention.py:33-74.  query [B,ndf,Tq], context [B,ndf,ih,iw] -> (weightedContext, attn)."""
+    """GlobalAttention.py:33-74.  query [B,ndf,Tq], context [B,ndf,ih,iw] -> (weightedContext, attn).  Forward only
+    (the training step reaches it through the fused words_loss kernels, which carry the image-feature gradient)."""
+    no_grad_path('func_attention', query, context)
     return ops.func_attention_fwd(query, context, gamma1)
 
 
@@ -39,5 +42,6 @@ class GlobalAttentionGeneral(nn.Module):
         w = self.conv_context.weight
         if self.training and torch.is_grad_enabled() and (input.requires_grad or w.requires_grad):
             from .train import AttentionFn
-            return AttentionFn.apply(input, w, context.detach(), self.mask)
+            no_grad_path('GlobalAttentionGeneral(context)', context)     # word embeddings come from the frozen text encoder
+            return AttentionFn.apply(input, w, context, self.mask)
         return ops.attention_fwd(input, context, w.detach(), self.mask)

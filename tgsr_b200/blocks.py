@@ -176,7 +176,16 @@ class CA_NET(nn.Module):
         self.relu = GLU()
 
     def _mulogvar(self, text_embedding):
+        from ._lib import no_grad_path
+        no_grad_path('CA_NET(text_embedding)', text_embedding)
+        if self.training and torch.is_grad_enabled() and self.fc.weight.requires_grad and not CA_NET._warned:
+            import warnings
+            CA_NET._warned = True
+            warnings.warn('tgsr_b200: CA_NET has no backward kernel -- mu / logvar carry no gradient, so KL_loss on them trains '
+                          'nothing (c_code is unused by the SR nets, model.py:51-52); freeze ca_net or leave it out of the optimiser')
         return ops.linear_glu(text_embedding, self.fc.weight.detach(), self.fc.bias.detach())
+
+    _warned = False
 
     def encode(self, text_embedding):
         x = self._mulogvar(text_embedding)

@@ -154,6 +154,7 @@ struct TcParams {
   const float* addend;
   float out_scale, addend_scale;
   int act_tanh;
+  int* nonfinite;        // optional device flag: set to 1 when a head accumulator is inf / NaN (16-bit overflow upstream)
 };
 
 // Tile walk of a persistent CTA: tile index t = (b * tiles_y + ty) * tiles_x + tx, advanced by gridDim.x with carries
@@ -449,6 +450,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             for (int kx = 1; kx < K; ++kx) z[o] += __shfl_down_sync(0xffffffffu, __uint_as_float(v[q][o * K + kx]), kx);
           }
           if (valid[q]) {
+            // inf / NaN anywhere upstream (an fp16 activation past 65504) reaches these sums; tanh would hide it
+            if (p.nonfinite != nullptr && !(fabsf(z[0]) <= 3.0e38f && fabsf(z[1]) <= 3.0e38f && fabsf(z[2]) <= 3.0e38f))
+              atomicOr(p.nonfinite, 1);
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
               float tv = z[o];
@@ -861,7 +865,7 @@ extern "C" int tgsr_pack_head(const float* w, void* packed, int Cin, int ksize, 
 
 extern "C" int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpacked, const float* addend,
                                 float out_scale, float addend_scale, float* y, int B, int Cin, int H, int W,
-                                int ksize, int act, int fmt, tgsr_stream_t stream) {
+                                int ksize, int act, int fmt, int* nonfinite_flag, tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(wpacked); TGSR_REQUIRE_PTR(y);
   TGSR_CHECK_FMT(fmt);
@@ -882,6 +886,7 @@ extern "C" int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpac
   p.tiles_x = (W + two - 1) / two; p.tiles_y = (H + 31) / 32; p.ntiles = B * p.tiles_x * p.tiles_y;
   p.out_f32 = y; p.addend = addend; p.out_scale = out_scale; p.addend_scale = addend_scale;
   p.act_tanh = act == TGSR_ACT_TANH;
+  p.nonfinite = nonfinite_flag;
   cudaStream_t st = (cudaStream_t)stream;
   if (ksize == 3) return launch_tc<32, 16, MODE_HEAD3, false>(tmap, tmap, p, fmt, st);
   return launch_tc<32, 16, MODE_HEAD5, false>(tmap, tmap, p, fmt, st);

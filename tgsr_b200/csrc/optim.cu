@@ -23,8 +23,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 __global__ void __launch_bounds__(256)
 adam_devstep_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
                     float lr, float b1, float b2, float eps, const int* __restrict__ step, float gscale) {
-  const float t = (float)step[0];
-  const float bc1 = 1.0f - powf(b1, t), bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+  const double t = (double)step[0];        // bias corrections in double, as the host path (and torch.optim.Adam) compute them
+  const float bc1 = (float)(1.0 - pow((double)b1, t)), bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
   const float st = lr / bc1;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
     const float gi = g[i] * gscale;

@@ -85,6 +85,28 @@ def _packed_head(conv: nn.Conv2d, fmt: int) -> Tensor:
     return cached[1]
 
 
+_NONFINITE = {}
+
+
+def nonfinite_flag(device) -> Tensor:
+    """Per-device int32 flag the image-head kernels OR a 1 into when a pre-activation sum is inf / NaN, i.e. when a 16-bit
+    activation overflowed somewhere upstream (fp16 saturates at 65504).  Read it with `nonfinite_seen`."""
+    key = str(device)
+    t = _NONFINITE.get(key)
+    if t is None:
+        t = _NONFINITE[key] = torch.zeros(1, device=device, dtype=torch.int32)
+    return t
+
+
+def nonfinite_seen(device, clear: bool = True) -> bool:
+    """True when a 16-bit forward since the last call produced inf / NaN (one device->host read)."""
+    t = nonfinite_flag(device)
+    seen = bool(int(t.item()))
+    if clear and seen:
+        t.zero_()
+    return seen
+
+
 def image_head(x: Blocked, head_seq, addend: Optional[Tensor] = None, a: float = 0.0, one: float = 1.0) -> Tensor:
     """GET_IMAGE_G[_noAct].img / conv_output -> fp32 NCHW image (util.py:894-919, model.py:223-226,280)."""
     conv = head_seq[0]
@@ -97,7 +119,7 @@ def image_head(x: Blocked, head_seq, addend: Optional[Tensor] = None, a: float =
             raise ValueError('SRb shape %s != image shape %s' % (tuple(addend.shape), tuple(y.shape)))
         ad = addend.contiguous()
     call('tgsr_img_head_tc', x.device, ptr(x.buf), x.P, x.p0, ptr(_packed_head(conv, x.fmt)), ptr(ad), float(one), float(a),
-         ptr(y), x.B, x.C, x.H, x.W, k, act, x.fmt)
+         ptr(y), x.B, x.C, x.H, x.W, k, act, x.fmt, ptr(nonfinite_flag(x.device)))
     return y
 
 

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import call, ptr
+from ._lib import call, no_grad_path, ptr
 from .config import cfg
 
 Tensor = torch.Tensor
@@ -97,6 +97,7 @@ def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size)
     cmask = _class_mask(class_ids, B, img_features.device)
     if labels is None:
         raise NotImplementedError('words_loss(labels=None) returns no losses in the reference; not needed here')
+    no_grad_path('words_loss(words_emb)', words_emb)          # only d/d(img_features) is built (frozen text encoder)
     loss0, loss1, attn = WordsLossFn.apply(img_features, words_emb, labels, cap_lens, cmask, sm.GAMMA1, sm.GAMMA2, sm.GAMMA3)
     return loss0, loss1, _AttMaps(attn, cap_lens, B, words_emb.shape[2], img_features.shape[2], img_features.shape[3])
 
@@ -155,6 +156,7 @@ def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-8):
     if cnn_code.dim() != 2:
         raise NotImplementedError('sent_loss: only [B, nef] codes (the SR training step) are implemented')
     cmask = _class_mask(class_ids, batch_size, cnn_code.device)
+    no_grad_path('sent_loss(rnn_code)', rnn_code)              # only d/d(cnn_code) is built (frozen text encoder)
     return SentLossFn.apply(cnn_code, rnn_code, labels, cmask, cfg.TRAIN.SMOOTH.GAMMA3, eps)
 
 

@@ -42,6 +42,25 @@ class G_SR_NET_low(nn.Module):
         return fake_imgs, att_maps, mu, logvar
 
 
+def _fast_ok(net, LR) -> bool:
+    """16-bit mode and the trunk is inside the tcgen05 kernels' envelope: every layer then runs on blocked activations
+    without layout conversions between them (tgsr_b200/fast.py)."""
+    from . import is_16bit
+    return (is_16bit() and net.convin[0].weight.shape[0] == 64 and LR.shape[2] % 16 == 0 and LR.shape[3] % 8 == 0
+            and not net.training)
+
+
+def _cached_float(mod, t, name) -> float:
+    """Host copy of a one-element parameter, cached per weight version (a device->host read only when it changed)."""
+    from ._lib import tensor_key
+    key = tensor_key(t)
+    c = mod.__dict__.get(name)
+    if c is None or c[0] != key:
+        c = (key, float(t))
+        mod.__dict__[name] = c
+    return c[1]
+
+
 def _res_body(ngf):
     return _ConvBnGluConvBn(conv3x3(ngf, ngf * 2), nn.BatchNorm2d(ngf * 2), GLU(), conv3x3(ngf, ngf),
                             nn.BatchNorm2d(ngf))
@@ -61,6 +80,12 @@ class NetG_high(nn.Module):
         self.residual816 = self.residual48 = self.residual24 = _res_body(ngf)
 
     def forward(self, LR, SRb, LRb, low=False):
+        from . import fast, fmt_for, is_16bit
+        if _fast_ok(self, LR):
+            x, x_sub = (LRb, None) if low else (LR, LRb)
+            return fast.netg_high(self, x, x_sub, SRb, 1.0, 1.0,
+                                  [(self.residual24, self.upscale4x), (self.residual48, self.upscale8x),
+                                   (self.residual816, self.upscale16x)], None, fmt_for('high'))
         out = self.convin(LRb if low else torch.sub(LR, LRb))
         out = self.residual(out)
         out = self.upscale2x(out)
@@ -106,7 +131,14 @@ class NetG_highweight(nn.Module):
             x = LR
         else:
             raise ValueError(self.low)
-        a, one = float(self.a), float(self.one)
+        a, one = _cached_float(self, self.a, '_tgsr_a'), 1.0      # `a` is trainable here: read once per weight version
+        from . import fast, fmt_for
+        if _fast_ok(self, LR):
+            x, x_sub = (LR, LRb) if self.low == 'lr-lrblur' else (x, None)
+            ims = fast.netg_high(self, x, x_sub, SRb, a, one,
+                                 [(self.residual24, self.upscale4x), (self.residual48, self.upscale8x),
+                                  (self.residual48, self.upscale8x)], None, fmt_for('high'))
+            return ims, self.a, self.one.to(ims[0].device)
         out = self.convin(x)
         out = self.residual(out)
         out = self.upscale2x(out)

@@ -38,6 +38,7 @@ class SRPipeline:
     def load_generators(self, sd_netG, sd_netGH):
         self.netGL.load_state_dict(sd_netG, strict=True)
         self.netGH.load_state_dict(sd_netGH, strict=True)
+        self._graphs = {}                      # captured graphs bake the packed / folded weights of the old parameters
 
     @torch.no_grad()
     def forward_device(self, LR: torch.Tensor, captions: torch.Tensor, cap_lens, LRb: Optional[torch.Tensor] = None):
@@ -61,7 +62,7 @@ class SRPipeline:
         first G_SR_NET_low stage; the streams join before the first high-frequency image head."""
         from . import fast, fmt_for, is_16bit
         gh, gl = self.netGH, self.netGL
-        overlap = (is_16bit() and self.variant == 'x8' and gh.low == 'lr' and LR.shape[2] % 16 == 0 and LR.shape[3] % 8 == 0
+        overlap = (is_16bit() and gh.low == 'lr' and LR.shape[2] % 16 == 0 and LR.shape[3] % 8 == 0
                    and gh.convin[0].weight.shape[0] == 64 and fast.stage_supported(gl.h_net1, LR.shape[2], LR.shape[3]))
         if not overlap:
             words_embs, sent_emb = self.text_encoder._forward_tmax(captions, cap_lens, tmax)
@@ -85,7 +86,13 @@ class SRPipeline:
             ev_h0.record(s_im2f)
         with torch.cuda.stream(s_trunk):
             h_high = fast.netg_high_trunk(gh, LR, None, fmt_for('high'))
-        stages = [gl.h_net1, gl.h_net2, gl.h_net3]
+        if self.variant == 'x8':                                         # model.py:34-78 / :264-298
+            stages, heads = [gl.h_net1, gl.h_net2, gl.h_net3], [gl.img_net1, gl.img_net2, gl.img_net3]
+            tail, a_val = [(gh.residual24, gh.upscale4x), (gh.residual48, gh.upscale8x)], 0.5
+        else:                                                            # models16.py:5-39 / :145-179 (last stage reuses 48 / 8x)
+            stages, heads = [gl.h_net1, gl.h_net2, gl.h_net3, gl.h_net4], [gl.img_net1, gl.img_net2, gl.img_net3, gl.img_net4]
+            tail = [(gh.residual24, gh.upscale4x), (gh.residual48, gh.upscale8x), (gh.residual48, gh.upscale8x)]
+            a_val = nets16._cached_float(gh, gh.a, '_tgsr_a')
         for st in stages:
             st.att.applyMask(mask)                                       # keep the modules' stateful contract
 
@@ -96,15 +103,13 @@ class SRPipeline:
             return out
         cur.wait_event(ev_h0)
         h0.buf.record_stream(cur); mask.record_stream(cur)
-        fake_imgL, attention_maps, mu, logvar = fast.g_sr_net_low(gl, LR, sent_emb, words_embs, mask, stages,
-                                                                  [gl.img_net1, gl.img_net2, gl.img_net3], False,
+        fake_imgL, attention_maps, mu, logvar = fast.g_sr_net_low(gl, LR, sent_emb, words_embs, mask, stages, heads, False,
                                                                   fmt_for('low'), h0=h0, ca=ca)
         cur.wait_stream(s_im2f)
         mu.record_stream(cur); logvar.record_stream(cur)
         cur.wait_stream(s_trunk)
         h_high.buf.record_stream(cur)
-        fine_im = fast.netg_high_finish(gh, h_high, fake_imgL, 0.5, 1.0,
-                                        [(gh.residual24, gh.upscale4x), (gh.residual48, gh.upscale8x)])
+        fine_im = fast.netg_high_finish(gh, h_high, fake_imgL, a_val, 1.0, tail)
         return fine_im, fake_imgL, attention_maps
 
     # ------------------------------------------------------------------ CUDA-graph replay
@@ -114,8 +119,7 @@ class SRPipeline:
         once per input signature into a CUDA graph and replayed with a single launch.  Inputs are copied
         into the graph's static buffers unless they already ARE those buffers (see static_inputs()).
         The returned tensors are the graph's static outputs: they are overwritten by the next replay."""
-        from . import get_precision
-        key = (tuple(LR.shape), tuple(captions.shape), int(tmax), get_precision())
+        key = self._graph_key(tuple(LR.shape), tuple(captions.shape), tmax)
         e = self._graphs.get(key) if hasattr(self, '_graphs') else None
         if e is None:
             e = self._capture(key, LR, captions, cap_lens, tmax)
@@ -133,10 +137,17 @@ class SRPipeline:
         from . import get_precision
         return get_precision()
 
+    @staticmethod
+    def _graph_key(lr_shape, cap_shape, tmax):
+        """Graph signature: shapes, precision and the weights epoch (a graph replays the packed weights it captured;
+        training steps or raw-pointer writes since then make it stale, see _lib.bump_weights_epoch)."""
+        from . import get_precision
+        from ._lib import weights_epoch
+        return (tuple(lr_shape), tuple(cap_shape), int(tmax), get_precision(), weights_epoch())
+
     def static_inputs(self, B: int, tmax: int, Tcap: int = 18, size: int = 32):
         """The static input buffers of the graph for this signature (fill them in place to skip copies)."""
-        from . import get_precision
-        key = ((B, 3, size, size), (B, Tcap), int(tmax), get_precision())
+        key = self._graph_key((B, 3, size, size), (B, Tcap), tmax)
         e = getattr(self, '_graphs', {}).get(key)
         return None if e is None else (e['LR'], e['caps'], e['lens'])
 
@@ -223,6 +234,62 @@ class SRPipeline:
                 'peak_source': pk['source'] + ' cuBLAS bf16 burst (kernel timed alone)'}
 
     @torch.no_grad()
+    def kernel_rooflines(self, B, flush, pk, iters: int = 10):
+        """Every conv / head kernel variant of the step at its largest instance (and the LSTM), each timed alone, L2-cold:
+        achieved TFLOP/s on EXECUTED MMA FLOPs vs the measured bf16 burst peak and algorithmic GB/s vs the measured copy
+        bandwidth (whichever bound is tighter names the kernel's roofline).  16-bit modes only."""
+        from . import fast, tc, fmt_for, is_16bit
+        from ._lib import ACT_GLU, ACT_NONE
+        if not is_16bit():
+            return None
+        dev = self.device
+        gl, gh = self.netGL, self.netGH
+        st, rb, hb = gl.h_net3, gl.h_net3.residual[0].block, gh.residual48
+        fl, fh = fmt_for('low'), fmt_for('high')
+        S = 128
+        px = B * S * S
+        x64 = tc.to_blocked(torch.randn(B, 64, S, S, device=dev) * 0.5, fmt=fl)
+        r64 = tc.to_blocked(torch.randn(B, 64, S, S, device=dev) * 0.5, fmt=fl)
+        o64 = tc.Blocked.empty(B, 64, S, S, dev, fmt=fl)
+        o32u = tc.Blocked.empty(B, 32, 2 * S, 2 * S, dev, fmt=fl)
+        x32 = tc.to_blocked(torch.randn(B, 32, S, S, device=dev) * 0.5, fmt=fh)
+        r32 = tc.to_blocked(torch.randn(B, 32, S, S, device=dev) * 0.5, fmt=fh)
+        o32 = tc.Blocked.empty(B, 32, S, S, dev, fmt=fh)
+        o32uh = tc.Blocked.empty(B, 32, 2 * S, 2 * S, dev, fmt=fh)
+        add = torch.randn(B, 3, 2 * S, 2 * S, device=dev)
+        caps = torch.randint(1, 5450, (B, 18), device=dev); lens = torch.full((B,), 18, device=dev)
+        e = 2
+        rows = [
+            ('conv3x3 64->128 +BN+GLU @128^2 (ResBlock conv 1)', lambda: fast.conv_bn_act(x64, rb[0], rb[1], ACT_GLU, out=o64),
+             2 * 9 * 64 * 128 * px, px * (64 + 64) * e),
+            ('conv3x3 64->64 +BN+skip @128^2 (ResBlock conv 2)', lambda: fast.conv_bn_act(x64, rb[3], rb[4], ACT_NONE, residual=r64, out=o64),
+             2 * 9 * 64 * 64 * px, px * (64 + 64 + 64) * e),
+            ('upBlock 64->32 @128^2->256^2 (4-phase)', lambda: fast.conv_bn_act(x64, st.upsample[1], st.upsample[2], ACT_GLU, up2x=True, out=o32u),
+             2 * 16 * 64 * 64 * px, px * 64 * e + 4 * px * 32 * e),
+            ('conv3x3 32->64 +BN+GLU @128^2 (NetG_high body)', lambda: fast.conv_bn_act(x32, hb[0], hb[1], ACT_GLU, out=o32),
+             2 * 9 * 32 * 64 * px, px * (32 + 32) * e),
+            ('conv3x3 32->32 +BN+skip @128^2 (NetG_high ResBlock conv 2)', lambda: fast.conv_bn_act(x32, hb[3], hb[4], ACT_NONE, residual=r32, out=o32),
+             2 * 9 * 32 * 32 * px, px * (32 + 32 + 32) * e),
+            ('upBlock 32->32 @128^2->256^2 (4-phase)', lambda: fast.conv_bn_act(x32, gh.upscale8x[1], gh.upscale8x[2], ACT_GLU, up2x=True, out=o32uh),
+             2 * 16 * 32 * 64 * px, px * 32 * e + 4 * px * 32 * e),
+            ('image head 3x3 32->3 @256^2', lambda: fast.image_head(o32u, gl.img_net3.img),
+             2 * 9 * 32 * 3 * 4 * px, 4 * px * (32 * e + 12)),
+            ('image head 5x5 32->3 + tanh + 0.5*SRb @256^2', lambda: fast.image_head(o32uh, gh.conv_output, add, 0.5, 1.0),
+             2 * 25 * 32 * 3 * 4 * px, 4 * px * (32 * e + 12 + 12)),
+            ('bi-LSTM text encoder, 18 steps', lambda: self.text_encoder._forward_tmax(caps, lens, 18), 15.78e6 * B, None),
+        ]
+        out = []
+        for name, fn, flops, nbytes in rows:
+            ms = self._time_kernel(fn, flush, iters=iters)
+            tf = flops / (ms * 1e-3) / 1e12
+            row = {'kernel': name, 'ms': ms, 'tflops': tf, 'frac_tensor': tf / pk['bf16']}
+            if nbytes:
+                gbs = nbytes / (ms * 1e-3) / 1e9
+                row.update({'gbs': gbs, 'frac_hbm': gbs / pk['hbm']})
+            out.append(row)
+        return out
+
+    @torch.no_grad()
     def attention_roofline(self, B, flush, pk):
         """Fused word attention at the h_net3 shape (Q=128^2, idf 32, cdf 256, T 18), timed alone.
         Algorithmic bytes per SURVEY.md 8d: B*Q*(idf*e_in + idf*e_out + 4*T) + B*cdf*T*4 + idf*cdf*4 + B*T."""
@@ -277,7 +344,7 @@ class SRPipeline:
         cur = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
-        ent = self._graphs[((B, 3, size, size), (B, Tcap), int(tmax), self._precision())]
+        ent = self._graphs[self._graph_key((B, 3, size, size), (B, Tcap), tmax)]
         if packed is not None and packed.numel() == ent['blob'].numel():
             # One H2D for the whole batch, issued on its own stream into one of two staging blobs so that it crosses PCIe
             # while the previous batch still computes; the compute stream then moves it into the graph's inputs with a
@@ -313,6 +380,7 @@ class SRPipeline:
                 s.dev = torch.empty(sr.shape, device=self.device, dtype=dt)
                 s.host = torch.empty(sr.shape, dtype=dt, pin_memory=True)
                 s.done = torch.cuda.Event(); s.copied = torch.cuda.Event()
+                s.flag_host = torch.zeros(1, dtype=torch.int32, pin_memory=True) if self._precision() != 'fp32' else None
                 s.copied.record(cur)
                 slots.append(s)
             self._slots[key] = slots
@@ -328,14 +396,23 @@ class SRPipeline:
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(s.done)
             s.host.copy_(s.dev, non_blocking=True)
+            if s.flag_host is not None:
+                from . import fast
+                s.flag_host.copy_(fast.nonfinite_flag(self.device), non_blocking=True)
             s.copied.record(self._copy_stream)
         self._tickets[self._ticket] = s
         return self._ticket
 
     def result(self, ticket: int) -> torch.Tensor:
-        """Block until the batch of `ticket` is in host memory; the buffer is reused two submits later."""
+        """Block until the batch of `ticket` is in host memory; the buffer is reused two submits later.  Raises
+        FloatingPointError when the 16-bit forward of that batch overflowed (inf / NaN reached an image head)."""
         s = self._tickets.pop(ticket)
         s.copied.synchronize()
+        if s.flag_host is not None and int(s.flag_host[0]) != 0:
+            from . import fast
+            fast.nonfinite_flag(self.device).zero_()
+            raise FloatingPointError('tgsr_b200: inf/NaN in the 16-bit forward (an activation exceeded the fp16 / bf16 range); '
+                                     'use set_precision("fp32") or "bf16" for this checkpoint')
         return s.host
 
     @torch.no_grad()
@@ -368,7 +445,7 @@ class SRPipeline:
 
 
 class _Slot:
-    __slots__ = ('dev', 'host', 'done', 'copied')
+    __slots__ = ('dev', 'host', 'done', 'copied', 'flag_host')
 
 
 def _ncu_traffic(key: str):

@@ -120,6 +120,8 @@ class BnActFn(torch.autograd.Function):
         ws = torch.empty(2 * Cc, device=x.device, dtype=torch.float64)
         call('tgsr_bn_stats_f32', x.device, ptr(x), ptr(mean), ptr(invstd), ptr(bn.running_mean if track else None),
              ptr(bn.running_var if track else None), mom, float(bn.eps), ptr(ws), B, Cc, H * W)
+        if track:
+            _lib.bump_weights_epoch()          # running stats were written through raw pointers: folded-BN caches are stale
         if track and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
         Cf = Cc // 2 if act == ACT_GLU else Cc

@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import losses
-from ._lib import call, ptr
+from ._lib import bump_weights_epoch, call, ptr
 
 
 class FlatBucket:
@@ -62,33 +62,33 @@ class FlatBucket:
 
 
 class FusedAdam:
-    """torch.optim.Adam semantics on a FlatBucket, one kernel per step (csrc/optim.cu)."""
+    """torch.optim.Adam semantics on a FlatBucket, one kernel per step (csrc/optim.cu).
+
+    The step count lives on the device (`step_t`, one int32) as the single source of truth, so eager steps, captured
+    steps and CUDA-graph replays can be mixed: the bias corrections are computed in-kernel from it.  `t` mirrors it on
+    the host for reporting only (replays advance it through `note_replay`)."""
 
     def __init__(self, bucket: FlatBucket, lr: float = 2e-4, betas=(0.5, 0.999), eps: float = 1e-8):
         self.b, self.lr, self.betas, self.eps, self.t = bucket, lr, betas, eps, 0
         self.m = torch.zeros_like(bucket.flat); self.v = torch.zeros_like(bucket.flat)
-        self.step_t = None
+        self.step_t = torch.zeros(1, device=bucket.flat.device, dtype=torch.int32)
 
     def step(self, grad_scale: float = 1.0) -> None:
-        self.t += 1
-        bc1 = 1.0 - self.betas[0] ** self.t
-        bc2 = math.sqrt(1.0 - self.betas[1] ** self.t)
+        """One update; safe both eagerly and inside a CUDA-graph capture (no host-side constant changes between steps)."""
         b = self.b
-        if self.step_t is not None:
-            self.step_t.fill_(self.t)
-        call('tgsr_adam_f32', b.flat.device, ptr(b.flat), ptr(b.grad), ptr(self.m), ptr(self.v), C.c_size_t(b.numel), self.lr,
-             self.betas[0], self.betas[1], self.eps, bc1, bc2, float(grad_scale))
-
-    def step_capturable(self, grad_scale: float = 1.0) -> None:
-        """Same update with the step count kept on the device (no host-side constants change between steps), for a
-        training step captured in a CUDA graph."""
-        b = self.b
-        if self.step_t is None:
-            self.step_t = torch.full((1,), self.t, device=b.flat.device, dtype=torch.int32)
         self.step_t += 1
-        self.t += 1
+        if not torch.cuda.is_current_stream_capturing():
+            self.t += 1
         call('tgsr_adam_devstep_f32', b.flat.device, ptr(b.flat), ptr(b.grad), ptr(self.m), ptr(self.v), C.c_size_t(b.numel), self.lr,
              self.betas[0], self.betas[1], self.eps, ptr(self.step_t), float(grad_scale))
+        bump_weights_epoch()                   # parameters were written through raw pointers: packed / folded caches are stale
+
+    step_capturable = step
+
+    def note_replay(self) -> None:
+        """A captured step was replayed: the device counter advanced by itself; keep the host mirror and the caches in step."""
+        self.t += 1
+        bump_weights_epoch()
 
 
 class FrozenImageEncoder(nn.Module):
@@ -139,9 +139,22 @@ class GeneratorTrainStep:
         self.opt = FusedAdam(self.bucket, lr, betas)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1:
+            self.sync_replicas()
         self.ev = None
         self._lab = None
         self._graph = None
+
+    def sync_replicas(self) -> None:
+        """Rank 0's parameters and BatchNorm buffers become every rank's (what DDP does at construction).  BatchNorm
+        running statistics are per-replica during training, as in plain DDP; call this again before evaluating or
+        checkpointing from a rank other than 0."""
+        dist.broadcast(self.bucket.flat, 0, group=self.group)
+        for net in (self.netGL, self.netGH):
+            for buf in net.buffers():
+                if buf.is_floating_point() or buf.dtype == torch.int64:
+                    dist.broadcast(buf, 0, group=self.group)
+        bump_weights_epoch()
 
     def _fwd_bwd(self, LR, real, captions, cap_lens, tmax: int):
         """Zero the flat gradient, forward (train-mode BN), losses, backward: everything before the exchange step."""
@@ -168,10 +181,7 @@ class GeneratorTrainStep:
             e.record(); self.ev = (s, e)
 
     def _update(self, capturable: bool) -> None:
-        if capturable:
-            self.opt.step_capturable(1.0 / self.world)
-        else:
-            self.opt.step(1.0 / self.world)
+        self.opt.step(1.0 / self.world)
 
     def _step_impl(self, LR, real, captions, cap_lens, tmax: int, capturable: bool, time_allreduce: bool = False):
         out = self._fwd_bwd(LR, real, captions, cap_lens, tmax)
@@ -226,7 +236,10 @@ class GeneratorTrainStep:
 
     # ------------------------------------------------------------------ whole-step CUDA graph
     def _capture_graphs(self, body_inputs, tmax: int, warmup: int):
-        """Capture one step.  On one GPU the whole step is ONE graph; with N > 1 ranks the NCCL all-reduce stays outside:
+        """Capture one step.  NOTE: the `warmup` eager steps that precede the capture (they size every workspace and warm the
+        allocator) are REAL optimiser steps on the static batch: parameters, Adam moments and BatchNorm running statistics
+        advance by `warmup` steps (the step counter counts them).
+        On one GPU the whole step is ONE graph; with N > 1 ranks the NCCL all-reduce stays outside:
         graph A = zero-grad + forward + losses + backward, the eager all-reduce of the flat bucket, graph B = fused Adam
         (capturing the collective itself hung the ranks in round 1, so it is not attempted)."""
         cur = torch.cuda.current_stream()
@@ -261,6 +274,7 @@ class GeneratorTrainStep:
         if g_b is not None:
             self._exchange(time_allreduce)
             g_b.replay()
+        self.opt.note_replay()
 
     def capture(self, LR, real, captions, cap_lens, tmax: int, warmup: int = 3) -> None:
         """Capture forward + losses + backward (+ Adam) of one step into CUDA graphs (static shapes).  The ~1400 launches
