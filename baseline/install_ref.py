@@ -3,7 +3,8 @@
     python baseline/install_ref.py [--src /root/reference]
 
 The reference is plain Python without packaging (`pip install /root/reference` has nothing to build), so the install is
-a byte-for-byte copy of the six modules the hot path lives in plus the package marker, with a sha256 manifest.
+a byte-for-byte copy of the six modules the hot path lives in, the package marker and the eval driver
+(trainer_objective.py with its datasets.py / miscc/utils.py helpers), with a sha256 manifest.
 baseline/_ref/ is git-ignored (never in history) but travels to the GPU box with the snapshot, where
 `bench.py --impl reference` and the `cpu_baseline` leg import it through baseline/ref_arm.py.  Nothing of the product
 (tgsr_b200/) reads it.
@@ -16,7 +17,10 @@ import shutil
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DST = os.path.join(HERE, '_ref')
-FILES = ['GlobalAttention.py', 'util.py', 'model.py', 'models16.py', 'miscc/__init__.py', 'miscc/config.py', 'miscc/losses.py']
+FILES = ['GlobalAttention.py', 'util.py', 'model.py', 'models16.py', 'miscc/__init__.py', 'miscc/config.py', 'miscc/losses.py',
+         # the eval driver and its helpers: tests/test_gpu_reference_driver.py runs the UNMODIFIED condGANTrainer.gen_exampleSRHL
+         # against tgsr_b200/compat
+         'trainer_objective.py', 'datasets.py', 'miscc/utils.py']
 
 
 def install(src: str = '/root/reference', quiet: bool = False) -> bool:

@@ -250,6 +250,67 @@ def gen_x16_gf32(ns):
                os.path.join(OUT, 'x16_gf32.pt'))
 
 
+def gen_attn_stats(ns):
+    """Pins ops.attention_word_stats / the oracle's restatement by EXECUTING the unmodified miscc/utils.py: build_super_images
+    (the per-pixel max over words it prepends, :122-131) and build_super_imagesall (the thresholded confidence sums,
+    :378-392).  Both keep those values in locals, so the module's `np` is wrapped for the duration of the calls to record the
+    operands of `np.transpose` (the [max-map, word maps] stack) and the results of `np.sum` (conf_score); skimage (absent) is
+    an import shim and the hard-coded Windows font falls back to PIL's default -- neither touches the recorded arithmetic."""
+    import numpy as np
+    shims = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', 'shims')
+    if shims not in sys.path:
+        sys.path.insert(0, shims)
+    from PIL import ImageFont
+    truetype = ImageFont.truetype
+    default_font = ImageFont.load_default()
+    ImageFont.truetype = lambda *a, **k: default_font
+    from miscc import utils as U
+
+    class NpProxy(object):
+        def __init__(self):
+            self.sums, self.transposed = [], []
+
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+        def sum(self, a, *args, **kw):
+            r = np.sum(a, *args, **kw)
+            self.sums.append(float(r))
+            return r
+
+        def transpose(self, a, *args, **kw):
+            self.transposed.append(np.array(a, copy=True))
+            return np.transpose(a, *args, **kw)
+
+    g = torch.Generator().manual_seed(1404)
+    B, T, s = 2, 18, 32
+    attn = torch.softmax(torch.randn(B, T, s, s, generator=g) * 2.0, dim=1)
+    attn[0, :, 0, 0] = 1.0 / T                                     # an exact tie
+    lens = [18, 13]
+    caps = torch.zeros(B, T, dtype=torch.int64)
+    for b in range(B):
+        caps[b, :lens[b]] = torch.randint(1, 40, (lens[b],), generator=g)
+    imgs = torch.rand(B, 3, 256, 256, generator=g) * 2 - 1
+    ixtoword = {i: 'w%d' % i for i in range(64)}
+    proxy = NpProxy()
+    U.np = proxy
+    try:
+        U.build_super_images(imgs.clone(), caps, ixtoword, [attn[b:b + 1] for b in range(B)], s, batch_size=B, max_word_num=T)
+        stacks = [a for a in proxy.transposed if a.ndim == 4 and a.shape[1] == 3 and a.shape[0] == T + 1]
+        assert len(stacks) == B
+        max_maps = torch.from_numpy(np.stack([a[0, 0] for a in stacks]))          # [B, s, s]
+        conf = []
+        for b in range(B):
+            proxy.sums = []
+            U.build_super_imagesall(imgs[b:b + 1].clone(), caps[b:b + 1], [lens[b]], ixtoword, [attn[b, :lens[b]]], s)
+            conf.append(torch.tensor(proxy.sums[:lens[b]], dtype=torch.float64))
+            assert len(proxy.sums) >= lens[b]
+    finally:
+        U.np = np
+        ImageFont.truetype = truetype
+    torch.save(dict(attn=attn, lens=lens, max_maps=max_maps, conf=conf), os.path.join(OUT, 'attn_stats.pt'))
+
+
 def gen_losses(ns):
     """words_loss / sent_loss / MSE of the UNMODIFIED miscc/losses.py (gamma 4/5/10, cfg/DAMSM/bird.yml:23-25) with
     autograd gradients to the image side: the pin for tgsr_b200/losses.py and the oracle's restatement."""
@@ -391,6 +452,10 @@ def main():
         gen_pyramid(ns)
         print('pyramid.npz', os.path.getsize(os.path.join(OUT, 'pyramid.npz')))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'attn_stats':
+        gen_attn_stats(ns)
+        print('attn_stats.pt', os.path.getsize(os.path.join(OUT, 'attn_stats.pt')))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'x16':
         gen_x16_gf32(ns)
         print('x16_gf32.pt', os.path.getsize(os.path.join(OUT, 'x16_gf32.pt')))
@@ -410,6 +475,7 @@ def main():
     gen_face_x8(ns)
     gen_x16(ns)
     gen_x16_gf32(ns)
+    gen_attn_stats(ns)
     gen_losses(ns)
     gen_train(ns)
     gen_pyramid(ns)

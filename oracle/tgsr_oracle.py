@@ -381,8 +381,8 @@ def attention_word_stats(attn, thresh=0.0):
     """Word-axis reductions of attention maps [B,T,ih,iw] as the reference's visualisation computes them on the host:
     miscc/utils.py:122-125 `attn.max(dim=1, keepdim=True)` (values, indices) and :389-392
     `conf_score[j] = np.sum(one_map * (one_map > 2*thresh))` over the 3-channel replica of [max-map, word maps...].
-    (miscc/utils.py imports skimage, absent from the image, so this restatement is not pinned by executing the reference;
-    it is three numpy/torch calls.)"""
+    Pinned by executing the unmodified miscc/utils.py behind a skimage import shim: tests/golden/attn_stats.pt
+    (oracle/make_golden.py gen_attn_stats records the max-map stack and the conf_score values of the reference's own calls)."""
     import numpy as np
     mx, am = attn.max(dim=1, keepdim=True)
     maps = torch.cat([mx, attn], 1)                                   # utils.py:125

@@ -284,9 +284,10 @@ def test_fp16_range_netg_high(golden):
     assert peak < 65504 / 128
     assert all(torch.isfinite(i).all() for i in ims) and not fast.nonfinite_seen(DEV)
     # scaled gains: 1e3 per BatchNorm compounds past the fp16 range within two layers
-    for m in gh.modules():
-        if isinstance(m, torch.nn.BatchNorm2d):
-            m.weight.data.mul_(1e3)
+    with torch.no_grad():
+        for m in gh.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.mul_(1e3)
     ims2 = gh(LR, SRb, LR, low=True)
     torch.cuda.synchronize()
     assert fast.nonfinite_seen(DEV), 'fp16 overflow went unnoticed'
@@ -298,7 +299,8 @@ def test_pipeline_result_raises_on_overflow():
     pipe = SRPipeline(50, device=DEV, seed=3, randomize_bn=True)
     for m in pipe.netGH.modules():
         if isinstance(m, torch.nn.BatchNorm2d):
-            m.weight.data.mul_(1e3)
+            m.weight.data.mul_(1e3)          # a write through .data bumps no version counter ...
+    tgsr_b200.invalidate_caches()            # ... so the derived-parameter caches are told explicitly
     LR = O.synth_lr(2, 32, seed=7).pin_memory()
     caps, lens = O.synth_captions(2, 50, seed=8, words_num=18)
     t = pipe.submit(LR, caps.pin_memory(), lens.pin_memory(), out='fp32')

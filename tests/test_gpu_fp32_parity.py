@@ -285,6 +285,19 @@ def test_attention_all_masked_caption_is_nan_like_torch():
         tgsr_b200.set_precision('fp32')
 
 
+def test_attention_word_stats_pinned(golden):
+    """The kernel against values recorded from the unmodified miscc/utils.py (tests/golden/attn_stats.pt)."""
+    from tgsr_b200 import ops
+    g = golden('attn_stats.pt')
+    attn = g['attn']
+    gmx, gam, _ = ops.attention_word_stats(attn.cuda(), 0.0)
+    assert torch.equal(gmx.cpu()[:, 0], g['max_maps'])
+    assert torch.equal(gam.cpu()[:, 0], attn.argmax(1))
+    for b, n in enumerate(g['lens']):
+        _, _, conf = ops.attention_word_stats(attn[b:b + 1, :n].contiguous().cuda(), 2.0 / n)
+        torch.testing.assert_close(conf.cpu()[0, 1:], g['conf'][b], rtol=1e-6, atol=1e-9)
+
+
 def test_attention_word_stats():
     """Per-pixel max / arg-max over words and thresholded confidence sums (miscc/utils.py:122-125, 389-392) against the oracle."""
     from tgsr_b200 import ops

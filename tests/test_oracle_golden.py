@@ -140,6 +140,19 @@ def test_x16_production_width(golden):
         close(finew[k][:, :, ::sub, ::sub], g['finew'][k], rtol=1e-4, atol=5e-5)
 
 
+def test_attention_word_stats_pinned(golden):
+    """attention_word_stats against values recorded while the UNMODIFIED miscc/utils.py ran (build_super_images :122-131 for
+    the max over words, build_super_imagesall :378-392 for the confidence sums)."""
+    g = golden('attn_stats.pt')
+    attn = g['attn']
+    mx, am, _ = O.attention_word_stats(attn, 0.0)
+    assert torch.equal(mx[:, 0], g['max_maps'])
+    assert torch.equal(am[:, 0], attn.argmax(1))
+    for b, n in enumerate(g['lens']):
+        _, _, conf = O.attention_word_stats(attn[b:b + 1, :n], 2.0 / n)          # thresh = 2 / num_attn, mask0 = map > 2 * thresh
+        close(conf[0, 1:], g['conf'][b], rtol=1e-12, atol=0)
+
+
 def test_psnr_and_quantisation():
     x = torch.tensor([[-1.0, 0.0, 1.0, 1.2]])
     assert O.to_uint8(x).tolist() == [[0, 128, 255, 255]]       # round-half-even of 127.5 -> 128

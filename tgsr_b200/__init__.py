@@ -23,6 +23,15 @@ def set_precision(mode: str) -> None:
     _PRECISION = mode
 
 
+def invalidate_caches() -> None:
+    """Drop every derived-parameter cache (folded BatchNorm, packed 16-bit operands, LSTM tables, captured eval graphs).
+    The caches follow `tensor._version`, `load_state_dict`, the library's own optimiser and BatchNorm updates; writes that
+    bypass the version counter -- `param.data.copy_(...)` / `.data.mul_(...)` as in the reference's `load_params`
+    (miscc/utils.py:462-464), or raw-pointer writes from other libraries -- need this call before the next eval forward."""
+    from ._lib import bump_weights_epoch
+    bump_weights_epoch()
+
+
 def get_precision() -> str:
     return _PRECISION
 

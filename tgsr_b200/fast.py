@@ -91,6 +91,9 @@ _NONFINITE = {}
 def nonfinite_flag(device) -> Tensor:
     """Per-device int32 flag the image-head kernels OR a 1 into when a pre-activation sum is inf / NaN, i.e. when a 16-bit
     activation overflowed somewhere upstream (fp16 saturates at 65504).  Read it with `nonfinite_seen`."""
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device(device.type, torch.cuda.current_device())
     key = str(device)
     t = _NONFINITE.get(key)
     if t is None:

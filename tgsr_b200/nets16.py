@@ -56,7 +56,7 @@ def _cached_float(mod, t, name) -> float:
     key = tensor_key(t)
     c = mod.__dict__.get(name)
     if c is None or c[0] != key:
-        c = (key, float(t))
+        c = (key, float(t.detach()))
         mod.__dict__[name] = c
     return c[1]
 
