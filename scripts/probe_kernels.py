@@ -48,6 +48,23 @@ def main():
         out = tc.Blocked.empty(B, 32, 2 * S, 2 * S, dev)
         fn = lambda: fast.conv_bn_act(x, st.upsample[1], st.upsample[2], ACT_GLU, up2x=True, out=out)
         flops = 2 * 9 * 64 * 64 * 4 * S * S * B          # reference FLOPs (executed: 4/9 of it)
+    elif a.what in ('body32', 'res32', 'up32'):      # NetG_high layers (fp16 operands) at 128x128
+        gh = pipe.netGH
+        hb = gh.residual48
+        x = tc.to_blocked(torch.randn(B, 32, S, S, device=dev) * 0.5, fmt=1)
+        r = tc.to_blocked(torch.randn(B, 32, S, S, device=dev) * 0.5, fmt=1)
+        if a.what == 'body32':
+            out = tc.Blocked.empty(B, 32, S, S, dev, fmt=1)
+            fn = lambda: fast.conv_bn_act(x, hb[0], hb[1], ACT_GLU, out=out)
+            flops = 2 * 9 * 32 * 64 * S * S * B
+        elif a.what == 'res32':
+            out = tc.Blocked.empty(B, 32, S, S, dev, fmt=1)
+            fn = lambda: fast.conv_bn_act(x, hb[3], hb[4], ACT_NONE, residual=r, out=out)
+            flops = 2 * 9 * 32 * 32 * S * S * B
+        else:
+            out = tc.Blocked.empty(B, 32, 2 * S, 2 * S, dev, fmt=1)
+            fn = lambda: fast.conv_bn_act(x, gh.upscale8x[1], gh.upscale8x[2], ACT_GLU, up2x=True, out=out)
+            flops = 2 * 9 * 32 * 64 * 4 * S * S * B
     elif a.what in ('head5', 'head3'):
         x = tc.to_blocked(torch.randn(B, 32, 2 * S, 2 * S, device=dev) * 0.5, fmt=1)
         seq = pipe.netGH.conv_output if a.what == 'head5' else pipe.netGL.img_net3.img

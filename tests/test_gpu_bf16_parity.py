@@ -29,7 +29,8 @@ def _cfg():
 
 @pytest.mark.parametrize('k,tanh,with_add,B,H,W', [(3, False, False, 2, 32, 32), (3, True, False, 1, 16, 8),
                                                     (5, True, True, 2, 32, 16), (5, False, True, 1, 64, 64),
-                                                    (5, True, True, 3, 128, 128)])
+                                                    (5, True, True, 3, 128, 128), (3, False, False, 2, 40, 136),
+                                                    (5, True, True, 1, 200, 144), (3, True, True, 2, 72, 120)])
 def test_image_head_tc(k, tanh, with_add, B, H, W):
     from tgsr_b200 import fast, tc
     g = torch.Generator().manual_seed(k * 100 + H)

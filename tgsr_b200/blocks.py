@@ -245,7 +245,7 @@ def _run_stage_bf16(stage, h_code, LR, word_embs, mask):
     if h_code is not None:
         B, C, H, W = h_code.shape
         hb = tc.to_blocked(h_code, out=tc.Blocked.empty(B, C, H, W, h_code.device, planes=2 * C // 8, fmt=_fmt()))
-    out, att = fast.stage(stage, hb, LR, word_embs, mask, None, _fmt())
+    out, att, _ = fast.stage(stage, hb, LR, word_embs, mask, None, _fmt())
     return tc.to_nchw(out), att
 
 

@@ -29,6 +29,7 @@
 #include "ptx_sm100.cuh"
 #include "fmt16.cuh"
 #include <cstdlib>
+#include <type_traits>
 
 namespace tgsr {
 
@@ -41,6 +42,8 @@ constexpr int MODE_CONV = 0;    // conv3x3 (+BN, +GLU, +residual) -> blocked bf1
 constexpr int MODE_UP = 1;      // nearest-x2 + conv3x3 + BN + GLU as four sub-pixel phases -> blocked bf16 at 2H x 2W
 constexpr int MODE_HEAD3 = 2;   // conv3x3 32->3 image head -> fp32 NCHW (+tanh, one*y + a*addend)
 constexpr int MODE_HEAD5 = 3;   // conv5x5 32->3 image head -> fp32 NCHW (+tanh, one*y + a*addend)
+constexpr int MODE_HEAD3W = 4;  // the same heads on 32-pixel-wide patches (images >= 128 wide): half the TMA rows per output
+constexpr int MODE_HEAD5W = 5;
 constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -68,6 +71,8 @@ template <> struct OpTable<MODE_HEAD5> {
   static constexpr int NOPS = 5;
   __host__ __device__ static constexpr TcOp op(int i) { return TcOp{i, 0, 1, 0}; }
 };
+template <> struct OpTable<MODE_HEAD3W> : OpTable<MODE_HEAD3> {};
+template <> struct OpTable<MODE_HEAD5W> : OpTable<MODE_HEAD5> {};
 // 4-phase nearest-x2 + conv3x3: low-res tap (r,c) in {0,1,2}^2 (offset -1..+1) feeds the output
 // parities ph = py*2+px listed below (see pack kernel for the pre-summed weights).
 template <> struct OpTable<MODE_UP> {
@@ -85,18 +90,23 @@ template <> struct OpTable<MODE_UP> {
 template <int CIN, int NPRE, int MODE, bool GLU>
 struct TcCfg {
   static constexpr bool UP = MODE == MODE_UP;
-  static constexpr bool HEAD = MODE == MODE_HEAD3 || MODE == MODE_HEAD5;
-  static constexpr int R = MODE == MODE_HEAD5 ? 2 : 1;         // halo radius
+  static constexpr bool HEAD = MODE >= MODE_HEAD3;
+  static constexpr bool WIDE = MODE == MODE_HEAD3W || MODE == MODE_HEAD5W;
+  static constexpr int R = (MODE == MODE_HEAD5 || MODE == MODE_HEAD5W) ? 2 : 1;         // halo radius
   static constexpr int KS = 2 * R + 1;                         // filter size
   // Conv/up tiles: 16 rows x 8 cols; accumulator row m = (y, x), 8-row groups are PW*16 B apart.
-  // Head tiles: the patch is 16 pixels wide and M walks it LINEARLY (m = y*16 + x', 8 rows of 16, 8-row groups
-  // 128 B apart).  Columns x' < TWO = 16-2R are outputs, the rest is halo, so every output's kx neighbours
-  // (x'+kx <= 15) sit in the same patch row = the same warp (a warp owns 2 rows): the epilogue combines the
-  // kx-folded partial sums with warp shuffles, no shared-memory exchange.
-  static constexpr int PW = HEAD ? 16 : TC_TW + 2 * R;
-  static constexpr int TWO = HEAD ? 16 - 2 * R : TC_TW;        // output columns per tile (12 / 14 for 5x5 / 3x3 heads)
-  static constexpr int MB = HEAD ? 4 : 1;                      // M=128 blocks per tile (heads: 4 x (8 rows x 16 px))
-  static constexpr int TH = HEAD ? 8 * MB : TC_TH;             // output rows per tile
+  // Head tiles: the patch is HPW = 16 (or 32) pixels wide and M walks it LINEARLY (m = y*HPW + x', 8-pixel groups
+  // 128 B apart).  Columns x' < TWO = HPW-2R are outputs, the rest is halo, so every output's kx neighbours
+  // (x'+kx < HPW) sit in the same patch row = the same warp (a warp owns 2 rows of 16 or 1 row of 32): the epilogue
+  // combines the kx-folded partial sums with warp shuffles, no shared-memory exchange.  The TMA engine spends ~10
+  // cycles per box ROW whatever its length, and a head is bound by exactly that (136 rows per tile): the 32-wide
+  // variant brings 2.1x the outputs per row and is used whenever the image is at least 128 wide.
+  static constexpr int HPW = WIDE ? 32 : 16;
+  static constexpr int PW = HEAD ? HPW : TC_TW + 2 * R;
+  static constexpr int TWO = HEAD ? HPW - 2 * R : TC_TW;       // output columns per tile
+  static constexpr int RB = HEAD ? 128 / HPW : TC_TH;          // patch rows per M=128 block (heads: 8 or 4)
+  static constexpr int MB = HEAD ? 32 / RB : 1;                // M=128 blocks per tile (heads: 32 output rows)
+  static constexpr int TH = HEAD ? RB * MB : TC_TH;            // output rows per tile
   static constexpr int PH = TH + 2 * R;
   static constexpr int SBO_A = HEAD ? 128 : PW * 16;
   static constexpr int PLANE_BYTES = PH * PW * 16;             // one 8-channel plane of the halo patch
@@ -323,6 +333,45 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     const uint32_t w_addr = smem_u32(w_s);
+    // One tile's MMAs.  Descriptors are "per-tile base + compile-time constant": only the 14-bit start-address field of
+    // the low word changes between MMAs.  FIRST (the CTA's first tile) also waits for the weight blocks, which land in
+    // issue order; it is a separate instantiation so that the steady-state sequence is ONE basic block (with the waits
+    // inline every op re-materialised its operands through R2UR and the issue thread spent ~58 cycles per MMA).
+    auto issue_tile = [&](auto first_c, const uint32_t a_lo0, const uint32_t d_base) {
+      constexpr bool FIRST = decltype(first_c)::value;
+      constexpr uint32_t a_hi = (uint32_t)(Cfg::SBO_A >> 4) | (1u << 14);
+      constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
+      const uint32_t b_lo0 = w_addr >> 4;
+      if constexpr (Cfg::BIAS) {
+        // accumulators start at the folded-BN shift: ones[128 x 16] (8-row groups 128 B apart, K chunks 2 KB apart)
+        // times the shift block [NBIAS x 16]
+        constexpr int NB = Cfg::NBIAS;
+        if constexpr (FIRST) { mbar_wait(&wbar[Ops::NOPS], 0); tc_fence_after(); }
+        const uint32_t one_lo = b_lo0 + (uint32_t)((Cfg::WBYTES_TAPS + Cfg::BIAS_BYTES) >> 4) + ((uint32_t)(2048 >> 4) << 16);
+        const uint32_t bias_lo = b_lo0 + (uint32_t)(Cfg::WBYTES_TAPS >> 4) + ((uint32_t)((NB * 16) >> 4) << 16);
+        umma_f16(d_base, make_desc64(one_lo, b_hi), make_desc64(bias_lo, b_hi),
+                 make_idesc_f16(128, NB, Fmt16<FMT>::kUmmaFormat), 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < Cfg::MB; ++j) {         // heads: MB M-blocks of RB patch rows each per tile
+        uint32_t b_off = 0;                       // compile-time after unrolling
+#pragma unroll
+        for (int o = 0; o < Ops::NOPS; ++o) {
+          const TcOp op = Ops::op(o);
+          const int N = op.n_mul * NPRE;
+          const uint32_t idesc = make_idesc_f16(128, N, Fmt16<FMT>::kUmmaFormat);
+          if constexpr (FIRST) { if (j == 0) { mbar_wait(&wbar[o], 0); tc_fence_after(); } }
+#pragma unroll
+          for (int k = 0; k < Cfg::KSTEPS; ++k) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)((((j * Cfg::RB + op.tap_r) * TC_PW + op.tap_c) * 16 + k * 2 * TC_PLANE_BYTES) >> 4);
+            const uint32_t b_lo = b_lo0 + (uint32_t)((b_off + k * (N * 32)) >> 4) + ((uint32_t)((N * 16) >> 4) << 16);
+            umma_f16(d_base + op.dcol_mul * NPRE + j * 32, make_desc64(a_lo, a_hi), make_desc64(b_lo, b_hi), idesc,
+                     (Cfg::BIAS || (o | k) != 0) ? 1u : 0u);
+          }
+          b_off += CIN * N * 2;
+        }
+      }
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1;
@@ -330,44 +379,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       mbar_wait(&tempty[acc], aph ^ 1);            // epilogue has drained this accumulator stage
       mbar_wait(&full[s], ph);                     // patch landed
       tc_fence_after();
-      const bool first = it == 0;                  // weight blocks land in issue order; later tiles find them resident
       if (elect_one()) {
-        // Descriptors are "per-tile base + compile-time constant": only the 14-bit start-address field of
-        // the low word changes between MMAs, so each one costs a single 32-bit add on the issuing thread.
         const uint32_t a_lo0 = (smem_u32(patch_s + s * Cfg::PATCH_BYTES) >> 4) | ((uint32_t)(TC_PLANE_BYTES >> 4) << 16);
-        constexpr uint32_t a_hi = (uint32_t)(Cfg::SBO_A >> 4) | (1u << 14);
-        constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
-        const uint32_t b_lo0 = w_addr >> 4;
         const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
-        if constexpr (Cfg::BIAS) {
-          // accumulators start at the folded-BN shift: ones[128 x 16] (8-row groups 128 B apart, K chunks 2 KB apart)
-          // times the shift block [NBIAS x 16]
-          constexpr int NB = Cfg::NBIAS;
-          if (first) { mbar_wait(&wbar[Ops::NOPS], 0); tc_fence_after(); }
-          const uint32_t one_lo = b_lo0 + (uint32_t)((Cfg::WBYTES_TAPS + Cfg::BIAS_BYTES) >> 4) + ((uint32_t)(2048 >> 4) << 16);
-          const uint32_t bias_lo = b_lo0 + (uint32_t)(Cfg::WBYTES_TAPS >> 4) + ((uint32_t)((NB * 16) >> 4) << 16);
-          umma_f16(d_base, make_desc64(one_lo, b_hi), make_desc64(bias_lo, b_hi),
-                   make_idesc_f16(128, NB, Fmt16<FMT>::kUmmaFormat), 0u);
-        }
-#pragma unroll
-        for (int j = 0; j < Cfg::MB; ++j) {         // heads: 4 M-blocks of 8 patch rows each per tile
-          uint32_t b_off = 0;                       // compile-time after unrolling
-#pragma unroll
-          for (int o = 0; o < Ops::NOPS; ++o) {
-            const TcOp op = Ops::op(o);
-            const int N = op.n_mul * NPRE;
-            const uint32_t idesc = make_idesc_f16(128, N, Fmt16<FMT>::kUmmaFormat);
-            if (first && j == 0) { mbar_wait(&wbar[o], 0); tc_fence_after(); }
-#pragma unroll
-            for (int k = 0; k < Cfg::KSTEPS; ++k) {
-              const uint32_t a_lo = a_lo0 + (uint32_t)((((j * 8 + op.tap_r) * TC_PW + op.tap_c) * 16 + k * 2 * TC_PLANE_BYTES) >> 4);
-              const uint32_t b_lo = b_lo0 + (uint32_t)((b_off + k * (N * 32)) >> 4) + ((uint32_t)((N * 16) >> 4) << 16);
-              umma_f16(d_base + op.dcol_mul * NPRE + j * 32, make_desc64(a_lo, a_hi), make_desc64(b_lo, b_hi), idesc,
-                       (Cfg::BIAS || (o | k) != 0) ? 1u : 0u);
-            }
-            b_off += CIN * N * 2;
-          }
-        }
+        if (it == 0) issue_tile(std::true_type{}, a_lo0, d_base);
+        else issue_tile(std::false_type{}, a_lo0, d_base);
         umma_commit(&empty[s]);                      // patch slot reusable once these MMAs retire
         umma_commit(&tfull[acc]);                    // accumulator ready for the epilogue
       }
@@ -383,7 +399,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const int half = (warp - 2) >> 2;                // 0: warps 2..5, 1: warps 6..9
     const int m = quad * 32 + lane;                  // accumulator row = pixel within the tile
     const int ty = m >> 3, tx = m & 7;
-    float adnext[2][3];                              // image-head addend of the next tile
+    float adnext[Cfg::MB > 1 ? Cfg::MB / 2 : 1][3];  // image-head addend of the next tile
     TileIter t; t.init(blockIdx.x, p);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it, t.next(p)) {
@@ -393,27 +409,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + ((uint32_t)(quad * 32) << 16);
 
       if constexpr (HEAD) {
-        // Image head.  A tile is MB=4 accumulator blocks (columns j*32..) of 8 patch rows each; accumulator row
-        // m = (y, x') = (m/16, m%16) of the 16-wide patch; column o*K + kx holds the partial sum over (ky, c):
+        // Image head.  A tile is MB accumulator blocks (columns j*32..) of RB patch rows each; accumulator row
+        // m = (y, x') = (m / HPW, m % HPW) of the HPW-wide patch; column o*K + kx holds the partial sum over (ky, c):
         //   out[y][x'][o] = sum_kx P[(y, x'+kx)][o*K + kx]  -> lane shuffles by kx inside the warp.
-        // Warp group `half` produces blocks 2*half and 2*half+1.
+        // Warp group `half` produces blocks half*NQ .. half*NQ + NQ-1.
         constexpr int K = Cfg::KS;
-        const int hy = m >> 4, hx = m & 15;
+        constexpr int NQ = Cfg::MB / 2;
+        const int hy = m / Cfg::HPW, hx = m % Cfg::HPW;
         const int ox = t.tx * Cfg::TWO + hx;
         const size_t hw = (size_t)p.H * p.W;
-        bool valid[2]; size_t oi[2]; float ad[2][3];
+        bool valid[NQ]; size_t oi[NQ]; float ad[NQ][3];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int oy = t.ty * Cfg::TH + (half * 2 + q) * 8 + hy;
+        for (int q = 0; q < NQ; ++q) {
+          const int oy = t.ty * Cfg::TH + (half * NQ + q) * Cfg::RB + hy;
           valid[q] = hx < Cfg::TWO && ox < p.W && oy < p.H;
           oi[q] = (size_t)b * 3 * hw + (size_t)oy * p.W + ox;
         }
         // the addend (SRb, fp32) of this tile was requested one tile ago: no DRAM round trip in the per-tile critical path
-        auto load_addend = [&](const TileIter& tt, float (&dst)[2][3]) {
+        auto load_addend = [&](const TileIter& tt, float (&dst)[NQ][3]) {
           const int xx = tt.tx * Cfg::TWO + hx;
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int yy = tt.ty * Cfg::TH + (half * 2 + q) * 8 + hy;
+          for (int q = 0; q < NQ; ++q) {
+            const int yy = tt.ty * Cfg::TH + (half * NQ + q) * Cfg::RB + hy;
             const bool ok = hx < Cfg::TWO && xx < p.W && yy < p.H;
             const size_t o0 = (size_t)tt.b * 3 * hw + (size_t)yy * p.W + xx;
 #pragma unroll
@@ -423,25 +440,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         if (p.addend) {
           if (it == 0) load_addend(t, adnext);
 #pragma unroll
-          for (int q = 0; q < 2; ++q)
+          for (int q = 0; q < NQ; ++q)
 #pragma unroll
             for (int o = 0; o < 3; ++o) ad[q][o] = adnext[q][o];
           if (tile + (int)gridDim.x < p.ntiles) { TileIter tn = t; tn.next(p); load_addend(tn, adnext); }
         } else {
 #pragma unroll
-          for (int q = 0; q < 2; ++q) ad[q][0] = ad[q][1] = ad[q][2] = 0.f;
+          for (int q = 0; q < NQ; ++q) ad[q][0] = ad[q][1] = ad[q][2] = 0.f;
         }
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
-        uint32_t v[2][16];
-        tmem_ld16(t_base + (half * 2) * 32, v[0]);
-        tmem_ld16(t_base + (half * 2 + 1) * 32, v[1]);
+        uint32_t v[NQ][16];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) tmem_ld16(t_base + (half * NQ + q) * 32, v[q]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);               // TMEM stage is free again
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < NQ; ++q) {
           float z[3];
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
@@ -716,6 +733,8 @@ int init_conv_tc() {
   if ((s = set_tc_attr<32, 64, MODE_UP, true>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<32, 16, MODE_HEAD3, false>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<32, 16, MODE_HEAD5, false>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<32, 16, MODE_HEAD3W, false>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<32, 16, MODE_HEAD5W, false>()) != TGSR_OK) return s;
   return TGSR_OK;
 }
 
@@ -736,8 +755,8 @@ static int make_box_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int
 }
 
 static int make_patch_tmap(CUtensorMap* m, const void* x, int B, int P, int H, int W, int npl, int fmt, int R = 1,
-                           int head = 0) {
-  return make_box_tmap(m, x, B, P, H, W, npl, fmt, head ? 16 : TC_TW + 2 * R, (head ? 32 : TC_TH) + 2 * R);
+                           int head_pw = 0) {
+  return make_box_tmap(m, x, B, P, H, W, npl, fmt, head_pw ? head_pw : TC_TW + 2 * R, (head_pw ? 32 : TC_TH) + 2 * R);
 }
 
 template <int CIN, int NPRE, int MODE, bool GLU>
@@ -875,19 +894,24 @@ extern "C" int tgsr_img_head_tc(const void* x, int xP, int xp0, const void* wpac
   TGSR_REQUIRE(act == TGSR_ACT_NONE || act == TGSR_ACT_TANH, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(xp0 >= 0 && xp0 + Cin / 8 <= xP, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE((long long)B * xP < (1LL << 31), TGSR_ERR_UNSUPPORTED);
+  const int hpw = W >= 128 ? 32 : 16;                        // patch width: 32-pixel rows once the image is wide enough
   CUtensorMap tmap;
-  int s = make_patch_tmap(&tmap, x, B, xP, H, W, Cin / 8, fmt, ksize / 2, 1);
+  int s = make_patch_tmap(&tmap, x, B, xP, H, W, Cin / 8, fmt, ksize / 2, hpw);
   if (s != TGSR_OK) return s;
   TcParams p = {};
   p.wpacked = wpacked; p.out = nullptr; p.has_res = 0;
   p.rP = p.rp0 = p.yP = p.yp0 = 0; p.xP = xP; p.xp0 = xp0;
   p.B = B; p.H = H; p.W = W;
-  const int two = 16 - 2 * (ksize / 2);                      // output columns per head tile (32 rows x two cols)
+  const int two = hpw - 2 * (ksize / 2);                     // output columns per head tile (32 rows x two cols)
   p.tiles_x = (W + two - 1) / two; p.tiles_y = (H + 31) / 32; p.ntiles = B * p.tiles_x * p.tiles_y;
   p.out_f32 = y; p.addend = addend; p.out_scale = out_scale; p.addend_scale = addend_scale;
   p.act_tanh = act == TGSR_ACT_TANH;
   p.nonfinite = nonfinite_flag;
   cudaStream_t st = (cudaStream_t)stream;
+  if (hpw == 32) {
+    if (ksize == 3) return launch_tc<32, 16, MODE_HEAD3W, false>(tmap, tmap, p, fmt, st);
+    return launch_tc<32, 16, MODE_HEAD5W, false>(tmap, tmap, p, fmt, st);
+  }
   if (ksize == 3) return launch_tc<32, 16, MODE_HEAD3, false>(tmap, tmap, p, fmt, st);
   return launch_tc<32, 16, MODE_HEAD5, false>(tmap, tmap, p, fmt, st);
 }

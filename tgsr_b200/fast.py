@@ -62,13 +62,32 @@ def body_noskip(x: Blocked, seq) -> Blocked:
     return conv_bn_act(y, seq[3], seq[4], ACT_NONE)
 
 
-def up_block(x: Blocked, seq, out_planes: Optional[int] = None) -> Blocked:
+def up_block(x: Blocked, seq, out_planes: Optional[int] = None, out: Optional[Blocked] = None) -> Blocked:
     """upBlock (util.py:74-80) as the 4-phase sub-pixel kernel; the output may be allocated with
     extra planes so the next stage's attention can append c_code in place."""
     conv, bn = seq[1], seq[2]
     C = conv.weight.shape[0] // 2
-    out = Blocked.empty(x.B, C, 2 * x.H, 2 * x.W, x.device, planes=out_planes, fmt=x.fmt)
+    if out is None:
+        out = Blocked.empty(x.B, C, 2 * x.H, 2 * x.W, x.device, planes=out_planes, fmt=x.fmt)
     return conv_bn_act(x, conv, bn, ACT_GLU, up2x=True, out=out, reverse=True)
+
+
+import os as _os
+# 0 = off (default).  Measured on B200 (profiles/r2_experiments.md): with 2 / 4 chunks of the batch-32 step the layers'
+# tensors fit in L2, yet every half-size kernel takes more than half the time (per-kernel fixed cost ~3-4 us) and the step
+# slows from 0.72 to 0.76 / 0.83 ms -- the conv chain is not HBM-bound enough for the saved traffic to pay.
+L2_CHUNK_BYTES = int(_os.environ.get('TGSR_L2_CHUNK_MB', '0')) << 20
+
+
+def batch_chunks(B: int, bytes_per_image: int):
+    """Split a batch so that the largest tensor a producer hands to its consumer stays L2-resident (126 MB L2 shared by
+    reads, dirty writes and weights): the conv chain of a high-resolution stage streams ~3x fewer HBM bytes when each
+    layer finds its input still in L2.  Returns [(b0, b1), ...] with equal power-of-two chunk counts."""
+    n = 1
+    while L2_CHUNK_BYTES > 0 and B % (2 * n) == 0 and (B // n) * bytes_per_image > L2_CHUNK_BYTES:
+        n *= 2
+    step = B // n
+    return [(i * step, (i + 1) * step) for i in range(n)]
 
 
 def _packed_head(conv: nn.Conv2d, fmt: int) -> Tensor:
@@ -110,12 +129,14 @@ def nonfinite_seen(device, clear: bool = True) -> bool:
     return seen
 
 
-def image_head(x: Blocked, head_seq, addend: Optional[Tensor] = None, a: float = 0.0, one: float = 1.0) -> Tensor:
+def image_head(x: Blocked, head_seq, addend: Optional[Tensor] = None, a: float = 0.0, one: float = 1.0,
+               out: Optional[Tensor] = None) -> Tensor:
     """GET_IMAGE_G[_noAct].img / conv_output -> fp32 NCHW image (util.py:894-919, model.py:223-226,280)."""
     conv = head_seq[0]
     act = ACT_TANH if any(isinstance(m, nn.Tanh) for m in head_seq) else ACT_NONE
     k = conv.weight.shape[2]
-    y = torch.empty((x.B, 3, x.H, x.W), device=x.device, dtype=torch.float32)
+    y = torch.empty((x.B, 3, x.H, x.W), device=x.device, dtype=torch.float32) if out is None else out
+    assert y.is_contiguous() and tuple(y.shape) == (x.B, 3, x.H, x.W)
     ad = None
     if addend is not None:
         if tuple(addend.shape) != tuple(y.shape):
@@ -182,9 +203,13 @@ def stage_im2f(st, LR: Tensor, fmt: int = 0) -> Blocked:
 
 
 def stage(st, h: Optional[Blocked], LR: Optional[Tensor], words: Tensor, mask, out_planes: Optional[int],
-          fmt: int = 0, sfrag: Optional[Tensor] = None):
+          fmt: int = 0, sfrag: Optional[Tensor] = None, head=None):
     """INIT_STAGE_GImgup (LR given) / NEXT_STAGE_G (h given); util.py:763-777 / :807-823.
-    `h` must be the first 32-channel view of a 64-channel buffer: c_code is appended in place."""
+    `h` must be the first 32-channel view of a 64-channel buffer: c_code is appended in place.
+    With `head` (the stage's image head, model.py:55-73) the stage also returns its image, and the conv chain behind the
+    attention -- residual blocks, up-block, head -- runs per batch chunk so that it stays in L2 (`batch_chunks`).  The
+    attention itself always sees the whole batch: its caption mask is indexed with the reference's row-order quirk
+    (GlobalAttention.py:109-112), which depends on the batch size."""
     ngf = st.gf_dim
     if h is None:
         h = stage_im2f(st, LR, fmt)
@@ -193,10 +218,19 @@ def stage(st, h: Optional[Blocked], LR: Optional[Tensor], words: Tensor, mask, o
         assert h.p0 == 0 and h.P * 8 >= 2 * ngf, 'h_code must live in a concat-sized buffer'
         cat = Blocked(h.buf, 0, 2 * ngf)
     att = attention(h, st.att, words, mask, out=cat.slice(ngf, ngf), sfrag=sfrag)
-    x = cat
-    for rb in st.residual:
-        x = res_block(x, rb)
-    return up_block(x, st.upsample, out_planes=out_planes), att
+    B, H, W = cat.B, cat.H, cat.W
+    up_conv = st.upsample[1]
+    Cup = up_conv.weight.shape[0] // 2
+    out = Blocked.empty(B, Cup, 2 * H, 2 * W, cat.device, planes=out_planes, fmt=cat.fmt)
+    img = torch.empty((B, 3, 2 * H, 2 * W), device=cat.device, dtype=torch.float32) if head is not None else None
+    for b0, b1 in batch_chunks(B, 4 * H * W * Cup * 2):                   # largest tensor of the chain: the up-block output
+        x = cat.batch(b0, b1)
+        for rb in st.residual:
+            x = res_block(x, rb)
+        o = up_block(x, st.upsample, out=out.batch(b0, b1))
+        if head is not None:
+            image_head(o, head.img, out=img[b0:b1])
+    return out, att, img
 
 
 def stage_supported(st, H: int, W: int) -> bool:
@@ -219,8 +253,8 @@ def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, hea
     n = len(stages)
     for i, (st, hd) in enumerate(zip(stages, heads)):
         planes = 8 if i + 1 < n else 4                     # leave room for the next stage's c_code
-        h, att = stage(st, h, LR if (i == 0 and h0 is None) else None, words, mask, planes, fmt, sfrags[i])
-        imgs.append(image_head(h, hd.img))
+        h, att, img = stage(st, h, LR if (i == 0 and h0 is None) else None, words, mask, planes, fmt, sfrags[i], head=hd)
+        imgs.append(img)
         atts.append(att)
         feats.append(h)
     if outmiddle:
@@ -254,13 +288,25 @@ def netg_high_trunk(net, x: Tensor, x_sub: Optional[Tensor], fmt: int = 0) -> Bl
 
 def netg_high_finish(net, h: Blocked, SRb, a: float, one: float, tail, feats=None) -> List[Tensor]:
     """Rest of the trunk (model.py:280-298): image heads with the fused `one*y + a*SRb`, residual24/48 bodies and
-    upscale4x/8x.  `tail` = [(body, upscale), ...] after the first upscale."""
+    upscale4x/8x.  `tail` = [(body, upscale), ...] after the first upscale.  Each level's chain (body, up-block, head) runs
+    per batch chunk so that it stays in L2 (`batch_chunks`)."""
     if feats is not None: feats.append(tc.to_nchw(h))
     ims = [image_head(h, net.conv_output, SRb[0], a, one)]
     for k, (body, up) in enumerate(tail):
-        h = up_block(body_noskip(h, body), up)
+        B, H, W = h.B, h.H, h.W
+        Cup = up[1].weight.shape[0] // 2
+        out = Blocked.empty(B, Cup, 2 * H, 2 * W, h.device, fmt=h.fmt)
+        img = torch.empty((B, 3, 2 * H, 2 * W), device=h.device, dtype=torch.float32)
+        srb = SRb[k + 1]
+        if tuple(srb.shape) != tuple(img.shape):
+            raise ValueError('SRb shape %s != image shape %s' % (tuple(srb.shape), tuple(img.shape)))
+        srb = srb.contiguous()
+        for b0, b1 in batch_chunks(B, 4 * H * W * Cup * 2):
+            o = up_block(body_noskip(h.batch(b0, b1), body), up, out=out.batch(b0, b1))
+            image_head(o, net.conv_output, srb[b0:b1], a, one, out=img[b0:b1])
+        h = out
         if feats is not None: feats.append(tc.to_nchw(h))
-        ims.append(image_head(h, net.conv_output, SRb[k + 1], a, one))
+        ims.append(img)
     return ims
 
 

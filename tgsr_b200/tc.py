@@ -48,6 +48,10 @@ class Blocked:
         assert c0 % 8 == 0
         return Blocked(self.buf, self.p0 + c0 // 8, C)
 
+    def batch(self, b0: int, b1: int) -> 'Blocked':
+        """Images b0..b1-1 of this view (a contiguous slice of the buffer)."""
+        return Blocked(self.buf[b0:b1], self.p0, self.C)
+
 
 def to_blocked(x: Tensor, out: Optional[Blocked] = None, fmt: int = FMT_BF16) -> Blocked:
     """NCHW fp32 -> blocked 16-bit (round-to-nearest-even)."""
