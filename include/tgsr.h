@@ -154,8 +154,9 @@ int tgsr_pack_conv3x3(const float* w, const float* scale, const float* shift, vo
  * 16-bit operands, fp32 accumulation in TMEM; util.py:62-65, :45-53, :110-130, :74-80.
  * x view (xP,xp0) of Cin channels at HxW; y view (yP,yp0) of Cout (or Cout/2 with GLU) channels at
  * HxW, or at 2Hx2W when up2x (wpacked must then come from tgsr_pack_conv3x3(up2x=1)).
- * residual view (rP,rp0) or NULL (only with act NONE, no up2x).  Supported (Cin,Cout,act,up2x):
- * (64,128,GLU,0) (64,64,NONE,0) (32,64,GLU,0) (32,32,NONE,0) (64,64,GLU,1) (32,64,GLU,1);
+ * residual view (rP,rp0) or NULL (only with act NONE, no up2x, Cout <= 64).  Supported (Cin,Cout,act,up2x):
+ * (64,128,GLU,0) (64,64,NONE,0) (32,64,GLU,0) (32,32,NONE,0) (64,64,GLU,1) (32,64,GLU,1), and for the training step's
+ * raw convolutions (64,128,NONE,0) (32,64,NONE,0);
  * H % 16 == 0, W % 8 == 0.
  * flags: TGSR_CONV_REVERSE walks the output tiles from the last one backwards.  Results are identical; a kernel that
  * consumes what its predecessor just wrote in forward order finds the most recently written (still L2-resident) part
@@ -353,6 +354,24 @@ int tgsr_cosine_similarity_f32(const float* x1, const float* x2, float* out, flo
                                float eps, tgsr_stream_t stream);
 int tgsr_cosine_similarity_bwd_f32(const float* x1, const float* x2, const float* stats, const float* g, float* d1, float* d2,
                                    size_t outer, int D, int inner, float eps, tgsr_stream_t stream);
+
+
+/* ---- training step on blocked 16-bit activations [B][C/8][H][W][8] (csrc/train16.cu); statistics and gradients in fp32 /
+ * fp64, one 16-bit rounding per layer.  nn.BatchNorm2d train mode + GLU + skip (util.py:45-53,64,110-130), nn.Upsample(2)
+ * (util.py:76) and their adjoints. */
+/* mean / invstd [C] of z over (B, H*W); running stats updated like nn.BatchNorm2d(momentum) when given.  ws: 2*C doubles. */
+int tgsr_bn16_stats(const void* z, float* mean, float* invstd, float* running_mean, float* running_var, float momentum,
+                    float eps, double* ws, int B, int C, int HW, int fmt, tgsr_stream_t stream);
+/* y = act(gamma * (z - mean) * invstd + beta) (+ residual): act NONE -> C channels out (residual allowed), GLU -> C/2. */
+int tgsr_bn16_act(const void* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                  const void* residual, void* y, int B, int C, int HW, int act, int fmt, tgsr_stream_t stream);
+/* Backward of tgsr_bn16_act through the batch statistics: dz [B,C,..], dgamma / dbeta [C] from dy.  ws: 2*C doubles. */
+int tgsr_bn16_act_bwd(const void* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                      const void* dy, void* dz, float* dgamma, float* dbeta, double* ws, int B, int C, int HW, int act,
+                      int fmt, tgsr_stream_t stream);
+/* y [B,P,2H,2W,8] = nearest x2 of x [B,P,H,W,8];  y [B,P,H,W,8] = 2x2 block sums of x [B,P,2H,2W,8] (its adjoint). */
+int tgsr_upsample2x_blocked(const void* x, void* y, int B, int P, int H, int W, tgsr_stream_t stream);
+int tgsr_sumpool2x2_blocked(const void* x, void* y, int B, int P, int H, int W, int fmt, tgsr_stream_t stream);
 
 #ifdef __cplusplus
 }

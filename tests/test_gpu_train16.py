@@ -1,0 +1,215 @@
+"""bf16 training path (-m gpu): tcgen05 convolutions on blocked bf16 activations with fp32 BatchNorm statistics
+(tgsr_b200/train16.py, csrc/train16.cu) against torch.autograd over the same arithmetic in fp32 on bf16-rounded operands,
+and the whole generator step against the exact fp32 step."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import tgsr_b200
+from oracle import tgsr_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.fixture(autouse=True)
+def _cfg():
+    tgsr_b200.set_eval_defaults()
+    tgsr_b200.set_precision('bf16')
+    yield
+    tgsr_b200.set_precision('fp32')
+
+
+def _cos(a, b):
+    a, b = a.flatten().double(), b.flatten().double()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+@pytest.mark.parametrize('Cin,Cout,B,H,W', [(64, 128, 2, 32, 32), (64, 64, 2, 32, 16), (32, 64, 1, 16, 8), (32, 32, 3, 32, 32)])
+def test_conv16_forward_backward(Cin, Cout, B, H, W):
+    from tgsr_b200 import train16 as T
+    g = torch.Generator().manual_seed(Cin + Cout + H)
+    x = bf(torch.randn(B, Cin, H, W, generator=g) * 0.5)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * (1.0 / (3 * Cin ** 0.5))
+    dz = bf(torch.randn(B, Cout, H, W, generator=g) * 0.1)
+    xr = x.clone().requires_grad_(True); wr = bf(w).clone().requires_grad_(True)
+    zr = F.conv2d(xr, wr, None, 1, 1)
+    zr.backward(dz)
+    xd = x.to(DEV).requires_grad_(True); wd = w.to(DEV).requires_grad_(True)
+    xb = T.to_blocked(xd)
+    zb = T.Conv16Fn.apply(xb, wd)
+    z = T.to_nchw(zb)
+    z.backward(dz.to(DEV))
+    tol = 2 ** -8
+    assert (z.detach().cpu() - zr.detach()).abs().max() <= tol * max(1.0, zr.abs().max().item()) + 1e-4
+    # dx: bf16 operands (dz exact in bf16, weights rounded), one (two for Cout = 128) output rounding
+    assert (xd.grad.cpu() - xr.grad).abs().max() <= 2 * tol * max(1.0, xr.grad.abs().max().item()) * 0.25 + 2e-3
+    assert _cos(xd.grad.cpu(), xr.grad) > 0.9995
+    # dw: TF32 accumulation over fp32 copies of the bf16 tensors
+    assert _cos(wd.grad.cpu(), wr.grad) > 0.9995
+    torch.testing.assert_close(wd.grad.cpu(), wr.grad, rtol=2e-2, atol=2e-2 * wr.grad.abs().max().item())
+
+
+@pytest.mark.parametrize('act,with_res', [(1, False), (0, True), (0, False)])
+def test_bn_act16_forward_backward(act, with_res):
+    from tgsr_b200 import train16 as T
+    g = torch.Generator().manual_seed(11 + act)
+    B, C, H, W = 3, 64, 16, 24
+    z = bf(torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3)
+    Cf = C // 2 if act else C
+    res = bf(torch.randn(B, Cf, H, W, generator=g)) if with_res else None
+    dy = bf(torch.randn(B, Cf, H, W, generator=g) * 0.2)
+    bn = torch.nn.BatchNorm2d(C)
+    bn.weight.data.copy_(1 + 0.2 * torch.randn(C, generator=g)); bn.bias.data.copy_(0.1 * torch.randn(C, generator=g))
+    bn_d = torch.nn.BatchNorm2d(C).to(DEV); bn_d.load_state_dict(bn.state_dict()); bn_d.train()
+    # reference: torch autograd, fp32
+    zr = z.clone().requires_grad_(True)
+    rr = None if res is None else res.clone().requires_grad_(True)
+    u = bn(zr)
+    y = u[:, :Cf] * torch.sigmoid(u[:, Cf:]) if act else u
+    if rr is not None:
+        y = y + rr
+    y.backward(dy)
+    zd = z.to(DEV).requires_grad_(True)
+    rd = None if res is None else res.to(DEV).requires_grad_(True)
+    yb = T.BnAct16Fn.apply(T.to_blocked(zd), bn_d.weight, bn_d.bias, None if rd is None else T.to_blocked(rd), bn_d, act)
+    yd = T.to_nchw(yb)
+    yd.backward(dy.to(DEV))
+    assert (yd.detach().cpu() - y.detach()).abs().max() <= 2 ** -8 * max(1.0, y.abs().max().item()) + 1e-4
+    torch.testing.assert_close(bn_d.running_mean.cpu(), bn.running_mean, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(bn_d.running_var.cpu(), bn.running_var, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(bn_d.weight.grad.cpu(), bn.weight.grad, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(bn_d.bias.grad.cpu(), bn.bias.grad, rtol=2e-2, atol=2e-2)
+    assert _cos(zd.grad.cpu(), zr.grad) > 0.999
+    assert (zd.grad.cpu() - zr.grad).abs().max() <= 2 ** -7 * max(1.0, zr.grad.abs().max().item())
+    if rd is not None:
+        assert torch.equal(rd.grad.cpu(), dy)
+
+
+def test_upsample16_and_adjoint():
+    from tgsr_b200 import train16 as T
+    g = torch.Generator().manual_seed(3)
+    x = bf(torch.randn(2, 32, 16, 8, generator=g))
+    dy = bf(torch.randn(2, 32, 32, 16, generator=g) * 0.25)
+    xd = x.to(DEV).requires_grad_(True)
+    y = T.to_nchw(T.Up2x16Fn.apply(T.to_blocked(xd)))
+    assert torch.equal(y.detach().cpu(), F.interpolate(x, scale_factor=2, mode='nearest'))
+    y.backward(dy.to(DEV))
+    want = F.avg_pool2d(dy, 2) * 4
+    assert (xd.grad.cpu() - want).abs().max() <= 2 ** -8 * want.abs().max().item()
+
+
+def _grad_rows(g16, g32):
+    rows = []
+    for n, gref in g32.items():
+        if n.startswith('ca_net'):
+            continue
+        rows.append((_cos(g16[n], gref), float((g16[n] - gref).norm()), float(gref.norm()), n))
+    rows.sort()
+    return rows
+
+
+def test_generator_step_bf16_matches_fp32_step():
+    """One training step of the whole generator (G_SR_NET_low + NetG_highweight, train BN): the bf16 / tcgen05 path against
+    the exact fp32 path from the same weights and inputs.
+    (a) MSE on the six outputs (a smooth loss): every parameter gradient of non-negligible size points the same way
+        (cosine > 0.98, median > 0.999) and has the same length within 5 %.
+    (b) The full cfg-5 loss (MSE + DAMSM through a random-init Inception-v3): losses within 2 %.  The DAMSM part of the
+        image gradient comes through 48 random conv layers and a gamma = 10 softmax and is itself sensitive to 1e-3-level
+        changes of the image, so only the bulk of the gradients is asserted (median cosine > 0.97, none below 0.6)."""
+    import statistics
+    from tgsr_b200 import losses, nets
+    from tgsr_b200.text_encoder import RNN_ENCODER
+    from tgsr_b200.train_step import FrozenImageEncoder, GeneratorTrainStep
+    B = 4
+    LR = O.synth_lr(B, 32, seed=61).to(DEV)
+    real = [F.interpolate(LR, scale_factor=2 ** (k + 1), mode='bicubic').clamp(-1, 1) for k in range(3)]
+    caps, lens = O.synth_captions(B, 200, seed=62, words_num=18)
+    caps, lens = caps.to(DEV), lens.to(DEV)
+    torch.manual_seed(77)
+    enc = RNN_ENCODER(200, nhidden=256).to(DEV).eval()
+    img = FrozenImageEncoder().to(DEV)
+    out, grads, grads_mse, mse = {}, {}, {}, {}
+    sd = None
+    for mode in ('fp32', 'bf16'):
+        torch.manual_seed(78)
+        gl = nets.G_SR_NET_low().to(DEV); gh = nets.NetG_highweight(low='lr').to(DEV)
+        if sd is None:
+            sd = ({k: v.clone() for k, v in gl.state_dict().items()}, {k: v.clone() for k, v in gh.state_dict().items()})
+        gl.load_state_dict(sd[0]); gh.load_state_dict(sd[1])
+        ts = GeneratorTrainStep(gl, gh, enc, img, conv_precision=mode)
+        params = [(n, p) for n, p in list(gl.named_parameters()) + list(gh.named_parameters()) if p.requires_grad]
+        # (a) MSE only
+        ts.bucket.zero_grad()
+        with torch.no_grad():
+            words, sent = enc._forward_tmax(caps, lens, 18)
+        mask = (caps == 0)[:, :18]
+        imgsL, _a, _m, _l = gl(LR, sent, words, mask)
+        fine, _, _ = gh(LR, imgsL, LR)
+        l = losses.MSE(list(fine) + list(imgsL), list(real) + list(real))
+        l.backward()
+        mse[mode] = float(l)
+        grads_mse[mode] = {n: p.grad.detach().clone() for n, p in params}
+        # (b) the full step's forward + backward (second forward: running statistics move, batch statistics do not)
+        o = ts._fwd_bwd(LR, real, caps, lens, 18)
+        out[mode] = {k: float(v) for k, v in o.items()}
+        grads[mode] = {n: p.grad.detach().clone() for n, p in params}
+    print('MSE-only loss fp32 %.6f bf16 %.6f; full losses fp32 %s  bf16 %s' % (mse['fp32'], mse['bf16'], out['fp32'], out['bf16']))
+    assert abs(mse['bf16'] - mse['fp32']) <= 5e-3 * abs(mse['fp32'])
+    rows = _grad_rows(grads_mse['bf16'], grads_mse['fp32'])
+    scale = statistics.median(r[2] for r in rows if r[3].endswith('.weight') and r[2] > 0)
+    for c, e, nr, n in rows[:6]:
+        print('MSE-only: cos %.4f  |err| %.3e  |g| %.3e  %s' % (c, e, nr, n))
+    for c, e, nr, n in rows:
+        # (a BatchNorm shift / gain that the next BatchNorm removes again has an almost vanishing true gradient: absolute scale)
+        assert e <= 0.2 * nr + 2e-2 * scale, (n, c, e, nr)
+        if nr > 0.1 * scale:
+            assert c > 0.98, (n, c)
+            assert abs(e) <= 0.2 * nr
+    assert statistics.median(c for c, e, nr, n in rows if nr > 0.1 * scale) > 0.999
+    assert abs(out['bf16']['total'] - out['fp32']['total']) <= 2e-2 * abs(out['fp32']['total'])
+    assert abs(out['bf16']['mse'] - out['fp32']['mse']) <= 2e-2 * abs(out['fp32']['mse'])
+    rows = _grad_rows(grads['bf16'], grads['fp32'])
+    scale = statistics.median(r[2] for r in rows if r[3].endswith('.weight') and r[2] > 0)
+    for c, e, nr, n in rows[:6]:
+        print('full loss: cos %.4f  |err| %.3e  |g| %.3e  %s' % (c, e, nr, n))
+    big = [c for c, e, nr, n in rows if nr > 0.2 * scale]
+    # calibration: how far does the DAMSM image gradient itself move when the fp32 image changes by one bf16 rounding?
+    torch.manual_seed(5)
+    tgsr_b200.set_precision('fp32')
+    labels = torch.arange(B, device=DEV)
+    with torch.no_grad():
+        words, sent = enc._forward_tmax(caps, lens, 18)
+    base = real[2].clone()
+    gs = []
+    for pert in (0.0, 2.0 ** -9):
+        im = (base * (1.0 + pert * torch.randn_like(base))).requires_grad_(True)
+        errG, _ = losses.generator_lossor_wordsentOnly(img, [im], words, sent, labels, lens, None)
+        gs.append(torch.autograd.grad(errG, im)[0])
+    sens = _cos(gs[0], gs[1])
+    print('DAMSM image-gradient cosine under a bf16-rounding-sized change of the image (fp32 path): %.4f; '
+          'bf16-vs-fp32 parameter gradients: min %.4f median %.4f' % (sens, min(big), statistics.median(big)))
+    assert min(big) > 0.5 and statistics.median(big) > min(0.97, sens - 0.1)
+
+
+def test_training_run_bf16_learns():
+    from tgsr_b200 import nets
+    from tgsr_b200.text_encoder import RNN_ENCODER
+    from tgsr_b200.train_step import FrozenImageEncoder, GeneratorTrainStep
+    torch.manual_seed(31)
+    gl = nets.G_SR_NET_low().to(DEV); gh = nets.NetG_highweight(low='lr').to(DEV)
+    enc = RNN_ENCODER(200, nhidden=256).to(DEV).eval()
+    img = FrozenImageEncoder().to(DEV)
+    ts = GeneratorTrainStep(gl, gh, enc, img, lr=2e-3, conv_precision='bf16')
+    B = 4
+    LR = O.synth_lr(B, 32, seed=41).to(DEV)
+    real = [F.interpolate(LR, scale_factor=2 ** (k + 1), mode='bicubic').clamp(-1, 1) for k in range(3)]
+    caps, lens = O.synth_captions(B, 200, seed=42, words_num=18)
+    caps, lens = caps.to(DEV), lens.to(DEV)
+    outs = [float(ts.step(LR, real, caps, lens, 18)['mse']) for _ in range(8)]
+    assert all(v == v for v in outs)
+    assert min(outs[-3:]) < outs[0], outs

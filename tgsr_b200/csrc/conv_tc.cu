@@ -131,7 +131,7 @@ struct TcCfg {
   static constexpr int WB_PAD = ((WBYTES + 1023) / 1024) * 1024;
   // Skip-tensor ring (ResBlock second conv): the producer warp fetches the skip tile with TMA RSTAGE tiles ahead, so
   // the epilogue never waits for a DRAM round trip of its own.
-  static constexpr bool RES = MODE == MODE_CONV && !GLU;
+  static constexpr bool RES = MODE == MODE_CONV && !GLU && NPRE <= 64;   // (the 128-channel act-free conv is training-only: no skip)
   static constexpr int RSTAGE = RES ? 3 : 0;
   static constexpr int RES_BYTES = RES ? TC_TH * TC_TW * NPRE * 2 : 0;
   // Patch-ring depth: as many stages as fit next to the resident weights (TMA latency ~1-2 us must be
@@ -488,7 +488,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
         uint32_t va[CW], vg[GLU ? CW : 1];
-        if constexpr (CW == 32) {
+        if constexpr (CW == 64) {
+          tmem_ld32(t_base + c0, reinterpret_cast<uint32_t(&)[32]>(va[0]));
+          tmem_ld32(t_base + c0 + 32, reinterpret_cast<uint32_t(&)[32]>(va[32]));
+        } else if constexpr (CW == 32) {
           tmem_ld32(t_base + c0, va);
           if constexpr (GLU) tmem_ld32(t_base + COUT + c0, vg);
         } else {
@@ -727,6 +730,8 @@ int init_conv_tc() {
   int s;
   if ((s = set_tc_attr<64, 128, MODE_CONV, true>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<64, 64, MODE_CONV, false>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<64, 128, MODE_CONV, false>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<32, 64, MODE_CONV, false>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<32, 64, MODE_CONV, true>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<32, 32, MODE_CONV, false>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<64, 64, MODE_UP, true>()) != TGSR_OK) return s;
@@ -837,6 +842,8 @@ extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpack
   if (!up2x) {
     if (Cin == 64 && Cout == 128 && glu) return launch_tc<64, 128, MODE_CONV, true>(tmap, rmap, p, fmt, st);
     if (Cin == 64 && Cout == 64 && !glu) return launch_tc<64, 64, MODE_CONV, false>(tmap, rmap, p, fmt, st);
+    if (Cin == 64 && Cout == 128 && !glu && !residual) return launch_tc<64, 128, MODE_CONV, false>(tmap, rmap, p, fmt, st);
+    if (Cin == 32 && Cout == 64 && !glu && !residual) return launch_tc<32, 64, MODE_CONV, false>(tmap, rmap, p, fmt, st);
     if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, MODE_CONV, true>(tmap, rmap, p, fmt, st);
     if (Cin == 32 && Cout == 32 && !glu) return launch_tc<32, 32, MODE_CONV, false>(tmap, rmap, p, fmt, st);
   } else {

@@ -29,6 +29,12 @@ class G_SR_NET_low(nn.Module):
 
     def forward(self, LR, sent_emb, word_embs, mask, outmiddle=False):
         from . import fast, fmt_for, is_16bit
+        if self.training and is_16bit():                        # bf16 training step: tcgen05 convs on blocked activations
+            if outmiddle:
+                raise NotImplementedError('outmiddle is an eval-time option')
+            from . import train16
+            return train16.g_sr_net_low(self, LR, sent_emb, word_embs, mask, [self.h_net1, self.h_net2, self.h_net3],
+                                        [self.img_net1, self.img_net2, self.img_net3])
         if is_16bit() and fast.stage_supported(self.h_net1, LR.shape[2], LR.shape[3]):
             for st in (self.h_net1, self.h_net2, self.h_net3):
                 st.att.applyMask(mask)                              # keep the stateful contract
@@ -73,6 +79,12 @@ class _HighBase(nn.Module):
 
     def _trunk(self, x, SRb, a, one, feats=None, x_sub=None):
         from . import fast, fmt_for, is_16bit
+        if self.training and is_16bit():                        # bf16 training step (tgsr_b200/train16.py)
+            if feats is not None:
+                raise NotImplementedError('outmiddle is an eval-time option')
+            from . import train16
+            return train16.netg_high(self, x, x_sub, SRb, a, one,
+                                     [(self.residual24, self.upscale4x), (self.residual48, self.upscale8x)])
         if is_16bit() and self.convin[0].weight.shape[0] == 64 and x.shape[2] % 16 == 0 \
                 and x.shape[3] % 8 == 0:
             return fast.netg_high(self, x, x_sub, SRb, a, one,

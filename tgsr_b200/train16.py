@@ -1,0 +1,268 @@
+"""Training-mode execution of the generator on BLOCKED 16-bit activations: the bf16 / tcgen05 twin of train.py.
+
+Activations between layers are bf16 tensors [B, C/8, H, W, 8] (the layout of csrc/conv_tc.cu).  Per layer:
+  * conv3x3 forward and data gradient: the tcgen05 implicit-GEMM kernel (bf16 operands packed from the fp32 MASTER weights
+    every step, fp32 accumulation in TMEM); the data gradient is the same kernel on dz with the transposed, flipped weights
+    (input channels beyond 64 are fed in two accumulating passes through the kernel's skip input);
+  * weight gradient: fp32 accumulation over fp32 copies of x and dz (TF32 tensor-core kernel, csrc/conv_tf32.cu);
+  * BatchNorm (batch statistics) + GLU + skip, forward and backward: csrc/train16.cu, arithmetic in fp32 / fp64;
+  * nearest x2 upsample / 2x2 sum-pool adjoint: csrc/train16.cu.
+The image heads (3 output channels), im2f / convin (3 input channels) and the word attention keep their fp32 kernels
+(train.py); `to_blocked` / `to_nchw` convert at those edges and are differentiable.
+
+reference: the generator modules in train() mode under autograd (util.py:45-130,726-823, model.py:34-78,212-298); cfg 5 of
+BASELINE.json asks for this step in bf16.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, train
+from ._lib import ACT_GLU, ACT_NONE, ACT_TANH, FMT_BF16, call, ptr
+
+Tensor = torch.Tensor
+FMT = FMT_BF16
+DT = torch.bfloat16
+
+
+def _blk(B, C, H, W, dev) -> Tensor:
+    return torch.empty((B, C // 8, H, W, 8), device=dev, dtype=DT)
+
+
+# ---------------------------------------------------------------- layout edges (differentiable)
+class ToBlockedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor):
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        y = _blk(B, C, H, W, x.device)
+        call('tgsr_nchw_to_blocked', x.device, ptr(x), ptr(y), B, C, H, W, C // 8, 0, FMT)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        return ToNchwFn.forward(None, dy)
+
+
+class ToNchwFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xb: Tensor):
+        xb = xb.contiguous()
+        B, P, H, W, _ = xb.shape
+        y = torch.empty((B, P * 8, H, W), device=xb.device, dtype=torch.float32)
+        call('tgsr_blocked_to_nchw', xb.device, ptr(xb), ptr(y), B, P * 8, H, W, P, 0, FMT)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        return ToBlockedFn.forward(None, dy)
+
+
+def to_blocked(x: Tensor) -> Tensor:
+    return ToBlockedFn.apply(x)
+
+
+def to_nchw(xb: Tensor) -> Tensor:
+    return ToNchwFn.apply(xb)
+
+
+# ---------------------------------------------------------------- conv3x3 (raw: no BN, no activation)
+def _pack(w: Tensor) -> Tensor:
+    Cout, Cin = w.shape[0], w.shape[1]
+    n = _lib.load().tgsr_packed_conv3x3_elems(Cout, Cin, 0)
+    packed = torch.empty(n, device=w.device, dtype=DT)
+    call('tgsr_pack_conv3x3', w.device, ptr(w), None, None, ptr(packed), Cout, Cin, 0, ACT_NONE, FMT)
+    return packed
+
+
+def _conv_tc(xb: Tensor, p0: int, Cin: int, w: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+    """tcgen05 conv of planes [p0, p0 + Cin/8) of xb with fp32 weights w [Cout, Cin, 3, 3] (+ residual) -> blocked bf16."""
+    B, P, H, W, _ = xb.shape
+    Cout = w.shape[0]
+    y = _blk(B, Cout, H, W, xb.device)
+    rP = 0 if residual is None else residual.shape[1]
+    call('tgsr_conv3x3_tc', xb.device, ptr(xb), P, p0, ptr(_pack(w.contiguous())), ptr(residual), rP, 0, ptr(y), Cout // 8, 0,
+         B, Cin, H, W, Cout, 0, ACT_NONE, FMT, 0)
+    return y
+
+
+_TC_SHAPES = {(64, 128), (64, 64), (32, 64), (32, 32)}
+
+
+class Conv16Fn(torch.autograd.Function):
+    """z = conv3x3(x, w), stride 1, pad 1, no bias (util.py:62-65) on blocked bf16 activations."""
+
+    @staticmethod
+    def forward(ctx, xb: Tensor, w: Tensor):
+        xb = xb.contiguous()
+        Cout, Cin = w.shape[0], w.shape[1]
+        if (Cin, Cout) not in _TC_SHAPES or xb.shape[1] * 8 != Cin or xb.shape[2] % 16 or xb.shape[3] % 8:
+            raise NotImplementedError('train16 conv: unsupported shape Cin %d Cout %d at %s' % (Cin, Cout, tuple(xb.shape)))
+        ctx.save_for_backward(xb, w)
+        return _conv_tc(xb, 0, Cin, w.detach())
+
+    @staticmethod
+    def backward(ctx, dz: Tensor):
+        xb, w = ctx.saved_tensors
+        dz = dz.contiguous()
+        Cout, Cin = w.shape[0], w.shape[1]
+        B, _, H, W, _ = xb.shape
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            # data gradient = conv of dz with the transposed, flipped weights wt [Cin, Cout, 3, 3]; the kernel takes at most 64
+            # input channels, so Cout = 128 goes in two passes, the second accumulating onto the first through the skip input
+            wt = torch.empty((Cin, Cout, 3, 3), device=w.device, dtype=torch.float32)
+            call('tgsr_conv_weight_flip_f32', w.device, ptr(w.detach().contiguous()), ptr(wt), Cout, Cin, 3)
+            step = Cin if Cout == 2 * Cin else Cout               # input-channel slice per pass: an instantiated (Cin', Cout') pair
+            if (step, Cin) not in _TC_SHAPES:
+                step = Cout
+            for c0 in range(0, Cout, step):
+                dx = _conv_tc(dz, c0 // 8, step, wt[:, c0:c0 + step].contiguous(), residual=dx)
+        if ctx.needs_input_grad[1]:
+            x32 = ToNchwFn.forward(None, xb); dz32 = ToNchwFn.forward(None, dz)
+            dw = torch.empty_like(w)
+            name = 'tgsr_conv2d_wgrad_tf32' if _lib.load().tgsr_conv_tf32_supported(Cin, Cout, 3, 1) else 'tgsr_conv2d_wgrad_f32'
+            call(name, w.device, ptr(x32), ptr(dz32), ptr(dw), B, Cin, H, W, Cout, 3, 0)
+        return dx, dw
+
+
+# ---------------------------------------------------------------- BatchNorm (batch statistics) + GLU + residual
+class BnAct16Fn(torch.autograd.Function):
+    """y = act(BN_train(z)) (+ residual) on blocked bf16; updates the module's running statistics like nn.BatchNorm2d."""
+
+    @staticmethod
+    def forward(ctx, z: Tensor, gamma: Tensor, beta: Tensor, residual: Optional[Tensor], bn: nn.BatchNorm2d, act: int):
+        z = z.contiguous()
+        B, P, H, W, _ = z.shape
+        Cc = P * 8
+        dev = z.device
+        mean = torch.empty(Cc, device=dev, dtype=torch.float32); invstd = torch.empty(Cc, device=dev, dtype=torch.float32)
+        ws = torch.empty(2 * Cc, device=dev, dtype=torch.float64)
+        track = bn.track_running_stats and bn.running_mean is not None
+        mom = 0.1 if bn.momentum is None else float(bn.momentum)
+        call('tgsr_bn16_stats', dev, ptr(z), ptr(mean), ptr(invstd), ptr(bn.running_mean if track else None),
+             ptr(bn.running_var if track else None), mom, float(bn.eps), ptr(ws), B, Cc, H * W, FMT)
+        if track:
+            _lib.bump_weights_epoch()
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        Cf = Cc // 2 if act == ACT_GLU else Cc
+        y = _blk(B, Cf, H, W, dev)
+        res = None if residual is None else residual.contiguous()
+        call('tgsr_bn16_act', dev, ptr(z), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(res), ptr(y), B, Cc, H * W, act, FMT)
+        ctx.save_for_backward(z, mean, invstd, gamma, beta)
+        ctx.act, ctx.has_res = act, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        z, mean, invstd, gamma, beta = ctx.saved_tensors
+        dy = dy.contiguous()
+        B, P, H, W, _ = z.shape
+        Cc = P * 8
+        dz = torch.empty_like(z); dg = torch.empty_like(gamma); db = torch.empty_like(beta)
+        ws = torch.empty(2 * Cc, device=z.device, dtype=torch.float64)
+        call('tgsr_bn16_act_bwd', z.device, ptr(z), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(dy), ptr(dz), ptr(dg), ptr(db),
+             ptr(ws), B, Cc, H * W, ctx.act, FMT)
+        return dz, dg, db, (dy if ctx.has_res else None), None, None
+
+
+class Up2x16Fn(torch.autograd.Function):
+    """nn.Upsample(scale_factor=2, mode='nearest') (util.py:76) on blocked bf16; backward = 2x2 sum-pool."""
+
+    @staticmethod
+    def forward(ctx, xb: Tensor):
+        xb = xb.contiguous()
+        B, P, H, W, _ = xb.shape
+        y = torch.empty((B, P, 2 * H, 2 * W, 8), device=xb.device, dtype=DT)
+        call('tgsr_upsample2x_blocked', xb.device, ptr(xb), ptr(y), B, P, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        dy = dy.contiguous()
+        B, P, H2, W2, _ = dy.shape
+        dx = torch.empty((B, P, H2 // 2, W2 // 2, 8), device=dy.device, dtype=DT)
+        call('tgsr_sumpool2x2_blocked', dy.device, ptr(dy), ptr(dx), B, P, H2 // 2, W2 // 2, FMT)
+        return dx
+
+
+# ---------------------------------------------------------------- blocks (util.py:74-130)
+def conv_bn_act(xb: Tensor, conv: nn.Conv2d, bn: nn.BatchNorm2d, act: int, residual: Optional[Tensor] = None) -> Tensor:
+    if not bn.training:
+        raise RuntimeError('tgsr_b200: gradients through an eval-mode BatchNorm are not implemented; call .train()')
+    return BnAct16Fn.apply(Conv16Fn.apply(xb, conv.weight), bn.weight, bn.bias, residual, bn, act)
+
+
+def res_block(xb: Tensor, rb) -> Tensor:
+    blk = rb.block
+    y = conv_bn_act(xb, blk[0], blk[1], ACT_GLU)
+    return conv_bn_act(y, blk[3], blk[4], ACT_NONE, residual=xb)
+
+
+def body_noskip(xb: Tensor, seq) -> Tensor:
+    return conv_bn_act(conv_bn_act(xb, seq[0], seq[1], ACT_GLU), seq[3], seq[4], ACT_NONE)
+
+
+def up_block(xb: Tensor, seq) -> Tensor:
+    return conv_bn_act(Up2x16Fn.apply(xb), seq[1], seq[2], ACT_GLU)
+
+
+def conv_in(seq, x: Tensor, x_sub: Optional[Tensor] = None) -> Tensor:
+    """[conv3x3(3, 2C), BN, GLU] from the fp32 image: fp32 training kernels (K = 27), then into the blocked layout."""
+    if x_sub is not None:
+        x = torch.sub(x, x_sub)
+    z = train.ConvFn.apply(x, seq[0].weight, False)
+    return to_blocked(train.BnActFn.apply(z, seq[1].weight, seq[1].bias, None, seq[1], ACT_GLU))
+
+
+def image_head(hb: Tensor, head_seq, addend: Optional[Tensor] = None, a: float = 0.0, one: float = 1.0) -> Tensor:
+    """GET_IMAGE_G[_noAct].img / conv_output (3 output channels): fp32 training kernels on the NCHW copy of h."""
+    h = to_nchw(hb)
+    if any(isinstance(m, nn.Tanh) for m in head_seq):
+        return train.TanhHeadFn.apply(h, head_seq[0].weight, addend, one, a)
+    y = train.ConvFn.apply(h, head_seq[0].weight, False)
+    if addend is not None or one != 1.0:
+        raise NotImplementedError('plain image heads take no addend')
+    return y
+
+
+def stage(st, hb: Optional[Tensor], LR: Optional[Tensor], words: Tensor, mask):
+    """INIT_STAGE_GImgup (LR given) / NEXT_STAGE_G (hb given) in train mode; util.py:763-777 / :807-823."""
+    if hb is None:
+        hb = conv_in(st.im2f, LR)
+    st.att.applyMask(mask)
+    c, att = train.AttentionFn.apply(to_nchw(hb), st.att.conv_context.weight, words, mask)
+    x = torch.cat((hb, to_blocked(c)), 1)                     # util.py:773,817: channel concat = plane concat
+    for rb in st.residual:
+        x = res_block(x, rb)
+    return up_block(x, st.upsample), att
+
+
+def g_sr_net_low(net, LR, sent, words, mask, stages, heads):
+    """G_SR_NET_low.forward in train mode (model.py:48-78 / models16.py:16-39)."""
+    imgs: List[Tensor] = []
+    atts: List[Tensor] = []
+    c_code, mu, logvar = net.ca_net(sent)
+    h = None
+    for i, (st, hd) in enumerate(zip(stages, heads)):
+        h, att = stage(st, h, LR if i == 0 else None, words, mask)
+        imgs.append(image_head(h, hd.img))
+        atts.append(att)
+    return imgs, atts, mu, logvar
+
+
+def netg_high(net, x: Tensor, x_sub: Optional[Tensor], SRb, a: float, one: float, tail) -> List[Tensor]:
+    """Trunk of NetG_high / NetG_highweight in train mode (model.py:264-298)."""
+    h = conv_in(net.convin, x, x_sub)
+    for rb in net.residual:
+        h = res_block(h, rb)
+    h = up_block(h, net.upscale2x)
+    ims = [image_head(h, net.conv_output, SRb[0], a, one)]
+    for k, (body, up) in enumerate(tail):
+        h = up_block(body_noskip(h, body), up)
+        ims.append(image_head(h, net.conv_output, SRb[k + 1], a, one))
+    return ims

@@ -129,8 +129,17 @@ class FrozenImageEncoder(nn.Module):
 class GeneratorTrainStep:
     def __init__(self, netGL: nn.Module, netGH: nn.Module, text_encoder: nn.Module, image_encoder: nn.Module, lr: float = 2e-4,
                  betas=(0.5, 0.999), group=None, conv_precision: str = 'tf32'):
-        from . import train
-        train.set_conv_precision(conv_precision)      # TF32 tensor-core convs by default, as PyTorch's cuDNN convs
+        """conv_precision: 'fp32' (exact CUDA-core convs), 'tf32' (mma.sync TF32, what PyTorch's cuDNN convs compute by
+        default) or 'bf16' (BASELINE.json configs[4]: tcgen05 convs on blocked bf16 activations with fp32 master weights,
+        fp32 BatchNorm statistics and fp32 weight-gradient accumulation; tgsr_b200/train16.py)."""
+        from . import set_precision, train
+        self.conv_precision = conv_precision
+        if conv_precision == 'bf16':
+            set_precision('bf16')
+            train.set_conv_precision('tf32')          # the fp32 edges (3-channel convs) and the weight gradients
+        else:
+            set_precision('fp32')
+            train.set_conv_precision(conv_precision)  # TF32 tensor-core convs by default, as PyTorch's cuDNN convs
         self.netGL, self.netGH, self.text_encoder, self.image_encoder = netGL, netGH, text_encoder, image_encoder
         netGL.train(); netGH.train(); text_encoder.eval(); image_encoder.eval()
         for p in netGL.ca_net.parameters():                                 # c_code is unused by the SR nets (model.py:51-52)
@@ -159,6 +168,10 @@ class GeneratorTrainStep:
     def _fwd_bwd(self, LR, real, captions, cap_lens, tmax: int):
         """Zero the flat gradient, forward (train-mode BN), losses, backward: everything before the exchange step."""
         B = LR.shape[0]
+        from . import get_precision, set_precision
+        want = 'bf16' if self.conv_precision == 'bf16' else 'fp32'
+        if get_precision() != want:
+            set_precision(want)
         self.bucket.zero_grad()
         with torch.no_grad():
             words, sent = self.text_encoder._forward_tmax(captions, cap_lens, tmax)
