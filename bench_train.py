@@ -29,6 +29,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=32, help='images per GPU')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying the captured step')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'tf32', 'fp32'],
+                    help="conv precision of the step: bf16 = tcgen05 convs on blocked bf16 activations (BASELINE configs[4]), tf32 / fp32 = round-1 paths")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -46,13 +48,16 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     tgsr_b200.set_eval_defaults(); tgsr_b200.set_precision('fp32')
+    import json as _json
+    _pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    bf16_peak = _json.load(open(_pk))['bf16_tflops'] if os.path.isfile(_pk) else 1590.0
     from tgsr_b200.config import cfg
     cfg.TRAIN.SMOOTH.GAMMA1, cfg.TRAIN.SMOOTH.GAMMA2, cfg.TRAIN.SMOOTH.GAMMA3 = 4.0, 5.0, 10.0
     torch.manual_seed(100)                                  # identical replicas
     gl = nets.G_SR_NET_low().to(dev); gh = nets.NetG_highweight(low='lr').to(dev)
     enc = RNN_ENCODER(5450, nhidden=256).to(dev).eval()
     img = FrozenImageEncoder().to(dev)
-    ts = GeneratorTrainStep(gl, gh, enc, img)
+    ts = GeneratorTrainStep(gl, gh, enc, img, conv_precision=a.precision)
     B = a.batch
     LR = O.synth_lr(B, 32, seed=201 + rank).to(dev)
     real = [torch.nn.functional.interpolate(LR, scale_factor=2 ** (k + 1), mode='bicubic').clamp(-1, 1) for k in range(3)]
@@ -130,20 +135,31 @@ def main():
         from tgsr_b200.timing import cold_time_ms, make_flush
         xq = torch.randn(B, 64, 128, 128, device=dev) * 0.5
         wq = torch.randn(128, 64, 3, 3, device=dev) * 0.05
-        cms = cold_time_ms(lambda: train._conv_raw(xq, wq, False), make_flush(dev), iters=5)
         fl = 2.0 * 9 * 64 * 128 * 128 * 128 * B
+        if a.precision == 'bf16':
+            from tgsr_b200 import train16
+            xb = train16.to_blocked(xq)
+            cms = cold_time_ms(lambda: train16._conv_tc(xb, 0, 64, wq), make_flush(dev), iters=5)
+            ach = fl / (cms * 1e-3) / 1e12
+            roof = {'bound': 'tensor', 'achieved': ach, 'peak': bf16_peak, 'unit': 'TFLOP/s', 'frac': ach / bf16_peak, 'traffic': None,
+                    'kernel': 'weight pack + conv3x3_tc_kernel<64,128,CONV,none> (tcgen05, bf16 operands, fp32 accumulate): the forward '
+                              'conv of ResBlock conv 1 at 128x128; the data gradient runs the same kernel',
+                    'ms_per_launch': cms, 'flops_per_launch': fl, 'peak_source': 'measured cuBLAS bf16 burst (MEASURED_PEAKS.json)'}
+        cms = cold_time_ms(lambda: train._conv_raw(xq, wq, False), make_flush(dev), iters=5)
         ach = fl / (cms * 1e-3) / 1e12
-        roof = {'bound': 'tensor', 'achieved': ach, 'peak': 275.0, 'unit': 'TFLOP/s', 'frac': ach / 275.0, 'traffic': None,
+        roof_tf32 = {'bound': 'tensor', 'achieved': ach, 'peak': 275.0, 'unit': 'TFLOP/s', 'frac': ach / 275.0, 'traffic': None,
                 'kernel': 'conv_prep_tf32_kernel + conv_tf32_kernel<3,64> (mma.sync m16n8k8 TF32, fp32 accumulate)', 'ms_per_launch': cms,
                 'flops_per_launch': fl, 'peak_source': 'measured HMMA TF32 issue rate on B200 (scripts/micro/hmma_rate.cu, profiles/r1_hmma_rate.md); '
-                                                       'the tcgen05 bf16 peak (1675 TFLOP/s) is the round-2 target for these convs'}
+                                                       'these kernels still compute the weight gradients and the tf32 / fp32 modes'}
+        if a.precision != 'bf16':
+            roof = roof_tf32
         del xq, wq
     if rank == 0:
         print(json.dumps({
             'metric': 'generator training images/sec (G fwd train-BN + DAMSM + MSE + bwd + all-reduce + Adam)',
             'value': world * B / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
             'ms_per_step': ms, 'allreduce_ms_last_step': (None if t[1] != t[1] else float(t[1])), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'tf32 tensor-core convs (fp32 accumulate), fp32 elsewhere', 'data': 'synthetic',
+            'dtype': {'bf16': 'bf16 (tcgen05 forward / data-gradient convs on bf16 activations, fp32 accumulate; fp32 master weights, fp32 BatchNorm statistics, TF32 weight gradients)', 'tf32': 'tf32 tensor-core convs (fp32 accumulate), fp32 elsewhere', 'fp32': 'f32'}[a.precision], 'data': 'synthetic',
             'config': {'workload': 'configs[4]: x8 generator training step, batch %d per GPU, 32->256, 18-word captions, '
                                    'gamma (4,5,10), Adam(2e-4,(0.5,0.999)), flat-bucket NCCL all-reduce of %d gradients'
                                    % (B, ts.bucket.numel), 'batch_per_gpu': B, 'launch': ('CUDA-graph replay of the whole step' if world == 1 else 'two CUDA graphs per step (fwd+bwd, Adam) around the eager NCCL all-reduce') if use_graph else 'per-kernel launches from Python',

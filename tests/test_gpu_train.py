@@ -14,9 +14,12 @@ DEV = 'cuda'
 
 @pytest.fixture(autouse=True)
 def _fp32():
+    from tgsr_b200 import train
     tgsr_b200.set_eval_defaults()
     tgsr_b200.set_precision('fp32')
+    train.set_conv_precision('fp32')             # (a GeneratorTrainStep built by an earlier test may have left 'tf32')
     yield
+    train.set_conv_precision('fp32')
 
 
 def close(a, b, rtol=2e-4, atol=2e-5):

@@ -21,7 +21,9 @@ def _cfg():
     tgsr_b200.set_eval_defaults()
     tgsr_b200.set_precision('bf16')
     yield
+    from tgsr_b200 import train
     tgsr_b200.set_precision('fp32')
+    train.set_conv_precision('fp32')
 
 
 def _cos(a, b):

@@ -30,20 +30,31 @@ bn16_stats_partial_kernel(const h16* __restrict__ z, double* __restrict__ ws, in
   double acc[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.0;
-  const size_t nchunk = ((size_t)B * HW + 64 * 256 - 1) / (64 * 256);      // chunk = 64 pixels per thread
+  const size_t n_items = (size_t)B * HW;
+  const size_t nchunk = (n_items + 64 * 256 - 1) / (64 * 256);             // chunk = 64 pixels per thread
   for (size_t ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
     float s[8], q[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
-    for (int it = 0; it < 64; ++it) {
-      const size_t i = (ch * 64 + it) * 256 + threadIdx.x;               // (b, pixel) index, coalesced across the CTA
-      if (i < (size_t)B * HW) {
-        const size_t b = i / HW, pix = i % HW;
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(z + ((b * P + p) * (size_t)HW + pix) * 8));
-        float v[8];
-        unpack8_16<FMT>(u, v);
+    for (int it = 0; it < 64; it += 4) {
+      uint4 u[4];
+      bool ok[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { s[e] += v[e]; q[e] = fmaf(v[e], v[e], q[e]); }
+      for (int k = 0; k < 4; ++k) {                                        // four independent 16-byte loads in flight
+        const size_t i = (ch * 64 + it + k) * 256 + threadIdx.x;           // (b, pixel) index, coalesced across the CTA
+        ok[k] = i < n_items;
+        const size_t ii = ok[k] ? i : 0;
+        const size_t b = ii / HW, pix = ii % HW;
+        u[k] = __ldg(reinterpret_cast<const uint4*>(z + ((b * P + p) * (size_t)HW + pix) * 8));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (ok[k]) {
+          float v[8];
+          unpack8_16<FMT>(u[k], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { s[e] += v[e]; q[e] = fmaf(v[e], v[e], q[e]); }
+        }
       }
     }
 #pragma unroll
@@ -177,13 +188,14 @@ bn16_bwd_reduce_kernel(const h16* __restrict__ z, const float* __restrict__ mean
     m_a[e] = mean[pf * 8 + e]; r_a[e] = invstd[pf * 8 + e];
     m_g[e] = GLU ? mean[(pf + Pf) * 8 + e] : 0.f; r_g[e] = GLU ? invstd[(pf + Pf) * 8 + e] : 0.f;
   }
-  const size_t nchunk = ((size_t)B * HW + 32 * 256 - 1) / (32 * 256);
+  const size_t nchunk = ((size_t)B * HW + 16 * 256 - 1) / (16 * 256);
   for (size_t ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
     float s[NA];
 #pragma unroll
     for (int k = 0; k < NA; ++k) s[k] = 0.f;
-    for (int it = 0; it < 32; ++it) {
-      const size_t i = (ch * 32 + it) * 256 + threadIdx.x;
+#pragma unroll 2
+    for (int it = 0; it < 16; ++it) {
+      const size_t i = (ch * 16 + it) * 256 + threadIdx.x;
       if (i < (size_t)B * HW) {
         const size_t b = i / HW, pix = i % HW;
         float xa[8], xg[8], dua[8], dug[8];
@@ -307,7 +319,7 @@ static inline int ew_blocks16(size_t total) {
 static inline int split16(int P, size_t n_items, int per_block) {
   // enough CTAs to fill the machine (~4 per SM) without leaving a CTA fewer than one chunk
   const size_t chunks = (n_items + per_block - 1) / per_block;
-  size_t want = (size_t)(g_sm_count > 0 ? g_sm_count : 148) * 4 / (P > 0 ? P : 1);
+  size_t want = (size_t)(g_sm_count > 0 ? g_sm_count : 148) * 8 / (P > 0 ? P : 1);
   if (want < 1) want = 1;
   return (int)(want < chunks ? want : (chunks ? chunks : 1));
 }
@@ -366,7 +378,7 @@ extern "C" int tgsr_bn16_act_bwd(const void* z, const float* mean, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   TGSR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
   const int P = C / 8, Pf = act == TGSR_ACT_GLU ? P / 2 : P;
-  const dim3 rgrid(Pf, split16(Pf, (size_t)B * HW, 32 * 256));
+  const dim3 rgrid(Pf, split16(Pf, (size_t)B * HW, 16 * 256));
   const int blocks = ew_blocks16((size_t)B * Pf * HW);
   const float inv_n = (float)(1.0 / ((double)B * HW));
   const h16* zz = reinterpret_cast<const h16*>(z); const h16* dd = reinterpret_cast<const h16*>(dy); h16* oo = reinterpret_cast<h16*>(dz);

@@ -219,15 +219,50 @@ def conv_in(seq, x: Tensor, x_sub: Optional[Tensor] = None) -> Tensor:
     return to_blocked(train.BnActFn.apply(z, seq[1].weight, seq[1].bias, None, seq[1], ACT_GLU))
 
 
+class Head16Fn(torch.autograd.Function):
+    """y = one * act(conv_kxk(h, w)) + a * srb with 3 output channels (GET_IMAGE_G[_noAct].img util.py:894-919, conv_output +
+    Tanh model.py:223-226,280): forward on the tcgen05 head kernel straight from the blocked features; the backward (K = 3
+    input channels for the data gradient) uses the fp32 kernels of train.py on the NCHW copy of h."""
+
+    @staticmethod
+    def forward(ctx, hb: Tensor, w: Tensor, srb: Optional[Tensor], one: float, a: float, tanh: bool):
+        hb = hb.contiguous()
+        B, P, H, W, _ = hb.shape
+        k = w.shape[2]
+        packed = torch.empty(k * 16 * w.shape[1], device=w.device, dtype=DT)
+        call('tgsr_pack_head', w.device, ptr(w.detach().contiguous()), ptr(packed), w.shape[1], k, FMT)
+        y = torch.empty((B, 3, H, W), device=hb.device, dtype=torch.float32)
+        srb_c = None if srb is None else srb.contiguous()
+        from .fast import nonfinite_flag
+        call('tgsr_img_head_tc', hb.device, ptr(hb), P, 0, ptr(packed), ptr(srb_c), float(one), float(a), ptr(y), B, P * 8, H, W, k,
+             ACT_TANH if tanh else ACT_NONE, FMT, ptr(nonfinite_flag(hb.device)))
+        ctx.save_for_backward(hb, w, y, srb_c)
+        ctx.one, ctx.a, ctx.tanh = float(one), float(a), tanh
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        import ctypes as C
+        hb, w, y, srb = ctx.saved_tensors
+        dy = dy.contiguous()
+        dsrb = None
+        if ctx.tanh:
+            dconv = torch.empty_like(y)
+            dsrb = torch.empty_like(y) if (srb is not None and ctx.needs_input_grad[2]) else None
+            call('tgsr_tanh_head_bwd_f32', y.device, ptr(y), ptr(srb), ptr(dy), ctx.one, ctx.a, ptr(dconv), ptr(dsrb),
+                 C.c_size_t(y.numel()))
+        else:
+            dconv = dy if ctx.one == 1.0 else dy * ctx.one
+            if srb is not None and ctx.needs_input_grad[2]:
+                dsrb = dy * ctx.a
+        dh = ToBlockedFn.forward(None, train._conv_dgrad(dconv, w.detach(), False)) if ctx.needs_input_grad[0] else None
+        dw = train._conv_wgrad(ToNchwFn.forward(None, hb), dconv, w.shape, False) if ctx.needs_input_grad[1] else None
+        return dh, dw, dsrb, None, None, None
+
+
 def image_head(hb: Tensor, head_seq, addend: Optional[Tensor] = None, a: float = 0.0, one: float = 1.0) -> Tensor:
-    """GET_IMAGE_G[_noAct].img / conv_output (3 output channels): fp32 training kernels on the NCHW copy of h."""
-    h = to_nchw(hb)
-    if any(isinstance(m, nn.Tanh) for m in head_seq):
-        return train.TanhHeadFn.apply(h, head_seq[0].weight, addend, one, a)
-    y = train.ConvFn.apply(h, head_seq[0].weight, False)
-    if addend is not None or one != 1.0:
-        raise NotImplementedError('plain image heads take no addend')
-    return y
+    tanh = any(isinstance(m, nn.Tanh) for m in head_seq)
+    return Head16Fn.apply(hb, head_seq[0].weight, addend, one, a, tanh)
 
 
 def stage(st, hb: Optional[Tensor], LR: Optional[Tensor], words: Tensor, mask):

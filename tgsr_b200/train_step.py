@@ -113,6 +113,17 @@ class FrozenImageEncoder(nn.Module):
         self.eval()
 
     def forward(self, x):
+        if self.autocast_bf16 and x.is_cuda:
+            # library code outside the hot path: let cuDNN run it the way a mixed-precision trainer would (bf16 autocast,
+            # channels-last), so that it does not dominate the bf16 step; features return as fp32
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                f, c = self._forward(x.contiguous(memory_format=torch.channels_last))
+            return f.float().contiguous(), c.float()
+        return self._forward(x)
+
+    autocast_bf16 = False
+
+    def _forward(self, x):
         x = F.interpolate(x, size=(299, 299), mode='bilinear', align_corners=False)
         x = self.Conv2d_2b_3x3(self.Conv2d_2a_3x3(self.Conv2d_1a_3x3(x)))
         x = F.max_pool2d(x, kernel_size=3, stride=2)
@@ -136,6 +147,9 @@ class GeneratorTrainStep:
         self.conv_precision = conv_precision
         if conv_precision == 'bf16':
             set_precision('bf16')
+            if hasattr(image_encoder, 'autocast_bf16'):
+                image_encoder.autocast_bf16 = True
+                image_encoder.to(memory_format=torch.channels_last)
             train.set_conv_precision('tf32')          # the fp32 edges (3-channel convs) and the weight gradients
         else:
             set_precision('fp32')
