@@ -369,6 +369,12 @@ int tgsr_bn16_act(const void* z, const float* mean, const float* invstd, const f
 int tgsr_bn16_act_bwd(const void* z, const float* mean, const float* invstd, const float* gamma, const float* beta,
                       const void* dy, void* dz, float* dgamma, float* dbeta, double* ws, int B, int C, int HW, int act,
                       int fmt, tgsr_stream_t stream);
+/* Weight gradient of conv3x3 (pad 1, no bias) on tcgen05: dw [Cout,Cin,3,3] fp32 (overwritten) from the blocked 16-bit
+ * views x (xP,xp0; Cin channels) and dz (zP,zp0; Cout channels) at HxW.  Both operands are read from the blocked layout
+ * as MN-major UMMA operands (K = pixels); fp32 accumulation in TMEM, per-CTA partial sums added with fp32 atomics.
+ * Cin in {32,64}, Cout in {32,64,128}, H % 16 == 0, W % 8 == 0. */
+int tgsr_conv3x3_wgrad_tc(const void* x, int xP, int xp0, const void* dz, int zP, int zp0, float* dw, int B, int Cin, int H,
+                          int W, int Cout, int fmt, tgsr_stream_t stream);
 /* y [B,P,2H,2W,8] = nearest x2 of x [B,P,H,W,8];  y [B,P,H,W,8] = 2x2 block sums of x [B,P,2H,2W,8] (its adjoint). */
 int tgsr_upsample2x_blocked(const void* x, void* y, int B, int P, int H, int W, tgsr_stream_t stream);
 int tgsr_sumpool2x2_blocked(const void* x, void* y, int B, int P, int H, int W, int fmt, tgsr_stream_t stream);

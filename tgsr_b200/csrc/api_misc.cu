@@ -16,6 +16,7 @@ int init_attention_bwd(void);      // attention_bwd.cu
 int init_damsm(void);              // damsm.cu
 int init_conv_tf32(void);          // conv_tf32.cu
 int init_pyramid(void);            // pyramid.cu
+int init_wgrad_tc(void);           // wgrad_tc.cu
 }  // namespace tgsr
 
 extern "C" {
@@ -60,6 +61,8 @@ int tgsr_init(int device) {
   s = tgsr::init_conv_tf32();
   if (s != TGSR_OK) return s;
   s = tgsr::init_pyramid();
+  if (s != TGSR_OK) return s;
+  s = tgsr::init_wgrad_tc();
   if (s != TGSR_OK) return s;
   return tgsr::init_lstm();
 }

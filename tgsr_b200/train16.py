@@ -4,7 +4,8 @@ Activations between layers are bf16 tensors [B, C/8, H, W, 8] (the layout of csr
   * conv3x3 forward and data gradient: the tcgen05 implicit-GEMM kernel (bf16 operands packed from the fp32 MASTER weights
     every step, fp32 accumulation in TMEM); the data gradient is the same kernel on dz with the transposed, flipped weights
     (input channels beyond 64 are fed in two accumulating passes through the kernel's skip input);
-  * weight gradient: fp32 accumulation over fp32 copies of x and dz (TF32 tensor-core kernel, csrc/conv_tf32.cu);
+  * weight gradient: tcgen05 as well (csrc/wgrad_tc.cu): both operands read from the blocked tensors as MN-major UMMA
+    operands with the pixels as K, fp32 accumulation in TMEM over all tiles of a CTA;
   * BatchNorm (batch statistics) + GLU + skip, forward and backward: csrc/train16.cu, arithmetic in fp32 / fp64;
   * nearest x2 upsample / 2x2 sum-pool adjoint: csrc/train16.cu.
 The image heads (3 output channels), im2f / convin (3 input channels) and the word attention keep their fp32 kernels
@@ -90,6 +91,8 @@ def _conv_tc(xb: Tensor, p0: int, Cin: int, w: Tensor, residual: Optional[Tensor
 
 
 _TC_SHAPES = {(64, 128), (64, 64), (32, 64), (32, 32)}
+import os as _os
+WGRAD_TC = _os.environ.get('TGSR_WGRAD_TC', '1') != '0'      # 0: weight gradients on the TF32 kernel (fp32 NCHW copies)
 
 
 class Conv16Fn(torch.autograd.Function):
@@ -122,10 +125,13 @@ class Conv16Fn(torch.autograd.Function):
             for c0 in range(0, Cout, step):
                 dx = _conv_tc(dz, c0 // 8, step, wt[:, c0:c0 + step].contiguous(), residual=dx)
         if ctx.needs_input_grad[1]:
-            x32 = ToNchwFn.forward(None, xb); dz32 = ToNchwFn.forward(None, dz)
             dw = torch.empty_like(w)
-            name = 'tgsr_conv2d_wgrad_tf32' if _lib.load().tgsr_conv_tf32_supported(Cin, Cout, 3, 1) else 'tgsr_conv2d_wgrad_f32'
-            call(name, w.device, ptr(x32), ptr(dz32), ptr(dw), B, Cin, H, W, Cout, 3, 0)
+            if WGRAD_TC:                                            # tcgen05, straight from the blocked bf16 tensors
+                call('tgsr_conv3x3_wgrad_tc', w.device, ptr(xb), Cin // 8, 0, ptr(dz), Cout // 8, 0, ptr(dw), B, Cin, H, W, Cout, FMT)
+            else:                                                   # TF32 kernel on fp32 NCHW copies
+                x32 = ToNchwFn.forward(None, xb); dz32 = ToNchwFn.forward(None, dz)
+                name = 'tgsr_conv2d_wgrad_tf32' if _lib.load().tgsr_conv_tf32_supported(Cin, Cout, 3, 1) else 'tgsr_conv2d_wgrad_f32'
+                call(name, w.device, ptr(x32), ptr(dz32), ptr(dw), B, Cin, H, W, Cout, 3, 0)
         return dx, dw
 
 
