@@ -52,6 +52,7 @@ def parse():
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of CUDA-graph replay')
     ap.add_argument('--no-kernel-table', action='store_true', help='skip the per-kernel roofline table (roofline_per_kernel)')
     ap.add_argument('--sustained-s', type=float, default=3.0, help='seconds of back-to-back replays for the `sustained` leg (0 = skip)')
+    ap.add_argument('--no-train', action='store_true', help='skip the `train` block (configs[4]: 3 timed generator training steps)')
     return ap.parse_args()
 
 
@@ -377,6 +378,24 @@ def run_ours(args):
                      'seconds': float(t3.item()) * 1e-3, 'ms_per_step': float(t3.item()) / n_rep, 'clocks': s_samp.stop(),
                      'l2': 'not flushed (a step streams ~1.3 GB through the 126 MB L2)'}
 
+    # ---- configs[4] in the same run, at every N: 3 timed steps of the bf16 generator training step (per-GPU batch 32,
+    # NCCL all-reduce of the flat gradient bucket between the two captured graphs when N > 1)
+    train_block = None
+    if not args.no_train:
+        import bench_train
+        del flush
+        torch.cuda.empty_cache()
+        ta = argparse.Namespace(gpus=world, steps=3, warmup=3, batch=BATCH_PER_GPU, no_graph=False, precision='bf16')
+        try:
+            r = bench_train.run(ta, e2e=False, kernel_roofline=False)
+            if r is not None:
+                train_block = {k: r[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'allreduce_ms_last_step', 'steps', 'warmup',
+                                                 'dtype', 'gpu_launches', 'loss')}
+                train_block['config'] = r['config']
+        except Exception as e:                              # noqa: BLE001  (the headline line must survive a failure here)
+            train_block = {'error': repr(e)[:300]}
+        tgsr_b200.set_precision(precision)
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference_leg()
@@ -395,7 +414,7 @@ def run_ours(args):
                               'neighbouring steps; every result waited for on the host',
                     'fp32_result': {'value': e2e_fp32, 'unit': 'images/s', 'd2h_bytes_per_step': d2h_fp32}},
             'gpu_launches': int(launches),
-            'roofline': roof, 'roofline_attention': attn_roof, 'roofline_per_kernel': per_kernel, 'sustained': sustained,
+            'roofline': roof, 'roofline_attention': attn_roof, 'roofline_per_kernel': per_kernel, 'sustained': sustained, 'train': train_block,
             'model_tflops': value * GFLOP_PER_IMAGE / 1e3, 'peaks': pk,
         }
         if cpu_base is not None:

@@ -22,7 +22,7 @@ if os.environ.get('NCCL_DEBUG', 'VERSION').upper() in ('VERSION', 'WARN'):
     os.environ['NCCL_DEBUG'] = 'NONE'      # keep stdout to the single JSON line (NCCL prints its version there from VERSION up)
 
 
-def main():
+def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
@@ -31,7 +31,12 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying the captured step')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'tf32', 'fp32'],
                     help="conv precision of the step: bf16 = tcgen05 convs on blocked bf16 activations (BASELINE configs[4]), tf32 / fp32 = round-1 paths")
-    a = ap.parse_args()
+    return ap.parse_args()
+
+
+def run(a, e2e: bool = True, kernel_roofline: bool = True):
+    """One measurement of the training step with the settings in `a` (steps, warmup, batch, no_graph, precision); returns
+    the result dict on rank 0 (None elsewhere).  Uses the default process group when one is initialised."""
     import torch
     import torch.distributed as dist
     import tgsr_b200
@@ -45,8 +50,10 @@ def main():
         raise SystemExit('bench_train.py: no CUDA device -- the product path has no CPU fallback')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    if world > 1:
+    own_group = world > 1 and not dist.is_initialized()
+    if own_group:
         dist.init_process_group('nccl', device_id=dev)
+    prev_precision = tgsr_b200.get_precision()
     tgsr_b200.set_eval_defaults(); tgsr_b200.set_precision('fp32')
     import json as _json
     _pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
@@ -97,6 +104,34 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0]) / a.steps
+    result = None
+    e2e_block = None
+    roof = None
+    if e2e:
+        e2e_block = _e2e_leg(a, ts, use_graph, B, rank, world, dev, caps, lens, barrier, O, dist, torch)
+    if rank == 0 and kernel_roofline:
+        roof = _conv_roofline(a, B, dev, bf16_peak, torch)
+    if rank == 0:
+        result = {
+            'metric': 'generator training images/sec (G fwd train-BN + DAMSM + MSE + bwd + all-reduce + Adam)',
+            'value': world * B / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
+            'ms_per_step': ms, 'allreduce_ms_last_step': (None if t[1] != t[1] else float(t[1])), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': {'bf16': 'bf16 (tcgen05 forward / data-gradient / weight-gradient convs on blocked bf16 activations, fp32 accumulate; fp32 master weights, fp32 BatchNorm statistics)', 'tf32': 'tf32 tensor-core convs (fp32 accumulate), fp32 elsewhere', 'fp32': 'f32'}[a.precision], 'data': 'synthetic',
+            'config': {'workload': 'configs[4]: x8 generator training step, batch %d per GPU, 32->256, 18-word captions, '
+                                   'gamma (4,5,10), Adam(2e-4,(0.5,0.999)), flat-bucket NCCL all-reduce of %d gradients'
+                                   % (B, ts.bucket.numel), 'batch_per_gpu': B, 'launch': ('CUDA-graph replay of the whole step' if world == 1 else 'two CUDA graphs per step (fwd+bwd, Adam) around the eager NCCL all-reduce') if use_graph else 'per-kernel launches from Python',
+                       'image_encoder': 'frozen random-init Inception-v3 on torchvision/cuDNN (library, out of scope)' + (', bf16 autocast, channels-last' if a.precision == 'bf16' else '')},
+            'gpu_launches': launches, 'roofline': roof,
+            'loss': {k: float(v) for k, v in out.items()}}
+        if e2e_block is not None:
+            result['e2e'] = e2e_block
+    tgsr_b200.set_precision(prev_precision)
+    if own_group:
+        dist.destroy_process_group()
+    return result
+
+
+def _e2e_leg(a, ts, use_graph, B, rank, world, dev, caps, lens, barrier, O, dist, torch):
     # ---- end to end from decoded images: per step the H2D copy of a pinned uint8 [B,256,256,3] batch + captions, the input
     # pyramid on the device (the reference's per-sample PIL work, datasets.py:112-148), the step, and the D2H of the loss.
     hr = torch.nn.functional.interpolate(O.synth_lr(B, 32, seed=201 + rank), size=(256, 256), mode='bicubic').clamp(-1, 1)
@@ -128,8 +163,15 @@ def main():
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_ms = float(t2[0]) / a.steps
+    return {'value': world * B / (e2e_ms * 1e-3), 'unit': 'images/s', 'ms_per_step': e2e_ms,
+            'h2d_bytes_per_step': hr_h.numel() + caps_h.numel() * 8 + lens_h.numel() * 8, 'd2h_bytes_per_step': 4,
+            'input': 'pinned uint8 [B,256,256,3] decoded images + int64 captions; input pyramid (PIL-exact resize, '
+                     'normalise) on the device inside the step', 'loss': last_loss}
+
+
+def _conv_roofline(a, B, dev, bf16_peak, torch):
     roof = None
-    if rank == 0:
+    if True:
         # dominant library kernel of the step: the TF32 implicit-GEMM conv (64 -> 128 at 128x128), timed alone, L2-cold
         from tgsr_b200 import train
         from tgsr_b200.timing import cold_time_ms, make_flush
@@ -154,24 +196,14 @@ def main():
         if a.precision != 'bf16':
             roof = roof_tf32
         del xq, wq
-    if rank == 0:
-        print(json.dumps({
-            'metric': 'generator training images/sec (G fwd train-BN + DAMSM + MSE + bwd + all-reduce + Adam)',
-            'value': world * B / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
-            'ms_per_step': ms, 'allreduce_ms_last_step': (None if t[1] != t[1] else float(t[1])), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': {'bf16': 'bf16 (tcgen05 forward / data-gradient convs on bf16 activations, fp32 accumulate; fp32 master weights, fp32 BatchNorm statistics, TF32 weight gradients)', 'tf32': 'tf32 tensor-core convs (fp32 accumulate), fp32 elsewhere', 'fp32': 'f32'}[a.precision], 'data': 'synthetic',
-            'config': {'workload': 'configs[4]: x8 generator training step, batch %d per GPU, 32->256, 18-word captions, '
-                                   'gamma (4,5,10), Adam(2e-4,(0.5,0.999)), flat-bucket NCCL all-reduce of %d gradients'
-                                   % (B, ts.bucket.numel), 'batch_per_gpu': B, 'launch': ('CUDA-graph replay of the whole step' if world == 1 else 'two CUDA graphs per step (fwd+bwd, Adam) around the eager NCCL all-reduce') if use_graph else 'per-kernel launches from Python',
-                       'image_encoder': 'frozen random-init Inception-v3 on torchvision/cuDNN (library, out of scope)'},
-            'e2e': {'value': world * B / (e2e_ms * 1e-3), 'unit': 'images/s', 'ms_per_step': e2e_ms,
-                    'h2d_bytes_per_step': hr_h.numel() + caps_h.numel() * 8 + lens_h.numel() * 8, 'd2h_bytes_per_step': 4,
-                    'input': 'pinned uint8 [B,256,256,3] decoded images + int64 captions; input pyramid (PIL-exact resize, '
-                             'normalise) on the device inside the step', 'loss': last_loss},
-            'gpu_launches': launches, 'roofline': roof,
-            'loss': {k: float(v) for k, v in out.items()}}))
-    if world > 1:
-        dist.destroy_process_group()
+    return roof
+
+
+def main():
+    a = parse()
+    res = run(a)
+    if res is not None:
+        print(json.dumps(res))
 
 
 if __name__ == '__main__':

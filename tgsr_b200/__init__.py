@@ -28,8 +28,8 @@ def invalidate_caches() -> None:
     The caches follow `tensor._version`, `load_state_dict`, the library's own optimiser and BatchNorm updates; writes that
     bypass the version counter -- `param.data.copy_(...)` / `.data.mul_(...)` as in the reference's `load_params`
     (miscc/utils.py:462-464), or raw-pointer writes from other libraries -- need this call before the next eval forward."""
-    from ._lib import bump_weights_epoch
-    bump_weights_epoch()
+    from ._lib import bump_manual_epoch
+    bump_manual_epoch()
 
 
 def get_precision() -> str:

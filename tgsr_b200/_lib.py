@@ -176,8 +176,20 @@ def no_grad_path(what: str, *tensors) -> None:
                     'trains the generator against frozen text / image-text encoders); detach() it or freeze its parameters' % what)
 
 
-def tensor_key(t):
-    return None if t is None else (t.data_ptr(), t._version, str(t.device), _weights_epoch)
+_manual_epoch = 0
+
+
+def bump_manual_epoch() -> None:
+    """invalidate_caches(): also drops the caches of modules the library's own writers never touch (frozen encoders)."""
+    global _manual_epoch
+    _manual_epoch += 1
+    bump_weights_epoch()
+
+
+def tensor_key(t, trained: bool = True):
+    """Cache key of a parameter / buffer.  trained=False: a tensor only the user can change (the frozen text encoder's
+    weights): it ignores the epoch the optimiser and BatchNorm kernels bump every training step."""
+    return None if t is None else (t.data_ptr(), t._version, str(t.device), _weights_epoch if trained else _manual_epoch)
 
 
 def stream_ptr():

@@ -57,14 +57,15 @@ class RNN_ENCODER(nn.Module):
         r = self.rnn
         src = (r.weight_ih_l0, r.weight_ih_l0_reverse, r.weight_hh_l0, r.weight_hh_l0_reverse,
                r.bias_ih_l0, r.bias_ih_l0_reverse, r.bias_hh_l0, r.bias_hh_l0_reverse)
-        key = tuple(tensor_key(t) for t in src)
+        trained = self.training or any(t.requires_grad and t.grad is not None for t in src)   # frozen encoder: per-step epochs do not apply
+        key = tuple(tensor_key(t, trained) for t in src)
         cached = self.__dict__.get('_tgsr_stacked')
         if cached is None or cached[0] != key:
             d = [t.detach() for t in src]
             cached = [key, torch.stack((d[0], d[1])).contiguous(), torch.stack((d[2], d[3])).contiguous(),
                       torch.stack((d[4], d[5])).contiguous(), torch.stack((d[6], d[7])).contiguous(), None, None]
             self.__dict__['_tgsr_stacked'] = cached
-        ek = tensor_key(self.encoder.weight)
+        ek = tensor_key(self.encoder.weight, trained)
         if self.nhidden == 128 and cached[1].is_cuda and (cached[5] is None or cached[6] != ek):
             # weight prep (derived, not in state_dict): input-projection lookup table
             cached[5] = ops.lstm_prepare(self.encoder.weight.detach(), cached[1], cached[3], cached[4])
