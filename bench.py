@@ -354,6 +354,9 @@ def run_ours(args):
     pk = peaks()
     roof = pipe.dominant_kernel_roofline(B, flush, pk) if rank == 0 else None
     attn_roof = pipe.attention_roofline(B, flush, pk) if rank == 0 else None
+    # the same kernel with the grid filled 3x deeper (96 images: 4.5 waves of 148 CTAs x 4 resident): separates the
+    # kernel's own efficiency from the one-and-a-half-wave tail of the batch-32 launch
+    attn_roof_b96 = pipe.attention_roofline(96, flush, pk) if (rank == 0 and not args.no_kernel_table) else None
 
     per_kernel = pipe.kernel_rooflines(B, flush, pk) if (rank == 0 and not args.no_kernel_table) else None
 
@@ -414,7 +417,7 @@ def run_ours(args):
                               'neighbouring steps; every result waited for on the host',
                     'fp32_result': {'value': e2e_fp32, 'unit': 'images/s', 'd2h_bytes_per_step': d2h_fp32}},
             'gpu_launches': int(launches),
-            'roofline': roof, 'roofline_attention': attn_roof, 'roofline_per_kernel': per_kernel, 'sustained': sustained, 'train': train_block,
+            'roofline': roof, 'roofline_attention': attn_roof, 'roofline_attention_b96': attn_roof_b96, 'roofline_per_kernel': per_kernel, 'sustained': sustained, 'train': train_block,
             'model_tflops': value * GFLOP_PER_IMAGE / 1e3, 'peaks': pk,
         }
         if cpu_base is not None:
