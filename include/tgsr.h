@@ -375,6 +375,12 @@ int tgsr_bn16_act_bwd(const void* z, const float* mean, const float* invstd, con
  * Cin in {32,64}, Cout in {32,64,128}, H % 16 == 0, W % 8 == 0. */
 int tgsr_conv3x3_wgrad_tc(const void* x, int xP, int xp0, const void* dz, int zP, int zp0, float* dw, int B, int Cin, int H,
                           int W, int Cout, int fmt, tgsr_stream_t stream);
+/* Weight gradient of a 3-output-channel image head (GET_IMAGE_G[_noAct].img util.py:894-919, conv_output model.py:223-226;
+ * autograd in the reference): dw [3][Cin][k][k] fp32 = sum over pixels of dz [B,3,H,W] fp32 (x) the blocked 16-bit features
+ * (view xP,xp0), zero padding.  Warp-level tensor-core path, dz enters as a 16-bit value + 16-bit residual.  Cin == 32,
+ * k in {3,5}; dw is overwritten. */
+int tgsr_head_wgrad16(const void* x, int xP, int xp0, const float* dz, float* dw, int B, int Cin, int H, int W, int ksize,
+                      int fmt, tgsr_stream_t stream);
 /* y [B,P,2H,2W,8] = nearest x2 of x [B,P,H,W,8];  y [B,P,H,W,8] = 2x2 block sums of x [B,P,2H,2W,8] (its adjoint). */
 int tgsr_upsample2x_blocked(const void* x, void* y, int B, int P, int H, int W, tgsr_stream_t stream);
 int tgsr_sumpool2x2_blocked(const void* x, void* y, int B, int P, int H, int W, int fmt, tgsr_stream_t stream);

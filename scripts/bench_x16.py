@@ -72,9 +72,9 @@ def main():
     line = {'metric': 'SR images/sec (eval fwd, x16 16->256, batch %d/GPU)' % B, 'value': B * a.steps / (t_ms * 1e-3),
             'unit': 'images/s', 'n_gpus': 1, 'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': t_ms / a.steps,
             'higher_is_better': True, 'dtype': 'bf16+f16 (16-bit tcgen05 operands, f32 accumulate)', 'data': 'synthetic',
-            'config': {'workload': 'models16.py nets at GF_DIM 64: text encoder + G_SR_NET_low (4 weight-shared stages, 16->128) + '
+            'config': {'workload': 'models16.py nets at GF_DIM %d: text encoder + G_SR_NET_low (4 weight-shared stages, 16->256) + '
                                    'NetG_highweight (16->256), batch %d, 18-word captions, ntoken %d, random-init, randomised BN stats'
-                                   % (B, NTOKEN),
+                                   % (tgsr_b200.cfg.GAN.GF_DIM, B, NTOKEN),
                        'l2': 'flushed between timed iterations (256 MiB write)', 'launch': 'CUDA-graph replay'},
             'gpu_launches': pipe.last_graph_kernels * a.steps,
             'e2e': {'value': B * a.steps / (s2.elapsed_time(e2) * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': packed_h.numel(),

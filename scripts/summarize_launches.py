@@ -10,7 +10,8 @@ def main(path, title=''):
     hdr = rows[hi]; ki = hdr.index('Kernel Name'); vi = hdr.index('Metric Value')
     data = [(r[ki], float(r[vi].replace(',', ''))) for r in rows[hi + 1:] if len(r) > vi]
     idx = [i for i, (k, _) in enumerate(data) if 'lstm_cluster' in k or 'lstm_transpose' in k]
-    step = data[idx[0]:idx[1]] if len(idx) > 1 else data
+    # the LAST complete step of the list: the first one also holds the one-time weight packing / BatchNorm folding
+    step = data[idx[-2]:idx[-1]] if len(idx) > 1 else data
     tot = sum(v for _, v in step)
     print('%s\nkernels per step: %d, sum of durations %.1f us\n' % (title, len(step), tot / 1e3))
     print('| us | share | launches | kernel |\n|---:|---:|---:|---|')

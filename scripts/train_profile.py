@@ -45,7 +45,7 @@ def main():
     agg = collections.defaultdict(lambda: [0, 0.0])
     for e in prof.events():
         if e.device_type == torch.autograd.DeviceType.CUDA:
-            k = e.name.split('(')[0][:80]
+            k = e.name.replace('(anonymous namespace)::', '').split('(')[0][:130]
             agg[k][0] += 1
             agg[k][1] += e.time_range.end - e.time_range.start
     tot = sum(v[1] for v in agg.values())

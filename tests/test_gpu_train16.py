@@ -115,6 +115,48 @@ def _grad_rows(g16, g32):
     return rows
 
 
+@pytest.mark.parametrize('k,B,H,W', [(3, 2, 64, 64), (5, 2, 64, 64), (5, 3, 48, 40), (3, 1, 16, 32), (5, 1, 128, 128)])
+def test_head_wgrad16(k, B, H, W):
+    """Weight gradient of the 3-channel image heads from the blocked bf16 features (csrc/head_wgrad16.cu) against fp32
+    autograd on the same bf16-rounded features: dz enters as value + residual, so the result is fp32-accurate up to the
+    accumulation order (ragged sizes exercise the zero padding and the partial tiles)."""
+    import ctypes as C
+    from tgsr_b200 import train16 as T
+    from tgsr_b200._lib import call, ptr, FMT_BF16
+    g = torch.Generator().manual_seed(k * 100 + H)
+    h = bf(torch.randn(B, 32, H, W, generator=g) * 0.5)
+    dz = torch.randn(B, 3, H, W, generator=g) * 0.1
+    w = torch.zeros(3, 32, k, k, requires_grad=True)
+    F.conv2d(h.double(), w.double(), None, 1, k // 2).backward(dz.double())
+    hb = T.to_blocked(h.to(DEV)).contiguous()
+    dw = torch.full((3, 32, k, k), float('nan'), device=DEV)
+    call('tgsr_head_wgrad16', hb.device, ptr(hb), 4, 0, ptr(dz.to(DEV)), ptr(dw), B, 32, H, W, k, FMT_BF16)
+    ref = w.grad
+    assert torch.isfinite(dw).all()
+    assert (dw.cpu() - ref).abs().max() <= 2e-4 * ref.abs().max() + 1e-5
+    assert _cos(dw.cpu(), ref) > 0.999999
+
+
+def test_head16_backward_uses_blocked_features():
+    """Head16Fn end to end: dW, dh and d(srb) against autograd on the plain module arithmetic."""
+    from tgsr_b200 import train16 as T
+    g = torch.Generator().manual_seed(77)
+    B, H, W = 2, 32, 32
+    h = bf(torch.randn(B, 32, H, W, generator=g) * 0.5)
+    w = bf(torch.randn(3, 32, 5, 5, generator=g) * 0.05)
+    srb = torch.randn(B, 3, H, W, generator=g) * 0.3
+    dy = torch.randn(B, 3, H, W, generator=g) * 0.1
+    hr, wr, sr = h.clone().requires_grad_(True), w.clone().requires_grad_(True), srb.clone().requires_grad_(True)
+    (1.0 * torch.tanh(F.conv2d(hr, wr, None, 1, 2)) + 0.5 * sr).backward(dy)
+    hd, wd, sd = h.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True), srb.to(DEV).requires_grad_(True)
+    y = T.Head16Fn.apply(T.to_blocked(hd), wd, sd, 1.0, 0.5, True)
+    y.backward(dy.to(DEV))
+    assert _cos(wd.grad.cpu(), wr.grad) > 0.9999
+    torch.testing.assert_close(wd.grad.cpu(), wr.grad, rtol=1e-2, atol=1e-2 * wr.grad.abs().max().item())
+    assert _cos(hd.grad.cpu(), hr.grad) > 0.999
+    torch.testing.assert_close(sd.grad.cpu(), sr.grad, rtol=1e-5, atol=1e-6)
+
+
 def test_generator_step_bf16_matches_fp32_step():
     """One training step of the whole generator (G_SR_NET_low + NetG_highweight, train BN): the bf16 / tcgen05 path against
     the exact fp32 path from the same weights and inputs.

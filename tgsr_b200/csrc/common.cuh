@@ -30,4 +30,20 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// n / d and n % d for n < 2^31 with one 64-bit multiply: m = ceil(2^p / d), p = 31 + ceil(log2 d); the product error
+// n * (m*d - 2^p) stays below 2^p for every n < 2^31, so the quotient is exact (elementwise kernels decompose their
+// linear index with it instead of 64-bit divisions, which cost more than the arithmetic they index).
+struct FastDiv {
+  uint32_t d, m, p;
+  FastDiv() : d(1), m(1u << 31), p(31) {}
+  explicit FastDiv(uint32_t dd) : d(dd) {
+    uint32_t s = 0;
+    while ((1ull << s) < dd) ++s;
+    p = 31 + s;
+    m = (uint32_t)(((1ull << p) + dd - 1) / dd);
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return (uint32_t)(((uint64_t)n * m) >> p); }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
 }  // namespace tgsr

@@ -25,14 +25,14 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // ws [2 * 8P] = (sum, sum of squares) per channel; bn16_stats_final turns them into mean / invstd (+ running stats).
 template <int FMT>
 __global__ void __launch_bounds__(256)
-bn16_stats_partial_kernel(const h16* __restrict__ z, double* __restrict__ ws, int B, int P, int HW) {
+bn16_stats_partial_kernel(const h16* __restrict__ z, double* __restrict__ ws, int B, int P, int HW, FastDiv dHW) {
   const int p = blockIdx.x;
   double acc[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.0;
-  const size_t n_items = (size_t)B * HW;
-  const size_t nchunk = (n_items + 64 * 256 - 1) / (64 * 256);             // chunk = 64 pixels per thread
-  for (size_t ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
+  const uint32_t n_items = (uint32_t)B * HW;                               // < 2^31 (checked by the launcher)
+  const uint32_t nchunk = (n_items + 64 * 256 - 1) / (64 * 256);           // chunk = 64 pixels per thread
+  for (uint32_t ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
     float s[8], q[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
@@ -41,11 +41,11 @@ bn16_stats_partial_kernel(const h16* __restrict__ z, double* __restrict__ ws, in
       bool ok[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {                                        // four independent 16-byte loads in flight
-        const size_t i = (ch * 64 + it + k) * 256 + threadIdx.x;           // (b, pixel) index, coalesced across the CTA
+        const uint32_t i = (ch * 64 + it + k) * 256 + threadIdx.x;         // (b, pixel) index, coalesced across the CTA
         ok[k] = i < n_items;
-        const size_t ii = ok[k] ? i : 0;
-        const size_t b = ii / HW, pix = ii % HW;
-        u[k] = __ldg(reinterpret_cast<const uint4*>(z + ((b * P + p) * (size_t)HW + pix) * 8));
+        uint32_t b, pix;
+        dHW.divmod(ok[k] ? i : 0u, b, pix);
+        u[k] = __ldg(reinterpret_cast<const uint4*>(z + (((size_t)b * P + p) * (size_t)HW + pix) * 8));
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -101,7 +101,7 @@ template <int FMT, bool GLU>
 __global__ void __launch_bounds__(256)
 bn16_act_kernel(const h16* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const h16* __restrict__ residual,
-                h16* __restrict__ y, int B, int P, int HW) {
+                h16* __restrict__ y, int B, int P, int HW, FastDiv dHW, FastDiv dPf) {
   extern __shared__ float coef[];                               // [2][C]
   const int C = P * 8;
   for (int c = threadIdx.x; c < C; c += 256) {
@@ -110,25 +110,26 @@ bn16_act_kernel(const h16* __restrict__ z, const float* __restrict__ mean, const
   }
   __syncthreads();
   const int Pf = GLU ? P / 2 : P;
-  const size_t total = (size_t)B * Pf * HW;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-    const size_t pix = i % HW, pf = (i / HW) % Pf, b = i / ((size_t)HW * Pf);
+  const uint32_t total = (uint32_t)B * Pf * HW;                 // < 2^31 (checked by the launcher)
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    uint32_t pix, pf, b, t;
+    dHW.divmod(i, t, pix); dPf.divmod(t, b, pf);
     float a[8], o[8];
-    unpack8_16<FMT>(__ldg(reinterpret_cast<const uint4*>(z + ((b * P + pf) * (size_t)HW + pix) * 8)), a);
+    unpack8_16<FMT>(__ldg(reinterpret_cast<const uint4*>(z + (((size_t)b * P + pf) * (size_t)HW + pix) * 8)), a);
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = fmaf(a[e], coef[pf * 8 + e], coef[C + pf * 8 + e]);
     if (GLU) {
       float g[8];
-      unpack8_16<FMT>(__ldg(reinterpret_cast<const uint4*>(z + ((b * P + pf + Pf) * (size_t)HW + pix) * 8)), g);
+      unpack8_16<FMT>(__ldg(reinterpret_cast<const uint4*>(z + (((size_t)b * P + pf + Pf) * (size_t)HW + pix) * 8)), g);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float gg = fmaf(g[e], coef[(pf + Pf) * 8 + e], coef[C + (pf + Pf) * 8 + e]);
-        o[e] *= 1.0f / (1.0f + __expf(-gg));
+        o[e] *= __fdividef(1.0f, 1.0f + __expf(-gg));
       }
     }
     if (residual) {
       float r[8];
-      unpack8_16<FMT>(__ldg(reinterpret_cast<const uint4*>(residual + i * 8)), r);
+      unpack8_16<FMT>(__ldg(reinterpret_cast<const uint4*>(residual + (size_t)i * 8)), r);
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] += r[e];
     }
@@ -154,7 +155,7 @@ __device__ __forceinline__ void bn16_du(const h16* __restrict__ z, const h16* __
       const int ca = (int)pf * 8 + e, cg = ca + Pf * 8;
       const float a = fmaf(xa[e], coef[ca], coef[C + ca]);
       const float g = fmaf(xg[e], coef[cg], coef[C + cg]);
-      const float s = 1.0f / (1.0f + __expf(-g));
+      const float s = __fdividef(1.0f, 1.0f + __expf(-g));
       dua[e] = d[e] * s;
       dug[e] = d[e] * a * s * (1.0f - s);
     }
@@ -168,7 +169,7 @@ template <int FMT, bool GLU>
 __global__ void __launch_bounds__(256)
 bn16_bwd_reduce_kernel(const h16* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
                        const float* __restrict__ gamma, const float* __restrict__ beta, const h16* __restrict__ dy,
-                       double* __restrict__ ws, int B, int P, int HW) {
+                       double* __restrict__ ws, int B, int P, int HW, FastDiv dHW) {
   extern __shared__ float coef[];
   const int C = P * 8;
   for (int c = threadIdx.x; c < C; c += 256) {
@@ -188,31 +189,42 @@ bn16_bwd_reduce_kernel(const h16* __restrict__ z, const float* __restrict__ mean
     m_a[e] = mean[pf * 8 + e]; r_a[e] = invstd[pf * 8 + e];
     m_g[e] = GLU ? mean[(pf + Pf) * 8 + e] : 0.f; r_g[e] = GLU ? invstd[(pf + Pf) * 8 + e] : 0.f;
   }
-  const size_t nchunk = ((size_t)B * HW + 16 * 256 - 1) / (16 * 256);
-  for (size_t ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
+  const uint32_t n_items = (uint32_t)B * HW;                     // < 2^31 (checked by the launcher)
+  const uint32_t nchunk = (n_items + 16 * 256 - 1) / (16 * 256);
+  for (uint32_t ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
     float s[NA];
 #pragma unroll
     for (int k = 0; k < NA; ++k) s[k] = 0.f;
 #pragma unroll 2
     for (int it = 0; it < 16; ++it) {
-      const size_t i = (ch * 16 + it) * 256 + threadIdx.x;
-      if (i < (size_t)B * HW) {
-        const size_t b = i / HW, pix = i % HW;
+      const uint32_t i = (ch * 16 + it) * 256 + threadIdx.x;
+      if (i < n_items) {
+        uint32_t b, pix;
+        dHW.divmod(i, b, pix);
         float xa[8], xg[8], dua[8], dug[8];
         bn16_du<FMT, GLU>(z, dy, coef, C, P, Pf, b, pf, pix, HW, xa, xg, dua, dug);
+        // S2 = sum du * xhat = invstd * (sum du * x - mean * sum du): the raw moment costs one FMA per element here, the
+        // affine correction is applied once per chunk below
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           s[e] += dua[e];
-          s[8 + e] = fmaf(dua[e], (xa[e] - m_a[e]) * r_a[e], s[8 + e]);
+          s[8 + e] = fmaf(dua[e], xa[e], s[8 + e]);
           if (GLU) {
             s[16 + e] += dug[e];
-            s[24 + e] = fmaf(dug[e], (xg[e] - m_g[e]) * r_g[e], s[24 + e]);
+            s[24 + e] = fmaf(dug[e], xg[e], s[24 + e]);
           }
         }
       }
     }
 #pragma unroll
-    for (int k = 0; k < NA; ++k) acc[k] += s[k];
+    for (int e = 0; e < 8; ++e) {
+      acc[e] += s[e];
+      acc[8 + e] += ((double)s[8 + e] - (double)m_a[e] * (double)s[e]) * (double)r_a[e];
+      if (GLU) {
+        acc[16 + e] += s[16 + e];
+        acc[24 + e] += ((double)s[24 + e] - (double)m_g[e] * (double)s[16 + e]) * (double)r_g[e];
+      }
+    }
   }
   __shared__ double red[NA][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -244,7 +256,7 @@ __global__ void __launch_bounds__(256)
 bn16_bwd_apply_kernel(const h16* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
                       const float* __restrict__ gamma, const float* __restrict__ beta, const h16* __restrict__ dy,
                       const float* __restrict__ dgamma, const float* __restrict__ dbeta, h16* __restrict__ dz, int B, int P,
-                      int HW, float inv_n) {
+                      int HW, float inv_n, FastDiv dHW, FastDiv dPf) {
   extern __shared__ float coef[];                               // [2][C] affine + [4][C]: mean, invstd, S1/N, S2/N
   const int C = P * 8;
   float* mu = coef + 2 * C; float* rs = mu + C; float* s1 = rs + C; float* s2 = s1 + C;
@@ -255,9 +267,10 @@ bn16_bwd_apply_kernel(const h16* __restrict__ z, const float* __restrict__ mean,
   }
   __syncthreads();
   const int Pf = GLU ? P / 2 : P;
-  const size_t total = (size_t)B * Pf * HW;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-    const size_t pix = i % HW, pf = (i / HW) % Pf, b = i / ((size_t)HW * Pf);
+  const uint32_t total = (uint32_t)B * Pf * HW;                 // < 2^31 (checked by the launcher)
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    uint32_t pix, pf, b, t;
+    dHW.divmod(i, t, pix); dPf.divmod(t, b, pf);
     float xa[8], xg[8], dua[8], dug[8], o[8];
     bn16_du<FMT, GLU>(z, dy, coef, C, P, Pf, b, pf, pix, HW, xa, xg, dua, dug);
 #pragma unroll
@@ -266,7 +279,7 @@ bn16_bwd_apply_kernel(const h16* __restrict__ z, const float* __restrict__ mean,
       const float xh = (xa[e] - mu[c]) * rs[c];
       o[e] = coef[c] * (dua[e] - s1[c] - xh * s2[c]);
     }
-    *reinterpret_cast<uint4*>(dz + ((b * P + pf) * (size_t)HW + pix) * 8) = pack8_16<FMT>(o);
+    *reinterpret_cast<uint4*>(dz + (((size_t)b * P + pf) * (size_t)HW + pix) * 8) = pack8_16<FMT>(o);
     if (GLU) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -274,32 +287,33 @@ bn16_bwd_apply_kernel(const h16* __restrict__ z, const float* __restrict__ mean,
         const float xh = (xg[e] - mu[c]) * rs[c];
         o[e] = coef[c] * (dug[e] - s1[c] - xh * s2[c]);
       }
-      *reinterpret_cast<uint4*>(dz + ((b * P + pf + Pf) * (size_t)HW + pix) * 8) = pack8_16<FMT>(o);
+      *reinterpret_cast<uint4*>(dz + (((size_t)b * P + pf + Pf) * (size_t)HW + pix) * 8) = pack8_16<FMT>(o);
     }
   }
 }
 
 // ---------------------------------------------------------------- nearest x2 upsample and its adjoint
 __global__ void __launch_bounds__(256)
-upsample2x_blocked_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, size_t planes, int H, int W) {
-  const size_t total = planes * 4 * H * W;
-  const int Wo = 2 * W, Ho = 2 * H;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-    const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
-    const size_t pl = i / ((size_t)Wo * Ho);
-    y[i] = __ldg(x + (pl * H + (oy >> 1)) * W + (ox >> 1));
+upsample2x_blocked_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint32_t planes, int H, int W, FastDiv dWo,
+                          FastDiv dHo) {
+  const uint32_t total = planes * 4u * H * W;                    // < 2^31 (checked by the launcher)
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    uint32_t ox, oy, pl, t;
+    dWo.divmod(i, t, ox); dHo.divmod(t, pl, oy);
+    y[i] = __ldg(x + ((size_t)pl * H + (oy >> 1)) * W + (ox >> 1));
   }
 }
 
 template <int FMT>
 __global__ void __launch_bounds__(256)
-sumpool2x2_blocked_kernel(const h16* __restrict__ x, h16* __restrict__ y, size_t planes, int H, int W) {
-  const size_t total = planes * H * W;                           // output pixels
+sumpool2x2_blocked_kernel(const h16* __restrict__ x, h16* __restrict__ y, uint32_t planes, int H, int W, FastDiv dW,
+                          FastDiv dH) {
+  const uint32_t total = planes * H * W;                         // output pixels; < 2^29 (checked by the launcher)
   const int Wi = 2 * W;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-    const int ox = (int)(i % W), oy = (int)((i / W) % H);
-    const size_t pl = i / ((size_t)W * H);
-    const h16* p = x + ((pl * 2 * H + 2 * oy) * (size_t)Wi + 2 * ox) * 8;
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    uint32_t ox, oy, pl, t;
+    dW.divmod(i, t, ox); dH.divmod(t, pl, oy);
+    const h16* p = x + (((size_t)pl * 2 * H + 2 * oy) * (size_t)Wi + 2 * ox) * 8;
     float a[8], b[8], c[8], d[8], o[8];
     unpack8_16<FMT>(__ldg(reinterpret_cast<const uint4*>(p)), a);
     unpack8_16<FMT>(__ldg(reinterpret_cast<const uint4*>(p + 8)), b);
@@ -307,7 +321,7 @@ sumpool2x2_blocked_kernel(const h16* __restrict__ x, h16* __restrict__ y, size_t
     unpack8_16<FMT>(__ldg(reinterpret_cast<const uint4*>(p + (size_t)Wi * 8 + 8)), d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = (a[e] + b[e]) + (c[e] + d[e]);
-    *reinterpret_cast<uint4*>(y + i * 8) = pack8_16<FMT>(o);
+    *reinterpret_cast<uint4*>(y + (size_t)i * 8) = pack8_16<FMT>(o);
   }
 }
 
@@ -333,14 +347,14 @@ extern "C" int tgsr_bn16_stats(const void* z, float* mean, float* invstd, float*
   using namespace tgsr;
   TGSR_REQUIRE_PTR(z); TGSR_REQUIRE_PTR(mean); TGSR_REQUIRE_PTR(invstd); TGSR_REQUIRE_PTR(ws);
   TGSR16_FMT(fmt);
-  TGSR_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && HW > 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && HW > 0 && (long long)B * HW < (1ll << 31) - 64 * 256, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE((running_mean == nullptr) == (running_var == nullptr), TGSR_ERR_NULL);
   cudaStream_t st = (cudaStream_t)stream;
   TGSR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
   const int P = C / 8;
   const dim3 grid(P, split16(P, (size_t)B * HW, 64 * 256));
-  if (fmt == TGSR_FMT_F16) bn16_stats_partial_kernel<TGSR_FMT_F16><<<grid, 256, 0, st>>>(reinterpret_cast<const h16*>(z), ws, B, P, HW);
-  else bn16_stats_partial_kernel<TGSR_FMT_BF16><<<grid, 256, 0, st>>>(reinterpret_cast<const h16*>(z), ws, B, P, HW);
+  if (fmt == TGSR_FMT_F16) bn16_stats_partial_kernel<TGSR_FMT_F16><<<grid, 256, 0, st>>>(reinterpret_cast<const h16*>(z), ws, B, P, HW, FastDiv((uint32_t)HW));
+  else bn16_stats_partial_kernel<TGSR_FMT_BF16><<<grid, 256, 0, st>>>(reinterpret_cast<const h16*>(z), ws, B, P, HW, FastDiv((uint32_t)HW));
   bn16_stats_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, mean, invstd, running_mean, running_var, momentum, eps, C,
                                                             (double)B * HW);
   return launch_status(2);
@@ -354,12 +368,13 @@ extern "C" int tgsr_bn16_act(const void* z, const float* mean, const float* invs
   TGSR_REQUIRE(act == TGSR_ACT_NONE || act == TGSR_ACT_GLU, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && HW > 0 && (act != TGSR_ACT_GLU || C % 16 == 0) && C <= 1024, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE(!(residual && act == TGSR_ACT_GLU), TGSR_ERR_UNSUPPORTED);
+  TGSR_REQUIRE((long long)B * (C / 8) * HW < (1ll << 31) - (1 << 24), TGSR_ERR_BAD_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
   const int P = C / 8, Pf = act == TGSR_ACT_GLU ? P / 2 : P;
   const int blocks = ew_blocks16((size_t)B * Pf * HW);
   const size_t sm = sizeof(float) * 2 * C;
   const h16* zz = reinterpret_cast<const h16*>(z); const h16* rr = reinterpret_cast<const h16*>(residual); h16* yy = reinterpret_cast<h16*>(y);
-#define TGSR16_LAUNCH(F, G) bn16_act_kernel<F, G><<<blocks, 256, sm, st>>>(zz, mean, invstd, gamma, beta, rr, yy, B, P, HW)
+#define TGSR16_LAUNCH(F, G) bn16_act_kernel<F, G><<<blocks, 256, sm, st>>>(zz, mean, invstd, gamma, beta, rr, yy, B, P, HW, FastDiv((uint32_t)HW), FastDiv((uint32_t)Pf))
   if (fmt == TGSR_FMT_F16) { if (act == TGSR_ACT_GLU) TGSR16_LAUNCH(TGSR_FMT_F16, true); else TGSR16_LAUNCH(TGSR_FMT_F16, false); }
   else { if (act == TGSR_ACT_GLU) TGSR16_LAUNCH(TGSR_FMT_BF16, true); else TGSR16_LAUNCH(TGSR_FMT_BF16, false); }
 #undef TGSR16_LAUNCH
@@ -375,9 +390,11 @@ extern "C" int tgsr_bn16_act_bwd(const void* z, const float* mean, const float* 
   TGSR16_FMT(fmt);
   TGSR_REQUIRE(act == TGSR_ACT_NONE || act == TGSR_ACT_GLU, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && HW > 0 && (act != TGSR_ACT_GLU || C % 16 == 0) && C <= 1024, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE((long long)B * (C / 8) * HW < (1ll << 31) - (1 << 24), TGSR_ERR_BAD_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
   TGSR_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
   const int P = C / 8, Pf = act == TGSR_ACT_GLU ? P / 2 : P;
+  const FastDiv dHW((uint32_t)HW), dPf((uint32_t)Pf);
   const dim3 rgrid(Pf, split16(Pf, (size_t)B * HW, 16 * 256));
   const int blocks = ew_blocks16((size_t)B * Pf * HW);
   const float inv_n = (float)(1.0 / ((double)B * HW));
@@ -385,9 +402,9 @@ extern "C" int tgsr_bn16_act_bwd(const void* z, const float* mean, const float* 
   const size_t sm2 = sizeof(float) * 2 * C, sm6 = sizeof(float) * 6 * C;
 #define TGSR16_BWD(F, G)                                                                                               \
   do {                                                                                                                 \
-    bn16_bwd_reduce_kernel<F, G><<<rgrid, 256, sm2, st>>>(zz, mean, invstd, gamma, beta, dd, ws, B, P, HW);             \
+    bn16_bwd_reduce_kernel<F, G><<<rgrid, 256, sm2, st>>>(zz, mean, invstd, gamma, beta, dd, ws, B, P, HW, dHW);             \
     bn16_bwd_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, dgamma, dbeta, C);                                     \
-    bn16_bwd_apply_kernel<F, G><<<blocks, 256, sm6, st>>>(zz, mean, invstd, gamma, beta, dd, dgamma, dbeta, oo, B, P, HW, inv_n); \
+    bn16_bwd_apply_kernel<F, G><<<blocks, 256, sm6, st>>>(zz, mean, invstd, gamma, beta, dd, dgamma, dbeta, oo, B, P, HW, inv_n, dHW, dPf); \
   } while (0)
   if (fmt == TGSR_FMT_F16) { if (act == TGSR_ACT_GLU) TGSR16_BWD(TGSR_FMT_F16, true); else TGSR16_BWD(TGSR_FMT_F16, false); }
   else { if (act == TGSR_ACT_GLU) TGSR16_BWD(TGSR_FMT_BF16, true); else TGSR16_BWD(TGSR_FMT_BF16, false); }
@@ -398,10 +415,10 @@ extern "C" int tgsr_bn16_act_bwd(const void* z, const float* mean, const float* 
 extern "C" int tgsr_upsample2x_blocked(const void* x, void* y, int B, int P, int H, int W, tgsr_stream_t stream) {
   using namespace tgsr;
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(y);
-  TGSR_REQUIRE(B > 0 && P > 0 && H > 0 && W > 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE(B > 0 && P > 0 && H > 0 && W > 0 && (long long)B * P * 4 * H * W < (1ll << 31) - (1 << 24), TGSR_ERR_BAD_SHAPE);
   const size_t planes = (size_t)B * P;
   upsample2x_blocked_kernel<<<ew_blocks16(planes * 4 * H * W), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), planes, H, W);
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), (uint32_t)planes, H, W, FastDiv(2u * W), FastDiv(2u * H));
   return launch_status();
 }
 
@@ -409,12 +426,13 @@ extern "C" int tgsr_sumpool2x2_blocked(const void* x, void* y, int B, int P, int
   using namespace tgsr;
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(y);
   TGSR16_FMT(fmt);
-  TGSR_REQUIRE(B > 0 && P > 0 && H > 0 && W > 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE(B > 0 && P > 0 && H > 0 && W > 0 && (long long)B * P * H * W < (1ll << 29), TGSR_ERR_BAD_SHAPE);
   const size_t planes = (size_t)B * P;
   const int blocks = ew_blocks16(planes * H * W);
+  const FastDiv dW((uint32_t)W), dH((uint32_t)H);
   if (fmt == TGSR_FMT_F16)
-    sumpool2x2_blocked_kernel<TGSR_FMT_F16><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const h16*>(x), reinterpret_cast<h16*>(y), planes, H, W);
+    sumpool2x2_blocked_kernel<TGSR_FMT_F16><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const h16*>(x), reinterpret_cast<h16*>(y), (uint32_t)planes, H, W, dW, dH);
   else
-    sumpool2x2_blocked_kernel<TGSR_FMT_BF16><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const h16*>(x), reinterpret_cast<h16*>(y), planes, H, W);
+    sumpool2x2_blocked_kernel<TGSR_FMT_BF16><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const h16*>(x), reinterpret_cast<h16*>(y), (uint32_t)planes, H, W, dW, dH);
   return launch_status();
 }

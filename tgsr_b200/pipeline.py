@@ -289,6 +289,28 @@ class SRPipeline:
             out.append(row)
         return out
 
+    @staticmethod
+    def step_roofline_bound(B: int, pk, T: int = 18):
+        """Analytic lower bound of one x8 step with ONE kernel per layer (no cross-layer fusion): for every conv / head /
+        attention layer max(executed MMA FLOP / measured bf16 peak, algorithmic bytes / measured copy bandwidth), summed
+        along the dependent chain (the text encoder and NetG_high's 32x32 trunk run beside G_SR_NET_low's first stages and
+        are left out).  `ms_per_step / bound_ms` says how far the whole step is from the sum of its per-kernel rooflines."""
+        e, tf, bw = 2, pk['bf16'] * 1e12, pk['hbm'] * 1e9
+        t = lambda flops, nbytes: max(flops / tf, nbytes / bw)
+        conv = lambda ci, co, px, skip: t(2 * 9 * ci * co * px, px * (ci + (co // 2 if not skip else co) + (co if skip else 0)) * e)
+        up = lambda ci, co, px: t(2 * 16 * ci * 2 * co * px, px * ci * e + 4 * px * co * e)
+        head = lambda k, px, add: t(2 * k * k * 32 * 3 * px, px * (32 * e + 12 + (12 if add else 0)))
+        attn = lambda px: t(0, px * (32 * e + 32 * e + 4 * T))
+        total = 0.0
+        for S in (32, 64, 128):                                   # G_SR_NET_low stages 1..3 (64 channels, 2 ResBlocks)
+            px = B * S * S
+            total += attn(px) + 2 * (conv(64, 128, px, False) + conv(64, 64, px, True)) + up(64, 32, px) + head(3, 4 * px, False)
+        for S in (64, 128):                                       # NetG_high tail after the trunk (32 channels)
+            px = B * S * S
+            total += conv(32, 64, px, False) + t(2 * 9 * 32 * 32 * px, px * 64 * e) + up(32, 32, px) + head(5, 4 * px, True)
+        total += head(5, B * 64 * 64, True)
+        return total * 1e3
+
     @torch.no_grad()
     def attention_roofline(self, B, flush, pk):
         """Fused word attention at the h_net3 shape (Q=128^2, idf 32, cdf 256, T 18), timed alone.

@@ -262,7 +262,14 @@ class Head16Fn(torch.autograd.Function):
             if srb is not None and ctx.needs_input_grad[2]:
                 dsrb = dy * ctx.a
         dh = ToBlockedFn.forward(None, train._conv_dgrad(dconv, w.detach(), False)) if ctx.needs_input_grad[0] else None
-        dw = train._conv_wgrad(ToNchwFn.forward(None, hb), dconv, w.shape, False) if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            if w.shape[1] == 32:
+                B, P, H, W, _ = hb.shape
+                dw = torch.empty(tuple(w.shape), device=w.device, dtype=torch.float32)
+                call('tgsr_head_wgrad16', hb.device, ptr(hb), P, 0, ptr(dconv.contiguous()), ptr(dw), B, P * 8, H, W, w.shape[2], FMT)
+            else:
+                dw = train._conv_wgrad(ToNchwFn.forward(None, hb), dconv, w.shape, False)
         return dh, dw, dsrb, None, None, None
 
 

@@ -114,17 +114,51 @@ class FrozenImageEncoder(nn.Module):
 
     def forward(self, x):
         if self.autocast_bf16 and x.is_cuda:
-            # library code outside the hot path: let cuDNN run it the way a mixed-precision trainer would (bf16 autocast,
-            # channels-last), so that it does not dominate the bf16 step; features return as fp32
-            with torch.autocast('cuda', dtype=torch.bfloat16):
-                f, c = self._forward(x.contiguous(memory_format=torch.channels_last))
+            # library code outside the hot path: let cuDNN run it the way a mixed-precision inference stack would -- eval-mode
+            # BatchNorm folded into the conv weights (the encoder is frozen), bf16 channels-last tensors end to end -- so that
+            # it does not dominate the bf16 step; features return as fp32
+            self._fold_bf16(x.device)
+            f, c = self._forward(x, torch.bfloat16)
             return f.float().contiguous(), c.float()
         return self._forward(x)
 
     autocast_bf16 = False
+    _folded_on = None
 
-    def _forward(self, x):
+    def _load_from_state_dict(self, *a, **k):
+        self._folded_on = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def _fold_bf16(self, device):
+        """conv(bias=False) -> BatchNorm(eval) -> ReLU of every torchvision BasicConv2d becomes one bf16 conv with bias + ReLU:
+        w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps).  The folded tensors live outside the
+        state dict (rebuilt after load_state_dict or a device move)."""
+        if self._folded_on == device:
+            return
+        import types
+        from torchvision.models.inception import BasicConv2d
+
+        def folded(m, x):
+            if x.dtype != torch.bfloat16:                    # the fp32 path keeps conv -> BatchNorm -> ReLU
+                return BasicConv2d.forward(m, x)
+            return F.relu(F.conv2d(x, m._fw, m._fb, m.conv.stride, m.conv.padding), inplace=True)
+
+        with torch.no_grad():
+            for m in self.modules():
+                if isinstance(m, BasicConv2d):
+                    s = m.bn.weight / torch.sqrt(m.bn.running_var + m.bn.eps)
+                    m._fw = (m.conv.weight * s.view(-1, 1, 1, 1)).to(device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+                    m._fb = (m.bn.bias - m.bn.running_mean * s).to(device, torch.bfloat16)
+                    m.forward = types.MethodType(folded, m)
+            self._ef_w = self.emb_features.weight.to(device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            self._ec_w = self.emb_cnn_code.weight.to(device, torch.bfloat16)
+            self._ec_b = self.emb_cnn_code.bias.to(device, torch.bfloat16)
+        self._folded_on = device
+
+    def _forward(self, x, dtype=None):
         x = F.interpolate(x, size=(299, 299), mode='bilinear', align_corners=False)
+        if dtype is not None:
+            x = x.to(dtype).contiguous(memory_format=torch.channels_last)
         x = self.Conv2d_2b_3x3(self.Conv2d_2a_3x3(self.Conv2d_1a_3x3(x)))
         x = F.max_pool2d(x, kernel_size=3, stride=2)
         x = self.Conv2d_4a_3x3(self.Conv2d_3b_1x1(x))
@@ -134,6 +168,8 @@ class FrozenImageEncoder(nn.Module):
         features = x
         x = self.Mixed_7c(self.Mixed_7b(self.Mixed_7a(x)))
         x = F.avg_pool2d(x, kernel_size=8).view(x.size(0), -1)
+        if dtype is not None:
+            return F.conv2d(features, self._ef_w), F.linear(x, self._ec_w, self._ec_b)
         return self.emb_features(features), self.emb_cnn_code(x)
 
 
