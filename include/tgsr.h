@@ -372,9 +372,10 @@ int tgsr_bn16_act_bwd(const void* z, const float* mean, const float* invstd, con
 /* Weight gradient of conv3x3 (pad 1, no bias) on tcgen05: dw [Cout,Cin,3,3] fp32 (overwritten) from the blocked 16-bit
  * views x (xP,xp0; Cin channels) and dz (zP,zp0; Cout channels) at HxW.  Both operands are read from the blocked layout
  * as MN-major UMMA operands (K = pixels); fp32 accumulation in TMEM, per-CTA partial sums added with fp32 atomics.
- * Cin in {32,64}, Cout in {32,64,128}, H % 16 == 0, W % 8 == 0. */
-int tgsr_conv3x3_wgrad_tc(const void* x, int xP, int xp0, const void* dz, int zP, int zp0, float* dw, int B, int Cin, int H,
-                          int W, int Cout, int fmt, tgsr_stream_t stream);
+ * Cin in {32,64}, Cout in {32,64,128}, H % 16 == 0, W % 8 == 0.  ws: caller's scratch of 9*Cin*Cout floats (the partial sums
+ * are accumulated there as [tap][ci][co], one 128-byte line per warp-wide atomic, then transposed into dw). */
+int tgsr_conv3x3_wgrad_tc(const void* x, int xP, int xp0, const void* dz, int zP, int zp0, float* dw, float* ws, int B, int Cin,
+                          int H, int W, int Cout, int fmt, tgsr_stream_t stream);
 /* Weight gradient of a 3-output-channel image head (GET_IMAGE_G[_noAct].img util.py:894-919, conv_output model.py:223-226;
  * autograd in the reference): dw [3][Cin][k][k] fp32 = sum over pixels of dz [B,3,H,W] fp32 (x) the blocked 16-bit features
  * (view xP,xp0), zero padding.  Warp-level tensor-core path, dz enters as a 16-bit value + 16-bit residual.  Cin == 32,

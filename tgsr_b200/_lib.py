@@ -90,7 +90,7 @@ _SIGS = {
     'tgsr_bn16_stats': ([C.c_void_p] * 5 + [C.c_float, C.c_float, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p], C.c_int),
     'tgsr_bn16_act': ([C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p], C.c_int),
     'tgsr_bn16_act_bwd': ([C.c_void_p] * 10 + [C.c_int] * 5 + [C.c_void_p], C.c_int),
-    'tgsr_conv3x3_wgrad_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p], C.c_int),
+    'tgsr_conv3x3_wgrad_tc': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p], C.c_int),
     'tgsr_head_wgrad16': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p], C.c_int),
     'tgsr_upsample2x_blocked': ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p], C.c_int),
     'tgsr_sumpool2x2_blocked': ([C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p], C.c_int),

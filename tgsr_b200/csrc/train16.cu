@@ -23,24 +23,39 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // grid (P, SPLIT): CTA (p, s) sums the 8 channels of plane p over pixel chunks s, s + SPLIT, ...; every thread keeps
 // 8 + 8 fp32 partials over at most 64 pixels before folding them into fp64, a CTA adds 16 doubles to ws with atomics.
 // ws [2 * 8P] = (sum, sum of squares) per channel; bn16_stats_final turns them into mean / invstd (+ running stats).
-template <int FMT>
-__global__ void __launch_bounds__(256)
-bn16_stats_partial_kernel(const h16* __restrict__ z, double* __restrict__ ws, int B, int P, int HW, FastDiv dHW) {
-  const int p = blockIdx.x;
-  double acc[16];
+// Fold per-thread fp32 partials (at most 64 elements each) into the CTA's fp64 accumulators in shared memory: warp
+// shuffle reduction in fp32, lane 0 adds in fp64.  Keeping the fp64 state out of the register file is what lets two CTAs
+// share an SM with several 16-byte loads in flight per thread (these kernels are latency-bound otherwise).
+template <int NA>
+__device__ __forceinline__ void fold_partials(float (&s)[NA], double (*sacc)[NA], int warp, int lane) {
 #pragma unroll
-  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  for (int k = 0; k < NA; ++k) {
+    float v = s[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sacc[warp][k] += (double)v;
+    s[k] = 0.f;
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256, 2)
+bn16_stats_partial_kernel(const h16* __restrict__ z, double* __restrict__ ws, int B, int P, int HW, FastDiv dHW) {
+  __shared__ double sacc[8][16];
+  const int p = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 128) sacc[threadIdx.x >> 4][threadIdx.x & 15] = 0.0;
+  __syncthreads();
   const uint32_t n_items = (uint32_t)B * HW;                               // < 2^31 (checked by the launcher)
   const uint32_t nchunk = (n_items + 64 * 256 - 1) / (64 * 256);           // chunk = 64 pixels per thread
+  float sq[16];                                                            // sums | sums of squares
+#pragma unroll
+  for (int e = 0; e < 16; ++e) sq[e] = 0.f;
   for (uint32_t ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
-    float s[8], q[8];
+    for (int it = 0; it < 64; it += 8) {
+      uint4 u[8];
+      bool ok[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
-    for (int it = 0; it < 64; it += 4) {
-      uint4 u[4];
-      bool ok[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {                                        // four independent 16-byte loads in flight
+      for (int k = 0; k < 8; ++k) {                                        // eight independent 16-byte loads in flight
         const uint32_t i = (ch * 64 + it + k) * 256 + threadIdx.x;         // (b, pixel) index, coalesced across the CTA
         ok[k] = i < n_items;
         uint32_t b, pix;
@@ -48,30 +63,22 @@ bn16_stats_partial_kernel(const h16* __restrict__ z, double* __restrict__ ws, in
         u[k] = __ldg(reinterpret_cast<const uint4*>(z + (((size_t)b * P + p) * (size_t)HW + pix) * 8));
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         if (ok[k]) {
           float v[8];
           unpack8_16<FMT>(u[k], v);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { s[e] += v[e]; q[e] = fmaf(v[e], v[e], q[e]); }
+          for (int e = 0; e < 8; ++e) { sq[e] += v[e]; sq[8 + e] = fmaf(v[e], v[e], sq[8 + e]); }
         }
       }
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { acc[e] += s[e]; acc[8 + e] += q[e]; }
-  }
-  __shared__ double red[16][8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const double t = warp_sum_d(acc[k]);
-    if (lane == 0) red[k][warp] = t;
+    fold_partials<16>(sq, sacc, warp, lane);
   }
   __syncthreads();
   if (threadIdx.x < 16) {
     double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    for (int w = 0; w < 8; ++w) t += sacc[w][threadIdx.x];
     const int e = threadIdx.x & 7, which = threadIdx.x >> 3;
     atomicAdd(ws + 2 * (p * 8 + e) + which, t);
   }
@@ -166,36 +173,30 @@ __device__ __forceinline__ void bn16_du(const h16* __restrict__ z, const h16* __
 }
 
 template <int FMT, bool GLU>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn16_bwd_reduce_kernel(const h16* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ invstd,
                        const float* __restrict__ gamma, const float* __restrict__ beta, const h16* __restrict__ dy,
                        double* __restrict__ ws, int B, int P, int HW, FastDiv dHW) {
   extern __shared__ float coef[];
+  constexpr int NA = GLU ? 32 : 16;                             // (S1 | raw S2) x (value | gate) x 8 channels
+  __shared__ double sacc[8][NA];
   const int C = P * 8;
   for (int c = threadIdx.x; c < C; c += 256) {
     const float a = gamma[c] * invstd[c];
     coef[c] = a; coef[C + c] = beta[c] - mean[c] * a;
   }
+  for (int k = threadIdx.x; k < 8 * NA; k += 256) sacc[k / NA][k % NA] = 0.0;
   __syncthreads();
   const int Pf = GLU ? P / 2 : P;
   const int pf = blockIdx.x;                                     // grid (Pf, SPLIT)
-  constexpr int NA = GLU ? 32 : 16;
-  double acc[NA];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float s[NA];
 #pragma unroll
-  for (int k = 0; k < NA; ++k) acc[k] = 0.0;
-  float m_a[8], r_a[8], m_g[8], r_g[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    m_a[e] = mean[pf * 8 + e]; r_a[e] = invstd[pf * 8 + e];
-    m_g[e] = GLU ? mean[(pf + Pf) * 8 + e] : 0.f; r_g[e] = GLU ? invstd[(pf + Pf) * 8 + e] : 0.f;
-  }
+  for (int k = 0; k < NA; ++k) s[k] = 0.f;
   const uint32_t n_items = (uint32_t)B * HW;                     // < 2^31 (checked by the launcher)
   const uint32_t nchunk = (n_items + 16 * 256 - 1) / (16 * 256);
   for (uint32_t ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
-    float s[NA];
-#pragma unroll
-    for (int k = 0; k < NA; ++k) s[k] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (int it = 0; it < 16; ++it) {
       const uint32_t i = (ch * 16 + it) * 256 + threadIdx.x;
       if (i < n_items) {
@@ -204,7 +205,7 @@ bn16_bwd_reduce_kernel(const h16* __restrict__ z, const float* __restrict__ mean
         float xa[8], xg[8], dua[8], dug[8];
         bn16_du<FMT, GLU>(z, dy, coef, C, P, Pf, b, pf, pix, HW, xa, xg, dua, dug);
         // S2 = sum du * xhat = invstd * (sum du * x - mean * sum du): the raw moment costs one FMA per element here, the
-        // affine correction is applied once per chunk below
+        // affine correction is applied once per CTA below
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           s[e] += dua[e];
@@ -216,30 +217,16 @@ bn16_bwd_reduce_kernel(const h16* __restrict__ z, const float* __restrict__ mean
         }
       }
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      acc[e] += s[e];
-      acc[8 + e] += ((double)s[8 + e] - (double)m_a[e] * (double)s[e]) * (double)r_a[e];
-      if (GLU) {
-        acc[16 + e] += s[16 + e];
-        acc[24 + e] += ((double)s[24 + e] - (double)m_g[e] * (double)s[16 + e]) * (double)r_g[e];
-      }
-    }
-  }
-  __shared__ double red[NA][8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < NA; ++k) {
-    const double t = warp_sum_d(acc[k]);
-    if (lane == 0) red[k][warp] = t;
+    fold_partials<NA>(s, sacc, warp, lane);                      // fp32 over 16 elements per thread, fp64 from there on
   }
   __syncthreads();
   if (threadIdx.x < NA) {
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
     const int k = threadIdx.x, e = k & 7, which = (k >> 3) & 1, gate = k >> 4;     // (S1 | S2) x (value | gate)
+    double t = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { t += sacc[w][k]; t1 += sacc[w][k & ~8]; }
     const int c = (pf + (gate ? Pf : 0)) * 8 + e;
+    if (which) t = (t - (double)mean[c] * t1) * (double)invstd[c];
     atomicAdd(ws + 2 * c + which, t);
   }
 }

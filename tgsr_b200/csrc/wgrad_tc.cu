@@ -34,7 +34,7 @@ typedef CUresult (*EncodeTiledFnW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 static EncodeTiledFnW g_encode_w = nullptr;
 
 struct WgParams {
-  float* dw;                      // [Cout][Cin][3][3] fp32, accumulated with atomics
+  float* ws;                      // [9 taps][Cin][Cout] fp32 partial sums, accumulated with atomics (coalesced over Cout)
   int Cout, B, H, W;
   int tiles_x, tiles_y, ntiles;
   int zP, zp0, xP, xp0;           // plane counts / offsets of the dz and x views
@@ -158,9 +158,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant_
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + t * CIN + c0, v);
           tmem_ld_wait();
+          // lanes = consecutive output channels: every warp-wide atomic covers one 128-byte line of ws[tap][ci][:]
           if (co < p.Cout) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(p.dw + ((size_t)co * CIN + c0 + j) * 9 + tap, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) atomicAdd(p.ws + ((size_t)tap * CIN + c0 + j) * p.Cout + co, __uint_as_float(v[j]));
           }
         }
       }
@@ -169,6 +170,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ws [9][Cin][Cout] -> dw [Cout][Cin][3][3]
+__global__ void wgrad_tc_finish_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cin, int Cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // index into dw
+  if (i >= Cout * Cin * 9) return;
+  const int tap = i % 9, ci = (i / 9) % Cin, co = i / (9 * Cin);
+  dw[i] = ws[((size_t)tap * Cin + ci) * Cout + co];
 }
 
 int init_wgrad_tc() {
@@ -202,10 +211,10 @@ static int make_box_w(CUtensorMap* m, const void* x, int B, int P, int H, int W,
 
 }  // namespace tgsr
 
-extern "C" int tgsr_conv3x3_wgrad_tc(const void* x, int xP, int xp0, const void* dz, int zP, int zp0, float* dw, int B,
-                                     int Cin, int H, int W, int Cout, int fmt, tgsr_stream_t stream) {
+extern "C" int tgsr_conv3x3_wgrad_tc(const void* x, int xP, int xp0, const void* dz, int zP, int zp0, float* dw, float* ws,
+                                     int B, int Cin, int H, int W, int Cout, int fmt, tgsr_stream_t stream) {
   using namespace tgsr;
-  TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(dz); TGSR_REQUIRE_PTR(dw);
+  TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(dz); TGSR_REQUIRE_PTR(dw); TGSR_REQUIRE_PTR(ws);
   TGSR_REQUIRE(fmt == TGSR_FMT_BF16 || fmt == TGSR_FMT_F16, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(g_sm_count > 0 && g_encode_w != nullptr, TGSR_ERR_NOT_INIT);
   TGSR_REQUIRE(B > 0 && H > 0 && W > 0, TGSR_ERR_BAD_SHAPE);
@@ -219,17 +228,21 @@ extern "C" int tgsr_conv3x3_wgrad_tc(const void* x, int xP, int xp0, const void*
   if (s != TGSR_OK) return s;
   s = make_box_w(&xmap, x, B, xP, H, W, Cin / 8, fmt, WG_TW + 2, WG_TH + 2);
   if (s != TGSR_OK) return s;
-  TGSR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * 9, st));
+  TGSR_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)Cout * Cin * 9, st));
   WgParams p;
-  p.dw = dw; p.Cout = Cout; p.B = B; p.H = H; p.W = W;
+  p.ws = ws; p.Cout = Cout; p.B = B; p.H = H; p.W = W;
   p.tiles_x = W / WG_TW; p.tiles_y = H / WG_TH; p.ntiles = B * p.tiles_x * p.tiles_y;
   p.zP = zP; p.zp0 = zp0; p.xP = xP; p.xp0 = xp0;
   const int groups = Cin == 64 ? 2 : 1;
+  // every CTA ends with 9 * Cin * Cout / groups atomics whatever its share of the tiles: small layers get fewer CTAs (at
+  // least 4 tiles each) so that this fixed cost does not exceed the MMA work
   int grid = g_sm_count / groups * groups;
-  if (p.ntiles * groups < grid) grid = p.ntiles * groups;
+  const int by_tiles = ((p.ntiles + 3) / 4) * groups;
+  if (by_tiles < grid) grid = by_tiles;
 #define TGSR_WG_LAUNCH(C, F) wgrad_tc_kernel<C, F><<<grid, WG_THREADS, WgCfg<C>::SMEM, st>>>(zmap, xmap, p)
   if (Cin == 64) { if (fmt == TGSR_FMT_F16) TGSR_WG_LAUNCH(64, TGSR_FMT_F16); else TGSR_WG_LAUNCH(64, TGSR_FMT_BF16); }
   else { if (fmt == TGSR_FMT_F16) TGSR_WG_LAUNCH(32, TGSR_FMT_F16); else TGSR_WG_LAUNCH(32, TGSR_FMT_BF16); }
 #undef TGSR_WG_LAUNCH
-  return launch_status();
+  wgrad_tc_finish_kernel<<<ceil_div(Cout * Cin * 9, 256), 256, 0, st>>>(ws, dw, Cin, Cout);
+  return launch_status(2);
 }

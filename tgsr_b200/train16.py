@@ -127,7 +127,8 @@ class Conv16Fn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
             if WGRAD_TC:                                            # tcgen05, straight from the blocked bf16 tensors
-                call('tgsr_conv3x3_wgrad_tc', w.device, ptr(xb), Cin // 8, 0, ptr(dz), Cout // 8, 0, ptr(dw), B, Cin, H, W, Cout, FMT)
+                call('tgsr_conv3x3_wgrad_tc', w.device, ptr(xb), Cin // 8, 0, ptr(dz), Cout // 8, 0, ptr(dw), ptr(torch.empty_like(dw)), B, Cin, H,
+                     W, Cout, FMT)
             else:                                                   # TF32 kernel on fp32 NCHW copies
                 x32 = ToNchwFn.forward(None, xb); dz32 = ToNchwFn.forward(None, dz)
                 name = 'tgsr_conv2d_wgrad_tf32' if _lib.load().tgsr_conv_tf32_supported(Cin, Cout, 3, 1) else 'tgsr_conv2d_wgrad_f32'
