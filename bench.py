@@ -359,6 +359,7 @@ def run_ours(args):
     attn_roof_b96 = pipe.attention_roofline(96, flush, pk) if (rank == 0 and not args.no_kernel_table) else None
 
     per_kernel = pipe.kernel_rooflines(B, flush, pk) if (rank == 0 and not args.no_kernel_table) else None
+    attn_sweep = SRPipeline.attention_sweep(pk, flush, dev) if (rank == 0 and not args.no_kernel_table) else None
     bound_ms = SRPipeline.step_roofline_bound(B, pk)
     step_roof = {'bound_ms': bound_ms, 'frac': bound_ms / (t_ms / args.steps),
                  'what': 'sum over the layers of the dependent chain of max(executed MMA FLOP / measured bf16 peak, algorithmic bytes / '
@@ -421,7 +422,7 @@ def run_ours(args):
                               'neighbouring steps; every result waited for on the host',
                     'fp32_result': {'value': e2e_fp32, 'unit': 'images/s', 'd2h_bytes_per_step': d2h_fp32}},
             'gpu_launches': int(launches),
-            'roofline': roof, 'roofline_attention': attn_roof, 'roofline_attention_b96': attn_roof_b96, 'roofline_per_kernel': per_kernel, 'roofline_step': step_roof, 'sustained': sustained, 'train': train_block,
+            'roofline': roof, 'roofline_attention': attn_roof, 'roofline_attention_b96': attn_roof_b96, 'attention_sweep': attn_sweep, 'roofline_per_kernel': per_kernel, 'roofline_step': step_roof, 'sustained': sustained, 'train': train_block,
             'model_tflops': value * GFLOP_PER_IMAGE / 1e3, 'peaks': pk,
         }
         if cpu_base is not None:

@@ -188,15 +188,17 @@ int tgsr_conv_in_blocked(const float* x, const float* x_sub, const float* w, con
 
 /* a1 on blocked activations (GlobalAttention.py:87-130), two entry points.
  * tgsr_attn_project: the word projection S[b] = w_ctx . context[b] (conv_context, GlobalAttention.py:99-101) in
- * fp32, written as the per-lane tensor-core operand image `sfrag` (tgsr_attn_sfrag_bytes(B) bytes, caller-owned
- * workspace).  It depends on the caption only: one call per (captions, conv_context weight), reused by every
- * pixel tile.  context fp32 [B,cdf,T], w_ctx fp32 [idf,cdf]; idf == 32, T <= 24, cdf % 4 == 0.
+ * fp32, written as the per-lane tensor-core operand image `sfrag` (tgsr_attn_sfrag_bytes_t(B, T) bytes, caller-owned
+ * workspace; tgsr_attn_sfrag_bytes(B) is the T <= 24 size).  It depends on the caption only: one call per (captions,
+ * conv_context weight), reused by every pixel tile.  context fp32 [B,cdf,T], w_ctx fp32 [idf,cdf]; idf == 32, T <= 48
+ * (three kernel variants: word tiles for T <= 24, <= 32, <= 48), cdf % 4 == 0.
  * tgsr_attn_fwd_blocked: reads the idf=32 channel view (xP,xp0), writes weightedContext (16-bit) into the view
  * (yP,yp0) -- normally the next planes of the same concat buffer -- and the attention map attn fp32 [B,T,Q]; caption
  * mask uint8 [B,T] or NULL with the reference's row-order quirk (pixel q of image b uses caption (b*Q+q) % B).
  * Logits, mask, softmax and the weighted sum are one persistent kernel (TMA-fed, warp-level tensor cores, S split
  * into three 16-bit pieces so the fp32 maps keep fp32 accuracy).  Q % 32 == 0. */
 size_t tgsr_attn_sfrag_bytes(int B);
+size_t tgsr_attn_sfrag_bytes_t(int B, int T);
 int tgsr_attn_project(const float* context, const float* w_ctx, void* sfrag, int B, int idf, int cdf, int T,
                       int fmt, tgsr_stream_t stream);
 /* n (1..3) projections of the same captions with different conv_context weights in ONE launch (a forward computes the

@@ -65,7 +65,11 @@ def test_conv_in_bf16(golden):
 
 
 @pytest.mark.parametrize('B,ih,iw,T,ragged', [(1, 32, 32, 18, False), (4, 64, 64, 18, True), (3, 16, 8, 7, True),
-                                               (5, 17, 3, 20, True)])
+                                               (5, 17, 3, 20, True), (2, 32, 32, 24, True),
+                                               # long captions: the T <= 32 and T <= 48 variants of the kernel
+                                               (3, 32, 32, 25, True), (4, 64, 32, 32, True), (2, 32, 32, 32, False),
+                                               (3, 32, 64, 33, True), (5, 16, 16, 41, True), (2, 64, 64, 48, True),
+                                               (1, 32, 32, 48, False)])
 def test_attention_blocked(B, ih, iw, T, ragged):
     from tgsr_b200 import fast, tc
     g = torch.Generator().manual_seed(B * 10 + T)

@@ -83,6 +83,7 @@ _SIGS = {
     'tgsr_pyramid_supported': ([C.c_int] * 5, C.c_int),
     'tgsr_pyramid_levels_u8': ([C.c_void_p] + [C.c_int] * 5 + [C.c_void_p] * 5 + [C.c_float, C.c_void_p], C.c_int),
     'tgsr_attn_sfrag_bytes': ([C.c_int], C.c_size_t),
+    'tgsr_attn_sfrag_bytes_t': ([C.c_int, C.c_int], C.c_size_t),
     'tgsr_attn_project': ([C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p], C.c_int),
     'tgsr_attn_project_multi': ([C.c_void_p] * 7 + [C.c_int] * 6 + [C.c_void_p], C.c_int),
     'tgsr_attn_fwd_blocked': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

@@ -34,12 +34,20 @@ namespace tgsr {
 typedef uint16_t h16;
 
 constexpr int AM_IDF = 32;
-constexpr int AM_NT = 3;              // word tiles of 8 -> T <= 24
-constexpr int AM_TP = AM_NT * 8;
-constexpr int AM_NFRAG = 48;          // 32-bit operand words per lane: 36 (logits, 3 pieces) + 12 (weighted sum)
-constexpr int AM_THREADS = 512;
-constexpr int AM_WARPS = AM_THREADS / 32;
-constexpr int AM_DEPTH = 3;           // TMA ring depth per warp (pixel tiles in flight)
+// NT = word tiles of 8: 3 (T <= 24, the production captions), 4 (T <= 32) or 6 (T <= 48).  The operand words of a caption
+// live in registers (16 * NT per lane), so the long-caption variants run 8 warps per CTA with a deeper ring instead of 16.
+template <int NT>
+struct AmCfg {
+  static constexpr int TP = NT * 8;
+  static constexpr int NL = 12 * NT;          // logits operand words per lane: 2 K-steps x NT x 3 pieces x (b0, b1)
+  static constexpr int NFRAG = 16 * NT;       // + weighted-sum operand: 4 planes x NT words
+  static constexpr int THREADS = NT == 3 ? 512 : 256;
+  static constexpr int WARPS = THREADS / 32;
+  static constexpr int DEPTH = NT == 3 ? 3 : 6;   // TMA ring depth per warp (pixel tiles in flight)
+};
+template <int NT, bool WIDE = (NT * 8 > 32)> struct AmMask { typedef uint32_t type; };
+template <int NT> struct AmMask<NT, true> { typedef unsigned long long type; };
+__host__ __device__ constexpr int am_nt_for(int T) { return T <= 24 ? 3 : (T <= 32 ? 4 : 6); }
 constexpr int AM_PLANE_B = 512;       // 32 pixels * 16 B
 constexpr int AM_TILE_B = 4 * AM_PLANE_B;
 constexpr int AM_LDP = 36;            // padded row (32 pixels) of the per-warp attention-map staging tile
@@ -107,8 +115,8 @@ __device__ __forceinline__ uint4 ldg128_keep(const uint4* p) {
 }
 
 // sfrag word f of lane l of caption b
-__host__ __device__ inline size_t sfrag_index(int b, int f, int lane) {
-  return (((size_t)b * (AM_NFRAG / 4) + (f >> 2)) * 32 + lane) * 4 + (f & 3);
+__host__ __device__ inline size_t sfrag_index(int b, int f, int lane, int nfrag) {
+  return (((size_t)b * (nfrag / 4) + (f >> 2)) * 32 + lane) * 4 + (f & 3);
 }
 
 // =====================================================================================================
@@ -121,11 +129,12 @@ constexpr int AP_THREADS = 256;
 constexpr int AP_ROWS = 8;
 constexpr int AP_KS = 16;
 
-template <int FMT>
+template <int FMT, int NT>
 __global__ void __launch_bounds__(AP_THREADS)
 attn_project_kernel(const float* __restrict__ context, const float* __restrict__ w_ctx0, const float* __restrict__ w_ctx1,
                     const float* __restrict__ w_ctx2, uint32_t* __restrict__ sfrag0, uint32_t* __restrict__ sfrag1,
                     uint32_t* __restrict__ sfrag2, int cdf, int T) {
+  constexpr int AM_NT = NT, AM_TP = AmCfg<NT>::TP, NL = AmCfg<NT>::NL, NFRAG = AmCfg<NT>::NFRAG;
   __shared__ float part[AP_KS][AP_ROWS][AM_TP];
   __shared__ float Srow[AP_ROWS][AM_TP + 1];
   const int tid = threadIdx.x, b = blockIdx.x, r = blockIdx.y;
@@ -171,8 +180,8 @@ attn_project_kernel(const float* __restrict__ context, const float* __restrict__
       for (int j = 0; j < AM_NT; ++j) part[ks][ig * 4 + i][tq + 8 * j] = acc[i][j];
   }
   __syncthreads();
-  if (tid < AP_ROWS * AM_TP) {
-    const int i = tid / AM_TP, t = tid - i * AM_TP;
+  for (int idx = tid; idx < AP_ROWS * AM_TP; idx += AP_THREADS) {
+    const int i = idx / AM_TP, t = idx - i * AM_TP;
     float v = 0.f;
     if (t < T) {
       float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
@@ -187,19 +196,21 @@ attn_project_kernel(const float* __restrict__ context, const float* __restrict__
   __syncthreads();
   // logits operand:  B[k][n] = log2(e) * S[16s + k][t = nt*8 + g]  (the log2(e) factor turns the softmax exponential
   // into a bare ex2).  Plane r = K-step s = r/2, register h = r%2 of the (b0,b1) pair; lane (g,tig) holds channels
-  // 8r + 2tig + {0,1}; word f = (((s*3 + nt)*3 + piece)*2 + h).
-  if (tid < 96) {
-    const int lane = tid & 31, nt = tid >> 5, g = lane >> 2, tig = lane & 3, sk = r >> 1, h = r & 1;
+  // 8r + 2tig + {0,1}; word f = (((s*NT + nt)*3 + piece)*2 + h).
+  for (int u = tid; u < 32 * AM_NT; u += AP_THREADS) {
+    const int lane = u & 31, nt = u >> 5, g = lane >> 2, tig = lane & 3, sk = r >> 1, h = r & 1;
     uint32_t p[3];
     split_pair<FMT, 3>(kLog2e * Srow[2 * tig][nt * 8 + g], kLog2e * Srow[2 * tig + 1][nt * 8 + g], p);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) sfrag[sfrag_index(b, ((sk * 3 + nt) * 3 + k) * 2 + h, lane)] = p[k];
-  } else if (tid < 192) {
-    // weighted-sum operand:  B[k = t][n = ch] = S[pl*8 + g][t], K-steps t 0..15 (k16: words rr 0,1) and 16..23 (k8)
-    const int u = tid - 96, lane = u & 31, rr = u >> 5, g = lane >> 2, tig = lane & 3;
+    for (int k = 0; k < 3; ++k) sfrag[sfrag_index(b, ((sk * AM_NT + nt) * 3 + k) * 2 + h, lane, NFRAG)] = p[k];
+  }
+  for (int u = tid; u < 32 * AM_NT; u += AP_THREADS) {
+    // weighted-sum operand:  B[k = t][n = ch] = S[pl*8 + g][t]; word rr holds words 8rr + 2tig, +1 (k16 steps take the
+    // words (2j, 2j+1) as (b0, b1); an odd last block is a k8 step)
+    const int lane = u & 31, rr = u >> 5, g = lane >> 2, tig = lane & 3;
     // always fp16 (11-bit mantissa; |S| < 65504 assumed): P lies in [0,1], so this contraction is 8x more accurate
     // than the 16-bit rounding of its result whatever the activation format
-    sfrag[sfrag_index(b, 36 + r * 3 + rr, lane)] =
+    sfrag[sfrag_index(b, NL + r * AM_NT + rr, lane, NFRAG)] =
         Fmt16<TGSR_FMT_F16>::pack2(Srow[g][rr * 8 + 2 * tig], Srow[g][rr * 8 + 2 * tig + 1]);
   }
 }
@@ -207,16 +218,19 @@ attn_project_kernel(const float* __restrict__ context, const float* __restrict__
 // =====================================================================================================
 // smem: ptile [16 warps][AM_TP][AM_LDP] f32 | ring [16 warps][AM_DEPTH][AM_TILE_B] | bars [16][AM_DEPTH] u64 |
 //       maskw [B] u32
-template <int FMT>
-__global__ void __launch_bounds__(AM_THREADS, 1)
+template <int FMT, int NT>
+__global__ void __launch_bounds__(AmCfg<NT>::THREADS, 1)
 attn_blocked_kernel(const h16* __restrict__ xin, int xP, int xp0, const uint32_t* __restrict__ sfrag,
                     const uint8_t* __restrict__ mask, h16* __restrict__ yout, int yP, int yp0,
                     float* __restrict__ attn, int B, int Q, int T, int tiles_img, int n_tiles) {
+  constexpr int AM_NT = NT, AM_TP = AmCfg<NT>::TP, NL = AmCfg<NT>::NL, AM_NFRAG = AmCfg<NT>::NFRAG;
+  constexpr int AM_THREADS = AmCfg<NT>::THREADS, AM_WARPS = AmCfg<NT>::WARPS, AM_DEPTH = AmCfg<NT>::DEPTH;
+  typedef typename AmMask<NT>::type MaskT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ptile = reinterpret_cast<float*>(smem_raw);
   unsigned char* ring = smem_raw + AM_WARPS * AM_TP * AM_LDP * 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + AM_WARPS * AM_DEPTH * AM_TILE_B);
-  uint32_t* maskw = reinterpret_cast<uint32_t*>(bars + AM_WARPS * AM_DEPTH);
+  MaskT* maskw = reinterpret_cast<MaskT*>(bars + AM_WARPS * AM_DEPTH);
 
   const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, tig = lane & 3;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler (uniform datapath)
@@ -267,12 +281,12 @@ attn_blocked_kernel(const h16* __restrict__ xin, int xP, int xp0, const uint32_t
   int cur_b = b;
   load_operands(cur_b);
 
-  const uint32_t pad_bits = ~((1u << T) - 1u);                 // words t >= T (T <= 24) are always masked
+  const MaskT pad_bits = T >= (int)(8 * sizeof(MaskT)) ? (MaskT)0 : (MaskT) ~(((MaskT)1 << T) - (MaskT)1);   // words t >= T are always masked
   if (mask) {
     for (int c = tid; c < B; c += AM_THREADS) {
-      uint32_t bits = pad_bits;
+      MaskT bits = pad_bits;
 #pragma unroll 6
-      for (int t = 0; t < T; ++t) bits |= (uint32_t)(__ldg(mask + c * T + t) != 0) << t;
+      for (int t = 0; t < T; ++t) bits |= (MaskT)(__ldg(mask + c * T + t) != 0) << t;
       maskw[c] = bits;
     }
     __syncthreads();
@@ -289,7 +303,7 @@ attn_blocked_kernel(const h16* __restrict__ xin, int xP, int xp0, const uint32_t
     cap = (uint32_t)(((unsigned long long)tile * 32u + (unsigned)g) % (unsigned)B);
     cap_step = (uint32_t)((AM_WARPS * 32) % B);
   }
-  const uint32_t my_pad = pad_bits >> (2 * tig);
+  const MaskT my_pad = pad_bits >> (2 * tig);
   float* const pt_w = ptile + warp * (AM_TP * AM_LDP) + (2 * tig) * AM_LDP + g;        // + (nt*8+j)*AM_LDP + row
   const float* const pt_r = ptile + warp * (AM_TP * AM_LDP) + (lane >> 3) * AM_LDP + (lane & 7) * 4;
   const uint32_t row_stride4 = 4u * (uint32_t)Q;                 // elements between rows t and t + 4
@@ -328,9 +342,9 @@ attn_blocked_kernel(const h16* __restrict__ xin, int xP, int xp0, const uint32_t
         for (int nt = 0; nt < AM_NT; ++nt)
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt)
-            MmaOp<FMT>::k16(acc[mt][nt], a[s][mt], fr[((s * 3 + nt) * 3 + sp) * 2], fr[((s * 3 + nt) * 3 + sp) * 2 + 1]);
+            MmaOp<FMT>::k16(acc[mt][nt], a[s][mt], fr[((s * AM_NT + nt) * 3 + sp) * 2], fr[((s * AM_NT + nt) * 3 + sp) * 2 + 1]);
     // ---- caption mask (row r = b*Q+q uses caption r % B: GlobalAttention.py:109-116) + softmax over words
-    uint32_t w[4] = {my_pad, my_pad, my_pad, my_pad};            // rows g, g+8, g+16, g+24
+    MaskT w[4] = {my_pad, my_pad, my_pad, my_pad};               // rows g, g+8, g+16, g+24
     if (has_mask) {
       const uint32_t inc8 = 8u % (unsigned)B;
       uint32_t c = cap;
@@ -348,8 +362,8 @@ attn_blocked_kernel(const h16* __restrict__ xin, int xP, int xp0, const uint32_t
       for (int nt = 0; nt < AM_NT; ++nt)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          if (w[2 * mt] & (1u << (nt * 8 + j))) acc[mt][nt][j] = -CUDART_INF_F;
-          if (w[2 * mt + 1] & (1u << (nt * 8 + j))) acc[mt][nt][2 + j] = -CUDART_INF_F;
+          if (w[2 * mt] & ((MaskT)1 << (nt * 8 + j))) acc[mt][nt][j] = -CUDART_INF_F;
+          if (w[2 * mt + 1] & ((MaskT)1 << (nt * 8 + j))) acc[mt][nt][2 + j] = -CUDART_INF_F;
           mx[2 * mt] = fmaxf(mx[2 * mt], acc[mt][nt][j]);
           mx[2 * mt + 1] = fmaxf(mx[2 * mt + 1], acc[mt][nt][2 + j]);
         }
@@ -390,22 +404,34 @@ attn_blocked_kernel(const h16* __restrict__ xin, int xP, int xp0, const uint32_t
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int pl = 0; pl < 4; ++pl) { o[mt][pl][0] = o[mt][pl][1] = o[mt][pl][2] = o[mt][pl][3] = 0.f; }
-    uint32_t pa[2][4], pb[2][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    {
       using H = Fmt16<TGSR_FMT_F16>;                             // P in [0,1] and S as fp16 (see attn_project_kernel)
-      pa[mt][0] = H::pack2(acc[mt][0][0], acc[mt][0][1]); pa[mt][1] = H::pack2(acc[mt][0][2], acc[mt][0][3]);
-      pa[mt][2] = H::pack2(acc[mt][1][0], acc[mt][1][1]); pa[mt][3] = H::pack2(acc[mt][1][2], acc[mt][1][3]);
-      pb[mt][0] = H::pack2(acc[mt][2][0], acc[mt][2][1]); pb[mt][1] = H::pack2(acc[mt][2][2], acc[mt][2][3]);
+#pragma unroll
+      for (int j = 0; j < AM_NT / 2; ++j) {                      // k16 steps: words 16j .. 16j+15
+        uint32_t pa[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          pa[mt][0] = H::pack2(acc[mt][2 * j][0], acc[mt][2 * j][1]); pa[mt][1] = H::pack2(acc[mt][2 * j][2], acc[mt][2 * j][3]);
+          pa[mt][2] = H::pack2(acc[mt][2 * j + 1][0], acc[mt][2 * j + 1][1]); pa[mt][3] = H::pack2(acc[mt][2 * j + 1][2], acc[mt][2 * j + 1][3]);
+        }
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl)
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+            MmaOp<TGSR_FMT_F16>::k16(o[mt][pl], pa[mt], fr[NL + pl * AM_NT + 2 * j], fr[NL + pl * AM_NT + 2 * j + 1]);
+      }
+      if (AM_NT & 1) {                                           // odd last block of 8 words: one k8 step
+        uint32_t pb[2][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          pb[mt][0] = H::pack2(acc[mt][AM_NT - 1][0], acc[mt][AM_NT - 1][1]); pb[mt][1] = H::pack2(acc[mt][AM_NT - 1][2], acc[mt][AM_NT - 1][3]);
+        }
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl)
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) MmaOp<TGSR_FMT_F16>::k8(o[mt][pl], pb[mt][0], pb[mt][1], fr[NL + pl * AM_NT + AM_NT - 1]);
+      }
     }
-#pragma unroll
-    for (int pl = 0; pl < 4; ++pl)
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) MmaOp<TGSR_FMT_F16>::k16(o[mt][pl], pa[mt], fr[36 + pl * 3], fr[36 + pl * 3 + 1]);
-#pragma unroll
-    for (int pl = 0; pl < 4; ++pl)
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) MmaOp<TGSR_FMT_F16>::k8(o[mt][pl], pb[mt][0], pb[mt][1], fr[36 + pl * 3 + 2]);
     {
       h16* const yp_base = yout + ((size_t)b * yP + yp0) * plane + (size_t)(q0 + g) * 8 + 2 * tig;
       uint32_t yoff = 0;
@@ -438,31 +464,47 @@ attn_blocked_kernel(const h16* __restrict__ xin, int xP, int xp0, const uint32_t
   }
 }
 
+template <int NT>
 static size_t attn_smem_bytes(int B, bool has_mask) {
-  return (size_t)AM_WARPS * AM_TP * AM_LDP * 4 + (size_t)AM_WARPS * AM_DEPTH * AM_TILE_B + (size_t)AM_WARPS * AM_DEPTH * 8 +
-         (has_mask ? (size_t)B * 4 : 0);
+  using Cfg = AmCfg<NT>;
+  return (size_t)Cfg::WARPS * Cfg::TP * AM_LDP * 4 + (size_t)Cfg::WARPS * Cfg::DEPTH * AM_TILE_B + (size_t)Cfg::WARPS * Cfg::DEPTH * 8 +
+         (has_mask ? (size_t)B * sizeof(typename AmMask<NT>::type) : 0);
+}
+
+template <int NT>
+static cudaError_t set_attn_attr() {
+  cudaError_t e = cudaFuncSetAttribute(attn_blocked_kernel<TGSR_FMT_BF16, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(attn_blocked_kernel<TGSR_FMT_F16, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 int init_attention_mma() {
-  cudaError_t e = cudaFuncSetAttribute(attn_blocked_kernel<TGSR_FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (e != cudaSuccess) return cuda_fail(e);
-  e = cudaFuncSetAttribute(attn_blocked_kernel<TGSR_FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = set_attn_attr<3>();
+  if (e == cudaSuccess) e = set_attn_attr<4>();
+  if (e == cudaSuccess) e = set_attn_attr<6>();
   return e == cudaSuccess ? TGSR_OK : cuda_fail(e);
 }
 
 }  // namespace tgsr
 
-extern "C" size_t tgsr_attn_sfrag_bytes(int B) { return (size_t)B * tgsr::AM_NFRAG * 32 * 4; }
+extern "C" size_t tgsr_attn_sfrag_bytes(int B) { return (size_t)B * tgsr::AmCfg<3>::NFRAG * 32 * 4; }
+/* operand image of B captions of T words (T <= 48) */
+extern "C" size_t tgsr_attn_sfrag_bytes_t(int B, int T) { return (size_t)B * 16 * tgsr::am_nt_for(T) * 32 * 4; }
 
 static int attn_project_launch(const float* context, const float* const w[3], void* const sf[3], int n, int B, int idf, int cdf,
                                int T, int fmt, cudaStream_t st) {
   using namespace tgsr;
   dim3 grid(B, AM_IDF / AP_ROWS, n);
   auto s0 = reinterpret_cast<uint32_t*>(sf[0]); auto s1 = reinterpret_cast<uint32_t*>(sf[1]); auto s2 = reinterpret_cast<uint32_t*>(sf[2]);
-  if (fmt == TGSR_FMT_F16)
-    attn_project_kernel<TGSR_FMT_F16><<<grid, AP_THREADS, 0, st>>>(context, w[0], w[1], w[2], s0, s1, s2, cdf, T);
-  else
-    attn_project_kernel<TGSR_FMT_BF16><<<grid, AP_THREADS, 0, st>>>(context, w[0], w[1], w[2], s0, s1, s2, cdf, T);
+#define TGSR_AP_LAUNCH(F, N) attn_project_kernel<F, N><<<grid, AP_THREADS, 0, st>>>(context, w[0], w[1], w[2], s0, s1, s2, cdf, T)
+#define TGSR_AP_FMT(N) do { if (fmt == TGSR_FMT_F16) TGSR_AP_LAUNCH(TGSR_FMT_F16, N); else TGSR_AP_LAUNCH(TGSR_FMT_BF16, N); } while (0)
+  switch (am_nt_for(T)) {
+    case 3: TGSR_AP_FMT(3); break;
+    case 4: TGSR_AP_FMT(4); break;
+    default: TGSR_AP_FMT(6); break;
+  }
+#undef TGSR_AP_FMT
+#undef TGSR_AP_LAUNCH
   return launch_status();
 }
 
@@ -472,7 +514,7 @@ extern "C" int tgsr_attn_project(const float* context, const float* w_ctx, void*
   TGSR_REQUIRE(fmt == TGSR_FMT_BF16 || fmt == TGSR_FMT_F16, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE_PTR(context); TGSR_REQUIRE_PTR(w_ctx); TGSR_REQUIRE_PTR(sfrag);
   TGSR_REQUIRE(B > 0 && idf > 0 && cdf > 0 && T > 0, TGSR_ERR_BAD_SHAPE);
-  TGSR_REQUIRE(idf == AM_IDF && T <= AM_TP && cdf % 4 == 0 && B <= 65535, TGSR_ERR_UNSUPPORTED);
+  TGSR_REQUIRE(idf == AM_IDF && T <= 48 && cdf % 4 == 0 && B <= 65535, TGSR_ERR_UNSUPPORTED);
   const float* w[3] = {w_ctx, w_ctx, w_ctx};
   void* sf[3] = {sfrag, sfrag, sfrag};
   return attn_project_launch(context, w, sf, 1, B, idf, cdf, T, fmt, (cudaStream_t)stream);
@@ -489,7 +531,7 @@ extern "C" int tgsr_attn_project_multi(const float* context, const float* w0, co
   if (n > 1) { TGSR_REQUIRE_PTR(w1); TGSR_REQUIRE_PTR(sfrag1); }
   if (n > 2) { TGSR_REQUIRE_PTR(w2); TGSR_REQUIRE_PTR(sfrag2); }
   TGSR_REQUIRE(B > 0 && idf > 0 && cdf > 0 && T > 0, TGSR_ERR_BAD_SHAPE);
-  TGSR_REQUIRE(idf == AM_IDF && T <= AM_TP && cdf % 4 == 0 && B <= 65535, TGSR_ERR_UNSUPPORTED);
+  TGSR_REQUIRE(idf == AM_IDF && T <= 48 && cdf % 4 == 0 && B <= 65535, TGSR_ERR_UNSUPPORTED);
   const float* w[3] = {w0, n > 1 ? w1 : w0, n > 2 ? w2 : w0};
   void* sf[3] = {sfrag0, n > 1 ? sfrag1 : sfrag0, n > 2 ? sfrag2 : sfrag0};
   return attn_project_launch(context, w, sf, n, B, idf, cdf, T, fmt, (cudaStream_t)stream);
@@ -503,31 +545,38 @@ extern "C" int tgsr_attn_fwd_blocked(const void* x, int xP, int xp0, const void*
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(sfrag); TGSR_REQUIRE_PTR(y); TGSR_REQUIRE_PTR(attn);
   TGSR_REQUIRE(B > 0 && idf > 0 && Q > 0 && T > 0, TGSR_ERR_BAD_SHAPE);
   TGSR_REQUIRE(g_sm_count > 0, TGSR_ERR_NOT_INIT);
-  TGSR_REQUIRE(idf == AM_IDF && T <= AM_TP && B <= 4096 && Q % 32 == 0, TGSR_ERR_UNSUPPORTED);
+  TGSR_REQUIRE(idf == AM_IDF && T <= 48 && B <= 4096 && Q % 32 == 0, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(xp0 >= 0 && xp0 + idf / 8 <= xP && yp0 >= 0 && yp0 + idf / 8 <= yP, TGSR_ERR_BAD_SHAPE);
-  TGSR_REQUIRE((long long)B * Q < (1LL << 31) && (long long)24 * Q < (1LL << 30), TGSR_ERR_UNSUPPORTED);
-  const size_t smem = attn_smem_bytes(B, mask != nullptr);
+  TGSR_REQUIRE((long long)B * Q < (1LL << 31) && (long long)48 * Q < (1LL << 30), TGSR_ERR_UNSUPPORTED);
+  const int nt = am_nt_for(T);
+  const size_t smem = nt == 3 ? attn_smem_bytes<3>(B, mask != nullptr) : (nt == 4 ? attn_smem_bytes<4>(B, mask != nullptr) : attn_smem_bytes<6>(B, mask != nullptr));
   TGSR_REQUIRE(smem <= 200 * 1024, TGSR_ERR_UNSUPPORTED);
+  const int warps = nt == 3 ? AmCfg<3>::WARPS : AmCfg<4>::WARPS;
   const int tiles_img = Q / 32;
   const int n_tiles = B * tiles_img;
   // persistent CTAs, one per SM; every CTA owns an equal contiguous run of tiles (+-1)
-  const int grid = n_tiles < AM_WARPS * g_sm_count ? ceil_div(n_tiles, AM_WARPS) : g_sm_count;
+  const int grid = n_tiles < warps * g_sm_count ? ceil_div(n_tiles, warps) : g_sm_count;
   cudaStream_t st = (cudaStream_t)stream;
   auto xi = reinterpret_cast<const h16*>(x);
   auto yo = reinterpret_cast<h16*>(y);
   auto sf = reinterpret_cast<const uint32_t*>(sfrag);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(AM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(warps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   static const int use_pdl = [] { const char* e = getenv("TGSR_PDL"); return e ? atoi(e) : 1; }();
   cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
   cudaError_t e;
-  if (fmt == TGSR_FMT_F16)
-    e = cudaLaunchKernelEx(&cfg, attn_blocked_kernel<TGSR_FMT_F16>, xi, xP, xp0, sf, mask, yo, yP, yp0, attn, B, Q, T, tiles_img, n_tiles);
-  else
-    e = cudaLaunchKernelEx(&cfg, attn_blocked_kernel<TGSR_FMT_BF16>, xi, xP, xp0, sf, mask, yo, yP, yp0, attn, B, Q, T, tiles_img, n_tiles);
+#define TGSR_AB_LAUNCH(F, N) e = cudaLaunchKernelEx(&cfg, attn_blocked_kernel<F, N>, xi, xP, xp0, sf, mask, yo, yP, yp0, attn, B, Q, T, tiles_img, n_tiles)
+#define TGSR_AB_FMT(N) do { if (fmt == TGSR_FMT_F16) TGSR_AB_LAUNCH(TGSR_FMT_F16, N); else TGSR_AB_LAUNCH(TGSR_FMT_BF16, N); } while (0)
+  switch (nt) {
+    case 3: TGSR_AB_FMT(3); break;
+    case 4: TGSR_AB_FMT(4); break;
+    default: TGSR_AB_FMT(6); break;
+  }
+#undef TGSR_AB_FMT
+#undef TGSR_AB_LAUNCH
   if (e != cudaSuccess) return cuda_fail(e);
   return launch_status();
 }

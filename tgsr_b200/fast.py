@@ -147,12 +147,16 @@ def image_head(x: Blocked, head_seq, addend: Optional[Tensor] = None, a: float =
     return y
 
 
+def _sfrag_words(B: int, T: int) -> int:
+    return 16 * (3 if T <= 24 else 4 if T <= 32 else 6) * 32 * B      # = tgsr_attn_sfrag_bytes_t(B, T) / 4
+
+
 def attention_project(att, words: Tensor, fmt: int) -> Tensor:
     """S = conv_context(words) (GlobalAttention.py:99-101) as the tensor-core operand image of the blocked
     attention kernel; depends on the caption only, so a forward computes it once per stage up front."""
     B, cdf, T = words.shape
     w = att.conv_context.weight
-    sfrag = torch.empty(B * 48 * 32, device=words.device, dtype=torch.int32)
+    sfrag = torch.empty(_sfrag_words(B, T), device=words.device, dtype=torch.int32)
     call('tgsr_attn_project', words.device, ptr(words.contiguous()), ptr(w.detach().contiguous()), ptr(sfrag),
          B, w.shape[0], cdf, T, fmt)
     return sfrag
@@ -162,7 +166,7 @@ def attention_project_multi(atts, words: Tensor, fmt: int):
     """Operand images of up to three attention modules for the same captions, one launch."""
     B, cdf, T = words.shape
     ws = [a.conv_context.weight.detach().contiguous() for a in atts]
-    sf = [torch.empty(B * 48 * 32, device=words.device, dtype=torch.int32) for _ in atts]
+    sf = [torch.empty(_sfrag_words(B, T), device=words.device, dtype=torch.int32) for _ in atts]
     n = len(atts)
     p = lambda lst, k: ptr(lst[k]) if k < n else None
     call('tgsr_attn_project_multi', words.device, ptr(words.contiguous()), p(ws, 0), p(ws, 1), p(ws, 2), p(sf, 0), p(sf, 1), p(sf, 2),
@@ -171,7 +175,7 @@ def attention_project_multi(atts, words: Tensor, fmt: int):
 
 
 def attention_blocked_supported(idf: int, T: int, Q: int) -> bool:
-    return idf == 32 and T <= 24 and Q % 32 == 0
+    return idf == 32 and T <= 48 and Q % 32 == 0
 
 
 def attention(h: Blocked, att, words: Tensor, mask: Optional[Tensor], out: Blocked, sfrag: Optional[Tensor] = None) -> Tensor:

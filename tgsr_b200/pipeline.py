@@ -290,6 +290,45 @@ class SRPipeline:
         return out
 
     @staticmethod
+    @torch.no_grad()
+    def attention_sweep(pk, flush, device, quick: bool = True):
+        """BASELINE.json configs[2] inside the bench line: GlobalAttentionGeneral(idf 32, cdf 256) at Q in {64^2, 128^2} x
+        T in {18, 32, 48}, module API (fp32 NCHW I/O) and the 16-bit blocked path (word projection included), batch
+        chosen so that at least 256 MB move; algorithmic bytes / L2-cold device time vs the measured copy
+        bandwidth.  scripts/bench_attention.py is the full sweep (other widths, func_attention)."""
+        from . import GlobalAttentionGeneral, fast, tc
+        from .timing import cold_time_ms
+        idf, cdf = 32, 256
+        att = GlobalAttentionGeneral(idf, cdf).to(device)
+        att.conv_context.weight.data.normal_(0, 0.1)
+        rows = []
+        for T in (18, 32, 48):
+            for S in ((64, 128) if quick else (32, 64, 128, 256)):
+                Q = S * S
+                for variant, e in (('fp32', 4), ('blocked16', 2)):
+                    per_img = Q * (idf * e + idf * e + 4 * T) + cdf * T * 4 + T
+                    B = max(1, min(4096, -(-256_000_000 // per_img)))
+                    ctx = torch.randn(B, cdf, T, device=device) * 0.3
+                    mask = torch.zeros(B, T, dtype=torch.uint8, device=device)
+                    if variant == 'fp32':
+                        x = torch.randn(B, idf, S, S, device=device) * 0.5
+                        att.applyMask(mask)
+                        fn = lambda: att(x, ctx)
+                    else:
+                        cat = tc.Blocked.empty(B, 2 * idf, S, S, device); cat.buf.normal_(0, 0.5)
+                        fn = lambda: fast.attention(cat.slice(0, idf), att, ctx, mask, out=cat.slice(idf, idf))
+                    ms = cold_time_ms(fn, flush, iters=6, reps=2)
+                    nbytes = B * per_img + idf * cdf * 4
+                    rows.append({'variant': variant, 'B': B, 'Q': Q, 'T': T, 'idf': idf, 'cdf': cdf, 'us': ms * 1e3,
+                                 'gbs': nbytes / ms / 1e6, 'frac_hbm': nbytes / ms / 1e6 / pk['hbm']})
+                    del ctx, mask, fn
+                    if variant == 'fp32':
+                        del x
+                    else:
+                        del cat
+        return rows
+
+    @staticmethod
     def step_roofline_bound(B: int, pk, T: int = 18):
         """Analytic lower bound of one x8 step with ONE kernel per layer (no cross-layer fusion): for every conv / head /
         attention layer max(executed MMA FLOP / measured bf16 peak, algorithmic bytes / measured copy bandwidth), summed
