@@ -172,7 +172,13 @@ class SRPipeline:
         lib = _lib.load()
         n0 = lib.tgsr_launch_count()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # the critical chain (LSTM -> stage 1 -> 2 -> 3 -> NetG_high tail) is captured from a HIGH-priority stream, the two side
+        # chains (im2f + CA_NET, NetG_high's 32x32 trunk) from default-priority ones: kernel nodes inherit the priority, so when
+        # both have CTAs pending the block scheduler serves the critical chain first (the trunk is not needed for ~0.5 ms)
+        import os
+        prio = int(os.environ.get('TGSR_GRAPH_PRIO', '1'))
+        cap = torch.cuda.Stream(self.device, priority=-1) if prio else torch.cuda.Stream(self.device)
+        with torch.cuda.graph(g, stream=cap):
             ent['out'] = self.text_and_generate(ent['LR'], ent['caps'], ent['lens'], tmax)
         ent['graph'] = g
         ent['n_kernels'] = int(lib.tgsr_launch_count() - n0)     # libtgsr kernels inside one replay
