@@ -172,11 +172,12 @@ class SRPipeline:
         lib = _lib.load()
         n0 = lib.tgsr_launch_count()
         g = torch.cuda.CUDAGraph()
-        # the critical chain (LSTM -> stage 1 -> 2 -> 3 -> NetG_high tail) is captured from a HIGH-priority stream, the two side
-        # chains (im2f + CA_NET, NetG_high's 32x32 trunk) from default-priority ones: kernel nodes inherit the priority, so when
-        # both have CTAs pending the block scheduler serves the critical chain first (the trunk is not needed for ~0.5 ms)
+        # TGSR_GRAPH_PRIO=1 captures the critical chain (LSTM -> stage 1 -> 2 -> 3 -> NetG_high tail) from a HIGH-priority stream
+        # and the side chains from default-priority ones (kernel nodes inherit it).  Measured: stage 1 starts 7 us earlier and
+        # stage 3 ends 20 us earlier, but the deferred 32x32 trunk then overlaps the large kernels and the step gets SLOWER
+        # (0.730 vs 0.723 ms, profiles/r2_experiments.md) -- off by default.
         import os
-        prio = int(os.environ.get('TGSR_GRAPH_PRIO', '1'))
+        prio = int(os.environ.get('TGSR_GRAPH_PRIO', '0'))
         cap = torch.cuda.Stream(self.device, priority=-1) if prio else torch.cuda.Stream(self.device)
         with torch.cuda.graph(g, stream=cap):
             ent['out'] = self.text_and_generate(ent['LR'], ent['caps'], ent['lens'], tmax)
