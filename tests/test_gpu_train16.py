@@ -157,6 +157,53 @@ def test_head16_backward_uses_blocked_features():
     torch.testing.assert_close(sd.grad.cpu(), sr.grad, rtol=1e-5, atol=1e-6)
 
 
+def test_x16_nets_train_bf16_matches_fp32():
+    """models16.py nets (weight-shared stages / heads / upscales) in train mode: the bf16 tcgen05 path against the exact fp32
+    path, MSE on all eight outputs.  The shared parameters collect the gradients of every use through autograd."""
+    import statistics
+    from tgsr_b200 import losses, nets16, train
+    from tgsr_b200.text_encoder import RNN_ENCODER
+    B = 2
+    LR = O.synth_lr(B, 16, seed=71).to(DEV)
+    real = [F.interpolate(LR, scale_factor=2 ** (k + 1), mode='bicubic').clamp(-1, 1) for k in range(4)]
+    caps, lens = O.synth_captions(B, 200, seed=72, words_num=18)
+    caps, lens = caps.to(DEV), lens.to(DEV)
+    torch.manual_seed(79)
+    enc = RNN_ENCODER(200, nhidden=256).to(DEV).eval()
+    with torch.no_grad():
+        words, sent = enc._forward_tmax(caps, lens, 18)
+    mask = (caps == 0)[:, :18]
+    gl = nets16.G_SR_NET_low().to(DEV).train(); gh = nets16.NetG_highweight(low='lr').to(DEV).train()
+    for p in gl.ca_net.parameters():
+        p.requires_grad = False
+    sd = ({k: v.clone() for k, v in gl.state_dict().items()}, {k: v.clone() for k, v in gh.state_dict().items()})
+    params = [(n, p) for n, p in list(gl.named_parameters()) + list(gh.named_parameters()) if p.requires_grad and n != 'a']
+    grads, loss = {}, {}
+    for mode in ('fp32', 'bf16'):
+        gl.load_state_dict(sd[0]); gh.load_state_dict(sd[1])
+        tgsr_b200.set_precision(mode)
+        train.set_conv_precision('fp32' if mode == 'fp32' else 'tf32')
+        for _, p in params:
+            p.grad = None
+        imgsL, _a, _m, _l = gl(LR, sent, words, mask)
+        fine, _, _ = gh(LR, imgsL, LR)
+        assert len(imgsL) == 4 and len(fine) == 4 and fine[-1].shape == (B, 3, 256, 256)
+        l = losses.MSE(list(fine) + list(imgsL), list(real) + list(real))
+        l.backward()
+        loss[mode] = float(l.detach())
+        grads[mode] = {n: p.grad.detach().clone() for n, p in params if p.grad is not None}
+    assert set(grads['bf16']) == set(grads['fp32'])
+    assert abs(loss['bf16'] - loss['fp32']) <= 0.02 * abs(loss['fp32'])
+    cos = []
+    gmax = max(float(g.abs().max()) for g in grads['fp32'].values())
+    for n, g in grads['fp32'].items():
+        if float(g.abs().max()) < 1e-3 * gmax:
+            continue                                           # scale-invariant / near-zero gradients: direction undefined
+        cos.append(_cos(grads['bf16'][n], g))
+    print('x16 bf16-vs-fp32 gradient cosines: min %.4f median %.4f over %d tensors' % (min(cos), statistics.median(cos), len(cos)))
+    assert statistics.median(cos) > 0.995 and min(cos) > 0.95
+
+
 def test_generator_step_bf16_matches_fp32_step():
     """One training step of the whole generator (G_SR_NET_low + NetG_highweight, train BN): the bf16 / tcgen05 path against
     the exact fp32 path from the same weights and inputs.

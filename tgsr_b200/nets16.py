@@ -26,6 +26,11 @@ class G_SR_NET_low(nn.Module):
 
     def forward(self, LR, sent_emb, word_embs, mask):
         from . import fast, fmt_for, is_16bit
+        stages = [self.h_net1, self.h_net2, self.h_net3, self.h_net4]
+        heads = [self.img_net1, self.img_net2, self.img_net3, self.img_net4]
+        if self.training and is_16bit():                        # bf16 training step (tgsr_b200/train16.py); the shared
+            from . import train16                               # stage / head parameters accumulate their gradients in autograd
+            return train16.g_sr_net_low(self, LR, sent_emb, word_embs, mask, stages, heads)
         if is_16bit() and fast.stage_supported(self.h_net1, LR.shape[2], LR.shape[3]):
             self.h_net1.att.applyMask(mask); self.h_net2.att.applyMask(mask)
             return fast.g_sr_net_low(self, LR, sent_emb, word_embs, mask,
@@ -81,6 +86,12 @@ class NetG_high(nn.Module):
 
     def forward(self, LR, SRb, LRb, low=False):
         from . import fast, fmt_for, is_16bit
+        if self.training and is_16bit():                        # bf16 training step (tgsr_b200/train16.py)
+            from . import train16
+            x, x_sub = (LRb, None) if low else (LR, LRb)
+            return train16.netg_high(self, x, x_sub, SRb, 1.0, 1.0,
+                                     [(self.residual24, self.upscale4x), (self.residual48, self.upscale8x),
+                                      (self.residual816, self.upscale16x)])
         if _fast_ok(self, LR):
             x, x_sub = (LRb, None) if low else (LR, LRb)
             return fast.netg_high(self, x, x_sub, SRb, 1.0, 1.0,
@@ -132,7 +143,14 @@ class NetG_highweight(nn.Module):
         else:
             raise ValueError(self.low)
         a, one = _cached_float(self, self.a, '_tgsr_a'), 1.0      # `a` is trainable here: read once per weight version
-        from . import fast, fmt_for
+        from . import fast, fmt_for, is_16bit
+        if self.training and is_16bit():                        # bf16 training step; `a` enters as a constant, as in the x8 net
+            from . import train16
+            x, x_sub = (LR, LRb) if self.low == 'lr-lrblur' else (x, None)
+            ims = train16.netg_high(self, x, x_sub, SRb, a, one,
+                                    [(self.residual24, self.upscale4x), (self.residual48, self.upscale8x),
+                                     (self.residual48, self.upscale8x)])
+            return ims, self.a, self.one.to(ims[0].device)
         if _fast_ok(self, LR):
             x, x_sub = (LR, LRb) if self.low == 'lr-lrblur' else (x, None)
             ims = fast.netg_high(self, x, x_sub, SRb, a, one,
