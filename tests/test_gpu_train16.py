@@ -92,11 +92,12 @@ def test_bn_act16_forward_backward(act, with_res):
         assert torch.equal(rd.grad.cpu(), dy)
 
 
-def test_upsample16_and_adjoint():
+@pytest.mark.parametrize('H,W', [(16, 8), (12, 20), (7, 3)])
+def test_upsample16_and_adjoint(H, W):
     from tgsr_b200 import train16 as T
     g = torch.Generator().manual_seed(3)
-    x = bf(torch.randn(2, 32, 16, 8, generator=g))
-    dy = bf(torch.randn(2, 32, 32, 16, generator=g) * 0.25)
+    x = bf(torch.randn(2, 32, H, W, generator=g))
+    dy = bf(torch.randn(2, 32, 2 * H, 2 * W, generator=g) * 0.25)
     xd = x.to(DEV).requires_grad_(True)
     y = T.to_nchw(T.Up2x16Fn.apply(T.to_blocked(xd)))
     assert torch.equal(y.detach().cpu(), F.interpolate(x, scale_factor=2, mode='nearest'))

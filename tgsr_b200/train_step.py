@@ -133,7 +133,9 @@ class FrozenImageEncoder(nn.Module):
         """conv(bias=False) -> BatchNorm(eval) -> ReLU of every torchvision BasicConv2d becomes one bf16 conv with bias + ReLU:
         w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps).  The folded tensors live outside the
         state dict (rebuilt after load_state_dict or a device move)."""
-        if self._folded_on == device:
+        from ._lib import tensor_key
+        key = (device, tensor_key(self.Conv2d_1a_3x3.conv.weight, False), tensor_key(self.emb_features.weight, False))
+        if self._folded_on == key:                           # rebuilt after load_state_dict / invalidate_caches() / a device move
             return
         import types
         from torchvision.models.inception import BasicConv2d
@@ -191,7 +193,7 @@ class FrozenImageEncoder(nn.Module):
             self._ef_w = self.emb_features.weight.to(device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
             self._ec_w = self.emb_cnn_code.weight.to(device, torch.bfloat16)
             self._ec_b = self.emb_cnn_code.bias.to(device, torch.bfloat16)
-        self._folded_on = device
+        self._folded_on = key
 
     def _forward(self, x, dtype=None):
         x = F.interpolate(x, size=(299, 299), mode='bilinear', align_corners=False)
