@@ -60,6 +60,31 @@ __host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N, uint32_t fmt)
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// MMAs of one tile for the taps [TAP0, TAP0 + NTAP): accumulator t (TMEM columns t*CIN ..) += dz^T (16 pixels) . x shifted by
+// the tap.  Descriptor fields (no swizzle): [0,14) start >> 4, [16,30) LBO >> 4, [32,46) SBO >> 4, version 1 at bit 46.
+// MN-major: SBO steps along M / N (the next 8 channels = the next plane), LBO along K (the next 8 pixels) -- verified on
+// B200 against fp32 autograd (tests/test_gpu_train16.py); the swapped reading gives garbage.
+template <int CIN, int FMT, int TAP0, int NTAP>
+__device__ __forceinline__ void issue_tile(uint32_t tmem_base, uint32_t zaddr, bool accumulate) {
+  using Cfg = WgCfg<CIN>;
+  constexpr uint32_t idesc = make_idesc_mn(128, CIN, Fmt16<FMT>::kUmmaFormat);
+  constexpr uint32_t a_lbo = 128, a_sbo = Cfg::ZPLANE;
+  constexpr uint32_t b_lbo = Cfg::PW * 16, b_sbo = Cfg::XPLANE;
+  constexpr uint32_t a_hi = (a_sbo >> 4) | (1u << 14), b_hi = (b_sbo >> 4) | (1u << 14);
+  const uint32_t a0 = (zaddr >> 4) | ((a_lbo >> 4) << 16);
+  const uint32_t b0 = ((zaddr + Cfg::ZBYTES) >> 4) | ((b_lbo >> 4) << 16);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {                            // 16 pixels = tile rows 2ks, 2ks+1
+#pragma unroll
+    for (int t = 0; t < NTAP; ++t) {
+      const int tap = TAP0 + t, dy = tap / 3, dx = tap % 3;   // compile-time after unrolling
+      const uint32_t a_lo = a0 + (uint32_t)((ks * 256) >> 4);
+      const uint32_t b_lo = b0 + (uint32_t)((((2 * ks + dy) * Cfg::PW + dx) * 16) >> 4);
+      umma_f16(tmem_base + t * CIN, make_desc64(a_lo, a_hi), make_desc64(b_lo, b_hi), idesc, (accumulate || ks != 0) ? 1u : 0u);
+    }
+  }
+}
+
 template <int CIN, int FMT>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant__ CUtensorMap xmap, const WgParams p) {
@@ -113,7 +138,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    constexpr uint32_t idesc = make_idesc_mn(128, CIN, Fmt16<FMT>::kUmmaFormat);
+    // One elected thread issues 8 K-steps x ntap MMAs per tile.  An MMA takes ~40-49 tensor-core cycles, so the issue
+    // sequence must stay well below that per MMA: the tap loop is unrolled at compile time for each tap group (all
+    // descriptor offsets are immediates, one add per operand), as in conv_tc.cu.
     int it = 0;
     for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
       const int s = it % Cfg::NSTAGE, ph = (it / Cfg::NSTAGE) & 1;
@@ -121,22 +148,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant_
       tc_fence_after();
       if (elect_one()) {
         const uint32_t zaddr = smem_u32(stage_s + s * Cfg::STAGE);
-        const uint32_t xaddr = zaddr + Cfg::ZBYTES;
-        // descriptor fields (no swizzle): [0,14) start >> 4, [16,30) LBO >> 4, [32,46) SBO >> 4, version 1 at bit 46.
-        // MN-major: SBO steps along M / N (the next 8 channels = the next plane), LBO along K (the next 8 pixels) --
-        // verified on B200 against fp32 autograd (tests/test_gpu_train16.py); the swapped reading gives garbage.
-        constexpr uint32_t a_lbo = 128, a_sbo = Cfg::ZPLANE;
-        constexpr uint32_t b_lbo = Cfg::PW * 16, b_sbo = Cfg::XPLANE;
-        constexpr uint32_t a_hi = (a_sbo >> 4) | (1u << 14), b_hi = (b_sbo >> 4) | (1u << 14);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {                      // 16 pixels = tile rows 2ks, 2ks+1
-          const uint32_t a_lo = ((zaddr + ks * 256) >> 4) | ((a_lbo >> 4) << 16);
-          for (int t = 0; t < ntap; ++t) {
-            const int tap = tap0 + t, dy = tap / 3, dx = tap % 3;
-            const uint32_t b_lo = ((xaddr + ((2 * ks + dy) * Cfg::PW + dx) * 16) >> 4) | ((b_lbo >> 4) << 16);
-            umma_f16(tmem_base + t * CIN, make_desc64(a_lo, a_hi), make_desc64(b_lo, b_hi), idesc, (it | ks) != 0 ? 1u : 0u);
-          }
-        }
+        if (group == 0) issue_tile<CIN, FMT, 0, Cfg::TAPS0>(tmem_base, zaddr, it != 0);
+        else issue_tile<CIN, FMT, Cfg::TAPS0, 9 - Cfg::TAPS0>(tmem_base, zaddr, it != 0);
         umma_commit(&empty[s]);
       }
       __syncwarp();
