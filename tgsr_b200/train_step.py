@@ -91,6 +91,30 @@ class FusedAdam:
         bump_weights_epoch()
 
 
+import os as _os
+_FUSED_CONV_RELU = int(_os.environ.get('TGSR_ENCODER_FUSED_CONV', '1'))
+
+
+class _ConvBiasReluFn(torch.autograd.Function):
+    """relu(conv2d(x, w) + b) of the frozen image encoder as cuDNN's fused conv-bias-activation (one kernel instead of conv,
+    broadcast add and clamp); only the input gradient exists (the encoder's weights are frozen)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding):
+        y = torch.cudnn_convolution_relu(x, w, b, stride, padding, (1, 1), 1)
+        ctx.save_for_backward(x, w, y)
+        ctx.conf = (tuple(stride), tuple(padding))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        stride, padding = ctx.conf
+        g = torch.ops.aten.threshold_backward(gy, y, 0)
+        dx = torch.ops.aten.convolution_backward(g, x, w, None, stride, padding, (1, 1), False, (0, 0), 1, (True, False, False))[0]
+        return dx, None, None, None, None
+
+
 class FrozenImageEncoder(nn.Module):
     """CNN_ENCODER (util.py:262-368) with random-init Inception-v3 weights (no network for the pretrained file), frozen,
     eval mode.  Library code (torchvision + cuDNN) outside the hot path: only its input gradient is used."""
@@ -145,6 +169,8 @@ class FrozenImageEncoder(nn.Module):
         def folded(m, x):
             if x.dtype != torch.bfloat16:                    # the fp32 path keeps conv -> BatchNorm -> ReLU
                 return BasicConv2d.forward(m, x)
+            if x.is_cuda and _FUSED_CONV_RELU:
+                return _ConvBiasReluFn.apply(x, m._fw, m._fb, m.conv.stride, m._fpad)
             return F.relu(F.conv2d(x, m._fw, m._fb, m.conv.stride, m._fpad), inplace=True)
 
         # branch wiring of the blocks whose pooling branch is avg_pool2d(3, stride 1, pad 1) -> 1x1 conv: that pair is ONE 3x3
