@@ -384,6 +384,12 @@ int tgsr_conv3x3_wgrad_tc(const void* x, int xP, int xp0, const void* dz, int zP
  * k in {3,5}; dw is overwritten. */
 int tgsr_head_wgrad16(const void* x, int xP, int xp0, const float* dz, float* dw, int B, int Cin, int H, int W, int ksize,
                       int fmt, tgsr_stream_t stream);
+/* F.max_pool2d(x, 3, stride 2) (no padding, floor mode) of the frozen CNN_ENCODER (util.py:262-368, Inception-v3 stem and
+ * Mixed_6a / Mixed_7a) on channels-last 16-bit tensors [B,H,W,C], C % 8 == 0: y [B,Ho,Wo,C], idx uint8 [B,Ho,Wo,C] = window
+ * position of the first maximum; backward gathers gy through idx into gx [B,H,W,C] (no atomics). */
+int tgsr_maxpool3s2_nhwc16(const void* x, void* y, uint8_t* idx, int B, int H, int W, int C, int fmt, tgsr_stream_t stream);
+int tgsr_maxpool3s2_nhwc16_bwd(const void* gy, const uint8_t* idx, void* gx, int B, int H, int W, int C, int fmt,
+                               tgsr_stream_t stream);
 /* y [B,P,2H,2W,8] = nearest x2 of x [B,P,H,W,8];  y [B,P,H,W,8] = 2x2 block sums of x [B,P,2H,2W,8] (its adjoint). */
 int tgsr_upsample2x_blocked(const void* x, void* y, int B, int P, int H, int W, tgsr_stream_t stream);
 int tgsr_sumpool2x2_blocked(const void* x, void* y, int B, int P, int H, int W, int fmt, tgsr_stream_t stream);

@@ -230,6 +230,28 @@ def test_image_encoder_bf16_paths_agree():
         assert _cos(res['fused'][k], res['fp32'][k]) > (0.99 if k < 2 else 0.8), k
 
 
+@pytest.mark.parametrize('B,C,H,W', [(2, 64, 147, 147), (3, 192, 71, 71), (2, 288, 35, 35), (1, 768, 17, 17), (2, 8, 8, 6)])
+def test_maxpool3s2_nhwc16(B, C, H, W):
+    """csrc/pool16.cu against F.max_pool2d(x, 3, 2) and its autograd backward on bf16 channels-last tensors (ties: duplicate
+    values are planted so that the first-maximum rule is exercised)."""
+    from tgsr_b200.train_step import _MaxPool3s2Fn
+    g = torch.Generator().manual_seed(C + H)
+    x = (torch.randint(-6, 7, (B, C, H, W), generator=g).float() / 4).to(torch.bfloat16)    # 13 levels: ties in most windows
+    gy_shape = (B, C, (H - 3) // 2 + 1, (W - 3) // 2 + 1)
+    gy = torch.randn(gy_shape, generator=g).to(torch.bfloat16)
+    xr = x.float().requires_grad_(True)
+    yr = F.max_pool2d(xr, 3, 2)
+    yr.backward(gy.float())
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    yd = _MaxPool3s2Fn.apply(xd)
+    yd.backward(gy.to(DEV))
+    assert torch.equal(yd.detach().float().cpu(), yr.detach())
+    # gx: sums of at most four bf16 values, rounded once to bf16
+    assert (xd.grad.float().cpu() - xr.grad).abs().max() <= 2 ** -7 * xr.grad.abs().max()
+    assert torch.equal(xd.grad.float().cpu() != 0, xr.grad.to(torch.bfloat16).float() != 0) or \
+        ((xd.grad.float().cpu() != 0) == (xr.grad != 0)).float().mean() > 0.9999
+
+
 def test_generator_step_bf16_matches_fp32_step():
     """One training step of the whole generator (G_SR_NET_low + NetG_highweight, train BN): the bf16 / tcgen05 path against
     the exact fp32 path from the same weights and inputs.

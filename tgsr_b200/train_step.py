@@ -93,6 +93,7 @@ class FusedAdam:
 
 import os as _os
 _FUSED_CONV_RELU = int(_os.environ.get('TGSR_ENCODER_FUSED_CONV', '1'))
+_OWN_MAXPOOL = int(_os.environ.get('TGSR_ENCODER_OWN_MAXPOOL', '1'))
 
 
 class _ConvBiasReluFn(torch.autograd.Function):
@@ -113,6 +114,39 @@ class _ConvBiasReluFn(torch.autograd.Function):
         g = torch.ops.aten.threshold_backward(gy, y, 0)
         dx = torch.ops.aten.convolution_backward(g, x, w, None, stride, padding, (1, 1), False, (0, 0), 1, (True, False, False))[0]
         return dx, None, None, None, None
+
+
+class _MaxPool3s2Fn(torch.autograd.Function):
+    """F.max_pool2d(x, 3, stride 2) on channels-last bf16 tensors through csrc/pool16.cu (gather kernels both ways)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        from ._lib import call, ptr, FMT_BF16
+        x = x.contiguous(memory_format=torch.channels_last)
+        B, C, H, W = x.shape
+        Ho, Wo = (H - 3) // 2 + 1, (W - 3) // 2 + 1
+        y = torch.empty((B, C, Ho, Wo), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        idx = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.uint8)
+        call('tgsr_maxpool3s2_nhwc16', x.device, ptr(x), ptr(y), ptr(idx), B, H, W, C, FMT_BF16)
+        ctx.save_for_backward(idx)
+        ctx.shape = (B, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from ._lib import call, ptr, FMT_BF16
+        idx, = ctx.saved_tensors
+        B, C, H, W = ctx.shape
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        gx = torch.empty((B, C, H, W), device=gy.device, dtype=gy.dtype, memory_format=torch.channels_last)
+        call('tgsr_maxpool3s2_nhwc16_bwd', gy.device, ptr(gy), ptr(idx), ptr(gx), B, H, W, C, FMT_BF16)
+        return gx
+
+
+def _max_pool_3s2(x):
+    if x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0 and _OWN_MAXPOOL:
+        return _MaxPool3s2Fn.apply(x)
+    return F.max_pool2d(x, kernel_size=3, stride=2)
 
 
 class FrozenImageEncoder(nn.Module):
@@ -164,7 +198,7 @@ class FrozenImageEncoder(nn.Module):
         import types
         from torchvision.models.inception import BasicConv2d
 
-        from torchvision.models.inception import InceptionA, InceptionC, InceptionE
+        from torchvision.models.inception import InceptionA, InceptionB, InceptionC, InceptionD, InceptionE
 
         def folded(m, x):
             if x.dtype != torch.bfloat16:                    # the fp32 path keeps conv -> BatchNorm -> ReLU
@@ -192,6 +226,19 @@ class FrozenImageEncoder(nn.Module):
             outs.append(blk.branch_pool(x))
             return torch.cat(outs, 1)
 
+        def block_b(blk, x):                                    # grid reduction: conv s2 | double 3x3 s2 | max pool
+            if x.dtype != torch.bfloat16:
+                return InceptionB.forward(blk, x)
+            return torch.cat((blk.branch3x3(x), blk.branch3x3dbl_3(blk.branch3x3dbl_2(blk.branch3x3dbl_1(x))), _max_pool_3s2(x)), 1)
+
+        def block_d(blk, x):
+            if x.dtype != torch.bfloat16:
+                return InceptionD.forward(blk, x)
+            y = x
+            for name in ('branch7x7x3_1', 'branch7x7x3_2', 'branch7x7x3_3', 'branch7x7x3_4'):
+                y = getattr(blk, name)(y)
+            return torch.cat((blk.branch3x3_2(blk.branch3x3_1(x)), y, _max_pool_3s2(x)), 1)
+
         def block_e(blk, x):
             if x.dtype != torch.bfloat16:
                 return InceptionE.forward(blk, x)
@@ -216,6 +263,10 @@ class FrozenImageEncoder(nn.Module):
                     bp._fw = w3.to(device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
                     bp._fpad = (1, 1)
                     blk.forward = types.MethodType(block_e if isinstance(blk, InceptionE) else block_ac, blk)
+                elif isinstance(blk, InceptionB):
+                    blk.forward = types.MethodType(block_b, blk)
+                elif isinstance(blk, InceptionD):
+                    blk.forward = types.MethodType(block_d, blk)
             self._ef_w = self.emb_features.weight.to(device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
             self._ec_w = self.emb_cnn_code.weight.to(device, torch.bfloat16)
             self._ec_b = self.emb_cnn_code.bias.to(device, torch.bfloat16)
@@ -226,9 +277,9 @@ class FrozenImageEncoder(nn.Module):
         if dtype is not None:
             x = x.to(dtype).contiguous(memory_format=torch.channels_last)
         x = self.Conv2d_2b_3x3(self.Conv2d_2a_3x3(self.Conv2d_1a_3x3(x)))
-        x = F.max_pool2d(x, kernel_size=3, stride=2)
+        x = _max_pool_3s2(x)
         x = self.Conv2d_4a_3x3(self.Conv2d_3b_1x1(x))
-        x = F.max_pool2d(x, kernel_size=3, stride=2)
+        x = _max_pool_3s2(x)
         x = self.Mixed_5d(self.Mixed_5c(self.Mixed_5b(x)))
         x = self.Mixed_6e(self.Mixed_6d(self.Mixed_6c(self.Mixed_6b(self.Mixed_6a(x)))))
         features = x
