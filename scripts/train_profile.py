@@ -43,17 +43,23 @@ def main():
         ts.step(LR, real, caps, lens, 18)
         torch.cuda.synchronize()
     agg = collections.defaultdict(lambda: [0, 0.0])
+    each = collections.defaultdict(list)
     for e in prof.events():
         if e.device_type == torch.autograd.DeviceType.CUDA:
             k = e.name.replace('(anonymous namespace)::', '').split('(')[0][:130]
             agg[k][0] += 1
             agg[k][1] += e.time_range.end - e.time_range.start
+            each[k].append(e.time_range.end - e.time_range.start)
     tot = sum(v[1] for v in agg.values())
     ours = sum(v[1] for k, v in agg.items() if 'tgsr::' in k)
     print('kernels %d, sum of durations %.2f ms (tgsr:: kernels %.2f ms)' % (sum(v[0] for v in agg.values()), tot / 1e3, ours / 1e3))
     print('| ms | share | launches | kernel |\n|---:|---:|---:|---|')
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
         print('| %.2f | %.1f%% | %d | `%s` |' % (t / 1e3, 100 * t / tot, c, k))
+    print('\nlargest launches (us) of this library\'s kernels:')
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+        if 'tgsr::' in k:
+            print('%-60s %s' % (k[:60], ' '.join('%.0f' % v for v in sorted(each[k], reverse=True)[:8])))
 
 
 if __name__ == '__main__':

@@ -291,7 +291,7 @@ def test_generator_step_bf16_matches_fp32_step():
         fine, _, _ = gh(LR, imgsL, LR)
         l = losses.MSE(list(fine) + list(imgsL), list(real) + list(real))
         l.backward()
-        mse[mode] = float(l)
+        mse[mode] = float(l.detach())
         grads_mse[mode] = {n: p.grad.detach().clone() for n, p in params}
         # (b) the full step's forward + backward (second forward: running statistics move, batch statistics do not)
         o = ts._fwd_bwd(LR, real, caps, lens, 18)

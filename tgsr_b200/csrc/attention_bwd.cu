@@ -16,7 +16,19 @@ namespace tgsr {
 
 constexpr int AB_PIX = 256;
 
-// smem: S [idf][TP] | Ps [256][TP+1] | dLs [256][TP+1]
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// smem: S [idf][TP] | Ps [256][TP+1] | dLs [256][TP+1] | dSs [idf][TP]
 template <int TP>
 __global__ void __launch_bounds__(AB_PIX)
 attn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ S, const float* __restrict__ attn,
@@ -26,6 +38,7 @@ attn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ S, const 
   float* Ss = sm;
   float* Ps = Ss + idf * TP;
   float* dLs = Ps + AB_PIX * (TP + 1);
+  float* dSs = dLs + AB_PIX * (TP + 1);                            // [idf][TP] partial dS of this CTA
   const int tid = threadIdx.x, b = blockIdx.y, q = blockIdx.x * AB_PIX + tid;
   const bool live = q < Q;
   for (int i = tid; i < idf * TP; i += AB_PIX) Ss[i] = __ldg(S + (size_t)b * idf * TP + i);
@@ -61,18 +74,63 @@ attn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ S, const 
     }
   }
   __syncthreads();
-  // dS partial sums of this chunk: thread -> (i, t) pairs
-  const int q0 = blockIdx.x * AB_PIX, nq = min(AB_PIX, Q - q0);
-  for (int o = tid; o < idf * T; o += AB_PIX) {
-    const int i = o / T, t = o - i * T;
-    const float* xr = xb + (size_t)i * Q + q0;
-    const float* dr = db + (size_t)i * Q + q0;
-    float a0 = 0.f, a1 = 0.f;
-    for (int k = 0; k < nq; ++k) {
-      a0 = fmaf(__ldg(dr + k), Ps[k * (TP + 1) + t], a0);
-      a1 = fmaf(__ldg(xr + k), dLs[k * (TP + 1) + t], a1);
+  // dS partial sums of this chunk: D[i][t] = sum_q dOut[i][q] P[q][t] + x[i][q] dL[q][t], a [idf x 256] . [256 x TP] product
+  // per term -> warp-level tensor cores (3xTF32 m16n8k8: fp32-grade products, fp32 accumulate).  Warp w owns the 32
+  // pixels [32w, 32w+32) as its K range; A fragments come straight from global memory (dOut was just read by this CTA,
+  // x is read here for the only time), B fragments from the staged P / dL rows (row stride TP+1: conflict-free).  The
+  // eight partial products meet in shared memory, then one atomic per (i, t) and CTA goes to dS.
+  const int q0 = blockIdx.x * AB_PIX;
+  {
+    constexpr int NT = TP / 8;
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, tig = lane & 3;
+    for (int i = tid; i < idf * TP; i += AB_PIX) dSs[i] = 0.f;
+    __syncthreads();
+    const int kb = warp * 32;
+    for (int m0 = 0; m0 < idf; m0 += 16) {
+      float acc[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+      const int r0 = m0 + g, r1 = m0 + g + 8;
+#pragma unroll
+      for (int term = 0; term < 2; ++term) {
+        const float* A = term == 0 ? db : xb;
+        const float* Bs = term == 0 ? Ps : dLs;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const int p0 = kb + ks * 8 + tig, p1 = p0 + 4;
+          const bool l0 = q0 + p0 < Q, l1 = q0 + p1 < Q;
+          // 3xTF32 (hi*hi + lo*hi + hi*lo): these sums cancel heavily, single-pass TF32 leaves 1e-3-level errors
+          float av[4];
+          av[0] = (l0 && r0 < idf) ? __ldg(A + (size_t)r0 * Q + q0 + p0) : 0.f;
+          av[1] = (l0 && r1 < idf) ? __ldg(A + (size_t)r1 * Q + q0 + p0) : 0.f;
+          av[2] = (l1 && r0 < idf) ? __ldg(A + (size_t)r0 * Q + q0 + p1) : 0.f;
+          av[3] = (l1 && r1 < idf) ? __ldg(A + (size_t)r1 * Q + q0 + p1) : 0.f;
+          uint32_t ah[4], al[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { ah[k] = f2tf32(av[k]); al[k] = f2tf32(av[k] - __uint_as_float(ah[k])); }
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const float bv0 = Bs[p0 * (TP + 1) + nt * 8 + g], bv1 = Bs[p1 * (TP + 1) + nt * 8 + g];
+            const uint32_t bh0 = f2tf32(bv0), bh1 = f2tf32(bv1);
+            const uint32_t bl0 = f2tf32(bv0 - __uint_as_float(bh0)), bl1 = f2tf32(bv1 - __uint_as_float(bh1));
+            mma_tf32_1688(acc[nt], ah, bh0, bh1);
+            mma_tf32_1688(acc[nt], al, bh0, bh1);
+            mma_tf32_1688(acc[nt], ah, bl0, bl1);
+          }
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int t0 = nt * 8 + 2 * tig;
+        if (r0 < idf) { atomicAdd(dSs + r0 * TP + t0, acc[nt][0]); atomicAdd(dSs + r0 * TP + t0 + 1, acc[nt][1]); }
+        if (r1 < idf) { atomicAdd(dSs + r1 * TP + t0, acc[nt][2]); atomicAdd(dSs + r1 * TP + t0 + 1, acc[nt][3]); }
+      }
     }
-    atomicAdd(dS + ((size_t)b * idf + i) * TP + t, a0 + a1);
+    __syncthreads();
+    for (int o = tid; o < idf * TP; o += AB_PIX) {
+      const int t = o % TP;
+      if (t < T) atomicAdd(dS + (size_t)b * idf * TP + o, dSs[o]);
+    }
   }
 }
 
@@ -129,7 +187,7 @@ extern "C" int tgsr_attn_bwd_f32(const float* input, const float* context, const
   TGSR_CUDA(cudaMemsetAsync(dS, 0, nws * sizeof(float), st));
   dim3 grid(ceil_div(Q, AB_PIX), B);
 #define TGSR_LAUNCH_AB(TPV)                                                                                      \
-  attn_bwd_kernel<TPV><<<grid, AB_PIX, ((size_t)idf * TPV + 2 * AB_PIX * (TPV + 1)) * 4, st>>>(input, S, attn, d_wctx, d_attn, \
+  attn_bwd_kernel<TPV><<<grid, AB_PIX, ((size_t)2 * idf * TPV + 2 * AB_PIX * (TPV + 1)) * 4, st>>>(input, S, attn, d_wctx, d_attn, \
                                                                                             d_input, dS, idf, Q, T)
   if (TP == 24) TGSR_LAUNCH_AB(24); else if (TP == 32) TGSR_LAUNCH_AB(32); else TGSR_LAUNCH_AB(48);
 #undef TGSR_LAUNCH_AB
