@@ -7,7 +7,7 @@
 //       so ldmatrix.x4.trans on (plane 2c, plane 2c+1) x (pixels 0-7, 8-15) IS the A fragment; the tap is an address shift.
 //   B = dz: columns 0..2 hold the 16-bit rounding of dz[co], columns 3..5 the rounding residual (N = 8 has room for both),
 //       so dz enters with ~16 mantissa bits at no extra MMA; the two partial sums meet in the final atomics.
-// A CTA owns 16 x 32 output pixels at a time; warp (kx, c) owns filter column kx and input channels 16c..16c+15 and walks the
+// A CTA owns 16 x 32 output pixels at a time (double-buffered through cp.async); warp (kx, c) owns filter column kx and input channels 16c..16c+15 and walks the
 // patch rows: one ldmatrix of patch row R serves the K taps ky (output row R - ky), whose B fragments slide through registers.
 // Accumulators stay in registers over all tiles of a CTA; the epilogue adds them to dW with fp32 atomics.
 #include "common.cuh"
@@ -40,62 +40,69 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
-// smem: patch [4 planes][PH][PW] x 16 B | bfrag [HW_TH][2 chunks][32 lanes] uint2
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;                                  // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
+// smem, two stages: patch [4 planes][PH][PW] x 16 B | dz tile [3][HW_TH][HW_TW] fp32.  Every byte arrives through cp.async
+// (zero-filled outside the image), so the loads of tile n+1 are in flight while tile n is multiplied.
 template <int K, int FMT>
 __global__ void __launch_bounds__(K * 2 * 32)
 head_wgrad16_kernel(const h16* __restrict__ x, int xP, int xp0, const float* __restrict__ dz, float* __restrict__ dw,
                     int B, int H, int W, int tiles_x, int tiles_y, int ntiles) {
   constexpr int R = K / 2, PH = HW_TH + K - 1, PW = HW_TW + K - 1, NPL = HW_CIN / 8, THREADS = K * 2 * 32;
+  constexpr int PATCH_B = NPL * PH * PW * 16, DZ_B = 3 * HW_TH * HW_TW * 4, STAGE_B = PATCH_B + DZ_B;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint4* patch = reinterpret_cast<uint4*>(smem_raw);
-  uint2* bfrag = reinterpret_cast<uint2*>(smem_raw + NPL * PH * PW * 16);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tig = lane & 3;
   const int kx = warp >> 1, cg = warp & 1;                      // filter column, input-channel group of 16
   const size_t plane = (size_t)H * W;
+  const uint32_t smem0 = ptx::smem_u32(smem_raw);
 
   float acc[K][4];
 #pragma unroll
   for (int ky = 0; ky < K; ++ky) { acc[ky][0] = acc[ky][1] = acc[ky][2] = acc[ky][3] = 0.f; }
 
-  // ldmatrix row address of this lane inside the patch: matrix j = lane/8: plane 2cg + (j & 1), pixels 8(j >> 1) + lane % 8
-  const uint32_t a_base = ptx::smem_u32(patch) +
-                          (uint32_t)((((2 * cg + ((lane >> 3) & 1)) * PH) * PW + kx + ((lane >> 4) << 3) + (lane & 7)) * 16);
+  // ldmatrix row address of this lane inside a patch: matrix j = lane/8: plane 2cg + (j & 1), pixels 8(j >> 1) + lane % 8
+  const uint32_t a_off = (uint32_t)((((2 * cg + ((lane >> 3) & 1)) * PH) * PW + kx + ((lane >> 4) << 3) + (lane & 7)) * 16);
+  // B fragment source of this lane: dz channel g % 3 (value for g < 3, rounding residual for g < 6, nothing above)
+  const int zco = g % 3;
+  const bool z_on = g < 6, z_lo = g >= 3;
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  auto prefetch = [&](int tile, int stage) {
     const int tx = tile % tiles_x, q = tile / tiles_x, ty = q % tiles_y, b = q / tiles_y;
     const int y0 = ty * HW_TH, x0 = tx * HW_TW;
-    __syncthreads();                                            // the previous tile's operands are no longer in use
-    // ---- halo patch of h (zero outside the image)
+    const uint32_t pbase = smem0 + stage * STAGE_B;
     const h16* xb = x + ((size_t)b * xP + xp0) * plane * 8;
     for (int e = tid; e < NPL * PH * PW; e += THREADS) {
       const int pc = e % PW, t = e / PW, pr = t % PH, pl = t / PH;
       const int yy = y0 - R + pr, xx = x0 - R + pc;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-        v = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)pl * plane + (size_t)yy * W + xx) * 8));
-      patch[e] = v;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      cp_async16_zfill(pbase + e * 16, xb + ((size_t)pl * plane + (size_t)(ok ? yy : 0) * W + (ok ? xx : 0)) * 8, ok);
     }
-    // ---- B fragments of dz: lane (g, tig) of (row, chunk) holds n = g: co = g % 3 (hi for g < 3, residual for g < 6),
-    //      k = 2tig, 2tig+1 (b0) and 2tig+8, 2tig+9 (b1) of the 16-pixel chunk
-    for (int e = tid; e < HW_TH * 2 * 32; e += THREADS) {
-      const int l = e & 31, ch = (e >> 5) & 1, r = e >> 6, gg = l >> 2, tg = l & 3;
-      uint2 v = make_uint2(0u, 0u);
-      const int yy = y0 + r;
-      if (gg < 6 && yy < H) {
-        const float* zp = dz + (((size_t)b * 3 + (gg % 3)) * H + yy) * W;
-        float f[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int xx = x0 + ch * 16 + 2 * tg + (i & 1) + (i >> 1) * 8;
-          f[i] = xx < W ? __ldg(zp + xx) : 0.f;
-          if (gg >= 3) f[i] -= Fmt16<FMT>::cvtf(f[i]);
-        }
-        v.x = Fmt16<FMT>::pack2(f[0], f[1]); v.y = Fmt16<FMT>::pack2(f[2], f[3]);
-      }
-      bfrag[e] = v;
+    for (int e = tid; e < 3 * HW_TH * (HW_TW / 4); e += THREADS) {             // 16-byte chunks = 4 pixels (W % 4 == 0)
+      const int c4 = e % (HW_TW / 4), t = e / (HW_TW / 4), r = t % HW_TH, co = t / HW_TH;
+      const int yy = y0 + r, xx = x0 + 4 * c4;
+      const bool ok = yy < H && xx < W;
+      cp_async16_zfill(pbase + PATCH_B + e * 16, dz + (((size_t)b * 3 + co) * H + (ok ? yy : 0)) * W + (ok ? xx : 0), ok);
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int stage = 0;
+  if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int next = tile + gridDim.x;
+    if (next < ntiles) {
+      prefetch(next, stage ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();                                            // this tile's bytes are visible to every warp
+    const uint32_t a_base = smem0 + stage * STAGE_B + a_off;
+    const float* zs = reinterpret_cast<const float*>(smem_raw + stage * STAGE_B + PATCH_B) + zco * (HW_TH * HW_TW) + 2 * tig;
     // ---- walk the patch rows; the B fragments of the last K output rows slide through registers
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
@@ -104,10 +111,19 @@ head_wgrad16_kernel(const h16* __restrict__ x, int xP, int xp0, const float* __r
       for (int i = 0; i < K; ++i) bw[i] = make_uint2(0u, 0u);
 #pragma unroll
       for (int pr = 0; pr < PH; ++pr) {
-        // window: bw[ky] = fragment of output row pr - ky
+        // window: bw[ky] = fragment of output row pr - ky: k = 2tig, 2tig+1 (b0) and 2tig+8, 2tig+9 (b1) of the chunk
 #pragma unroll
         for (int i = K - 1; i > 0; --i) bw[i] = bw[i - 1];
-        bw[0] = pr < HW_TH ? bfrag[(pr * 2 + ch) * 32 + lane] : make_uint2(0u, 0u);
+        bw[0] = make_uint2(0u, 0u);
+        if (pr < HW_TH && z_on) {
+          float2 f0 = *reinterpret_cast<const float2*>(zs + pr * HW_TW + ch * 16);
+          float2 f1 = *reinterpret_cast<const float2*>(zs + pr * HW_TW + ch * 16 + 8);
+          if (z_lo) {
+            f0.x -= Fmt16<FMT>::cvtf(f0.x); f0.y -= Fmt16<FMT>::cvtf(f0.y);
+            f1.x -= Fmt16<FMT>::cvtf(f1.x); f1.y -= Fmt16<FMT>::cvtf(f1.y);
+          }
+          bw[0] = make_uint2(Fmt16<FMT>::pack2(f0.x, f0.y), Fmt16<FMT>::pack2(f1.x, f1.y));
+        }
         uint32_t a[4];
         ldmatrix_x4_trans(a, a_base + (uint32_t)((pr * PW + ch * 16) * 16));
 #pragma unroll
@@ -115,14 +131,29 @@ head_wgrad16_kernel(const h16* __restrict__ x, int xP, int xp0, const float* __r
           if (pr - ky >= 0 && pr - ky < HW_TH) HwMma<FMT>::k16(acc[ky], a, bw[ky].x, bw[ky].y);
       }
     }
+    __syncthreads();                                            // everyone is done with this stage before it is refilled
+    stage ^= 1;
   }
-  // ---- D fragment: rows ci = 16cg + g (+8), columns n = 2tig, 2tig+1; n < 3: co = n, 3 <= n < 6: residual of co = n - 3
+  // ---- D fragment: rows ci = 16cg + g (+8), columns n = 2tig, 2tig+1; n < 3: co = n, 3 <= n < 6: residual part of co = n - 3.
+  // Value and residual columns of one co sit in different lanes of a quad: they are added through shuffles, so each
+  // (co, ci, tap) costs ONE atomic per CTA.
+  const int qbase = lane & ~3;
 #pragma unroll
   for (int ky = 0; ky < K; ++ky)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int n = 2 * tig + (i & 1), ci = 16 * cg + g + (i >> 1) * 8;
-      if (n < 6) atomicAdd(dw + (((size_t)(n % 3) * HW_CIN + ci) * K + ky) * K + kx, acc[ky][i]);
+    for (int r = 0; r < 2; ++r) {
+      const float v0 = acc[ky][2 * r], v1 = acc[ky][2 * r + 1];
+      const float t1v1 = __shfl_sync(0xffffffffu, v1, qbase + 1);
+      const float t2v0 = __shfl_sync(0xffffffffu, v0, qbase + 2);
+      const float t2v1 = __shfl_sync(0xffffffffu, v1, qbase + 2);
+      const int ci = 16 * cg + g + r * 8;
+      float* o = dw + ((size_t)ci * K + ky) * K + kx;              // + co * HW_CIN * K * K
+      if (tig == 0) {
+        atomicAdd(o, v0 + t1v1);                                   // co 0: n = 0 and n = 3
+        atomicAdd(o + (size_t)HW_CIN * K * K, v1 + t2v0);          // co 1: n = 1 and n = 4
+      } else if (tig == 1) {
+        atomicAdd(o + (size_t)2 * HW_CIN * K * K, v0 + t2v1);      // co 2: n = 2 and n = 5
+      }
     }
 }
 
@@ -134,7 +165,7 @@ extern "C" int tgsr_head_wgrad16(const void* x, int xP, int xp0, const float* dz
   TGSR_REQUIRE_PTR(x); TGSR_REQUIRE_PTR(dz); TGSR_REQUIRE_PTR(dw);
   TGSR_REQUIRE(fmt == TGSR_FMT_BF16 || fmt == TGSR_FMT_F16, TGSR_ERR_UNSUPPORTED);
   TGSR_REQUIRE(Cin == HW_CIN && (ksize == 3 || ksize == 5), TGSR_ERR_UNSUPPORTED);
-  TGSR_REQUIRE(B > 0 && H > 0 && W > 0 && xP >= xp0 + Cin / 8 && xp0 >= 0, TGSR_ERR_BAD_SHAPE);
+  TGSR_REQUIRE(B > 0 && H > 0 && W > 0 && W % 4 == 0 && xP >= xp0 + Cin / 8 && xp0 >= 0, TGSR_ERR_BAD_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
   TGSR_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 3 * Cin * ksize * ksize, st));
   const int tiles_x = ceil_div(W, HW_TW), tiles_y = ceil_div(H, HW_TH);
@@ -145,14 +176,16 @@ extern "C" int tgsr_head_wgrad16(const void* x, int xP, int xp0, const float* dz
 #define TGSR_HW_LAUNCH(KK, F)                                                                                          \
   do {                                                                                                                 \
     constexpr int PHh = HW_TH + KK - 1, PWw = HW_TW + KK - 1;                                                          \
-    constexpr size_t sm = (size_t)(HW_CIN / 8) * PHh * PWw * 16 + HW_TH * 2 * 32 * 8;                                  \
+    constexpr size_t sm = 2 * ((size_t)(HW_CIN / 8) * PHh * PWw * 16 + 3 * HW_TH * HW_TW * 4);   /* two stages */                                  \
     static bool attr_set = false;                                                                                      \
     if (!attr_set) {                                                                                                   \
       TGSR_CUDA(cudaFuncSetAttribute(head_wgrad16_kernel<KK, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
       attr_set = true;                                                                                                 \
     }                                                                                                                  \
     const int per_sm = (int)((220 * 1024) / (sm + 1024)) > 4 ? 4 : (int)((220 * 1024) / (sm + 1024));                  \
-    const int grid = ntiles < (g_sm_count > 0 ? g_sm_count : 148) * per_sm ? ntiles : (g_sm_count > 0 ? g_sm_count : 148) * per_sm;                                      \
+    const int cap = (g_sm_count > 0 ? g_sm_count : 148) * per_sm;                                                      \
+    int grid = (ntiles + 7) / 8;                 /* >= 8 tiles per CTA: every CTA ends with 3 * Cin * k * k atomics */   \
+    if (grid > cap) grid = cap;                                                                                        \
     head_wgrad16_kernel<KK, F><<<grid, KK * 2 * 32, sm, st>>>(xx, xP, xp0, dz, dw, B, H, W, tiles_x, tiles_y, ntiles);   \
   } while (0)
   if (ksize == 3) { if (fmt == TGSR_FMT_F16) TGSR_HW_LAUNCH(3, TGSR_FMT_F16); else TGSR_HW_LAUNCH(3, TGSR_FMT_BF16); }
