@@ -390,6 +390,11 @@ int tgsr_head_wgrad16(const void* x, int xP, int xp0, const float* dz, float* dw
 int tgsr_maxpool3s2_nhwc16(const void* x, void* y, uint8_t* idx, int B, int H, int W, int C, int fmt, tgsr_stream_t stream);
 int tgsr_maxpool3s2_nhwc16_bwd(const void* gy, const uint8_t* idx, void* gx, int B, int H, int W, int C, int fmt,
                                tgsr_stream_t stream);
+/* ReLU backward on channels-last 16-bit tensors: out[p][c] = y[p][c] > 0 ? gy[p][c] : 0 for npix pixels of C channels; gy's
+ * pixels are gy_pixel_stride elements apart (a channel slice of a wider tensor: the gradient of a concatenation), y and out
+ * are dense.  C % 8 == 0, stride % 8 == 0, 16-byte aligned pointers. */
+int tgsr_relu_bwd_nhwc16(const void* gy, long long gy_pixel_stride, const void* y, void* out, long long npix, int C, int fmt,
+                         tgsr_stream_t stream);
 /* y [B,P,2H,2W,8] = nearest x2 of x [B,P,H,W,8];  y [B,P,H,W,8] = 2x2 block sums of x [B,P,2H,2W,8] (its adjoint). */
 int tgsr_upsample2x_blocked(const void* x, void* y, int B, int P, int H, int W, tgsr_stream_t stream);
 int tgsr_sumpool2x2_blocked(const void* x, void* y, int B, int P, int H, int W, int fmt, tgsr_stream_t stream);

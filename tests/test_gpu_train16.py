@@ -252,6 +252,22 @@ def test_maxpool3s2_nhwc16(B, C, H, W):
         ((xd.grad.float().cpu() != 0) == (xr.grad != 0)).float().mean() > 0.9999
 
 
+def test_relu_bwd_nhwc16_on_channel_slices():
+    """gy * (y > 0) where gy is a channel slice of a wider channels-last tensor (the gradient of a concatenation): bit-exact
+    against torch's threshold_backward."""
+    from tgsr_b200.train_step import _relu_bwd
+    g = torch.Generator().manual_seed(9)
+    B, H, W = 3, 17, 13
+    wide = torch.randn(B, 64 + 96 + 32, H, W, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+    for c0, C in ((0, 64), (64, 96), (160, 32)):
+        y = torch.relu(torch.randn(B, C, H, W, generator=g)).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+        gy = wide[:, c0:c0 + C]
+        assert not gy.is_contiguous(memory_format=torch.channels_last)
+        out = _relu_bwd(gy, y)
+        assert torch.equal(out, torch.ops.aten.threshold_backward(gy, y, 0))
+        assert out.is_contiguous(memory_format=torch.channels_last)
+
+
 def test_generator_step_bf16_matches_fp32_step():
     """One training step of the whole generator (G_SR_NET_low + NetG_highweight, train BN): the bf16 / tcgen05 path against
     the exact fp32 path from the same weights and inputs.

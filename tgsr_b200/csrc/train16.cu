@@ -195,24 +195,46 @@ bn16_bwd_reduce_kernel(const h16* __restrict__ z, const float* __restrict__ mean
   for (int k = 0; k < NA; ++k) s[k] = 0.f;
   const uint32_t n_items = (uint32_t)B * HW;                     // < 2^31 (checked by the launcher)
   const uint32_t nchunk = (n_items + 16 * 256 - 1) / (16 * 256);
+  constexpr int NLD = GLU ? 3 : 2;                               // 16-byte loads per element: dy, z value plane (, z gate plane)
   for (uint32_t ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
-#pragma unroll 4
-    for (int it = 0; it < 16; ++it) {
-      const uint32_t i = (ch * 16 + it) * 256 + threadIdx.x;
-      if (i < n_items) {
+    for (int it = 0; it < 16; it += 4) {
+      // all loads of four elements first (8-12 independent 16-byte requests per thread), then the arithmetic
+      uint4 u[4][NLD];
+      bool ok[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t i = (ch * 16 + it + k) * 256 + threadIdx.x;
+        ok[k] = i < n_items;
         uint32_t b, pix;
-        dHW.divmod(i, b, pix);
-        float xa[8], xg[8], dua[8], dug[8];
-        bn16_du<FMT, GLU>(z, dy, coef, C, P, Pf, b, pf, pix, HW, xa, xg, dua, dug);
+        dHW.divmod(ok[k] ? i : 0u, b, pix);
+        u[k][0] = __ldg(reinterpret_cast<const uint4*>(dy + (((size_t)b * Pf + pf) * (size_t)HW + pix) * 8));
+        u[k][1] = __ldg(reinterpret_cast<const uint4*>(z + (((size_t)b * P + pf) * (size_t)HW + pix) * 8));
+        if (GLU) u[k][NLD - 1] = __ldg(reinterpret_cast<const uint4*>(z + (((size_t)b * P + pf + Pf) * (size_t)HW + pix) * 8));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!ok[k]) continue;
+        float d[8], xa[8], xg[8];
+        unpack8_16<FMT>(u[k][0], d);
+        unpack8_16<FMT>(u[k][1], xa);
+        if (GLU) unpack8_16<FMT>(u[k][NLD - 1], xg);
         // S2 = sum du * xhat = invstd * (sum du * x - mean * sum du): the raw moment costs one FMA per element here, the
         // affine correction is applied once per CTA below
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          s[e] += dua[e];
-          s[8 + e] = fmaf(dua[e], xa[e], s[8 + e]);
           if (GLU) {
-            s[16 + e] += dug[e];
-            s[24 + e] = fmaf(dug[e], xg[e], s[24 + e]);
+            const int ca = pf * 8 + e, cg = ca + Pf * 8;
+            const float a = fmaf(xa[e], coef[ca], coef[C + ca]);
+            const float gg = fmaf(xg[e], coef[cg], coef[C + cg]);
+            const float sg = __fdividef(1.0f, 1.0f + __expf(-gg));
+            const float dua = d[e] * sg, dug = d[e] * a * sg * (1.0f - sg);
+            s[e] += dua;
+            s[8 + e] = fmaf(dua, xa[e], s[8 + e]);
+            s[16 + e] += dug;
+            s[24 + e] = fmaf(dug, xg[e], s[24 + e]);
+          } else {
+            s[e] += d[e];
+            s[8 + e] = fmaf(d[e], xa[e], s[8 + e]);
           }
         }
       }

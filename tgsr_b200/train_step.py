@@ -94,6 +94,23 @@ class FusedAdam:
 import os as _os
 _FUSED_CONV_RELU = int(_os.environ.get('TGSR_ENCODER_FUSED_CONV', '1'))
 _OWN_MAXPOOL = int(_os.environ.get('TGSR_ENCODER_OWN_MAXPOOL', '1'))
+_OWN_RELU_BWD = int(_os.environ.get('TGSR_ENCODER_OWN_RELU_BWD', '1'))
+
+
+def _relu_bwd(gy, y):
+    """gy * (y > 0).  gy is often a channel slice of a concatenation's gradient (pixels strided): csrc/pool16.cu reads it with
+    16-byte vectors where the library falls back to a scalar strided kernel."""
+    B, C, H, W = y.shape
+    st = gy.stride()
+    if (_OWN_RELU_BWD and gy.dtype == torch.bfloat16 and C % 8 == 0 and st[1] == 1 and st[3] % 8 == 0 and st[2] == W * st[3]
+            and st[0] == H * st[2] and gy.data_ptr() % 16 == 0 and y.is_contiguous(memory_format=torch.channels_last)
+            and y.stride()[1] == 1):
+        from ._lib import call, ptr, FMT_BF16
+        import ctypes as C_
+        out = torch.empty_like(y)
+        call('tgsr_relu_bwd_nhwc16', y.device, ptr(gy), C_.c_longlong(st[3]), ptr(y), ptr(out), C_.c_longlong(B * H * W), C, FMT_BF16)
+        return out
+    return torch.ops.aten.threshold_backward(gy, y, 0)
 
 
 class _ConvBiasReluFn(torch.autograd.Function):
@@ -111,7 +128,7 @@ class _ConvBiasReluFn(torch.autograd.Function):
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
         stride, padding = ctx.conf
-        g = torch.ops.aten.threshold_backward(gy, y, 0)
+        g = _relu_bwd(gy, y)
         dx = torch.ops.aten.convolution_backward(g, x, w, None, stride, padding, (1, 1), False, (0, 0), 1, (True, False, False))[0]
         return dx, None, None, None, None
 
