@@ -390,6 +390,10 @@ int tgsr_head_wgrad16(const void* x, int xP, int xp0, const float* dz, float* dw
 int tgsr_maxpool3s2_nhwc16(const void* x, void* y, uint8_t* idx, int B, int H, int W, int C, int fmt, tgsr_stream_t stream);
 int tgsr_maxpool3s2_nhwc16_bwd(const void* gy, const uint8_t* idx, void* gx, int B, int H, int W, int C, int fmt,
                                tgsr_stream_t stream);
+/* Data gradient of the same heads into the blocked layout: dh (view hP,hp0; Cin = 32 channels, 16-bit) = transposed conv of
+ * dz [B,3,H,W] fp32 with w [3][Cin][k][k] fp32, zero padding; warp-level tensor cores, K = 3*k*k.  k in {3,5}. */
+int tgsr_head_dgrad16(const float* dz, const float* w, void* dh, int hP, int hp0, int B, int Cin, int H, int W, int ksize, int fmt,
+                      tgsr_stream_t stream);
 /* ReLU backward on channels-last 16-bit tensors: out[p][c] = y[p][c] > 0 ? gy[p][c] : 0 for npix pixels of C channels; gy's
  * pixels are gy_pixel_stride elements apart (a channel slice of a wider tensor: the gradient of a concatenation), y and out
  * are dense.  C % 8 == 0, stride % 8 == 0, 16-byte aligned pointers. */

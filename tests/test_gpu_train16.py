@@ -131,11 +131,32 @@ def test_head_wgrad16(k, B, H, W):
     F.conv2d(h.double(), w.double(), None, 1, k // 2).backward(dz.double())
     hb = T.to_blocked(h.to(DEV)).contiguous()
     dw = torch.full((3, 32, k, k), float('nan'), device=DEV)
-    call('tgsr_head_wgrad16', hb.device, ptr(hb), 4, 0, ptr(dz.to(DEV)), ptr(dw), B, 32, H, W, k, FMT_BF16)
+    dz_d = dz.to(DEV)                                     # raw-pointer API: the tensor must outlive the call
+    call('tgsr_head_wgrad16', hb.device, ptr(hb), 4, 0, ptr(dz_d), ptr(dw), B, 32, H, W, k, FMT_BF16)
     ref = w.grad
     assert torch.isfinite(dw).all()
     assert (dw.cpu() - ref).abs().max() <= 2e-4 * ref.abs().max() + 1e-5
     assert _cos(dw.cpu(), ref) > 0.999999
+
+
+@pytest.mark.parametrize('k,B,H,W', [(3, 2, 64, 64), (5, 2, 64, 64), (5, 3, 21, 40), (3, 1, 9, 33), (5, 1, 128, 128)])
+def test_head_dgrad16(k, B, H, W):
+    """Data gradient of the image heads straight into the blocked bf16 layout (csrc/head_dgrad16.cu) against fp32 autograd on
+    bf16-rounded dz and weights (ragged sizes: zero padding and partial tiles)."""
+    from tgsr_b200 import train16 as T
+    from tgsr_b200._lib import call, ptr, FMT_BF16
+    g = torch.Generator().manual_seed(k * 10 + W)
+    dz = bf(torch.randn(B, 3, H, W, generator=g) * 0.1)
+    w = bf(torch.randn(3, 32, k, k, generator=g) * 0.1)
+    h = torch.zeros(B, 32, H, W, dtype=torch.float64, requires_grad=True)
+    F.conv2d(h, w.double(), None, 1, k // 2).backward(dz.double())
+    dh = torch.full((B, 4, H, W, 8), float('nan'), device=DEV).to(torch.bfloat16)
+    dz_d, w_d = dz.to(DEV), w.to(DEV)                     # raw-pointer API: the tensors must outlive the call
+    call('tgsr_head_dgrad16', dh.device, ptr(dz_d), ptr(w_d), ptr(dh), 4, 0, B, 32, H, W, k, FMT_BF16)
+    got = T.to_nchw(dh).float().cpu()
+    ref = h.grad.float()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max() <= 2 ** -8 * ref.abs().max() + 1e-6
 
 
 def test_head16_backward_uses_blocked_features():

@@ -95,6 +95,7 @@ _SIGS = {
     'tgsr_head_wgrad16': ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p], C.c_int),
     'tgsr_maxpool3s2_nhwc16': ([C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p], C.c_int),
     'tgsr_maxpool3s2_nhwc16_bwd': ([C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p], C.c_int),
+    'tgsr_head_dgrad16': ([C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p], C.c_int),
     'tgsr_relu_bwd_nhwc16': ([C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p], C.c_int),
     'tgsr_upsample2x_blocked': ([C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p], C.c_int),
     'tgsr_sumpool2x2_blocked': ([C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p], C.c_int),

@@ -157,8 +157,8 @@ def attention_project(att, words: Tensor, fmt: int) -> Tensor:
     B, cdf, T = words.shape
     w = att.conv_context.weight
     sfrag = torch.empty(_sfrag_words(B, T), device=words.device, dtype=torch.int32)
-    call('tgsr_attn_project', words.device, ptr(words.contiguous()), ptr(w.detach().contiguous()), ptr(sfrag),
-         B, w.shape[0], cdf, T, fmt)
+    words, wc = words.contiguous(), w.detach().contiguous()                  # raw pointers: keep both alive across the call
+    call('tgsr_attn_project', words.device, ptr(words), ptr(wc), ptr(sfrag), B, w.shape[0], cdf, T, fmt)
     return sfrag
 
 

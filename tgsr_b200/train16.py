@@ -262,7 +262,15 @@ class Head16Fn(torch.autograd.Function):
             dconv = dy if ctx.one == 1.0 else dy * ctx.one
             if srb is not None and ctx.needs_input_grad[2]:
                 dsrb = dy * ctx.a
-        dh = ToBlockedFn.forward(None, train._conv_dgrad(dconv, w.detach(), False)) if ctx.needs_input_grad[0] else None
+        dh = None
+        if ctx.needs_input_grad[0]:
+            if w.shape[1] == 32:                                   # tensor cores, straight into the blocked layout
+                B, P, H, W, _ = hb.shape
+                dh = torch.empty_like(hb)
+                dconv, wc = dconv.contiguous(), w.detach().contiguous()      # raw pointers: keep both alive across the call
+                call('tgsr_head_dgrad16', hb.device, ptr(dconv), ptr(wc), ptr(dh), P, 0, B, P * 8, H, W, w.shape[2], FMT)
+            else:
+                dh = ToBlockedFn.forward(None, train._conv_dgrad(dconv, w.detach(), False))
         dw = None
         if ctx.needs_input_grad[1]:
             if w.shape[1] == 32:
