@@ -207,13 +207,15 @@ def stage_im2f(st, LR: Tensor, fmt: int = 0) -> Blocked:
 
 
 def stage(st, h: Optional[Blocked], LR: Optional[Tensor], words: Tensor, mask, out_planes: Optional[int],
-          fmt: int = 0, sfrag: Optional[Tensor] = None, head=None):
+          fmt: int = 0, sfrag: Optional[Tensor] = None, head=None, head_stream=None):
     """INIT_STAGE_GImgup (LR given) / NEXT_STAGE_G (h given); util.py:763-777 / :807-823.
     `h` must be the first 32-channel view of a 64-channel buffer: c_code is appended in place.
     With `head` (the stage's image head, model.py:55-73) the stage also returns its image, and the conv chain behind the
     attention -- residual blocks, up-block, head -- runs per batch chunk so that it stays in L2 (`batch_chunks`).  The
     attention itself always sees the whole batch: its caption mask is indexed with the reference's row-order quirk
-    (GlobalAttention.py:109-112), which depends on the batch size."""
+    (GlobalAttention.py:109-112), which depends on the batch size.
+    `head_stream`: the image head is enqueued there instead of the current stream -- nothing downstream in G_SR_NET_low reads
+    the image, so the (HBM-bound) head overlaps the next stage; the caller joins the stream where the image is consumed."""
     ngf = st.gf_dim
     if h is None:
         h = stage_im2f(st, LR, fmt)
@@ -233,7 +235,13 @@ def stage(st, h: Optional[Blocked], LR: Optional[Tensor], words: Tensor, mask, o
             x = res_block(x, rb)
         o = up_block(x, st.upsample, out=out.batch(b0, b1))
         if head is not None:
-            image_head(o, head.img, out=img[b0:b1])
+            if head_stream is None:
+                image_head(o, head.img, out=img[b0:b1])
+            else:
+                head_stream.wait_stream(torch.cuda.current_stream(cat.device))
+                with torch.cuda.stream(head_stream):
+                    image_head(o, head.img, out=img[b0:b1])
+                out.buf.record_stream(head_stream); img.record_stream(head_stream)
     return out, att, img
 
 
@@ -242,10 +250,11 @@ def stage_supported(st, H: int, W: int) -> bool:
 
 
 def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, heads, outmiddle: bool, fmt: int = 0,
-                 h0: Optional[Blocked] = None, ca=None):
+                 h0: Optional[Blocked] = None, ca=None, head_stream=None, head_events: Optional[list] = None):
     """G_SR_NET_low.forward (model.py:48-78) on blocked activations.  `h0`: stage_im2f(stages[0], LR) computed ahead;
     `ca`: callable returning ca_net(sent) = (c_code, mu, logvar), for callers that evaluate it off the critical path
-    (c_code is unused by the SR nets, model.py:51-52)."""
+    (c_code is unused by the SR nets, model.py:51-52).  `head_stream` + `head_events`: the image heads run on that stream and
+    one event per image is appended to `head_events`; the caller must wait for event k (or the stream) before reading image k."""
     imgs: List[Tensor] = []
     atts: List[Tensor] = []
     feats: List[Blocked] = []
@@ -257,7 +266,12 @@ def g_sr_net_low(net, LR: Tensor, sent: Tensor, words: Tensor, mask, stages, hea
     n = len(stages)
     for i, (st, hd) in enumerate(zip(stages, heads)):
         planes = 8 if i + 1 < n else 4                     # leave room for the next stage's c_code
-        h, att, img = stage(st, h, LR if (i == 0 and h0 is None) else None, words, mask, planes, fmt, sfrags[i], head=hd)
+        h, att, img = stage(st, h, LR if (i == 0 and h0 is None) else None, words, mask, planes, fmt, sfrags[i], head=hd,
+                            head_stream=head_stream)
+        if head_stream is not None and head_events is not None:
+            ev = torch.cuda.Event()
+            ev.record(head_stream)
+            head_events.append(ev)
         imgs.append(img)
         atts.append(att)
         feats.append(h)
@@ -290,11 +304,14 @@ def netg_high_trunk(net, x: Tensor, x_sub: Optional[Tensor], fmt: int = 0) -> Bl
     return up_block(h, net.upscale2x)
 
 
-def netg_high_finish(net, h: Blocked, SRb, a: float, one: float, tail, feats=None) -> List[Tensor]:
+def netg_high_finish(net, h: Blocked, SRb, a: float, one: float, tail, feats=None, srb_events=None) -> List[Tensor]:
     """Rest of the trunk (model.py:280-298): image heads with the fused `one*y + a*SRb`, residual24/48 bodies and
     upscale4x/8x.  `tail` = [(body, upscale), ...] after the first upscale.  Each level's chain (body, up-block, head) runs
     per batch chunk so that it stays in L2 (`batch_chunks`)."""
     if feats is not None: feats.append(tc.to_nchw(h))
+    cur = torch.cuda.current_stream(h.device)
+    if srb_events:                                              # SRb[k] was produced on another stream (see g_sr_net_low)
+        cur.wait_event(srb_events[0])
     ims = [image_head(h, net.conv_output, SRb[0], a, one)]
     for k, (body, up) in enumerate(tail):
         B, H, W = h.B, h.H, h.W
@@ -305,8 +322,10 @@ def netg_high_finish(net, h: Blocked, SRb, a: float, one: float, tail, feats=Non
         if tuple(srb.shape) != tuple(img.shape):
             raise ValueError('SRb shape %s != image shape %s' % (tuple(srb.shape), tuple(img.shape)))
         srb = srb.contiguous()
-        for b0, b1 in batch_chunks(B, 4 * H * W * Cup * 2):
+        for ci, (b0, b1) in enumerate(batch_chunks(B, 4 * H * W * Cup * 2)):
             o = up_block(body_noskip(h.batch(b0, b1), body), up, out=out.batch(b0, b1))
+            if srb_events and ci == 0:
+                cur.wait_event(srb_events[k + 1])               # as late as possible: only this head reads SRb[k + 1]
             image_head(o, net.conv_output, srb[b0:b1], a, one, out=img[b0:b1])
         h = out
         if feats is not None: feats.append(tc.to_nchw(h))

@@ -12,6 +12,10 @@ from .config import cfg
 from .text_encoder import RNN_ENCODER
 
 
+# TGSR_HEAD_STREAM=1: G_SR_NET_low's image heads on their own stream (measured: no gain, profiles/r2_experiments.md)
+_HEAD_STREAM = int(__import__('os').environ.get('TGSR_HEAD_STREAM', '0'))
+
+
 class SRPipeline:
     def __init__(self, n_words: int, device='cuda', variant: str = 'x8', low: str = 'lr', seed: Optional[int] = None,
                  randomize_bn: bool = False):
@@ -75,8 +79,10 @@ class SRPipeline:
         # critical path, so the other two run on their own streams and join where their results are consumed.
         cur = torch.cuda.current_stream(self.device)
         if self._side is None:
-            self._side = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
-        s_trunk, s_im2f = self._side
+            self._side = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        s_trunk, s_im2f, s_head = self._side
+        if not _HEAD_STREAM:
+            s_head = None
         s_trunk.wait_stream(cur); s_im2f.wait_stream(cur)                    # fork before anything of this step is enqueued
         words_embs, sent_emb = self.text_encoder._forward_tmax(captions, cap_lens, tmax)   # critical chain first
         with torch.cuda.stream(s_im2f):
@@ -103,13 +109,19 @@ class SRPipeline:
             return out
         cur.wait_event(ev_h0)
         h0.buf.record_stream(cur); mask.record_stream(cur)
+        # G_SR_NET_low's own image heads feed nothing inside that net: they run on a fourth stream and overlap the next stage;
+        # NetG_high's heads wait for image k right where they add it (one*y + a*SRb[k])
+        head_events: list = []
         fake_imgL, attention_maps, mu, logvar = fast.g_sr_net_low(gl, LR, sent_emb, words_embs, mask, stages, heads, False,
-                                                                  fmt_for('low'), h0=h0, ca=ca)
+                                                                  fmt_for('low'), h0=h0, ca=ca, head_stream=s_head,
+                                                                  head_events=head_events)
         cur.wait_stream(s_im2f)
         mu.record_stream(cur); logvar.record_stream(cur)
         cur.wait_stream(s_trunk)
         h_high.buf.record_stream(cur)
-        fine_im = fast.netg_high_finish(gh, h_high, fake_imgL, a_val, 1.0, tail)
+        fine_im = fast.netg_high_finish(gh, h_high, fake_imgL, a_val, 1.0, tail, srb_events=head_events or None)
+        if s_head is not None:
+            cur.wait_stream(s_head)                                      # join (a no-op after the last event wait)
         return fine_im, fake_imgL, attention_maps
 
     # ------------------------------------------------------------------ CUDA-graph replay
