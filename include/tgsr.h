@@ -162,6 +162,8 @@ int tgsr_pack_conv3x3(const float* w, const float* scale, const float* shift, vo
  * consumes what its predecessor just wrote in forward order finds the most recently written (still L2-resident) part
  * of its input first, which matters when a layer's tensors exceed the 126 MB L2 (64 channels at 128x128, batch 32). */
 #define TGSR_CONV_REVERSE 1
+#define TGSR_CONV_L2_IN_FIRST 2   /* the inputs (patch and skip tiles) are dead after this call: load them with L2 evict_first */
+#define TGSR_CONV_L2_OUT_LAST 4   /* the output is the next kernel's input: store it with L2 evict_last (plain conv mode) */
 int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpacked, const void* residual, int rP, int rp0,
                     void* y, int yP, int yp0, int B, int Cin, int H, int W, int Cout, int up2x, int act, int fmt,
                     int flags, tgsr_stream_t stream);

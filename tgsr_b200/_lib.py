@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libtgsr_sm100.so')
 ACT_NONE, ACT_GLU, ACT_TANH = 0, 1, 2
 FMT_BF16, FMT_F16 = 0, 1
 CONV_REVERSE = 1
+CONV_L2_IN_FIRST, CONV_L2_OUT_LAST = 2, 4
 
 _lib = None
 _lock = threading.Lock()

@@ -159,6 +159,7 @@ struct TcParams {
   int tiles_x, tiles_y, ntiles;
   int step_x, step_y, step_b;      // gridDim.x decomposed in (tile x, tile y, image) units: the per-CTA tile stride
   int reverse;                     // walk the tiles from the last one backwards (see tgsr_conv3x3_tc flags)
+  int l2_in_first, l2_out_last;    // L2 eviction hints: inputs are dead after this kernel / the output is read next (flags)
   // image-head epilogue (MODE_HEAD*): y = out_scale * act(conv) + addend_scale * addend, fp32 NCHW [B,3,H,W]
   float* out_f32;
   const float* addend;
@@ -302,13 +303,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     asm volatile("griddepcontrol.wait;" ::: "memory");      // weights are not produced by the predecessor; patches are
     TileIter t; t.init(blockIdx.x, p);
     TileIter tr = t;                                         // skip tiles trail the patches by RLAG tiles
+    const uint64_t pol_first = l2_policy_evict_first();
     constexpr int RLAG = 1;
     auto fetch_res = [&](int k) {
       const int rs = k % (RSTAGE > 0 ? RSTAGE : 1), rph = (k / (RSTAGE > 0 ? RSTAGE : 1)) & 1;
       mbar_wait(&rempty[rs], rph ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&rfull[rs], Cfg::RES_BYTES);
-        tma_load_3d(res_s + rs * Cfg::RES_BYTES, &rmap, &rfull[rs], tr.tx * Cfg::TWO * 8, tr.ty * Cfg::TH, tr.b * p.rP + p.rp0);
+        if (p.l2_in_first)
+          tma_load_3d_hint(res_s + rs * Cfg::RES_BYTES, &rmap, &rfull[rs], tr.tx * Cfg::TWO * 8, tr.ty * Cfg::TH, tr.b * p.rP + p.rp0, pol_first);
+        else
+          tma_load_3d(res_s + rs * Cfg::RES_BYTES, &rmap, &rfull[rs], tr.tx * Cfg::TWO * 8, tr.ty * Cfg::TH, tr.b * p.rP + p.rp0);
       }
       __syncwarp();
       tr.next(p);
@@ -320,7 +325,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       mbar_wait(&empty[s], ph ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&full[s], Cfg::PATCH_BYTES);
-        tma_load_3d(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], (x0 - Cfg::R) * 8, y0 - Cfg::R, t.b * p.xP + p.xp0);
+        if (p.l2_in_first)
+          tma_load_3d_hint(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], (x0 - Cfg::R) * 8, y0 - Cfg::R, t.b * p.xP + p.xp0, pol_first);
+        else
+          tma_load_3d(patch_s + s * Cfg::PATCH_BYTES, &tmap, &full[s], (x0 - Cfg::R) * 8, y0 - Cfg::R, t.b * p.xP + p.xp0);
       }
       __syncwarp();
       // The skip tile of tile k is only needed by the epilogue, after the MMAs of tile k: it is requested RLAG patches
@@ -400,6 +408,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const int m = quad * 32 + lane;                  // accumulator row = pixel within the tile
     const int ty = m >> 3, tx = m & 7;
     float adnext[Cfg::MB > 1 ? Cfg::MB / 2 : 1][3];  // image-head addend of the next tile
+    const uint64_t pol_last = l2_policy_evict_last();
     TileIter t; t.init(blockIdx.x, p);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it, t.next(p)) {
@@ -533,7 +542,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
               for (int e = 0; e < 8; ++e) o[e] += res[e];
             }
           }
-          *reinterpret_cast<uint4*>(obase + (size_t)j * plane_elems) = pack8_16<FMT>(o);
+          if (p.l2_out_last) stg128_hint(obase + (size_t)j * plane_elems, pack8_16<FMT>(o), pol_last);
+          else *reinterpret_cast<uint4*>(obase + (size_t)j * plane_elems) = pack8_16<FMT>(o);
         }
       } else {
         // 4-phase upsample: accumulator columns [ph*NPRE, (ph+1)*NPRE) hold output pixel
@@ -833,6 +843,8 @@ extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpack
   p.out = reinterpret_cast<h16*>(y);
   p.has_res = residual != nullptr;
   p.reverse = (flags & TGSR_CONV_REVERSE) != 0;
+  p.l2_in_first = (flags & TGSR_CONV_L2_IN_FIRST) != 0;
+  p.l2_out_last = (flags & TGSR_CONV_L2_OUT_LAST) != 0;
   p.rP = rP; p.rp0 = rp0; p.yP = yP; p.yp0 = yp0; p.xP = xP; p.xp0 = xp0;
   p.B = B; p.H = H; p.W = W;
   p.tiles_x = W / TC_TW; p.tiles_y = H / TC_TH; p.ntiles = B * p.tiles_x * p.tiles_y;

@@ -8,6 +8,8 @@ logvar out are NCHW fp32.
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Tuple
 
 import torch
@@ -27,9 +29,14 @@ def _fold(bn):
 
 # ---------------------------------------------------------------- single layers
 def conv_bn_act(x: Blocked, conv: nn.Conv2d, bn, act: int, residual: Optional[Blocked] = None, up2x: bool = False,
-                out: Optional[Blocked] = None, reverse: bool = False) -> Blocked:
+                out: Optional[Blocked] = None, reverse: bool = False, l2_flags: int = 0) -> Blocked:
     scale, shift = _fold(bn)
-    return tc.conv3x3_tc(x, conv, scale, shift, act, residual=residual, up2x=up2x, out=out, reverse=reverse)
+    return tc.conv3x3_tc(x, conv, scale, shift, act, residual=residual, up2x=up2x, out=out, reverse=reverse, l2_flags=l2_flags)
+
+
+# TGSR_L2_POLICY (experiment, profiles/r2_experiments.md): 1 = inside a ResBlock the intermediate tensor is stored with L2
+# evict_last and the second conv loads its (then dead) inputs with evict_first and stores evict_last; 2 = without the last hint
+_L2P = int(os.environ.get('TGSR_L2_POLICY', '0'))
 
 
 def conv_in(seq, x: Tensor, out: Blocked, x_sub: Optional[Tensor] = None) -> Blocked:
@@ -52,8 +59,10 @@ def res_block(x: Blocked, rb) -> Blocked:
     blk = rb.block
     # Tile order alternates along the chain (see TGSR_CONV_REVERSE): the first conv walks backwards, so the second one,
     # walking forwards, starts where the intermediate tensor and the skip tensor were touched last.
-    y = conv_bn_act(x, blk[0], blk[1], ACT_GLU, reverse=True)
-    return conv_bn_act(y, blk[3], blk[4], ACT_NONE, residual=x)
+    from ._lib import CONV_L2_IN_FIRST, CONV_L2_OUT_LAST
+    y = conv_bn_act(x, blk[0], blk[1], ACT_GLU, reverse=True, l2_flags=CONV_L2_OUT_LAST if _L2P else 0)
+    return conv_bn_act(y, blk[3], blk[4], ACT_NONE, residual=x,
+                       l2_flags=(CONV_L2_IN_FIRST | (CONV_L2_OUT_LAST if _L2P == 1 else 0)) if _L2P else 0)
 
 
 def body_noskip(x: Blocked, seq) -> Blocked:

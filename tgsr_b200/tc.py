@@ -101,7 +101,7 @@ def tc_supported(Cin: int, Cout: int, act: int, up2x: bool, H: int, W: int) -> b
 
 def conv3x3_tc(xb: Blocked, conv: nn.Conv2d, scale: Optional[Tensor], shift: Optional[Tensor], act: int,
                residual: Optional[Blocked] = None, up2x: bool = False, out: Optional[Blocked] = None,
-               reverse: bool = False) -> Blocked:
+               reverse: bool = False, l2_flags: int = 0) -> Blocked:
     Cout, Cin = conv.weight.shape[0], conv.weight.shape[1]
     assert Cin == xb.C, (Cin, xb.C)
     Cf = Cout // 2 if act == ACT_GLU else Cout
@@ -114,5 +114,5 @@ def conv3x3_tc(xb: Blocked, conv: nn.Conv2d, scale: Optional[Tensor], shift: Opt
     if residual is not None:
         assert residual.C == Cf and residual.H == Ho and residual.W == Wo and residual.fmt == xb.fmt
     call('tgsr_conv3x3_tc', xb.device, ptr(xb.buf), xb.P, xb.p0, ptr(wp), ptr(rbuf), rP, rp0,
-         ptr(out.buf), out.P, out.p0, xb.B, Cin, xb.H, xb.W, Cout, int(up2x), act, xb.fmt, int(reverse))
+         ptr(out.buf), out.P, out.p0, xb.B, Cin, xb.H, xb.W, Cout, int(up2x), act, xb.fmt, int(reverse) | l2_flags)
     return out
