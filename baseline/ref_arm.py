@@ -154,3 +154,66 @@ def torch_eager_gpu(ref, ntoken: int, words: int, B: int, iters: int = 10):
             e.record(); e.synchronize()
         out[name] = {'value': B * iters / (s.elapsed_time(e) * 1e-3), 'unit': 'images/s', 'batch': B}
     return out
+
+
+def torch_eager_train_gpu(ref, ntoken: int, words: int, B: int, iters: int = 5):
+    """Informational: BASELINE.json configs[4] (generator training step) composed from the UNMODIFIED reference modules under
+    torch eager + autograd on the GPU: G_SR_NET_low / NetG_highweight in train mode, the reference's own
+    generator_lossor_wordsentOnly (DAMSM words / sentence losses: a Python loop over the batch, miscc/losses.py:499-522) and
+    MSE (:779-784), Adam(2e-4, (0.5, 0.999)).  The image encoder is the reference's CNN_ENCODER (util.py:262-368) on a
+    random-init Inception-v3 (its pretrained download is replaced by the constructor's own weights: no network here)."""
+    import torch
+    import torch.nn.functional as F
+    import torchvision
+    util, cfg = ref['util'], ref['cfg']
+    from miscc import losses as ref_losses                       # the reference's file (baseline/_ref/miscc/losses.py)
+    cfg.CUDA = True
+    enc, gl, gh = build(ref, ntoken, device='cuda')
+    gl.train(); gh.train()
+    orig = util.model_zoo.load_url
+    util.model_zoo.load_url = lambda url, *a, **k: torchvision.models.inception_v3(weights=None, aux_logits=True,
+                                                                                   init_weights=False).state_dict()
+    try:
+        img_enc = util.CNN_ENCODER(cfg.TEXT.EMBEDDING_DIM)
+    finally:
+        util.model_zoo.load_url = orig
+    img_enc = img_enc.cuda().eval()
+    for p in img_enc.parameters():
+        p.requires_grad = False
+    LR, caps, lens = inputs(B, ntoken, words, device='cuda')
+    real = [F.interpolate(LR, scale_factor=2 ** (k + 1), mode='bicubic').clamp(-1, 1) for k in range(3)]
+    labels = torch.arange(B, device='cuda')
+    params = [p for p in list(gl.parameters()) + list(gh.parameters()) if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=2e-4, betas=(0.5, 0.999))
+
+    def step():
+        with torch.no_grad():
+            hidden = enc.init_hidden(B)
+            words_embs, sent_emb = enc(caps, lens, hidden)
+        mask = (caps == 0)[:, :words_embs.size(2)]
+        fake_imgL, _att, _mu, _logvar = gl(LR, sent_emb, words_embs, mask)
+        fine, _a, _one = gh(LR, fake_imgL, LR)
+        errG, _ = ref_losses.generator_lossor_wordsentOnly(img_enc, fine, words_embs, sent_emb, labels, lens, None)
+        mse = ref_losses.MSE(list(fine) + list(fake_imgL), list(real) + list(real))
+        opt.zero_grad(set_to_none=True)
+        (errG + mse).backward()
+        opt.step()
+
+    out = {}
+    for name, ctx in (('fp32_tf32_convs', contextlib.nullcontext), ('bf16_autocast', lambda: torch.autocast('cuda', dtype=torch.bfloat16))):
+        try:
+            for _ in range(2):
+                with ctx():
+                    step()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(iters):
+                with ctx():
+                    step()
+            e.record(); e.synchronize()
+            ms = s.elapsed_time(e) / iters
+            out[name] = {'value': B / (ms * 1e-3), 'unit': 'images/s', 'ms_per_step': ms, 'batch': B}
+        except Exception as ex:                                  # noqa: BLE001  (informational leg: report, do not fail the arm)
+            out[name] = {'error': repr(ex)[:200]}
+    return out

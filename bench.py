@@ -217,6 +217,10 @@ def run_reference(args):
             line['torch_eager_b200'] = ref_arm.torch_eager_gpu(ref, NTOKEN, WORDS, BATCH_PER_GPU)
         except Exception as e:                       # noqa: BLE001  (never let the extra leg break the reference arm)
             line['torch_eager_b200'] = {'error': repr(e)[:200]}
+        try:                                         # the same for configs[4]: the generator training step under eager + autograd
+            line['torch_eager_b200_train'] = ref_arm.torch_eager_train_gpu(ref, NTOKEN, WORDS, BATCH_PER_GPU)
+        except Exception as e:                       # noqa: BLE001
+            line['torch_eager_b200_train'] = {'error': repr(e)[:200]}
     print(json.dumps(line))
 
 
