@@ -56,6 +56,28 @@ def test_conv16_forward_backward(Cin, Cout, B, H, W):
     torch.testing.assert_close(wd.grad.cpu(), wr.grad, rtol=2e-2, atol=2e-2 * wr.grad.abs().max().item())
 
 
+@pytest.mark.parametrize('Cin,B,H,W', [(64, 2, 32, 32), (32, 2, 16, 24), (64, 1, 64, 64)])
+def test_upconv16_matches_explicit_upsample_conv(Cin, B, H, W):
+    """conv3x3(nearest_x2(x)) through the 4-phase sub-pixel kernel (act-free MODE_UP) against fp32 autograd: the forward uses
+    taps pre-summed per output parity (one rounding of the sum instead of one per tap), the backward is the explicit form."""
+    from tgsr_b200 import train16 as T
+    g = torch.Generator().manual_seed(Cin + H)
+    x = bf(torch.randn(B, Cin, H, W, generator=g) * 0.5)
+    w = torch.randn(64, Cin, 3, 3, generator=g) * (1.0 / (3 * Cin ** 0.5))
+    dz = bf(torch.randn(B, 64, 2 * H, 2 * W, generator=g) * 0.1)
+    xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True)
+    zr = F.conv2d(F.interpolate(xr, scale_factor=2, mode='nearest'), wr, None, 1, 1)
+    zr.backward(dz)
+    xd = x.to(DEV).requires_grad_(True); wd = w.to(DEV).requires_grad_(True)
+    z = T.to_nchw(T.UpConv16Fn.apply(T.to_blocked(xd), wd))
+    z.backward(dz.to(DEV))
+    assert (z.detach().cpu() - zr.detach()).abs().max() <= 2 ** -7 * max(1.0, zr.abs().max().item())
+    assert _cos(z.detach().cpu(), zr.detach()) > 0.9999
+    assert _cos(xd.grad.cpu(), xr.grad) > 0.9995
+    assert _cos(wd.grad.cpu(), wr.grad) > 0.9995
+    torch.testing.assert_close(wd.grad.cpu(), wr.grad, rtol=2e-2, atol=2e-2 * wr.grad.abs().max().item())
+
+
 @pytest.mark.parametrize('act,with_res', [(1, False), (0, True), (0, False)])
 def test_bn_act16_forward_backward(act, with_res):
     from tgsr_b200 import train16 as T

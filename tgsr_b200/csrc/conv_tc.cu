@@ -549,8 +549,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         // 4-phase upsample: accumulator columns [ph*NPRE, (ph+1)*NPRE) hold output pixel
         // (2*gy + ph/2, 2*gx + ph%2); GLU halves inside each phase block.  half h -> phases 2h, 2h+1
         // (= output row 2*gy + h, both columns: one 32-byte run per plane).
-        static_assert(!UP || (GLU && NPRE == 64), "upsample path is conv(C -> 64) + GLU -> 32 channels");
-        constexpr int COUT = NPRE / 2;                          // 32
+        static_assert(!UP || NPRE == 64, "upsample path is conv(C -> 64) [+ GLU -> 32 channels]");
         const int Ho = 2 * p.H, Wo = 2 * p.W;
         const size_t plane_elems = (size_t)Ho * Wo * 8;
         mbar_wait(&tfull[acc], aph);
@@ -560,29 +559,52 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const int oy = 2 * gy + half, ox = 2 * gx;
         h16* obase = p.out + ((size_t)b * p.yP + p.yp0) * plane_elems + ((size_t)oy * Wo + ox) * 8;
         const uint32_t t0 = t_base + (half * 2) * NPRE, t1 = t0 + NPRE;
-        // software pipeline over the four output planes: the TMEM loads of plane j+1 are in flight while plane j is
-        // evaluated and stored
-        uint32_t a0[2][8], g0[2][8], a1[2][8], g1[2][8];
-        tmem_ld8(t0, a0[0]); tmem_ld8(t0 + COUT, g0[0]); tmem_ld8(t1, a1[0]); tmem_ld8(t1 + COUT, g1[0]);
+        if constexpr (GLU) {
+          constexpr int COUT = NPRE / 2;                          // 32
+          // software pipeline over the four output planes: the TMEM loads of plane j+1 are in flight while plane j is
+          // evaluated and stored
+          uint32_t a0[2][8], g0[2][8], a1[2][8], g1[2][8];
+          tmem_ld8(t0, a0[0]); tmem_ld8(t0 + COUT, g0[0]); tmem_ld8(t1, a1[0]); tmem_ld8(t1 + COUT, g1[0]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int cur = j & 1, nxt = cur ^ 1;
-          tmem_ld_wait();
-          if (j < 3) {
-            tmem_ld8(t0 + (j + 1) * 8, a0[nxt]); tmem_ld8(t0 + COUT + (j + 1) * 8, g0[nxt]);
-            tmem_ld8(t1 + (j + 1) * 8, a1[nxt]); tmem_ld8(t1 + COUT + (j + 1) * 8, g1[nxt]);
-          } else {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);           // last plane is in registers: stage free
-          }
-          float o0[8], o1[8];
+          for (int j = 0; j < 4; ++j) {
+            const int cur = j & 1, nxt = cur ^ 1;
+            tmem_ld_wait();
+            if (j < 3) {
+              tmem_ld8(t0 + (j + 1) * 8, a0[nxt]); tmem_ld8(t0 + COUT + (j + 1) * 8, g0[nxt]);
+              tmem_ld8(t1 + (j + 1) * 8, a1[nxt]); tmem_ld8(t1 + COUT + (j + 1) * 8, g1[nxt]);
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[acc]);           // last plane is in registers: stage free
+            }
+            float o0[8], o1[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            o0[e] = glu_pair<FMT>(a0[cur][e], g0[cur][e]);
-            o1[e] = glu_pair<FMT>(a1[cur][e], g1[cur][e]);
+            for (int e = 0; e < 8; ++e) {
+              o0[e] = glu_pair<FMT>(a0[cur][e], g0[cur][e]);
+              o1[e] = glu_pair<FMT>(a1[cur][e], g1[cur][e]);
+            }
+            stg256(obase + (size_t)j * plane_elems, pack8_16<FMT>(o0), pack8_16<FMT>(o1));
           }
-          stg256(obase + (size_t)j * plane_elems, pack8_16<FMT>(o0), pack8_16<FMT>(o1));
+        } else {
+          // act-free (training forward: the pre-BatchNorm conv output of an up-block): all NPRE channels of both phases
+          uint32_t a0[2][8], a1[2][8];
+          tmem_ld8(t0, a0[0]); tmem_ld8(t1, a1[0]);
+#pragma unroll
+          for (int j = 0; j < NPRE / 8; ++j) {
+            const int cur = j & 1, nxt = cur ^ 1;
+            tmem_ld_wait();
+            if (j < NPRE / 8 - 1) {
+              tmem_ld8(t0 + (j + 1) * 8, a0[nxt]); tmem_ld8(t1 + (j + 1) * 8, a1[nxt]);
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+            float o0[8], o1[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { o0[e] = __uint_as_float(a0[cur][e]); o1[e] = __uint_as_float(a1[cur][e]); }
+            stg256(obase + (size_t)j * plane_elems, pack8_16<FMT>(o0), pack8_16<FMT>(o1));
+          }
         }
       }
     }
@@ -746,6 +768,8 @@ int init_conv_tc() {
   if ((s = set_tc_attr<32, 32, MODE_CONV, false>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<64, 64, MODE_UP, true>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<32, 64, MODE_UP, true>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<64, 64, MODE_UP, false>()) != TGSR_OK) return s;
+  if ((s = set_tc_attr<32, 64, MODE_UP, false>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<32, 16, MODE_HEAD3, false>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<32, 16, MODE_HEAD5, false>()) != TGSR_OK) return s;
   if ((s = set_tc_attr<32, 16, MODE_HEAD3W, false>()) != TGSR_OK) return s;
@@ -861,6 +885,8 @@ extern "C" int tgsr_conv3x3_tc(const void* x, int xP, int xp0, const void* wpack
   } else {
     if (Cin == 64 && Cout == 64 && glu) return launch_tc<64, 64, MODE_UP, true>(tmap, rmap, p, fmt, st);
     if (Cin == 32 && Cout == 64 && glu) return launch_tc<32, 64, MODE_UP, true>(tmap, rmap, p, fmt, st);
+    if (Cin == 64 && Cout == 64 && !glu && !residual) return launch_tc<64, 64, MODE_UP, false>(tmap, rmap, p, fmt, st);
+    if (Cin == 32 && Cout == 64 && !glu && !residual) return launch_tc<32, 64, MODE_UP, false>(tmap, rmap, p, fmt, st);
   }
   return TGSR_ERR_UNSUPPORTED;
 }

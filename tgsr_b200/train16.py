@@ -214,8 +214,55 @@ def body_noskip(xb: Tensor, seq) -> Tensor:
     return conv_bn_act(conv_bn_act(xb, seq[0], seq[1], ACT_GLU), seq[3], seq[4], ACT_NONE)
 
 
+class UpConv16Fn(torch.autograd.Function):
+    """z = conv3x3(nearest_x2(x), w) (util.py:74-80) without materialising the upsampled tensor in the forward pass: the
+    4-phase sub-pixel kernel of the eval path (conv_tc.cu MODE_UP, act-free instantiation; 16/36 of the MMAs).  Backward is
+    the explicit formulation: the data gradient at the output resolution followed by the 2x2 sum-pool (the adjoint of the
+    upsample), the weight gradient against the re-created upsampled input."""
+
+    @staticmethod
+    def forward(ctx, xb: Tensor, w: Tensor):
+        xb = xb.contiguous()
+        Cout, Cin = w.shape[0], w.shape[1]
+        B, P, H, W, _ = xb.shape
+        ctx.save_for_backward(xb, w)
+        n = _lib.load().tgsr_packed_conv3x3_elems(Cout, Cin, 1)
+        packed = torch.empty(n, device=w.device, dtype=DT)
+        wc = w.detach().contiguous()
+        call('tgsr_pack_conv3x3', w.device, ptr(wc), None, None, ptr(packed), Cout, Cin, 1, ACT_NONE, FMT)
+        z = _blk(B, Cout, 2 * H, 2 * W, xb.device)
+        call('tgsr_conv3x3_tc', xb.device, ptr(xb), P, 0, ptr(packed), None, 0, 0, ptr(z), Cout // 8, 0, B, Cin, H, W, Cout, 1,
+             ACT_NONE, FMT, 0)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz: Tensor):
+        xb, w = ctx.saved_tensors
+        dx = dw = None
+        with torch.no_grad():
+            x_up = Up2x16Fn.forward(None, xb)
+            need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+
+            class _C:                                              # reuse Conv16Fn.backward on the explicit tensors
+                saved_tensors = (x_up, w)
+                needs_input_grad = need
+            dx_up, dw = Conv16Fn.backward(_C, dz)
+            if dx_up is not None:
+                dx = Up2x16Fn.backward(None, dx_up)
+        return dx, dw
+
+
+_UPCONV = _os.environ.get('TGSR_TRAIN_UPCONV', '1') != '0'       # 0: explicit upsample + conv in the forward pass too
+
+
 def up_block(xb: Tensor, seq) -> Tensor:
-    return conv_bn_act(Up2x16Fn.apply(xb), seq[1], seq[2], ACT_GLU)
+    conv, bn = seq[1], seq[2]
+    Cout, Cin = conv.weight.shape[0], conv.weight.shape[1]
+    if _UPCONV and Cout == 64 and Cin in (32, 64) and xb.shape[1] * 8 == Cin and xb.shape[2] % 16 == 0 and xb.shape[3] % 8 == 0:
+        if not bn.training:
+            raise RuntimeError('tgsr_b200: gradients through an eval-mode BatchNorm are not implemented; call .train()')
+        return BnAct16Fn.apply(UpConv16Fn.apply(xb, conv.weight), bn.weight, bn.bias, None, bn, ACT_GLU)
+    return conv_bn_act(Up2x16Fn.apply(xb), conv, bn, ACT_GLU)
 
 
 def conv_in(seq, x: Tensor, x_sub: Optional[Tensor] = None) -> Tensor:
