@@ -118,3 +118,20 @@ def test_pyramid_module_has_no_cpu_path():
         pyramid.get_imgs_blur(torch.zeros(1, 64, 64, 3, dtype=torch.uint8), [16, 32, 64])
     with pytest.raises(RuntimeError, match='CUDA'):
         pyramid.resize(torch.zeros(1, 64, 64, 3, dtype=torch.uint8), 32)
+
+
+def test_host_side_size_helpers_agree_with_the_library():
+    """Pure host functions of the C ABI (no device work): workspace / operand-image sizes the Python side computes itself must
+    equal what the library reports."""
+    from tgsr_b200 import build, fast
+    build.build()
+    lib = _lib.load()
+    for B in (1, 7, 32):
+        for T in (1, 18, 24, 25, 32, 33, 48):
+            assert fast._sfrag_words(B, T) * 4 == lib.tgsr_attn_sfrag_bytes_t(B, T)
+        assert lib.tgsr_attn_sfrag_bytes(B) == lib.tgsr_attn_sfrag_bytes_t(B, 24)
+    # packed conv image = tap blocks + shift block + ones block (conv_tc.cu TcCfg::WBYTES / 2)
+    assert lib.tgsr_packed_conv3x3_elems(128, 64, 0) == 9 * 128 * 64 + 128 * 16 + 128 * 16
+    assert lib.tgsr_packed_conv3x3_elems(64, 64, 1) == 16 * 64 * 64 + 4 * 64 * 16 + 128 * 16
+    assert fast.attention_blocked_supported(32, 48, 1024) and not fast.attention_blocked_supported(32, 49, 1024)
+    assert not fast.attention_blocked_supported(64, 18, 1024) and not fast.attention_blocked_supported(32, 18, 51)
