@@ -53,7 +53,9 @@ head_wgrad16_kernel(const h16* __restrict__ x, int xP, int xp0, const float* __r
                     int B, int H, int W, int tiles_x, int tiles_y, int ntiles) {
   constexpr int R = K / 2, PH = HW_TH + K - 1, PW = HW_TW + K - 1, NPL = HW_CIN / 8, THREADS = K * 2 * 32;
   constexpr int PATCH_B = NPL * PH * PW * 16, DZ_B = 3 * HW_TH * HW_TW * 4, STAGE_B = PATCH_B + DZ_B;
+  constexpr int BFRAG_OFF = 2 * STAGE_B;                         // B fragments of the current tile: [HW_TH][2 chunks][32 lanes] uint2
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint2* bfrag = reinterpret_cast<uint2*>(smem_raw + BFRAG_OFF);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tig = lane & 3;
   const int kx = warp >> 1, cg = warp & 1;                      // filter column, input-channel group of 16
@@ -66,9 +68,6 @@ head_wgrad16_kernel(const h16* __restrict__ x, int xP, int xp0, const float* __r
 
   // ldmatrix row address of this lane inside a patch: matrix j = lane/8: plane 2cg + (j & 1), pixels 8(j >> 1) + lane % 8
   const uint32_t a_off = (uint32_t)((((2 * cg + ((lane >> 3) & 1)) * PH) * PW + kx + ((lane >> 4) << 3) + (lane & 7)) * 16);
-  // B fragment source of this lane: dz channel g % 3 (value for g < 3, rounding residual for g < 6, nothing above)
-  const int zco = g % 3;
-  const bool z_on = g < 6, z_lo = g >= 3;
 
   auto prefetch = [&](int tile, int stage) {
     const int tx = tile % tiles_x, q = tile / tiles_x, ty = q % tiles_y, b = q / tiles_y;
@@ -102,7 +101,26 @@ head_wgrad16_kernel(const h16* __restrict__ x, int xP, int xp0, const float* __r
     }
     __syncthreads();                                            // this tile's bytes are visible to every warp
     const uint32_t a_base = smem0 + stage * STAGE_B + a_off;
-    const float* zs = reinterpret_cast<const float*>(smem_raw + stage * STAGE_B + PATCH_B) + zco * (HW_TH * HW_TW) + 2 * tig;
+    // ---- B fragments of dz, built ONCE per tile for all warps: lane (g, tig) of (row, chunk) holds n = g: channel g % 3
+    //      (the 16-bit value for g < 3, the rounding residual for g < 6, zero above), k = 2tig, 2tig+1 (b0) and 2tig+8, 2tig+9 (b1)
+    {
+      const float* zt = reinterpret_cast<const float*>(smem_raw + stage * STAGE_B + PATCH_B);
+      for (int e = tid; e < HW_TH * 2 * 32; e += THREADS) {
+        const int l = e & 31, ch = (e >> 5) & 1, r = e >> 6, gg = l >> 2, tg = l & 3;
+        uint2 v = make_uint2(0u, 0u);
+        if (gg < 6) {
+          const float* zp = zt + (gg % 3) * (HW_TH * HW_TW) + r * HW_TW + ch * 16 + 2 * tg;
+          float2 f0 = *reinterpret_cast<const float2*>(zp), f1 = *reinterpret_cast<const float2*>(zp + 8);
+          if (gg >= 3) {
+            f0.x -= Fmt16<FMT>::cvtf(f0.x); f0.y -= Fmt16<FMT>::cvtf(f0.y);
+            f1.x -= Fmt16<FMT>::cvtf(f1.x); f1.y -= Fmt16<FMT>::cvtf(f1.y);
+          }
+          v = make_uint2(Fmt16<FMT>::pack2(f0.x, f0.y), Fmt16<FMT>::pack2(f1.x, f1.y));
+        }
+        bfrag[e] = v;
+      }
+    }
+    __syncthreads();
     // ---- walk the patch rows; the B fragments of the last K output rows slide through registers
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
@@ -111,19 +129,10 @@ head_wgrad16_kernel(const h16* __restrict__ x, int xP, int xp0, const float* __r
       for (int i = 0; i < K; ++i) bw[i] = make_uint2(0u, 0u);
 #pragma unroll
       for (int pr = 0; pr < PH; ++pr) {
-        // window: bw[ky] = fragment of output row pr - ky: k = 2tig, 2tig+1 (b0) and 2tig+8, 2tig+9 (b1) of the chunk
+        // window: bw[ky] = fragment of output row pr - ky
 #pragma unroll
         for (int i = K - 1; i > 0; --i) bw[i] = bw[i - 1];
-        bw[0] = make_uint2(0u, 0u);
-        if (pr < HW_TH && z_on) {
-          float2 f0 = *reinterpret_cast<const float2*>(zs + pr * HW_TW + ch * 16);
-          float2 f1 = *reinterpret_cast<const float2*>(zs + pr * HW_TW + ch * 16 + 8);
-          if (z_lo) {
-            f0.x -= Fmt16<FMT>::cvtf(f0.x); f0.y -= Fmt16<FMT>::cvtf(f0.y);
-            f1.x -= Fmt16<FMT>::cvtf(f1.x); f1.y -= Fmt16<FMT>::cvtf(f1.y);
-          }
-          bw[0] = make_uint2(Fmt16<FMT>::pack2(f0.x, f0.y), Fmt16<FMT>::pack2(f1.x, f1.y));
-        }
+        bw[0] = pr < HW_TH ? bfrag[(pr * 2 + ch) * 32 + lane] : make_uint2(0u, 0u);
         uint32_t a[4];
         ldmatrix_x4_trans(a, a_base + (uint32_t)((pr * PW + ch * 16) * 16));
 #pragma unroll
@@ -176,7 +185,7 @@ extern "C" int tgsr_head_wgrad16(const void* x, int xP, int xp0, const float* dz
 #define TGSR_HW_LAUNCH(KK, F)                                                                                          \
   do {                                                                                                                 \
     constexpr int PHh = HW_TH + KK - 1, PWw = HW_TW + KK - 1;                                                          \
-    constexpr size_t sm = 2 * ((size_t)(HW_CIN / 8) * PHh * PWw * 16 + 3 * HW_TH * HW_TW * 4);   /* two stages */                                  \
+    constexpr size_t sm = 2 * ((size_t)(HW_CIN / 8) * PHh * PWw * 16 + 3 * HW_TH * HW_TW * 4) + HW_TH * 2 * 32 * 8;   /* two stages + B fragments */                                  \
     static bool attr_set = false;                                                                                      \
     if (!attr_set) {                                                                                                   \
       TGSR_CUDA(cudaFuncSetAttribute(head_wgrad16_kernel<KK, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
